@@ -1,0 +1,165 @@
+/* tce_b200.h -- C ABI of libtce_b200.so: the B200-native (sm_100a) kernels of TCE's episodic
+ * policy-update path.
+ *
+ * The reference (BruceGeLi/TCE_RL) has no FFI: the seam this library sits behind is the duck-typed
+ * Python method surface of mprl.rl (policy / projection / agent classes created by the string
+ * factories, mprl/rl/policy/__init__.py:19, mprl/rl/projection/__init__.py:40,
+ * mprl/rl/agent/__init__.py:19).  Each entry point below cites the reference call it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to a contiguous row-major array unless a stride is passed;
+ *    float = fp32, double = fp64, indices int64, flags uint8 (torch.bool);
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing,
+ *    never synchronises the host and is CUDA-graph capturable; the only allocation is the tables
+ *    handle (explicit create / destroy);
+ *  - return value: 0 = TCE_OK, negative = tce_status; numerical failures (non positive pivots) are
+ *    reported LAPACK-style in device `info` arrays, never by aborting;
+ *  - "L" is a lower-triangular Cholesky factor stored as a dense [n, n] matrix; only the lower
+ *    triangle is read, gradients are written for the lower triangle (upper = 0);
+ *  - `ldb` arguments are batch strides in elements; 0 broadcasts one matrix over the batch (the
+ *    non-contextual covariance of every shipped TCE config, black_box_policy.py:53-55).
+ */
+#ifndef TCE_B200_H
+#define TCE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  TCE_OK = 0,
+  TCE_ERR_INVALID_ARGUMENT = -1,
+  TCE_ERR_UNSUPPORTED_SHAPE = -2, /* (num_dof, num_basis+1) not in the instantiated kernel list */
+  TCE_ERR_CUDA = -3,              /* a CUDA runtime call failed; see tce_last_cuda_error()        */
+  TCE_ERR_WORKSPACE = -4          /* workspace too small                                          */
+} tce_status;
+
+int tce_version(void);
+const char *tce_strerror(int status);
+const char *tce_last_cuda_error(void);
+
+/* ---- ProDMP configuration and pre-computed tables ------------------------------------------------
+ * Replaces mp_pytorch's ExpDecayPhaseGenerator + ProDMPBasisGenerator(pre_compute_length_factor=5)
+ * + ProDMP construction done by get_mp (mprl/util/util_mp.py:11-46).                              */
+typedef struct {
+  int32_t num_dof;
+  int32_t num_basis;            /* K; parameters per DoF = K + 1 (weights + goal)                 */
+  int32_t num_basis_outside;
+  int32_t pre_compute_length_factor; /* 5 in the reference (util_mp.py:33)                         */
+  int32_t auto_scale_basis;
+  int32_t relative_goal;
+  int32_t relative_goal_scaled; /* ambiguity switch; 0 = g_eff = scale*g + y0    */
+  int32_t reserved;
+  double tau, delay, dt, alpha, alpha_phase, basis_bandwidth_factor, weights_scale, goal_scale;
+} tce_mp_cfg;
+
+typedef struct tce_tables tce_tables_t;
+
+int tce_prodmp_tables_create(const tce_mp_cfg *cfg, void *stream, tce_tables_t **out);
+void tce_prodmp_tables_destroy(tce_tables_t *tables);
+int tce_prodmp_tables_num_pc(const tce_tables_t *tables);
+/* copy the fp64 tables to HOST buffers (any pointer may be NULL): y1,y2,dy1,dy2 [N_pc];
+ * pos_basis, vel_basis [N_pc, K+1]; scale [K+1] (= weights_goal_scale).  Synchronises.           */
+int tce_prodmp_tables_export(const tce_tables_t *tables, double *y1, double *y2, double *dy1,
+                             double *dy2, double *pos_basis, double *vel_basis, double *scale);
+
+/* ---- (1) trajectory synthesis ---------------------------------------------------------------------
+ * ProDMP.get_traj_pos / get_traj_vel as used by TemporalCorrelatedPolicy.sample
+ * (mprl/rl/policy/temporal_correlated_policy.py:76-100).
+ * params [B, D*(K+1)] (already sampled parameters, or the mean), times [B, T], init_time [B],
+ * init_pos / init_vel [B, D] -> traj [B, T, 2*D] (pos | vel).                                     */
+int tce_prodmp_traj_fwd(const tce_tables_t *tables, const float *params, const float *times,
+                        const float *init_time, const float *init_pos, const float *init_vel,
+                        float *traj, int64_t B, int64_t T, void *stream);
+/* backward: grad_traj [B,T,2D] -> grad_params [B,Dp], grad_init_pos [B,D], grad_init_vel [B,D]
+ * (any output may be NULL).  API-permitted, never exercised by the reference (sample runs under
+ * no_grad, temporal_correlated_sampler.py:91,200).                                                */
+int tce_prodmp_traj_bwd(const tce_tables_t *tables, const float *grad_traj, const float *times,
+                        const float *init_time, float *grad_params, float *grad_init_pos,
+                        float *grad_init_vel, int64_t B, int64_t T, void *stream);
+
+/* ---- (2) Gaussian policy over the MP parameters -----------------------------------------------------
+ * out = mean + L eps : MultivariateNormal(loc, scale_tril).rsample (black_box_policy.py:82-84 and
+ * mp_pytorch sample_trajectories).  eps [B, n] is injected when not NULL, otherwise drawn in-kernel
+ * from Philox4x32-10 (seed, offset) with Box-Muller.                                               */
+int tce_mvn_rsample(const float *mean, const float *L, int64_t ldb_L, const float *eps, uint64_t seed,
+                    uint64_t offset, float *out, int64_t B, int n, void *stream);
+/* Batched Cholesky A = L L^T, one CTA per matrix in shared memory, n <= 128
+ * (torch.linalg.cholesky via util_matrix.py:133 / the Frobenius + KL projections).                */
+int tce_chol_fwd(const float *A, float *L, int32_t *info, int64_t B, int n, void *stream);
+/* grad_A = sym(L^-T Phi(L^T grad_L) L^-1)                                           */
+int tce_chol_bwd(const float *L, const float *grad_L, float *grad_A, int64_t B, int n, void *stream);
+/* policy head: covariance vector [B or 1, n + n(n-1)/2] -> L [B, n, n]
+ * diag = softplus(v) + min_std, strictly lower filled row-major (abstract_policy.py:166-187,
+ * util_numerical.py:44-68, util_matrix.py:12-33); ldb_vec = 0 broadcasts one vector.              */
+int tce_policy_head_fwd(const float *vec, int64_t ldb_vec, float min_std, float *L, int64_t B, int n,
+                        void *stream);
+/* grad_vec [Bv, nvec]: Bv = B (ldb_vec != 0) or 1 (sum over the batch, ldb_vec == 0)               */
+int tce_policy_head_bwd(const float *vec, int64_t ldb_vec, const float *grad_L, float *grad_vec,
+                        int64_t B, int n, void *stream);
+/* per-episode Gaussian scalars used by every projection / KL / entropy call
+ * (black_box_policy.py:130-224, projection_utils.gaussian_kl):
+ *   out[b, 0] = maha(mean, mean_o, L_o) = |L_o^-1 (mean - mean_o)|^2
+ *   out[b, 1] = tr(Sigma_o^-1 Sigma)     = |L_o^-1 L|_F^2
+ *   out[b, 2] = logdet Sigma = 2 sum log L_ii ;  out[b, 3] = logdet Sigma_o
+ *   out[b, 4] = entropy(mean, L) = n/2 (1 + ln 2 pi) + sum log L_ii                                */
+int tce_gauss_stats(const float *mean, const float *L, int64_t ldb_L, const float *mean_o,
+                    const float *L_o, int64_t ldb_Lo, double *out, int64_t B, int n, void *stream);
+
+/* ---- (3) TCE segment-wise trajectory likelihood -----------------------------------------------------
+ * TemporalCorrelatedPolicy.log_prob (temporal_correlated_policy.py:104-203) = mp.update_inputs +
+ * get_traj_pos(flat) + get_traj_pos_cov + MultivariateNormal(covariance_matrix).log_prob.
+ *
+ * Stage 1 (gram):  per episode, C_bp = H_bp (L_b L_b^T) H_bp^T  (no regulariser) and the residual
+ *                  r_bp = x_bp - mu_bp, both fp64 into `work`; max_b,p,i C_bp[i,i] is folded into
+ *                  *diag_max (device double, caller zero-initialises) with an atomic max.
+ * (collective)     at >1 GPU the caller all-reduces(MAX) *diag_max here.
+ * Stage 2 (chol):  per segment, C += reg_rel * *diag_max * I, Cholesky, log-prob.  With grad_logp
+ *                  [B,P] != NULL it writes the per-segment adjoints used by stage 3 to `adj` (same
+ *                  size as `work`; may alias it).
+ *                  With logp_old/advantage [B,P] != NULL instead, the surrogate loss of
+ *                  temporal_correlated_agent.py:718-739 is fused: the upstream gradient is
+ *                  -exp(lp - lp_old) * adv * grad_scale and its sum is added to *loss_acc
+ *                  (grad_scale = 1 / (B_global * P) gives loss = -mean(ratio * adv)).
+ * Stage 3 (bwd):   per episode, from `adj`: grad_mean [B, Dp] and grad_L [B, Dp, Dp] (lower triangle).
+ *
+ * smp_traj [B, T, 2D] (only [:, pairs, :D] is read), mean [B, Dp], L [B, Dp, Dp] (batch stride
+ * ldb_L, 0 = shared), times [B, T], init_* as above, pred_pairs [P, 2] int64.                       */
+size_t tce_seglik_work_bytes(const tce_tables_t *tables, int64_t B, int64_t P);
+int tce_seglik_gram(const tce_tables_t *tables, const float *smp_traj, const float *mean, const float *L,
+                    int64_t ldb_L, const float *times, const float *init_time, const float *init_pos,
+                    const float *init_vel, const int64_t *pred_pairs, void *work, double *diag_max,
+                    int64_t B, int64_t T, int64_t P, void *stream);
+int tce_seglik_chol(const tce_tables_t *tables, const void *work, void *adj, const double *diag_max, double reg_rel,
+                    const float *grad_logp, const float *logp_old, const float *advantage,
+                    double grad_scale, double *loss_acc, float *logp, int32_t *info, int64_t B,
+                    int64_t P, void *stream);
+int tce_seglik_bwd(const tce_tables_t *tables, const void *work, const float *L, int64_t ldb_L,
+                   const float *times, const float *init_time, const int64_t *pred_pairs,
+                   float *grad_mean, float *grad_L, int64_t B, int64_t T, int64_t P, void *stream);
+
+/* ---- (4b) GAE and segment advantages ------------------------------------------------------------------
+ * TemporalCorrelatedAgent.get_advantage_return (temporal_correlated_agent.py:118-181).
+ * rewards [B,T], values [B,T+1], dones / time_limit_dones [B,T] uint8 -> adv, ret [B,T].            */
+int tce_gae(const float *rewards, const float *values, const uint8_t *dones, const uint8_t *tl_dones,
+            float gamma, float lam, int use_gae, float *adv, float *ret, int64_t B, int64_t T,
+            void *stream);
+/* get_segment_advantage (temporal_correlated_agent.py:183-321); mode 0 = accumulate (expects
+ * `advantages`), 1 = value_subtraction, 2 = accumulated_rewards (un-normalised part only).
+ * Writes raw segment advantages [B,P] and adds {count, sum, sum of squares} to stats[3] (device
+ * doubles, caller zero-initialises; all-reduced(SUM) by the caller at >1 GPU).                      */
+int tce_segment_advantage_raw(int mode, const float *rewards, const float *values, const float *advantages,
+                              const int64_t *pred_pairs, float gamma, float *seg, double *stats, int64_t B,
+                              int64_t T, int64_t P, void *stream);
+/* adds {count, sum, sum of squares} of x[N] to stats[3] */
+int tce_sum_stats(const float *x, double *stats, int64_t N, void *stream);
+/* (x - mean) / (std_unbiased + 1e-8) with mean/std from stats[3] (temporal_correlated_agent.py:281-284) */
+int tce_normalize_by_stats(float *x, const double *stats, int64_t N, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCE_B200_H */

@@ -1,0 +1,86 @@
+"""ctypes binding of libtce_b200.so (the C ABI declared in include/tce_b200.h).
+
+There is no CPU fallback: importing this module without the built library raises, and every
+wrapper raises ``TceError`` on a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtce_b200.so")
+
+
+class TceError(RuntimeError):
+    pass
+
+
+class MpCfg(C.Structure):
+    """Mirror of ``tce_mp_cfg``."""
+    _fields_ = [("num_dof", C.c_int32), ("num_basis", C.c_int32), ("num_basis_outside", C.c_int32),
+                ("pre_compute_length_factor", C.c_int32), ("auto_scale_basis", C.c_int32),
+                ("relative_goal", C.c_int32), ("relative_goal_scaled", C.c_int32), ("reserved", C.c_int32),
+                ("tau", C.c_double), ("delay", C.c_double), ("dt", C.c_double), ("alpha", C.c_double),
+                ("alpha_phase", C.c_double), ("basis_bandwidth_factor", C.c_double),
+                ("weights_scale", C.c_double), ("goal_scale", C.c_double)]
+
+
+_P, _I64, _I32, _U64, _F, _D = C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_float, C.c_double
+
+# name -> (restype, argtypes); the single source of truth for tests/test_abi.py
+SIGNATURES = {
+    "tce_version": (C.c_int, []),
+    "tce_strerror": (C.c_char_p, [C.c_int]),
+    "tce_last_cuda_error": (C.c_char_p, []),
+    "tce_prodmp_tables_create": (C.c_int, [C.POINTER(MpCfg), _P, C.POINTER(_P)]),
+    "tce_prodmp_tables_destroy": (None, [_P]),
+    "tce_prodmp_tables_num_pc": (C.c_int, [_P]),
+    "tce_prodmp_tables_export": (C.c_int, [_P] * 8),
+    "tce_prodmp_traj_fwd": (C.c_int, [_P] * 7 + [_I64, _I64, _P]),
+    "tce_prodmp_traj_bwd": (C.c_int, [_P] * 7 + [_I64, _I64, _P]),
+    "tce_mvn_rsample": (C.c_int, [_P, _P, _I64, _P, _U64, _U64, _P, _I64, _I32, _P]),
+    "tce_chol_fwd": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
+    "tce_chol_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
+    "tce_policy_head_fwd": (C.c_int, [_P, _I64, _F, _P, _I64, _I32, _P]),
+    "tce_policy_head_bwd": (C.c_int, [_P, _I64, _P, _P, _I64, _I32, _P]),
+    "tce_gauss_stats": (C.c_int, [_P, _P, _I64, _P, _P, _I64, _P, _I64, _I32, _P]),
+    "tce_seglik_work_bytes": (C.c_size_t, [_P, _I64, _I64]),
+    "tce_seglik_gram": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
+    "tce_seglik_chol": (C.c_int, [_P, _P, _P, _P, _D, _P, _P, _P, _D, _P, _P, _P, _I64, _I64, _P]),
+    "tce_seglik_bwd": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
+    "tce_gae": (C.c_int, [_P, _P, _P, _P, _F, _F, _I32, _P, _P, _I64, _I64, _P]),
+    "tce_segment_advantage_raw": (C.c_int, [_I32, _P, _P, _P, _P, _F, _P, _P, _I64, _I64, _I64, _P]),
+    "tce_sum_stats": (C.c_int, [_P, _P, _I64, _P]),
+    "tce_normalize_by_stats": (C.c_int, [_P, _P, _I64, _P]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TceError(f"{LIB_PATH} is missing: run `python -m tce_rl_b200._build` "
+                           "(or __graft_entry__.build()); there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        lib = load()
+        msg = lib.tce_strerror(status).decode()
+        if status == -3:
+            msg += " -- " + lib.tce_last_cuda_error().decode()
+        raise TceError(f"{what}: {msg} (status {status})")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args), name)

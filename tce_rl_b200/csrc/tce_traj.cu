@@ -1,0 +1,257 @@
+// (1) Batched ProDMP trajectory synthesis: params -> pos/vel over T steps.
+// Replaces ProDMP.get_traj_pos / get_traj_vel behind TemporalCorrelatedPolicy.sample
+// (mprl/rl/policy/temporal_correlated_policy.py:76-100); math: SURVEY App. A.5.
+//
+// HBM-bound (algorithmic bytes/episode = 4*[Dp + (1+2D) + T + 2D*T]).  The fp32 basis rows are staged
+// in shared memory once per (persistent) CTA; every thread owns one (episode, time) point, results go
+// through a shared tile so that the global stores are contiguous float4.
+#include "tce_common.cuh"
+
+namespace {
+
+constexpr int TRAJ_THREADS = 256;
+constexpr int MAX_EP_PER_CHUNK = 32;   // chunk of 256 time points spans <= 256/T + 2 episodes
+
+struct EpInit {     // per-episode values at init_time
+  float y1b, y2b, dy1b, dy2b, inv_det;
+  float pb[TCE_MAX_K1], vb[TCE_MAX_K1];
+};
+
+__device__ __forceinline__ const float *tab_row(const TabDev &tb, const float *srow, int staged_rows, int i) {
+  return i < staged_rows ? srow + (size_t)i * tb.row32_stride : tb.row32 + (size_t)i * tb.row32_stride;
+}
+
+template <int K1>
+__global__ void __launch_bounds__(TRAJ_THREADS)
+traj_fwd_kernel(TabDev tb, const float *__restrict__ params, const float *__restrict__ times,
+                const float *__restrict__ init_time, const float *__restrict__ init_pos,
+                const float *__restrict__ init_vel, float *__restrict__ traj, long long B, int T,
+                int staged_rows) {
+  extern __shared__ __align__(16) float smem[];
+  const int D = tb.D, D2 = 2 * D, stride = tb.row32_stride;
+  float *srow = smem;                                            // staged table rows
+  float *tile = srow + (size_t)staged_rows * stride;            // [TRAJ_THREADS][2D] output tile
+  EpInit *eps = reinterpret_cast<EpInit *>(tile + TRAJ_THREADS * D2);
+  __shared__ float s_scale[TCE_MAX_K1];
+
+  for (int i = threadIdx.x; i < staged_rows * stride; i += blockDim.x) srow[i] = tb.row32[i];
+  if (threadIdx.x < K1) s_scale[threadIdx.x] = (float)tb.scale[threadIdx.x];
+  __syncthreads();
+
+  const long long total = B * (long long)T;
+  const float tau = (float)tb.tau;
+  for (long long g0 = (long long)blockIdx.x * TRAJ_THREADS; g0 < total; g0 += (long long)gridDim.x * TRAJ_THREADS) {
+    const long long b_first = g0 / T;
+    long long g_last = g0 + TRAJ_THREADS - 1;
+    if (g_last >= total) g_last = total - 1;
+    const int n_ep = (int)(g_last / T - b_first) + 1;
+    // per-episode initial-condition values
+    for (int e = threadIdx.x; e < n_ep; e += blockDim.x) {
+      int i0; double w;
+      time_to_index(tb, (double)init_time[b_first + e], i0, w);
+      const float wf = (float)w;
+      const float *r0 = tab_row(tb, srow, staged_rows, i0), *r1 = tab_row(tb, srow, staged_rows, i0 + 1);
+      EpInit &E = eps[e];
+      E.y1b = lerp_t(r0[0], r1[0], wf); E.y2b = lerp_t(r0[1], r1[1], wf);
+      E.dy1b = lerp_t(r0[2], r1[2], wf); E.dy2b = lerp_t(r0[3], r1[3], wf);
+      E.inv_det = 1.0f / (E.y1b * E.dy2b - E.y2b * E.dy1b);
+#pragma unroll
+      for (int j = 0; j < K1; ++j) {
+        E.pb[j] = lerp_t(r0[4 + j], r1[4 + j], wf);
+        E.vb[j] = lerp_t(r0[4 + K1 + j], r1[4 + K1 + j], wf);
+      }
+    }
+    __syncthreads();
+    const long long g = g0 + threadIdx.x;
+    if (g < total) {
+      const long long b = g / T;
+      const EpInit &E = eps[(int)(b - b_first)];
+      int i0; double w;
+      time_to_index(tb, (double)times[g], i0, w);
+      const float wf = (float)w;
+      const float *r0 = tab_row(tb, srow, staged_rows, i0), *r1 = tab_row(tb, srow, staged_rows, i0 + 1);
+      const float y1 = lerp_t(r0[0], r1[0], wf), y2 = lerp_t(r0[1], r1[1], wf);
+      const float dy1 = lerp_t(r0[2], r1[2], wf), dy2 = lerp_t(r0[3], r1[3], wf);
+      const float xi1 = (E.dy2b * y1 - E.dy1b * y2) * E.inv_det, xi2 = (E.y1b * y2 - E.y2b * y1) * E.inv_det;
+      const float xi3 = (E.dy2b * dy1 - E.dy1b * dy2) * E.inv_det, xi4 = (E.y1b * dy2 - E.y2b * dy1) * E.inv_det;
+      float hp[K1], hv[K1];
+#pragma unroll
+      for (int j = 0; j < K1; ++j) {
+        const float pj = lerp_t(r0[4 + j], r1[4 + j], wf), vj = lerp_t(r0[4 + K1 + j], r1[4 + K1 + j], wf);
+        hp[j] = (pj - xi1 * E.pb[j] - xi2 * E.vb[j]) * s_scale[j];
+        hv[j] = (vj - xi3 * E.pb[j] - xi4 * E.vb[j]) * s_scale[j];
+      }
+      const float *th = params + b * (long long)(D * K1);
+      float *o = tile + threadIdx.x * D2;
+      for (int d = 0; d < D; ++d) {
+        const float y0 = init_pos[b * D + d], v0 = init_vel[b * D + d] * tau;
+        float p = xi1 * y0 + xi2 * v0, v = xi3 * y0 + xi4 * v0;
+#pragma unroll
+        for (int j = 0; j < K1; ++j) {
+          const float t = __ldg(th + d * K1 + j);
+          p = fmaf(hp[j], t, p);
+          v = fmaf(hv[j], t, v);
+        }
+        if (tb.relative_goal) {
+          const float shift = tb.relative_goal_scaled ? y0 : y0 / s_scale[K1 - 1];
+          p = fmaf(hp[K1 - 1], shift, p);
+          v = fmaf(hv[K1 - 1], shift, v);
+        }
+        o[d] = p;
+        o[D + d] = v / tau;
+      }
+    }
+    __syncthreads();
+    // contiguous store of the tile
+    const long long n_out = ((g_last - g0) + 1) * D2;
+    float *dst = traj + g0 * D2;
+    if ((n_out & 3) == 0 && ((g0 * D2) & 3) == 0) {
+      const float4 *s4 = reinterpret_cast<const float4 *>(tile);
+      float4 *d4 = reinterpret_cast<float4 *>(dst);
+      for (int i = threadIdx.x; i < n_out / 4; i += blockDim.x) d4[i] = s4[i];
+    } else {
+      for (int i = threadIdx.x; i < n_out; i += blockDim.x) dst[i] = tile[i];
+    }
+    __syncthreads();
+  }
+}
+
+// backward: one CTA per episode, thread (d, j) reduces over time.  Low priority path (the reference
+// only ever samples under no_grad), kept simple.
+template <int K1>
+__global__ void traj_bwd_kernel(TabDev tb, const float *__restrict__ grad_traj, const float *__restrict__ times,
+                                const float *__restrict__ init_time, float *__restrict__ grad_params,
+                                float *__restrict__ grad_init_pos, float *__restrict__ grad_init_vel, int T) {
+  const long long b = blockIdx.x;
+  const int D = tb.D, D2 = 2 * D;
+  const float tau = (float)tb.tau;
+  __shared__ float s_pb[TCE_MAX_K1], s_vb[TCE_MAX_K1], s_init[5];
+  if (threadIdx.x == 0) {
+    int i0; double w;
+    time_to_index(tb, (double)init_time[b], i0, w);
+    const float wf = (float)w;
+    const float *r0 = tb.row32 + (size_t)i0 * tb.row32_stride, *r1 = r0 + tb.row32_stride;
+    for (int q = 0; q < 4; ++q) s_init[q] = lerp_t(r0[q], r1[q], wf);
+    s_init[4] = 1.0f / (s_init[0] * s_init[3] - s_init[1] * s_init[2]);
+    for (int j = 0; j < K1; ++j) {
+      s_pb[j] = lerp_t(r0[4 + j], r1[4 + j], wf);
+      s_vb[j] = lerp_t(r0[4 + K1 + j], r1[4 + K1 + j], wf);
+    }
+  }
+  __syncthreads();
+  // threads [0, D*K1): params; [D*K1, D*K1 + D): init_pos; [.., +D): init_vel
+  const int tid = threadIdx.x, nP = D * K1;
+  if (tid >= nP + 2 * D) return;
+  const int kind = tid < nP ? 0 : (tid < nP + D ? 1 : 2);
+  const int d = kind == 0 ? tid / K1 : (tid - nP) % D;
+  const int j = kind == 0 ? tid % K1 : 0;
+  const float y1b = s_init[0], y2b = s_init[1], dy1b = s_init[2], dy2b = s_init[3], idet = s_init[4];
+  const float sc_j = (float)tb.scale[j], sc_g = (float)tb.scale[K1 - 1];
+  float acc = 0.f;
+  for (int t = 0; t < T; ++t) {
+    int i0; double w;
+    time_to_index(tb, (double)times[b * T + t], i0, w);
+    const float wf = (float)w;
+    const float *r0 = tb.row32 + (size_t)i0 * tb.row32_stride, *r1 = r0 + tb.row32_stride;
+    const float y1 = lerp_t(r0[0], r1[0], wf), y2 = lerp_t(r0[1], r1[1], wf);
+    const float dy1 = lerp_t(r0[2], r1[2], wf), dy2 = lerp_t(r0[3], r1[3], wf);
+    const float xi1 = (dy2b * y1 - dy1b * y2) * idet, xi2 = (y1b * y2 - y2b * y1) * idet;
+    const float xi3 = (dy2b * dy1 - dy1b * dy2) * idet, xi4 = (y1b * dy2 - y2b * dy1) * idet;
+    const float gp = grad_traj[(b * T + t) * D2 + d], gv = grad_traj[(b * T + t) * D2 + D + d] / tau;
+    if (kind == 0) {
+      const float hp = (lerp_t(r0[4 + j], r1[4 + j], wf) - xi1 * s_pb[j] - xi2 * s_vb[j]) * sc_j;
+      const float hv = (lerp_t(r0[4 + K1 + j], r1[4 + K1 + j], wf) - xi3 * s_pb[j] - xi4 * s_vb[j]) * sc_j;
+      acc += hp * gp + hv * gv;
+    } else if (kind == 1) {
+      float a = xi1 * gp + xi3 * gv;
+      if (tb.relative_goal) {
+        const int g = K1 - 1;
+        const float hp = (lerp_t(r0[4 + g], r1[4 + g], wf) - xi1 * s_pb[g] - xi2 * s_vb[g]) * sc_g;
+        const float hv = (lerp_t(r0[4 + K1 + g], r1[4 + K1 + g], wf) - xi3 * s_pb[g] - xi4 * s_vb[g]) * sc_g;
+        a += (hp * gp + hv * gv) * (tb.relative_goal_scaled ? 1.0f : 1.0f / sc_g);
+      }
+      acc += a;
+    } else {
+      acc += (xi2 * gp + xi4 * gv) * tau;
+    }
+  }
+  if (kind == 0 && grad_params) grad_params[b * nP + tid] = acc;
+  if (kind == 1 && grad_init_pos) grad_init_pos[b * D + d] = acc;
+  if (kind == 2 && grad_init_vel) grad_init_vel[b * D + d] = acc;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int K1>
+int launch_traj_fwd(const tce_tables *t, const float *params, const float *times, const float *init_time,
+                    const float *init_pos, const float *init_vel, float *traj, int64_t B, int64_t T,
+                    cudaStream_t st) {
+  const int stride = t->row32_stride;
+  const size_t row_bytes = (size_t)stride * sizeof(float);
+  const long long chunks = (B * T + TRAJ_THREADS - 1) / TRAJ_THREADS;
+  long long grid = 2LL * num_sms();
+  if (grid > chunks) grid = chunks;
+  // Staging the rows pays only when a persistent CTA reuses them over several chunks; short-lived
+  // CTAs read the (few, hot) rows through L1 instead.
+  int staged = (int)((96 * 1024) / row_bytes);
+  if (staged > t->num_pc) staged = t->num_pc;
+  if (chunks < 4 * grid) staged = 0;
+  const size_t smem = (size_t)staged * row_bytes + (size_t)TRAJ_THREADS * 2 * t->D * sizeof(float) +
+                      MAX_EP_PER_CHUNK * sizeof(EpInit) + 16;
+  if ((TRAJ_THREADS + T - 1) / T + 2 > MAX_EP_PER_CHUNK) return TCE_ERR_INVALID_ARGUMENT;  // T < 9
+  static bool attr_set = false;
+  if (!attr_set) {
+    TCE_CUDA(cudaFuncSetAttribute(traj_fwd_kernel<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024),
+             "traj smem attr");
+    attr_set = true;
+  }
+  traj_fwd_kernel<K1><<<(unsigned)grid, TRAJ_THREADS, smem, st>>>(tab_dev(t), params, times, init_time, init_pos,
+                                                                  init_vel, traj, B, (int)T, staged);
+  TCE_CHECK_LAUNCH("traj_fwd_kernel");
+  return TCE_OK;
+}
+
+}  // namespace
+
+#define TCE_DISPATCH_K1(K1v, CALL)                   \
+  switch (K1v) {                                     \
+    case 3: { constexpr int K1 = 3; CALL; } break;   \
+    case 4: { constexpr int K1 = 4; CALL; } break;   \
+    case 6: { constexpr int K1 = 6; CALL; } break;   \
+    case 9: { constexpr int K1 = 9; CALL; } break;   \
+    case 11: { constexpr int K1 = 11; CALL; } break; \
+    default: return TCE_ERR_UNSUPPORTED_SHAPE;       \
+  }
+
+extern "C" int tce_prodmp_traj_fwd(const tce_tables_t *t, const float *params, const float *times,
+                                   const float *init_time, const float *init_pos, const float *init_vel,
+                                   float *traj, int64_t B, int64_t T, void *stream) {
+  if (!t || !params || !times || !init_time || !init_pos || !init_vel || !traj || B < 0 || T < 1)
+    return TCE_ERR_INVALID_ARGUMENT;
+  if (B == 0) return TCE_OK;
+  TCE_DISPATCH_K1(t->K1, return launch_traj_fwd<K1>(t, params, times, init_time, init_pos, init_vel, traj, B, T,
+                                                    (cudaStream_t)stream));
+  return TCE_OK;
+}
+
+extern "C" int tce_prodmp_traj_bwd(const tce_tables_t *t, const float *grad_traj, const float *times,
+                                   const float *init_time, float *grad_params, float *grad_init_pos,
+                                   float *grad_init_vel, int64_t B, int64_t T, void *stream) {
+  if (!t || !grad_traj || !times || !init_time || B < 0 || T < 1) return TCE_ERR_INVALID_ARGUMENT;
+  if (B == 0) return TCE_OK;
+  const int threads = ((t->D * t->K1 + 2 * t->D + 31) / 32) * 32;
+  TCE_DISPATCH_K1(t->K1, (traj_bwd_kernel<K1><<<(unsigned)B, threads, 0, (cudaStream_t)stream>>>(
+                             tab_dev(t), grad_traj, times, init_time, grad_params, grad_init_pos, grad_init_vel,
+                             (int)T)));
+  TCE_CHECK_LAUNCH("traj_bwd_kernel");
+  return TCE_OK;
+}

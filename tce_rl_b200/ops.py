@@ -1,0 +1,451 @@
+"""PyTorch custom ops (``torch.ops.tce.*``) over the C ABI of libtce_b200.so.
+
+PyTorch is plumbing here: it owns device memory and streams; every op body is one or more calls
+into the hand-written sm_100a kernels.  There is no CPU or eager fallback: tensors must be CUDA
+fp32 (indices int64, flags bool/uint8) and the library must be built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import MpCfg, TceError
+
+Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------------------
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: Tensor, dtype=torch.float32, name="tensor") -> Tensor:
+    if not t.is_cuda:
+        raise TceError(f"{name} must be a CUDA tensor (tce_rl_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TceError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def _batched_matrix(L: Tensor, name="L") -> Tuple[Tensor, int]:
+    """Return (storage tensor, batch stride in elements); keeps a stride-0 batch expand un-materialised."""
+    if not L.is_cuda or L.dtype != torch.float32:
+        raise TceError(f"{name} must be a CUDA float32 tensor")
+    n = L.shape[-1]
+    if L.dim() == 3 and L.stride(0) == 0 and L.stride(1) == n and L.stride(2) == 1:
+        return L, 0
+    L = L.contiguous()
+    return L, n * n
+
+
+class Tables:
+    """Owner of a ``tce_tables_t`` handle (pre-computed ProDMP basis tables on the current device)."""
+
+    def __init__(self, *, num_dof, tau, dt, num_basis, alpha, alpha_phase, basis_bandwidth_factor,
+                 delay=0.0, num_basis_outside=0, auto_scale_basis=True, weights_scale=1.0, goal_scale=1.0,
+                 relative_goal=False, relative_goal_scaled=False, pre_compute_length_factor=5, **_ignored):
+        self.cfg = MpCfg(num_dof=int(num_dof), num_basis=int(num_basis), num_basis_outside=int(num_basis_outside),
+                         pre_compute_length_factor=int(pre_compute_length_factor),
+                         auto_scale_basis=int(bool(auto_scale_basis)), relative_goal=int(bool(relative_goal)),
+                         relative_goal_scaled=int(bool(relative_goal_scaled)), reserved=0, tau=float(tau),
+                         delay=float(delay), dt=float(dt), alpha=float(alpha), alpha_phase=float(alpha_phase),
+                         basis_bandwidth_factor=float(basis_bandwidth_factor), weights_scale=float(weights_scale),
+                         goal_scale=float(goal_scale))
+        self.num_dof, self.num_basis_g = int(num_dof), int(num_basis) + 1
+        self.dim_params = self.num_dof * self.num_basis_g
+        self.tau, self.delay, self.dt = float(tau), float(delay), float(dt)
+        self.factor = int(pre_compute_length_factor)
+        handle = C.c_void_p()
+        self.device = torch.cuda.current_device()
+        _lib.call("tce_prodmp_tables_create", C.byref(self.cfg), _stream(), C.byref(handle))
+        self.handle = handle.value
+        self.num_pc = _lib.load().tce_prodmp_tables_num_pc(self.handle)
+
+    def export(self):
+        """fp64 tables as CPU tensors (for tests / inspection)."""
+        n, k1 = self.num_pc, self.num_basis_g
+        out = {k: torch.empty(n, dtype=torch.float64) for k in ("y1", "y2", "dy1", "dy2")}
+        out["pos_basis"] = torch.empty(n, k1, dtype=torch.float64)
+        out["vel_basis"] = torch.empty(n, k1, dtype=torch.float64)
+        out["scale"] = torch.empty(k1, dtype=torch.float64)
+        _lib.call("tce_prodmp_tables_export", self.handle,
+                  *[out[k].data_ptr() for k in ("y1", "y2", "dy1", "dy2", "pos_basis", "vel_basis", "scale")])
+        return out
+
+    def max_time(self) -> float:
+        return self.delay + self.factor * self.tau
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().tce_prodmp_tables_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------------------------------
+# (1) trajectory synthesis
+# --------------------------------------------------------------------------------------------------
+@torch.library.custom_op("tce::prodmp_traj", mutates_args=())
+def prodmp_traj(params: Tensor, times: Tensor, init_time: Tensor, init_pos: Tensor, init_vel: Tensor,
+                tables: int, num_dof: int) -> Tensor:
+    params, times = _chk(params, name="params"), _chk(times, name="times")
+    init_time, init_pos, init_vel = _chk(init_time), _chk(init_pos), _chk(init_vel)
+    B, T = times.shape
+    traj = torch.empty(B, T, 2 * num_dof, device=params.device, dtype=torch.float32)
+    _lib.call("tce_prodmp_traj_fwd", tables, _p(params), _p(times), _p(init_time), _p(init_pos), _p(init_vel),
+              _p(traj), B, T, _stream())
+    return traj
+
+
+@prodmp_traj.register_fake
+def _(params, times, init_time, init_pos, init_vel, tables, num_dof):
+    return params.new_empty(times.shape[0], times.shape[1], 2 * num_dof)
+
+
+@torch.library.custom_op("tce::prodmp_traj_bwd", mutates_args=())
+def prodmp_traj_bwd(grad_traj: Tensor, times: Tensor, init_time: Tensor, tables: int, num_dof: int,
+                    dim_params: int) -> Tuple[Tensor, Tensor, Tensor]:
+    grad_traj, times, init_time = _chk(grad_traj), _chk(times), _chk(init_time)
+    B, T = times.shape
+    gp = torch.empty(B, dim_params, device=times.device, dtype=torch.float32)
+    gy = torch.empty(B, num_dof, device=times.device, dtype=torch.float32)
+    gv = torch.empty(B, num_dof, device=times.device, dtype=torch.float32)
+    _lib.call("tce_prodmp_traj_bwd", tables, _p(grad_traj), _p(times), _p(init_time), _p(gp), _p(gy), _p(gv),
+              B, T, _stream())
+    return gp, gy, gv
+
+
+def _traj_setup(ctx, inputs, output):
+    params, times, init_time, init_pos, init_vel, tables, num_dof = inputs
+    ctx.save_for_backward(times, init_time)
+    ctx.tables, ctx.num_dof, ctx.dim_params = tables, num_dof, params.shape[-1]
+
+
+def _traj_backward(ctx, grad):
+    times, init_time = ctx.saved_tensors
+    gp, gy, gv = prodmp_traj_bwd(grad, times, init_time, ctx.tables, ctx.num_dof, ctx.dim_params)
+    return gp, None, None, gy, gv, None, None
+
+
+prodmp_traj.register_autograd(_traj_backward, setup_context=_traj_setup)
+
+
+# --------------------------------------------------------------------------------------------------
+# (2) Gaussian sampling, Cholesky, head, stats
+# --------------------------------------------------------------------------------------------------
+@torch.library.custom_op("tce::mvn_rsample", mutates_args=())
+def mvn_rsample(mean: Tensor, L: Tensor, eps: Optional[Tensor], seed: int, offset: int) -> Tensor:
+    mean = _chk(mean, name="mean")
+    L, ldb = _batched_matrix(L)
+    eps_c = None if eps is None else _chk(eps, name="eps")
+    B, n = mean.shape
+    out = torch.empty_like(mean)
+    _lib.call("tce_mvn_rsample", _p(mean), _p(L), ldb, _p(eps_c), seed, offset, _p(out), B, n, _stream())
+    return out
+
+
+@mvn_rsample.register_fake
+def _(mean, L, eps, seed, offset):
+    return torch.empty_like(mean)
+
+
+@torch.library.custom_op("tce::chol_fwd", mutates_args=())
+def chol_fwd(A: Tensor) -> Tuple[Tensor, Tensor]:
+    A = _chk(A, name="A")
+    B, n = A.shape[0], A.shape[-1]
+    L = torch.empty_like(A)
+    info = torch.empty(B, device=A.device, dtype=torch.int32)
+    _lib.call("tce_chol_fwd", _p(A), _p(L), _p(info), B, n, _stream())
+    return L, info
+
+
+@chol_fwd.register_fake
+def _(A):
+    return torch.empty_like(A), A.new_empty(A.shape[0], dtype=torch.int32)
+
+
+@torch.library.custom_op("tce::chol_bwd", mutates_args=())
+def chol_bwd(L: Tensor, grad_L: Tensor) -> Tensor:
+    L, grad_L = _chk(L), _chk(grad_L)
+    gA = torch.empty_like(L)
+    _lib.call("tce_chol_bwd", _p(L), _p(grad_L), _p(gA), L.shape[0], L.shape[-1], _stream())
+    return gA
+
+
+@chol_bwd.register_fake
+def _(L, grad_L):
+    return torch.empty_like(L)
+
+
+def _chol_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[0])
+
+
+def _chol_backward(ctx, gL, ginfo):
+    (L,) = ctx.saved_tensors
+    return chol_bwd(L, gL)
+
+
+chol_fwd.register_autograd(_chol_backward, setup_context=_chol_setup)
+
+
+def cholesky(A: Tensor) -> Tensor:
+    """Batched Cholesky of [B, n, n] SPD matrices (differentiable)."""
+    return chol_fwd(A)[0]
+
+
+@torch.library.custom_op("tce::policy_head", mutates_args=())
+def policy_head(vec: Tensor, batch: int, dim: int, min_std: float) -> Tensor:
+    """cov vector [nvec] (shared) or [B, nvec] -> L [B, dim, dim]."""
+    vec = _chk(vec, name="cov vector")
+    ldb = 0 if vec.dim() == 1 else vec.shape[-1]
+    L = torch.empty(batch, dim, dim, device=vec.device, dtype=torch.float32)
+    _lib.call("tce_policy_head_fwd", _p(vec), ldb, float(min_std), _p(L), batch, dim, _stream())
+    return L
+
+
+@policy_head.register_fake
+def _(vec, batch, dim, min_std):
+    return vec.new_empty(batch, dim, dim)
+
+
+@torch.library.custom_op("tce::policy_head_bwd", mutates_args=())
+def policy_head_bwd(vec: Tensor, grad_L: Tensor) -> Tensor:
+    vec, grad_L = _chk(vec), _chk(grad_L)
+    ldb = 0 if vec.dim() == 1 else vec.shape[-1]
+    g = torch.empty_like(vec)
+    _lib.call("tce_policy_head_bwd", _p(vec), ldb, _p(grad_L), _p(g), grad_L.shape[0], grad_L.shape[-1], _stream())
+    return g
+
+
+@policy_head_bwd.register_fake
+def _(vec, grad_L):
+    return torch.empty_like(vec)
+
+
+def _head_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0])
+
+
+def _head_backward(ctx, gL):
+    (vec,) = ctx.saved_tensors
+    return policy_head_bwd(vec, gL), None, None, None
+
+
+policy_head.register_autograd(_head_backward, setup_context=_head_setup)
+
+
+@torch.library.custom_op("tce::gauss_stats", mutates_args=())
+def gauss_stats(mean: Tensor, L: Tensor, mean_o: Tensor, L_o: Tensor) -> Tensor:
+    """[B, 5] float64: maha, tr(Sigma_o^-1 Sigma), logdet Sigma, logdet Sigma_o, entropy(mean, L)."""
+    mean, mean_o = _chk(mean), _chk(mean_o)
+    L, ldb = _batched_matrix(L)
+    L_o, ldbo = _batched_matrix(L_o, "L_o")
+    B, n = mean.shape
+    out = torch.empty(B, 5, device=mean.device, dtype=torch.float64)
+    _lib.call("tce_gauss_stats", _p(mean), _p(L), ldb, _p(mean_o), _p(L_o), ldbo, _p(out), B, n, _stream())
+    return out
+
+
+@gauss_stats.register_fake
+def _(mean, L, mean_o, L_o):
+    return mean.new_empty(mean.shape[0], 5, dtype=torch.float64)
+
+
+# --------------------------------------------------------------------------------------------------
+# (3) segment-wise trajectory likelihood
+# --------------------------------------------------------------------------------------------------
+_REG_GROUP = None   # torch.distributed process group over which the regulariser max is reduced
+
+
+def set_regulariser_group(group) -> None:
+    """At >1 GPU, all-reduce(MAX) the batch-global regulariser seed over ``group``."""
+    global _REG_GROUP
+    _REG_GROUP = group
+
+
+def _reduce_diag_max(diag_max: Tensor) -> None:
+    if _REG_GROUP is not None:
+        import torch.distributed as dist
+        dist.all_reduce(diag_max, op=dist.ReduceOp.MAX, group=None if _REG_GROUP is True else _REG_GROUP)
+
+
+def _work(tables: int, B: int, P: int, device) -> Tensor:
+    nbytes = _lib.load().tce_seglik_work_bytes(tables, B, P)
+    return torch.empty(max(nbytes // 8, 1), device=device, dtype=torch.float64)
+
+
+@torch.library.custom_op("tce::seglik_fwd", mutates_args=())
+def seglik_fwd(smp_traj: Tensor, mean: Tensor, L: Tensor, times: Tensor, init_time: Tensor, init_pos: Tensor,
+               init_vel: Tensor, pred_pairs: Tensor, tables: int, reg_rel: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """-> (logp [B,P], work (fp64 gram matrices + residuals), diag_max [1] fp64, info [B,P] int32)."""
+    smp_traj, mean, times = _chk(smp_traj, name="smp_traj"), _chk(mean, name="mean"), _chk(times, name="times")
+    init_time, init_pos, init_vel = _chk(init_time), _chk(init_pos), _chk(init_vel)
+    pairs = _chk(pred_pairs, torch.int64, "pred_pairs")
+    L, ldb = _batched_matrix(L)
+    B, T = times.shape
+    P = pairs.shape[0]
+    dev = mean.device
+    work = _work(tables, B, P, dev)
+    diag_max = torch.zeros(1, device=dev, dtype=torch.float64)
+    logp = torch.empty(B, P, device=dev, dtype=torch.float32)
+    info = torch.empty(B, P, device=dev, dtype=torch.int32)
+    st = _stream()
+    _lib.call("tce_seglik_gram", tables, _p(smp_traj), _p(mean), _p(L), ldb, _p(times), _p(init_time), _p(init_pos),
+              _p(init_vel), _p(pairs), _p(work), _p(diag_max), B, T, P, st)
+    _reduce_diag_max(diag_max)
+    _lib.call("tce_seglik_chol", tables, _p(work), None, _p(diag_max), float(reg_rel), None, None, None, 0.0, None,
+              _p(logp), _p(info), B, P, st)
+    return logp, work, diag_max, info
+
+
+@seglik_fwd.register_fake
+def _(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, tables, reg_rel):
+    B, P = times.shape[0], pred_pairs.shape[0]
+    n = smp_traj.shape[-1]
+    return (mean.new_empty(B, P), mean.new_empty(B * P * (n * (n + 1) // 2 + n), dtype=torch.float64),
+            mean.new_empty(1, dtype=torch.float64), mean.new_empty(B, P, dtype=torch.int32))
+
+
+@torch.library.custom_op("tce::seglik_bwd", mutates_args=())
+def seglik_bwd(grad_logp: Tensor, work: Tensor, diag_max: Tensor, L: Tensor, times: Tensor, init_time: Tensor,
+               pred_pairs: Tensor, tables: int, reg_rel: float, dim_params: int) -> Tuple[Tensor, Tensor]:
+    grad_logp, times, init_time = _chk(grad_logp), _chk(times), _chk(init_time)
+    pairs = _chk(pred_pairs, torch.int64)
+    L, ldb = _batched_matrix(L)
+    B, T = times.shape
+    P = pairs.shape[0]
+    dev = times.device
+    adj = torch.empty_like(work)
+    g_mean = torch.empty(B, dim_params, device=dev, dtype=torch.float32)
+    g_L = torch.empty(B, dim_params, dim_params, device=dev, dtype=torch.float32)
+    st = _stream()
+    _lib.call("tce_seglik_chol", tables, _p(work), _p(adj), _p(diag_max), float(reg_rel), _p(grad_logp), None, None,
+              0.0, None, None, None, B, P, st)
+    _lib.call("tce_seglik_bwd", tables, _p(adj), _p(L), ldb, _p(times), _p(init_time), _p(pairs), _p(g_mean),
+              _p(g_L), B, T, P, st)
+    return g_mean, g_L
+
+
+@seglik_bwd.register_fake
+def _(grad_logp, work, diag_max, L, times, init_time, pred_pairs, tables, reg_rel, dim_params):
+    B = times.shape[0]
+    return times.new_empty(B, dim_params), times.new_empty(B, dim_params, dim_params)
+
+
+def _seglik_setup(ctx, inputs, output):
+    smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, tables, reg_rel = inputs
+    logp, work, diag_max, info = output
+    ctx.save_for_backward(work, diag_max, L, times, init_time, pred_pairs)
+    ctx.tables, ctx.reg_rel, ctx.dim_params = tables, reg_rel, mean.shape[-1]
+    ctx.L_expanded = L.dim() == 3 and L.stride(0) == 0
+    ctx.set_materialize_grads(False)
+
+
+def _seglik_backward(ctx, g_logp, g_work, g_diag, g_info):
+    work, diag_max, L, times, init_time, pred_pairs = ctx.saved_tensors
+    if g_logp is None:
+        return (None,) * 10
+    g_mean, g_L = seglik_bwd(g_logp, work, diag_max, L, times, init_time, pred_pairs, ctx.tables, ctx.reg_rel,
+                             ctx.dim_params)
+    return None, g_mean, g_L, None, None, None, None, None, None, None
+
+
+seglik_fwd.register_autograd(_seglik_backward, setup_context=_seglik_setup)
+
+
+def seg_logprob(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, tables: Tables,
+                reg_rel: float = 1e-4, return_info: bool = False):
+    """Segment-wise log-likelihood [B, P] (differentiable w.r.t. ``mean`` and ``L``)."""
+    logp, _work_, diag_max, info = seglik_fwd(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs,
+                                              tables.handle, reg_rel)
+    return (logp, info, diag_max) if return_info else logp
+
+
+# --------------------------------------------------------------------------------------------------
+# (4b) GAE and segment advantages
+# --------------------------------------------------------------------------------------------------
+@torch.library.custom_op("tce::gae", mutates_args=())
+def gae(rewards: Tensor, values: Tensor, dones: Tensor, time_limit_dones: Tensor, gamma: float, lam: float,
+        use_gae: bool) -> Tuple[Tensor, Tensor]:
+    rewards, values = _chk(rewards, name="rewards"), _chk(values, name="values")
+    dn = _chk(dones.view(torch.uint8) if dones.dtype == torch.bool else dones, torch.uint8, "dones")
+    tl = _chk(time_limit_dones.view(torch.uint8) if time_limit_dones.dtype == torch.bool else time_limit_dones,
+              torch.uint8, "time_limit_dones")
+    B, T = rewards.shape
+    adv, ret = torch.empty_like(rewards), torch.empty_like(rewards)
+    _lib.call("tce_gae", _p(rewards), _p(values), _p(dn), _p(tl), float(gamma), float(lam), int(use_gae), _p(adv),
+              _p(ret), B, T, _stream())
+    return adv, ret
+
+
+@gae.register_fake
+def _(rewards, values, dones, time_limit_dones, gamma, lam, use_gae):
+    return torch.empty_like(rewards), torch.empty_like(rewards)
+
+
+_STATS_GROUP = None
+
+
+def set_stats_group(group) -> None:
+    """At >1 GPU, all-reduce(SUM) {count, sum, sum sq} of the advantage normalisation over ``group``."""
+    global _STATS_GROUP
+    _STATS_GROUP = group
+
+
+def _reduce_stats(stats: Tensor) -> None:
+    if _STATS_GROUP is not None:
+        import torch.distributed as dist
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=None if _STATS_GROUP is True else _STATS_GROUP)
+
+
+@torch.library.custom_op("tce::segment_advantage", mutates_args=())
+def segment_advantage(mode: int, rewards: Tensor, values: Tensor, advantages: Tensor, pred_pairs: Tensor,
+                      gamma: float, normalize: bool) -> Tensor:
+    """mode 0 accumulate / 1 value_subtraction / 2 accumulated rewards (raw); optional global normalisation."""
+    rewards, values, advantages = _chk(rewards), _chk(values), _chk(advantages)
+    pairs = _chk(pred_pairs, torch.int64)
+    B, T = rewards.shape
+    P = pairs.shape[0]
+    seg = torch.empty(B, P, device=rewards.device, dtype=torch.float32)
+    stats = torch.zeros(3, device=rewards.device, dtype=torch.float64)
+    st = _stream()
+    _lib.call("tce_segment_advantage_raw", int(mode), _p(rewards), _p(values), _p(advantages), _p(pairs),
+              float(gamma), _p(seg), _p(stats), B, T, P, st)
+    if normalize:
+        _reduce_stats(stats)
+        _lib.call("tce_normalize_by_stats", _p(seg), _p(stats), B * P, st)
+    return seg
+
+
+@segment_advantage.register_fake
+def _(mode, rewards, values, advantages, pred_pairs, gamma, normalize):
+    return rewards.new_empty(rewards.shape[0], pred_pairs.shape[0])
+
+
+@torch.library.custom_op("tce::normalize", mutates_args=())
+def normalize(x: Tensor) -> Tensor:
+    """(x - mean) / (unbiased std + 1e-8) over all elements (advantage normalisation)."""
+    x = _chk(x).clone()
+    stats = torch.zeros(3, device=x.device, dtype=torch.float64)
+    st = _stream()
+    _lib.call("tce_sum_stats", _p(x), _p(stats), x.numel(), st)
+    _reduce_stats(stats)
+    _lib.call("tce_normalize_by_stats", _p(x), _p(stats), x.numel(), st)
+    return x
+
+
+@normalize.register_fake
+def _(x):
+    return torch.empty_like(x)
