@@ -334,7 +334,8 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
   constexpr int LD = NR + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *Gs = reinterpret_cast<double *>(smem_raw);              // [NT][P] staged adjoints (later: out tile)
-  double *hs = Gs + (size_t)NT * P;                               // [2P][K1]
+  const int gs_doubles = NT * P > (Dp * Dp + 1) / 2 ? NT * P : (Dp * Dp + 1) / 2;   // same rule as bwd_smem()
+  double *hs = Gs + gs_doubles;                                   // [2P][K1]
   double *xi = hs + 2 * P * K1;                                   // [2P][2]
   double *init_row = xi + 4 * P;                                  // [5 + 2 K1]
   float *Ls = reinterpret_cast<float *>(init_row + 5 + 2 * K1 + 1);  // [NR][LD]
@@ -391,7 +392,7 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
   __syncthreads();
 
   // ---- grad_L = 2 * tril(M L)  (fp32 FFMA, 2x2 tiles over the lower triangle), staged in the Gs buffer
-  float *out = reinterpret_cast<float *>(Gs);     // [Dp][Dp] dense; needs NT*P*8 >= Dp*Dp*4 (checked on the host)
+  float *out = reinterpret_cast<float *>(Gs);     // [Dp][Dp] dense (the Gs region is sized for it)
   for (int e = threadIdx.x; e < Dp * Dp; e += blockDim.x) out[e] = 0.f;
   __syncthreads();
   {
@@ -431,9 +432,8 @@ size_t gram_smem(int P) {
 template <int D, int K1>
 size_t bwd_smem(int P) {
   constexpr int Dp = D * K1, N = 2 * D, NT = tri(N), NR = (Dp + 1) & ~1, LD = NR + 1;
-  size_t g = sizeof(double) * (size_t)NT * P;
-  if (g < sizeof(float) * Dp * Dp) g = sizeof(float) * Dp * Dp;
-  g = (g + 7) & ~(size_t)7;
+  const size_t gs_doubles = (size_t)NT * P > (size_t)(Dp * Dp + 1) / 2 ? (size_t)NT * P : (size_t)(Dp * Dp + 1) / 2;
+  const size_t g = sizeof(double) * gs_doubles;
   return g + sizeof(double) * (2 * P * K1 + 4 * P + 5 + 2 * K1 + 1) + sizeof(float) * 2 * NR * LD + 16;
 }
 

@@ -29,9 +29,9 @@ traj_fwd_kernel(TabDev tb, const float *__restrict__ params, const float *__rest
                 int staged_rows) {
   extern __shared__ __align__(16) float smem[];
   const int D = tb.D, D2 = 2 * D, stride = tb.row32_stride;
-  float *srow = smem;                                            // staged table rows
-  float *tile = srow + (size_t)staged_rows * stride;            // [TRAJ_THREADS][2D] output tile
+  float *tile = smem;                                            // [TRAJ_THREADS][2D] output tile (16B aligned)
   EpInit *eps = reinterpret_cast<EpInit *>(tile + TRAJ_THREADS * D2);
+  float *srow = reinterpret_cast<float *>(eps + MAX_EP_PER_CHUNK);   // staged table rows
   __shared__ float s_scale[TCE_MAX_K1];
 
   for (int i = threadIdx.x; i < staged_rows * stride; i += blockDim.x) srow[i] = tb.row32[i];

@@ -119,7 +119,7 @@ def test_segment_logprob_parity(name, B):
     got, info, diag_max = ops.seg_logprob(c(smp), mean_g, L_g, c(times), c(inp["init_time"]), c(inp["init_pos"]),
                                           c(inp["init_vel"]), c(pairs), tabs, return_info=True)
     assert int(info.abs().max()) == 0
-    assert abs(diag_max.item() * 1e-4 - reg) <= 1e-9 * reg
+    assert abs(diag_max.item() * 1e-4 - reg) <= 1e-6 * reg      # Sigma = L L^T is accumulated in fp32
     assert (f64(got) - lp.detach()).abs().max() <= 1e-4
     (got * c(w.float())).sum().backward()
     assert (f64(mean_g.grad) - gm).abs().max() <= 2e-4 * gm.abs().max()
