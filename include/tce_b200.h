@@ -105,9 +105,59 @@ int tce_policy_head_bwd(const float *vec, int64_t ldb_vec, const float *grad_L, 
  *   out[b, 0] = maha(mean, mean_o, L_o) = |L_o^-1 (mean - mean_o)|^2
  *   out[b, 1] = tr(Sigma_o^-1 Sigma)     = |L_o^-1 L|_F^2
  *   out[b, 2] = logdet Sigma = 2 sum log L_ii ;  out[b, 3] = logdet Sigma_o
- *   out[b, 4] = entropy(mean, L) = n/2 (1 + ln 2 pi) + sum log L_ii                                */
+ *   out[b, 4] = entropy(mean, L) = n/2 (1 + ln 2 pi) + sum log L_ii
+ * L == NULL computes the Mahalanobis part only (out[b, 1] = out[b, 2] = 0).                          */
 int tce_gauss_stats(const float *mean, const float *L, int64_t ldb_L, const float *mean_o,
                     const float *L_o, int64_t ldb_Lo, double *out, int64_t B, int n, void *stream);
+/* gradient of the five scalars w.r.t. (mean, L) given grad_out [B,5] (the "other" distribution is data):
+ * grad_mean [B,n] (may be NULL), grad_L [B,n,n] lower (NULL = mean part only).                       */
+int tce_gauss_stats_bwd(const float *mean, const float *L, int64_t ldb_L, const float *mean_o,
+                        const float *L_o, int64_t ldb_Lo, const double *grad_out, float *grad_mean,
+                        float *grad_L, int64_t B, int n, void *stream);
+
+/* ---- (4a) differentiable trust-region projections ------------------------------------------------------
+ * Replace the trust_region_projections layers (BruceGeLi/trust-region-layers@TCE_ICLR24) created by
+ * projection_factory (mprl/rl/projection/__init__.py:19-40) and called at
+ * temporal_correlated_agent.py:530-533; KL covariance part replaces cpp_projection (ITPAL).  n <= 64.
+ *
+ * mean projection (all layers): mean_part [B] fp64 is the layer's mean distance (1/2 maha for KL, maha or
+ * squared Euclidean otherwise); proj = (mean + w mean_o) / (1 + w), w = sqrt(mean_part / eps) - 1 where
+ * mean_part > eps, identity elsewhere.  bwd returns the gradient w.r.t. mean and w.r.t. mean_part.      */
+int tce_proj_mean_fwd(const float *mean, const float *mean_o, const double *mean_part, double eps,
+                      float *proj_mean, int64_t B, int n, void *stream);
+int tce_proj_mean_bwd(const float *mean, const float *mean_o, const double *mean_part, double eps,
+                      const float *grad_out, float *grad_mean, double *grad_mean_part, int64_t B, int n,
+                      void *stream);
+/* entropy projection: L * exp((beta - H(L)) / n) where H(L) < beta (always if equality); beta [B] fp64
+ * (ldb_beta = 0 broadcasts one value); entropy [B] (optional) receives H(L) before the projection.       */
+int tce_proj_entropy_fwd(const float *L, const double *beta, int64_t ldb_beta, int equality, float *out,
+                         double *entropy, int64_t B, int n, void *stream);
+int tce_proj_entropy_bwd(const float *L, const double *beta, int64_t ldb_beta, int equality,
+                         const float *grad_out, float *grad_L, int64_t B, int n, void *stream);
+/* KL covariance projection: min KL(N(.,S)||N(.,S~)) s.t. KL_cov(S||S_old) <= eps_cov, solved exactly on
+ * the generalised eigenvalues (CTA-per-matrix Jacobi + safeguarded Newton); proj_L = chol(S_proj).
+ * `save` (tce_proj_kl_save_doubles(B, n) doubles) carries Q, lambda, eta to the backward (implicit
+ * differentiation of eta*).  info [B]: non positive pivot of the final Cholesky (0 = ok).               */
+size_t tce_proj_kl_save_doubles(int64_t B, int n);
+int tce_proj_kl_cov_fwd(const float *L, const float *L_o, double eps_cov, float *proj_L, double *save,
+                        int32_t *info, int64_t B, int n, void *stream);
+int tce_proj_kl_cov_bwd(const float *L, const float *L_o, const float *proj_L, const float *grad_out,
+                        const double *save, float *grad_L, int64_t B, int n, void *stream);
+/* Frobenius: S_new = (S + eta S_old) / (1 + eta), eta = sqrt(|S_old - S|_F^2 / eps_cov) - 1; save_sc [B,4] */
+int tce_proj_frob_cov_fwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov, float *proj_L,
+                          double *save_sc, int32_t *info, int64_t B, int n, void *stream);
+int tce_proj_frob_cov_bwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov,
+                          const float *proj_L, const float *grad_out, const double *save_sc, float *grad_L,
+                          int64_t B, int n, void *stream);
+/* W2 (commutative): proj = (L + eta L_old) / (1 + eta) on the factors that are passed; save_sc [B,4]      */
+int tce_proj_w2_cov_fwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov, int scale_prec,
+                        float *proj_L, double *save_sc, int64_t B, int n, void *stream);
+int tce_proj_w2_cov_bwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov, int scale_prec,
+                        const float *grad_out, float *grad_L, int64_t B, int n, void *stream);
+/* covariance distances of the Frobenius (kind 0) / W2 (kind 1) layers: val [B] when grad_val == NULL,
+ * otherwise grad_L [B,n,n] = grad_val[b] * d val / d L (used by get_trust_region_loss).                 */
+int tce_cov_distance(int kind, const float *L, const float *L_o, int64_t ldb_Lo, int scale_prec,
+                     const double *grad_val, double *val, float *grad_L, int64_t B, int n, void *stream);
 
 /* ---- (3) TCE segment-wise trajectory likelihood -----------------------------------------------------
  * TemporalCorrelatedPolicy.log_prob (temporal_correlated_policy.py:104-203) = mp.update_inputs +

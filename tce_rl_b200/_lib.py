@@ -45,6 +45,19 @@ SIGNATURES = {
     "tce_policy_head_fwd": (C.c_int, [_P, _I64, _F, _P, _I64, _I32, _P]),
     "tce_policy_head_bwd": (C.c_int, [_P, _I64, _P, _P, _I64, _I32, _P]),
     "tce_gauss_stats": (C.c_int, [_P, _P, _I64, _P, _P, _I64, _P, _I64, _I32, _P]),
+    "tce_gauss_stats_bwd": (C.c_int, [_P, _P, _I64, _P, _P, _I64, _P, _P, _P, _I64, _I32, _P]),
+    "tce_proj_mean_fwd": (C.c_int, [_P, _P, _P, _D, _P, _I64, _I32, _P]),
+    "tce_proj_mean_bwd": (C.c_int, [_P, _P, _P, _D, _P, _P, _P, _I64, _I32, _P]),
+    "tce_proj_entropy_fwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _I64, _I32, _P]),
+    "tce_proj_entropy_bwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _I64, _I32, _P]),
+    "tce_proj_kl_save_doubles": (C.c_size_t, [_I64, _I32]),
+    "tce_proj_kl_cov_fwd": (C.c_int, [_P, _P, _D, _P, _P, _P, _I64, _I32, _P]),
+    "tce_proj_kl_cov_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "tce_proj_frob_cov_fwd": (C.c_int, [_P, _P, _I64, _D, _P, _P, _P, _I64, _I32, _P]),
+    "tce_proj_frob_cov_bwd": (C.c_int, [_P, _P, _I64, _D, _P, _P, _P, _P, _I64, _I32, _P]),
+    "tce_proj_w2_cov_fwd": (C.c_int, [_P, _P, _I64, _D, _I32, _P, _P, _I64, _I32, _P]),
+    "tce_proj_w2_cov_bwd": (C.c_int, [_P, _P, _I64, _D, _I32, _P, _P, _I64, _I32, _P]),
+    "tce_cov_distance": (C.c_int, [_I32, _P, _P, _I64, _I32, _P, _P, _P, _I64, _I32, _P]),
     "tce_seglik_work_bytes": (C.c_size_t, [_P, _I64, _I64]),
     "tce_seglik_gram": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
     "tce_seglik_chol": (C.c_int, [_P, _P, _P, _P, _D, _P, _P, _P, _D, _P, _P, _P, _I64, _I64, _P]),

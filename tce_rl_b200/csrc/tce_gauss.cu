@@ -186,71 +186,6 @@ __global__ void head_bwd_kernel(const float *__restrict__ vec, long long ldb_vec
   }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// per-episode Gaussian scalars (fp64): maha, tr(Sigma_o^-1 Sigma), logdets, entropy
-// ---------------------------------------------------------------------------------------------------
-constexpr int GS_THREADS = 256;
-constexpr int GS_SUB = 4;          // lanes cooperating on one column of W = L_o^-1 L
-
-__global__ void __launch_bounds__(GS_THREADS)
-gauss_stats_kernel(const float *__restrict__ mean, const float *__restrict__ L, long long ldb_L,
-                   const float *__restrict__ mean_o, const float *__restrict__ L_o, long long ldb_Lo,
-                   double *__restrict__ out, int n) {
-  extern __shared__ double sd[];
-  const int LD = n + 1;
-  double *sLo = sd, *sW = sd + n * LD, *sz = sW + n * LD;   // sW starts as L, becomes W column by column
-  __shared__ double s_red[GS_THREADS / 32][3];
-  const long long b = blockIdx.x;
-  const float *Lb = L + b * ldb_L, *Lob = L_o + b * ldb_Lo;
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-    const int r = e / n, c = e % n;
-    sLo[r * LD + c] = c <= r ? (double)Lob[e] : 0.0;
-    sW[r * LD + c] = c <= r ? (double)Lb[e] : 0.0;
-  }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) sz[i] = (double)mean[b * n + i] - (double)mean_o[b * n + i];
-  __syncthreads();
-  double ld = 0.0, ldo = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) { ld += log(sW[i * LD + i]); ldo += log(sLo[i * LD + i]); }
-  // W[:, c] = L_o^-1 L[:, c]; column n is the mean difference.  GS_SUB lanes share one column.
-  const int sub = threadIdx.x % GS_SUB, grp = threadIdx.x / GS_SUB, ngrp = blockDim.x / GS_SUB;
-  const unsigned gmask = ((1u << GS_SUB) - 1u) << ((threadIdx.x & 31) & ~(GS_SUB - 1));   // lanes of my group
-  double fro = 0.0, maha = 0.0;
-  for (int c = grp; c <= n; c += ngrp) {
-    const bool is_mean = (c == n);
-    const int first = is_mean ? 0 : c;
-    double *col = is_mean ? sz : sW + c;
-    const int cs = is_mean ? 1 : LD;
-    double acc2 = 0.0;
-    for (int i = first; i < n; ++i) {
-      double part = 0.0;
-      for (int k = first + sub; k < i; k += GS_SUB) part = fma(sLo[i * LD + k], col[k * cs], part);
-#pragma unroll
-      for (int o = GS_SUB / 2; o > 0; o >>= 1) part += __shfl_xor_sync(gmask, part, o);
-      const double w = (col[i * cs] - part) / sLo[i * LD + i];
-      __syncwarp(gmask);
-      if (sub == 0) col[i * cs] = w;
-      __syncwarp(gmask);
-      acc2 = fma(w, w, acc2);
-    }
-    if (sub == 0) { if (is_mean) maha += acc2; else fro += acc2; }
-  }
-  // block reduction of (fro, ld, ldo); maha lives in a single lane
-  fro = warp_sum(fro); ld = warp_sum(ld); ldo = warp_sum(ldo); maha = warp_sum(maha);
-  __shared__ double s_maha[GS_THREADS / 32];
-  if ((threadIdx.x & 31) == 0) {
-    const int w = threadIdx.x >> 5;
-    s_red[w][0] = fro; s_red[w][1] = ld; s_red[w][2] = ldo; s_maha[w] = maha;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double a = 0, c1 = 0, c2 = 0, m = 0;
-    for (int w = 0; w < GS_THREADS / 32; ++w) { a += s_red[w][0]; c1 += s_red[w][1]; c2 += s_red[w][2]; m += s_maha[w]; }
-    double *o = out + b * 5;
-    o[0] = m; o[1] = a; o[2] = 2.0 * c1; o[3] = 2.0 * c2;
-    o[4] = 0.5 * n * (1.0 + 1.8378770664093453) + c1;
-  }
-}
-
 }  // namespace
 
 extern "C" int tce_mvn_rsample(const float *mean, const float *L, int64_t ldb_L, const float *eps, uint64_t seed,
@@ -304,16 +239,5 @@ extern "C" int tce_policy_head_bwd(const float *vec, int64_t ldb_vec, const floa
   dim3 grid((nvec + 127) / 128, (unsigned)((B + chunk - 1) / chunk));
   head_bwd_kernel<<<grid, 128, 0, st>>>(vec, ldb_vec, grad_L, grad_vec, B, n, chunk);
   TCE_CHECK_LAUNCH("head_bwd_kernel");
-  return TCE_OK;
-}
-
-extern "C" int tce_gauss_stats(const float *mean, const float *L, int64_t ldb_L, const float *mean_o,
-                               const float *L_o, int64_t ldb_Lo, double *out, int64_t B, int n, void *stream) {
-  if (!mean || !L || !mean_o || !L_o || !out || B < 0 || n < 1 || n > 96) return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
-  const size_t smem = (2 * (size_t)n * (n + 1) + n) * sizeof(double);
-  TCE_CUDA(cudaFuncSetAttribute(gauss_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "gs attr");
-  gauss_stats_kernel<<<(unsigned)B, GS_THREADS, smem, (cudaStream_t)stream>>>(mean, L, ldb_L, mean_o, L_o, ldb_Lo, out, n);
-  TCE_CHECK_LAUNCH("gauss_stats_kernel");
   return TCE_OK;
 }

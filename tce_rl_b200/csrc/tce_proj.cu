@@ -1,0 +1,789 @@
+// (4a) Differentiable trust-region projections (KL / Frobenius / W2) and the Gaussian distances they use.
+// Replaces the trust_region_projections layers instantiated at mprl/rl/projection/__init__.py:19-40 and
+// called at mprl/rl/agent/temporal_correlated_agent.py:530-533,561-567 (math: SURVEY App. B / App. F;
+// Otto et al., ICLR 2021), including the C++ cpp_projection (ITPAL) KL covariance projection, which the
+// reference runs on the CPU through numpy.  One CTA per matrix; all matrices live in shared memory in fp64
+// (bounds such as cov_bound = 5e-4 are differences of O(n) quantities -- fp32 cannot resolve them).
+#include <math.h>
+
+#include "tce_smem_la.cuh"
+
+namespace {
+
+constexpr int PJ_THREADS = 512;
+constexpr double LOG_2PI = 1.8378770664093453;
+
+__device__ inline int pad_even(int n) { return (n + 1) & ~1; }
+
+// load the lower triangle of a dense fp32 [n,n] matrix into an fp64 shared buffer (m x LD, zero elsewhere)
+__device__ inline void load_lower_d(Mat M, const float *__restrict__ src, int n, int m) {
+  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+    const int i = e / m, j = e % m;
+    M(i, j) = (i < n && j <= i) ? (double)src[(size_t)i * n + j] : 0.0;
+  }
+  __syncthreads();
+}
+__device__ inline void load_full_d(Mat M, const double *__restrict__ src, int n, int m) {
+  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+    const int i = e / m, j = e % m;
+    M(i, j) = (i < n && j < n) ? src[(size_t)i * n + j] : 0.0;
+  }
+  __syncthreads();
+}
+__device__ inline void store_lower_f(float *__restrict__ dst, Mat M, int n, double scale) {
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e % n;
+    dst[e] = j <= i ? (float)(scale * M(i, j)) : 0.f;
+  }
+}
+__device__ inline double block_sum(double v, double *red) {   // red: >= 32 doubles of shared scratch
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+  __syncthreads();
+  return t;
+}
+
+// grad_A (sym) of a Cholesky factor P with upstream G (lower): Sbar = sym(P^-T Phi(P^T G) P^-1)
+// P in bP, G in bG; result in bM (full symmetric); bG is destroyed.
+__device__ inline void chol_backward(Mat bP, Mat bG, Mat bM, double *inv_diag, int n) {
+  // M = Phi(P^T G)  (lower, halved diagonal, zero above)
+  la_gemm(bM, bP.T(), bG, n, n, n, TRI_UPPER, TRI_LOWER, TRI_FULL, 1.0, 0.0);
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e % n;
+    if (j > i) bM(i, j) = 0.0; else if (i == j) bM(i, j) *= 0.5;
+  }
+  __syncthreads();
+  la_inv_diag(bP, inv_diag, n);
+  la_trsm_lower_t(bP, inv_diag, bM, n, n);            // Y = P^-T M
+  la_trsm_lower_t(bP, inv_diag, bM.T(), n, n);        // X^T = P^-T Y^T  -> bM = X
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e % n;
+    if (j < i) { const double s = 0.5 * (bM(i, j) + bM(j, i)); bG(i, j) = s; }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e % n;
+    if (j < i) { bM(i, j) = bG(i, j); bM(j, i) = bG(i, j); }
+  }
+  __syncthreads();
+}
+
+// =====================================================================================================
+// Gaussian distances: per episode maha / trace / logdets / entropy, and their gradient w.r.t. (mean, L)
+// =====================================================================================================
+// fwd: out[b] = {maha, tr(Sigma_o^-1 Sigma), logdet Sigma, logdet Sigma_o, entropy(L)}
+// bwd: given gout[b][5] -> grad_mean[b] (n), grad_L[b] (n x n lower)
+//   d maha / d mean = 2 Sigma_o^-1 (mean - mean_o) ; d tr / d L = 2 Sigma_o^-1 L ; d logdet / d L_ii = 2 / L_ii ;
+//   d entropy / d L_ii = 1 / L_ii
+__global__ void __launch_bounds__(PJ_THREADS)
+gauss_kl_kernel(const float *__restrict__ mean, const float *__restrict__ L, long long ldb_L,
+                const float *__restrict__ mean_o, const float *__restrict__ L_o, long long ldb_Lo,
+                double *__restrict__ out, const double *__restrict__ gout, float *__restrict__ grad_mean,
+                float *__restrict__ grad_L, int n, int mean_only) {
+  extern __shared__ double sd[];
+  const int m = pad_even(n), LD = m + 1;
+  Mat Lo{sd, LD, 1}, W{sd + m * LD, LD, 1};
+  double *inv_diag = sd + 2 * m * LD, *red = inv_diag + m;
+  const long long b = blockIdx.x;
+  load_lower_d(Lo, L_o + b * ldb_Lo, n, m);
+  // W = [L | diff] : n x (n+1)
+  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+    const int i = e / m, j = e % m;
+    W(i, j) = (i < n && j <= i && !mean_only) ? (double)L[b * ldb_L + (size_t)i * n + j] : 0.0;
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) W(i, m) = (double)mean[b * n + i] - (double)mean_o[b * n + i];
+  __syncthreads();
+  double ld = 0.0, ldo = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { ld += mean_only ? 0.0 : log(W(i, i)); ldo += log(Lo(i, i)); }
+  ld = block_sum(ld, red);
+  ldo = block_sum(ldo, red);
+  la_inv_diag(Lo, inv_diag, n);
+  const bool backward = gout != nullptr;
+  double g_tr = 0.0, g_ld = 0.0, g_ent = 0.0, g_maha = 0.0;
+  if (backward) {
+    g_maha = gout[b * 5 + 0]; g_tr = gout[b * 5 + 1]; g_ld = gout[b * 5 + 2]; g_ent = gout[b * 5 + 4];
+    // dlogdet/dL_ii and dentropy/dL_ii need the ORIGINAL diagonal: stash it before the solves
+    for (int i = threadIdx.x; i < n; i += blockDim.x) red[64 + i] = mean_only ? 1.0 : W(i, i);
+    __syncthreads();
+  }
+  // mean column first (plain column), then the lower-triangular block
+  la_trsm_lower(Lo, inv_diag, Mat{W.p + m, LD, 1}, n, 1, false);
+  if (!mean_only) la_trsm_lower(Lo, inv_diag, W, n, n, true);
+  if (!backward) {
+    double fro = 0.0, maha = 0.0;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) { const double v = W(e / n, e % n); fro = fma(v, v, fro); }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const double v = W(i, m); maha = fma(v, v, maha); }
+    fro = block_sum(fro, red);
+    maha = block_sum(maha, red);
+    if (threadIdx.x == 0) {
+      double *o = out + b * 5;
+      o[0] = maha; o[1] = fro; o[2] = 2.0 * ld; o[3] = 2.0 * ldo; o[4] = 0.5 * n * (1.0 + LOG_2PI) + ld;
+    }
+    return;
+  }
+  // Sigma_o^-1 [L | diff] = L_o^-T W
+  la_trsm_lower_t(Lo, inv_diag, Mat{W.p + m, LD, 1}, n, 1);
+  if (!mean_only) la_trsm_lower_t(Lo, inv_diag, W, n, n);
+  if (grad_mean)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) grad_mean[b * n + i] = (float)(2.0 * g_maha * W(i, m));
+  if (grad_L && !mean_only) {
+    float *gl = grad_L + (size_t)b * n * n;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e % n;
+      double v = 0.0;
+      if (j <= i) v = 2.0 * g_tr * W(i, j);
+      if (i == j) v += (2.0 * g_ld + g_ent) / red[64 + i];
+      gl[e] = (float)v;
+    }
+  }
+}
+
+// =====================================================================================================
+// mean projection (closed form) -- elementwise, one warp per episode
+// =====================================================================================================
+__global__ void proj_mean_fwd_kernel(const float *__restrict__ mean, const float *__restrict__ mean_o,
+                                     const double *__restrict__ mean_part, double eps, float *__restrict__ out,
+                                     long long B, int n) {
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const double mp = mean_part[b];
+  const bool active = mp > eps;
+  const double om = active ? fabs(sqrt(mp / eps) - 1.0) : 0.0;
+  const double a = 1.0 / (1.0 + om + 1e-16);
+  for (int i = lane; i < n; i += 32) {
+    const double x = mean[b * n + i];
+    out[b * n + i] = active ? (float)((x + om * (double)mean_o[b * n + i]) * a) : (float)x;
+  }
+}
+// g [B,n] -> grad_mean [B,n], grad_mean_part [B]
+__global__ void proj_mean_bwd_kernel(const float *__restrict__ mean, const float *__restrict__ mean_o,
+                                     const double *__restrict__ mean_part, double eps, const float *__restrict__ g,
+                                     float *__restrict__ grad_mean, double *__restrict__ grad_part, long long B, int n) {
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const double mp = mean_part[b];
+  const bool active = mp > eps;
+  if (!active) {
+    for (int i = lane; i < n; i += 32) grad_mean[b * n + i] = g[b * n + i];
+    if (lane == 0) grad_part[b] = 0.0;
+    return;
+  }
+  const double om = sqrt(mp / eps) - 1.0;       // > 0 when active
+  const double a = 1.0 / (1.0 + om + 1e-16);
+  double dot = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    const double x = mean[b * n + i], xo = mean_o[b * n + i], gi = g[b * n + i];
+    const double proj = (x + om * xo) * a;
+    dot = fma(gi, a * (xo - proj), dot);
+    grad_mean[b * n + i] = (float)(gi * a);
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) grad_part[b] = dot / (2.0 * sqrt(mp * eps));
+}
+
+// =====================================================================================================
+// entropy projection: L <- L * exp((beta - H(L)) / n) where H(L) < beta (or always, equality variant)
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+proj_entropy_kernel(const float *__restrict__ L, const double *__restrict__ beta, long long ldb_beta, int equality,
+                    const float *__restrict__ gout, float *__restrict__ out, double *__restrict__ ent_out, int n) {
+  __shared__ double red[40];
+  const long long b = blockIdx.x;
+  const float *Lb = L + (size_t)b * n * n;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += log((double)Lb[(size_t)i * n + i]);
+  s = block_sum(s, red);
+  const double H = 0.5 * n * (1.0 + LOG_2PI) + s, bt = beta[b * ldb_beta];
+  const bool active = equality || (H < bt);
+  const double alpha = active ? exp((bt - H) / n) : 1.0;
+  float *ob = out + (size_t)b * n * n;
+  if (!gout) {                                   // forward
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) ob[e] = (e % n <= e / n) ? (float)(alpha * Lb[e]) : 0.f;
+    if (ent_out && threadIdx.x == 0) ent_out[b] = H;
+    return;
+  }
+  // backward: out = alpha(L) L ; d alpha / d L_ii = -alpha / (n L_ii)
+  const float *gb = gout + (size_t)b * n * n;
+  double dot = 0.0;
+  if (active)
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x)
+      if (e % n <= e / n) dot = fma((double)gb[e], (double)Lb[e], dot);
+  dot = block_sum(dot, red);
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e % n;
+    double v = 0.0;
+    if (j <= i) v = alpha * gb[e];
+    if (i == j && active) v -= dot * alpha / (n * (double)Lb[e]);
+    ob[e] = (float)v;
+  }
+}
+
+// =====================================================================================================
+// KL covariance projection (exact dual solve on the generalised eigenvalues)
+// =====================================================================================================
+struct KlScalars { double eta; double active; double kl0; double pad; };
+
+__device__ inline double kl_of_eta(const double *lam, int n, double eta, double *dfd_eta) {
+  // warp-cooperative: every lane of warp 0 calls this
+  double f = 0.0, df = 0.0;
+  for (int i = threadIdx.x & 31; i < n; i += 32) {
+    const double r = (lam[i] + eta) / (1.0 + eta);
+    f += 1.0 / r - 1.0 + log(r);
+    df += ((r - 1.0) / (r * r)) * ((1.0 - lam[i]) / ((1.0 + eta) * (1.0 + eta)));
+  }
+  f = warp_sum(f); df = warp_sum(df);
+  if (dfd_eta) *dfd_eta = 0.5 * df;
+  return 0.5 * f;
+}
+
+__global__ void __launch_bounds__(PJ_THREADS)
+proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_o, double eps_cov,
+                       float *__restrict__ proj_L, double *__restrict__ save_Q, double *__restrict__ save_lam,
+                       double *__restrict__ save_sc, int32_t *__restrict__ info, int n) {
+  extern __shared__ double sd[];
+  const int m = pad_even(n), LD = m + 1, MS = m * LD;
+  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
+  double *inv_diag = sd + 4 * MS, *lam = inv_diag + m, *rot = lam + m, *red = rot + 4 * m;   // red: 80 doubles
+  __shared__ double s_eta, s_active, s_kl0;
+  __shared__ int s_bad;
+  const long long b = blockIdx.x;
+  const float *Lt = L + (size_t)b * n * n, *Lo = L_o + (size_t)b * n * n;
+  if (threadIdx.x == 0) s_bad = 0;
+  load_lower_d(b0, Lt, n, m);
+  load_lower_d(b1, Lo, n, m);
+  la_inv_diag(b0, inv_diag, n);
+  la_trsm_lower(b0, inv_diag, b1, n, n, true);                                   // W = Lt^-1 Lo (lower)
+  la_gemm(b2, b1.T(), b1, n, n, n, TRI_UPPER, TRI_LOWER, TRI_FULL, 1.0, 0.0);     // N = W^T W
+  for (int e = threadIdx.x; e < m * m; e += blockDim.x) b3(e / m, e % m) = (e / m == e % m) ? 1.0 : 0.0;
+  __syncthreads();
+  la_jacobi(b2, b3, lam, n, rot, red);                                            // N = Q diag(lam) Q^T
+  if (threadIdx.x < 32) {
+    const double kl0 = kl_of_eta(lam, n, 0.0, nullptr);
+    double eta = 0.0;
+    const bool active = kl0 > eps_cov;
+    if (active) {
+      double lo = 0.0, hi = 1.0;
+      while (kl_of_eta(lam, n, hi, nullptr) > eps_cov && hi < 1e30) { lo = hi; hi *= 2.0; }
+      eta = 0.5 * (lo + hi);
+      for (int it = 0; it < 200; ++it) {
+        double df;
+        const double f = kl_of_eta(lam, n, eta, &df) - eps_cov;
+        if (f > 0.0) lo = eta; else hi = eta;
+        double nxt = (df != 0.0) ? eta - f / df : 0.5 * (lo + hi);
+        if (!(nxt > lo && nxt < hi)) nxt = 0.5 * (lo + hi);
+        if (fabs(nxt - eta) <= 1e-15 * fmax(1.0, fabs(eta)) || hi - lo <= 1e-15 * fmax(1.0, hi)) { eta = nxt; break; }
+        eta = nxt;
+      }
+    }
+    if (threadIdx.x == 0) { s_eta = eta; s_active = active ? 1.0 : 0.0; s_kl0 = kl0; }
+  }
+  __syncthreads();
+  const double eta = s_eta;
+  const bool active = s_active != 0.0;
+  if (save_sc && threadIdx.x == 0) {
+    save_sc[b * 4 + 0] = eta; save_sc[b * 4 + 1] = s_active; save_sc[b * 4 + 2] = s_kl0; save_sc[b * 4 + 3] = 0.0;
+  }
+  if (save_lam) for (int i = threadIdx.x; i < n; i += blockDim.x) save_lam[b * n + i] = lam[i];
+  if (save_Q) for (int e = threadIdx.x; e < n * n; e += blockDim.x) save_Q[(size_t)b * n * n + e] = b3(e / n, e % n);
+  float *out = proj_L + (size_t)b * n * n;
+  if (!active) {                                                                   // identity
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) out[e] = (e % n <= e / n) ? Lt[e] : 0.f;
+    if (info && threadIdx.x == 0) info[b] = 0;
+    return;
+  }
+  load_lower_d(b0, Lo, n, m);
+  la_gemm(b1, b0, b3, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);          // M = Lo Q
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int j = e % n;
+    b1(e / n, j) *= sqrt((1.0 + eta) / (lam[j] + eta));
+  }
+  __syncthreads();
+  la_gemm(b2, b1, b1.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_LOWER, 1.0, 0.0);      // Sigma_proj (lower)
+  la_chol(b2, n, &s_bad);
+  store_lower_f(out, b2, n, 1.0);
+  if (info && threadIdx.x == 0) info[b] = s_bad;
+}
+
+__global__ void __launch_bounds__(PJ_THREADS)
+proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ L_o, const float *__restrict__ proj_L,
+                       const float *__restrict__ gout, const double *__restrict__ save_Q,
+                       const double *__restrict__ save_lam, const double *__restrict__ save_sc,
+                       float *__restrict__ grad_L, int n) {
+  extern __shared__ double sd[];
+  const int m = pad_even(n), LD = m + 1, MS = m * LD;
+  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
+  double *inv_diag = sd + 4 * MS, *lam = inv_diag + m, *rho = lam + m, *red = rho + m;
+  const long long b = blockIdx.x;
+  const size_t off = (size_t)b * n * n;
+  float *gl = grad_L + off;
+  const double eta = save_sc[b * 4 + 0];
+  if (save_sc[b * 4 + 1] == 0.0) {                                                 // inactive: identity
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) gl[e] = (e % n <= e / n) ? gout[off + e] : 0.f;
+    return;
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { lam[i] = save_lam[b * n + i]; rho[i] = 1.0 / (lam[i] + eta); }
+  load_lower_d(b0, proj_L + off, n, m);
+  load_lower_d(b1, gout + off, n, m);
+  chol_backward(b0, b1, b2, inv_diag, n);                                          // b2 = Sbar (sym)
+  load_lower_d(b0, L_o + off, n, m);
+  la_gemm(b1, b2, b0, n, n, n, TRI_FULL, TRI_LOWER, TRI_FULL, 1.0, 0.0);          // T1 = Sbar Lo
+  la_gemm(b2, b0.T(), b1, n, n, n, TRI_UPPER, TRI_FULL, TRI_FULL, 1.0, 0.0);      // Fbar = Lo^T T1
+  // W = Lt^-1 Lo -> b3
+  load_lower_d(b1, L + off, n, m);
+  load_lower_d(b3, L_o + off, n, m);
+  la_inv_diag(b1, inv_diag, n);
+  la_trsm_lower(b1, inv_diag, b3, n, n, true);
+  load_full_d(b0, save_Q + off, n, m);                                             // Q
+  la_gemm(b1, b2, b0, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);           // Fbar Q
+  la_gemm(b2, b0.T(), b1, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);       // Ft = Q^T Fbar Q
+  // eigenbasis: Nt_ij = -(1+eta) rho_i rho_j Ft_ij ; implicit eta term on the diagonal
+  double eb = 0.0, dfe = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    eb += b2(i, i) * (rho[i] - (1.0 + eta) * rho[i] * rho[i]);
+    dfe += 2.0 * rho[i] - (1.0 + eta) * rho[i] * rho[i] - 1.0 / (1.0 + eta);
+  }
+  eb = block_sum(eb, red);
+  dfe = 0.5 * block_sum(dfe, red);
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e % n;
+    double v = -(1.0 + eta) * rho[i] * rho[j] * b2(i, j);
+    if (i == j) v -= eb * (0.5 * (rho[i] - (1.0 + eta) * rho[i] * rho[i])) / dfe;
+    b2(i, j) = v;
+  }
+  __syncthreads();
+  la_gemm(b1, b0, b2, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);           // Q Nt
+  la_gemm(b2, b1, b0.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);       // Nbar = Q Nt Q^T
+  la_gemm(b0, b3, b2, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 2.0, 0.0);          // Wbar = 2 W Nbar
+  la_gemm(b1, b0, b3.T(), n, n, n, TRI_FULL, TRI_UPPER, TRI_FULL, 1.0, 0.0);      // T2 = Wbar W^T
+  load_lower_d(b0, L + off, n, m);
+  la_inv_diag(b0, inv_diag, n);
+  la_trsm_lower_t(b0, inv_diag, b1, n, n);                                         // Z = Lt^-T T2
+  store_lower_f(gl, b1, n, -1.0);
+}
+
+// =====================================================================================================
+// Frobenius covariance projection
+// =====================================================================================================
+__global__ void __launch_bounds__(PJ_THREADS)
+proj_frob_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_o, long long ldb_Lo, double eps_cov,
+                         float *__restrict__ proj_L, double *__restrict__ save_sc, int32_t *__restrict__ info, int n) {
+  extern __shared__ double sd[];
+  const int m = pad_even(n), LD = m + 1, MS = m * LD;
+  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1};
+  double *red = sd + 3 * MS;
+  __shared__ int s_bad;
+  const long long b = blockIdx.x;
+  const size_t off = (size_t)b * n * n;
+  if (threadIdx.x == 0) s_bad = 0;
+  load_lower_d(b0, L + off, n, m);
+  la_gemm(b1, b0, b0.T(), n, n, n, TRI_LOWER, TRI_UPPER, TRI_FULL, 1.0, 0.0);     // Sigma
+  load_lower_d(b0, L_o + b * ldb_Lo, n, m);
+  la_gemm(b2, b0, b0.T(), n, n, n, TRI_LOWER, TRI_UPPER, TRI_FULL, 1.0, 0.0);     // Sigma_o
+  double cp = 0.0;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) { const double d = b2(e / n, e % n) - b1(e / n, e % n); cp = fma(d, d, cp); }
+  cp = block_sum(cp, red);
+  const bool active = cp > eps_cov;
+  const double eta = active ? fabs(sqrt(cp / eps_cov) - 1.0) : 0.0;
+  if (save_sc && threadIdx.x == 0) { save_sc[b * 4] = eta; save_sc[b * 4 + 1] = active ? 1.0 : 0.0; save_sc[b * 4 + 2] = cp; save_sc[b * 4 + 3] = 0.0; }
+  float *out = proj_L + off;
+  if (!active) {
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) out[e] = (e % n <= e / n) ? L[off + e] : 0.f;
+    if (info && threadIdx.x == 0) info[b] = 0;
+    return;
+  }
+  const double a = 1.0 / (1.0 + eta + 1e-16);
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) b1(e / n, e % n) = (b1(e / n, e % n) + eta * b2(e / n, e % n)) * a;
+  __syncthreads();
+  la_chol(b1, n, &s_bad);
+  store_lower_f(out, b1, n, 1.0);
+  if (info && threadIdx.x == 0) info[b] = s_bad;
+}
+
+__global__ void __launch_bounds__(PJ_THREADS)
+proj_frob_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ L_o, long long ldb_Lo, double eps_cov,
+                         const float *__restrict__ proj_L, const float *__restrict__ gout,
+                         const double *__restrict__ save_sc, float *__restrict__ grad_L, int n) {
+  extern __shared__ double sd[];
+  const int m = pad_even(n), LD = m + 1, MS = m * LD;
+  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
+  double *inv_diag = sd + 4 * MS, *red = inv_diag + m;
+  const long long b = blockIdx.x;
+  const size_t off = (size_t)b * n * n;
+  float *gl = grad_L + off;
+  const double eta = save_sc[b * 4];
+  if (save_sc[b * 4 + 1] == 0.0) {
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) gl[e] = (e % n <= e / n) ? gout[off + e] : 0.f;
+    return;
+  }
+  load_lower_d(b0, proj_L + off, n, m);
+  load_lower_d(b1, gout + off, n, m);
+  chol_backward(b0, b1, b2, inv_diag, n);                                          // b2 = Sbar_new (sym)
+  load_lower_d(b1, L + off, n, m);
+  la_gemm(b3, b1, b1.T(), n, n, n, TRI_LOWER, TRI_UPPER, TRI_FULL, 1.0, 0.0);     // Sigma
+  load_lower_d(b1, L_o + b * ldb_Lo, n, m);
+  la_gemm(b0, b1, b1.T(), n, n, n, TRI_LOWER, TRI_UPPER, TRI_FULL, 1.0, 0.0);     // Sigma_o
+  double dot = 0.0;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e % n;
+    const double d = b0(i, j) - b3(i, j);
+    b0(i, j) = d;                                                                  // Dm = Sigma_o - Sigma
+    dot = fma(b2(i, j), d, dot);
+  }
+  dot = block_sum(dot, red);
+  const double a = 1.0 / (1.0 + eta + 1e-16);
+  const double cp = save_sc[b * 4 + 2];
+  const double eta_bar = a * a * dot, deta_dcp = 1.0 / (2.0 * sqrt(cp * eps_cov));
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e % n;
+    b2(i, j) = a * b2(i, j) - 2.0 * eta_bar * deta_dcp * b0(i, j);                 // Sigma_bar
+  }
+  __syncthreads();
+  load_lower_d(b1, L + off, n, m);
+  la_gemm(b3, b2, b1, n, n, n, TRI_FULL, TRI_LOWER, TRI_LOWER, 2.0, 0.0);          // grad = 2 Sigma_bar L (lower)
+  store_lower_f(gl, b3, n, 1.0);
+}
+
+// =====================================================================================================
+// W2 (commutative) covariance projection on whatever "square roots" are passed (Cholesky factors in TCE)
+// =====================================================================================================
+// cov_part: scale_prec ? tr(I + A Sigma A - 2 A R) : tr(Sigma_o + Sigma - 2 S R), A = S^-1, S = L_o, R = L
+// mode 0: forward (proj + scalars); mode 1: backward
+__global__ void __launch_bounds__(PJ_THREADS)
+proj_w2_cov_kernel(const float *__restrict__ L, const float *__restrict__ L_o, long long ldb_Lo, double eps_cov,
+                   int scale_prec, const float *__restrict__ gout, float *__restrict__ out, double *__restrict__ save_sc,
+                   int n) {
+  extern __shared__ double sd[];
+  const int m = pad_even(n), LD = m + 1, MS = m * LD;
+  Mat R{sd, LD, 1}, S{sd + MS, LD, 1}, A{sd + 2 * MS, LD, 1}, T{sd + 3 * MS, LD, 1}, U{sd + 4 * MS, LD, 1};
+  double *inv_diag = sd + 5 * MS, *red = inv_diag + m;
+  const long long b = blockIdx.x;
+  const size_t off = (size_t)b * n * n;
+  load_lower_d(R, L + off, n, m);
+  load_lower_d(S, L_o + b * ldb_Lo, n, m);
+  double cp;
+  if (scale_prec) {
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) A(e / m, e % m) = (e / m == e % m && e / m < n) ? 1.0 : 0.0;
+    __syncthreads();
+    la_inv_diag(S, inv_diag, n);
+    la_trsm_lower(S, inv_diag, A, n, n, true);                                     // A = S^-1 (lower)
+    la_gemm(T, A, R, n, n, n, TRI_LOWER, TRI_LOWER, TRI_FULL, 1.0, 0.0);           // T = A R (lower)
+    la_gemm(U, A.T(), R, n, n, n, TRI_UPPER, TRI_LOWER, TRI_FULL, 1.0, 0.0);       // U = A^T R
+    double v = 0.0;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e % n;
+      v = fma(T(i, j), U(i, j), v);
+      if (i == j) v += 1.0 - 2.0 * T(i, i);
+    }
+    cp = block_sum(v, red);
+  } else {
+    la_gemm(T, S, R, n, n, n, TRI_LOWER, TRI_LOWER, TRI_FULL, 1.0, 0.0);           // S R
+    double v = 0.0;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e % n;
+      v += S(i, j) * S(i, j) + R(i, j) * R(i, j);
+      if (i == j) v -= 2.0 * T(i, i);
+    }
+    cp = block_sum(v, red);
+  }
+  const bool active = cp > eps_cov;
+  const double eta = active ? fabs(sqrt(cp / eps_cov) - 1.0) : 0.0;
+  const double a = 1.0 / (1.0 + eta + 1e-16);
+  float *ob = out + off;
+  if (!gout) {
+    if (save_sc && threadIdx.x == 0) { save_sc[b * 4] = eta; save_sc[b * 4 + 1] = active ? 1.0 : 0.0; save_sc[b * 4 + 2] = cp; save_sc[b * 4 + 3] = 0.0; }
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e % n;
+      ob[e] = j <= i ? (float)(active ? (R(i, j) + eta * S(i, j)) * a : R(i, j)) : 0.f;
+    }
+    return;
+  }
+  const float *gb = gout + off;
+  if (!active) {
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) ob[e] = (e % n <= e / n) ? gb[e] : 0.f;
+    return;
+  }
+  // eta_bar = <g, a (S - proj)>, proj = (R + eta S) a
+  double dot = 0.0;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e % n;
+    if (j <= i) dot = fma((double)gb[e], a * (S(i, j) - (R(i, j) + eta * S(i, j)) * a), dot);
+  }
+  dot = block_sum(dot, red);
+  const double coef = dot / (2.0 * sqrt(cp * eps_cov));
+  if (scale_prec) {
+    // d cp / d R = A T + A^T U - 2 A^T   (lower part)
+    la_gemm(S, A, T, n, n, n, TRI_LOWER, TRI_LOWER, TRI_LOWER, 1.0, 0.0);          // S <- A T (S no longer needed)
+    la_gemm(S, A.T(), U, n, n, n, TRI_UPPER, TRI_FULL, TRI_LOWER, 1.0, 1.0);       // += A^T U
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e % n;
+      double v = 0.0;
+      if (j <= i) v = a * gb[e] + coef * (S(i, j) - 2.0 * A(j, i));
+      ob[e] = (float)v;
+    }
+  } else {
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e % n;
+      double v = 0.0;
+      if (j <= i) v = a * gb[e] + coef * (2.0 * R(i, j) - 2.0 * S(j, i));
+      ob[e] = (float)v;
+    }
+  }
+}
+
+// gradient of the W2 / Frobenius covariance distances themselves (needed by the trust-region loss):
+// value only (gval == nullptr) or gradient w.r.t. L scaled by gval[b]
+__global__ void __launch_bounds__(PJ_THREADS)
+cov_distance_kernel(int kind /*0 frob, 1 w2*/, const float *__restrict__ L, const float *__restrict__ L_o,
+                    long long ldb_Lo, int scale_prec, const double *__restrict__ gval, double *__restrict__ val,
+                    float *__restrict__ grad_L, int n) {
+  extern __shared__ double sd[];
+  const int m = pad_even(n), LD = m + 1, MS = m * LD;
+  Mat R{sd, LD, 1}, S{sd + MS, LD, 1}, A{sd + 2 * MS, LD, 1}, T{sd + 3 * MS, LD, 1}, U{sd + 4 * MS, LD, 1};
+  double *inv_diag = sd + 5 * MS, *red = inv_diag + m;
+  const long long b = blockIdx.x;
+  const size_t off = (size_t)b * n * n;
+  load_lower_d(R, L + off, n, m);
+  load_lower_d(S, L_o + b * ldb_Lo, n, m);
+  double cp = 0.0;
+  if (kind == 0) {
+    la_gemm(T, R, R.T(), n, n, n, TRI_LOWER, TRI_UPPER, TRI_FULL, 1.0, 0.0);      // Sigma
+    la_gemm(U, S, S.T(), n, n, n, TRI_LOWER, TRI_UPPER, TRI_FULL, 1.0, 0.0);      // Sigma_o
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e % n;
+      const double d = U(i, j) - T(i, j);
+      U(i, j) = d;
+      cp = fma(d, d, cp);
+    }
+    cp = block_sum(cp, red);
+    if (gval) {                                                                    // d/dL = -4 (Sigma_o - Sigma) L
+      la_gemm(T, U, R, n, n, n, TRI_FULL, TRI_LOWER, TRI_LOWER, -4.0 * gval[b], 0.0);
+      store_lower_f(grad_L + off, T, n, 1.0);
+    }
+  } else if (scale_prec) {
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) A(e / m, e % m) = (e / m == e % m && e / m < n) ? 1.0 : 0.0;
+    __syncthreads();
+    la_inv_diag(S, inv_diag, n);
+    la_trsm_lower(S, inv_diag, A, n, n, true);
+    la_gemm(T, A, R, n, n, n, TRI_LOWER, TRI_LOWER, TRI_FULL, 1.0, 0.0);
+    la_gemm(U, A.T(), R, n, n, n, TRI_UPPER, TRI_LOWER, TRI_FULL, 1.0, 0.0);
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e % n;
+      cp = fma(T(i, j), U(i, j), cp);
+      if (i == j) cp += 1.0 - 2.0 * T(i, i);
+    }
+    cp = block_sum(cp, red);
+    if (gval) {
+      la_gemm(S, A, T, n, n, n, TRI_LOWER, TRI_LOWER, TRI_LOWER, 1.0, 0.0);
+      la_gemm(S, A.T(), U, n, n, n, TRI_UPPER, TRI_FULL, TRI_LOWER, 1.0, 1.0);
+      const double g = gval[b];
+      for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int i = e / n, j = e % n;
+        grad_L[off + e] = j <= i ? (float)(g * (S(i, j) - 2.0 * A(j, i))) : 0.f;
+      }
+    }
+  } else {
+    la_gemm(T, S, R, n, n, n, TRI_LOWER, TRI_LOWER, TRI_FULL, 1.0, 0.0);
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e % n;
+      cp += S(i, j) * S(i, j) + R(i, j) * R(i, j);
+      if (i == j) cp -= 2.0 * T(i, i);
+    }
+    cp = block_sum(cp, red);
+    if (gval) {
+      const double g = gval[b];
+      for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int i = e / n, j = e % n;
+        grad_L[off + e] = j <= i ? (float)(g * (2.0 * R(i, j) - 2.0 * S(j, i))) : 0.f;
+      }
+    }
+  }
+  if (val && threadIdx.x == 0) val[b] = cp;
+}
+
+size_t pj_smem(int n, int nbuf) {
+  const int m = (n + 1) & ~1;
+  return sizeof(double) * ((size_t)nbuf * m * (m + 1) + 8 * m + 160);
+}
+
+template <typename K>
+int set_smem(K kernel, size_t smem) {
+  if (smem > 220 * 1024) return TCE_ERR_UNSUPPORTED_SHAPE;
+  TCE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "proj smem attr");
+  return TCE_OK;
+}
+
+}  // namespace
+
+#define PJ_CHECK_N(n) if ((n) < 1 || (n) > 64) return TCE_ERR_UNSUPPORTED_SHAPE
+
+extern "C" int tce_gauss_stats(const float *mean, const float *L, int64_t ldb_L, const float *mean_o,
+                               const float *L_o, int64_t ldb_Lo, double *out, int64_t B, int n, void *stream) {
+  if (!mean || !mean_o || !L_o || !out || B < 0) return TCE_ERR_INVALID_ARGUMENT;
+  PJ_CHECK_N(n);
+  if (B == 0) return TCE_OK;
+  const size_t smem = pj_smem(n, 2);
+  int rc = set_smem(gauss_kl_kernel, smem);
+  if (rc) return rc;
+  gauss_kl_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(mean, L, ldb_L, mean_o, L_o, ldb_Lo, out,
+                                                                          nullptr, nullptr, nullptr, n, L ? 0 : 1);
+  TCE_CHECK_LAUNCH("gauss_kl_kernel");
+  return TCE_OK;
+}
+
+extern "C" int tce_gauss_stats_bwd(const float *mean, const float *L, int64_t ldb_L, const float *mean_o,
+                                   const float *L_o, int64_t ldb_Lo, const double *grad_out, float *grad_mean,
+                                   float *grad_L, int64_t B, int n, void *stream) {
+  if (!mean || !mean_o || !L_o || !grad_out || B < 0 || (grad_L && !L)) return TCE_ERR_INVALID_ARGUMENT;
+  PJ_CHECK_N(n);
+  if (B == 0) return TCE_OK;
+  const size_t smem = pj_smem(n, 2);
+  int rc = set_smem(gauss_kl_kernel, smem);
+  if (rc) return rc;
+  gauss_kl_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(mean, L, ldb_L, mean_o, L_o, ldb_Lo, nullptr,
+                                                                          grad_out, grad_mean, grad_L, n, grad_L ? 0 : 1);
+  TCE_CHECK_LAUNCH("gauss_kl_kernel(bwd)");
+  return TCE_OK;
+}
+
+extern "C" int tce_proj_mean_fwd(const float *mean, const float *mean_o, const double *mean_part, double eps,
+                                 float *proj_mean, int64_t B, int n, void *stream) {
+  if (!mean || !mean_o || !mean_part || !proj_mean || B < 0 || n < 1 || !(eps > 0)) return TCE_ERR_INVALID_ARGUMENT;
+  if (B == 0) return TCE_OK;
+  proj_mean_fwd_kernel<<<(unsigned)((B * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mean, mean_o, mean_part, eps,
+                                                                                          proj_mean, B, n);
+  TCE_CHECK_LAUNCH("proj_mean_fwd_kernel");
+  return TCE_OK;
+}
+
+extern "C" int tce_proj_mean_bwd(const float *mean, const float *mean_o, const double *mean_part, double eps,
+                                 const float *grad_out, float *grad_mean, double *grad_mean_part, int64_t B, int n,
+                                 void *stream) {
+  if (!mean || !mean_o || !mean_part || !grad_out || !grad_mean || !grad_mean_part || B < 0 || n < 1)
+    return TCE_ERR_INVALID_ARGUMENT;
+  if (B == 0) return TCE_OK;
+  proj_mean_bwd_kernel<<<(unsigned)((B * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      mean, mean_o, mean_part, eps, grad_out, grad_mean, grad_mean_part, B, n);
+  TCE_CHECK_LAUNCH("proj_mean_bwd_kernel");
+  return TCE_OK;
+}
+
+extern "C" int tce_proj_entropy_fwd(const float *L, const double *beta, int64_t ldb_beta, int equality, float *out,
+                                    double *entropy, int64_t B, int n, void *stream) {
+  if (!L || !beta || !out || B < 0 || n < 1) return TCE_ERR_INVALID_ARGUMENT;
+  if (B == 0) return TCE_OK;
+  proj_entropy_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(L, beta, ldb_beta, equality, nullptr, out, entropy, n);
+  TCE_CHECK_LAUNCH("proj_entropy_kernel");
+  return TCE_OK;
+}
+
+extern "C" int tce_proj_entropy_bwd(const float *L, const double *beta, int64_t ldb_beta, int equality,
+                                    const float *grad_out, float *grad_L, int64_t B, int n, void *stream) {
+  if (!L || !beta || !grad_out || !grad_L || B < 0 || n < 1) return TCE_ERR_INVALID_ARGUMENT;
+  if (B == 0) return TCE_OK;
+  proj_entropy_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(L, beta, ldb_beta, equality, grad_out, grad_L, nullptr, n);
+  TCE_CHECK_LAUNCH("proj_entropy_kernel(bwd)");
+  return TCE_OK;
+}
+
+extern "C" size_t tce_proj_kl_save_doubles(int64_t B, int n) { return (size_t)B * ((size_t)n * n + n + 4); }
+
+extern "C" int tce_proj_kl_cov_fwd(const float *L, const float *L_o, double eps_cov, float *proj_L, double *save,
+                                   int32_t *info, int64_t B, int n, void *stream) {
+  if (!L || !L_o || !proj_L || !save || B < 0 || !(eps_cov > 0)) return TCE_ERR_INVALID_ARGUMENT;
+  PJ_CHECK_N(n);
+  if (B == 0) return TCE_OK;
+  const size_t smem = pj_smem(n, 4);
+  int rc = set_smem(proj_kl_cov_fwd_kernel, smem);
+  if (rc) return rc;
+  double *Q = save, *lam = Q + (size_t)B * n * n, *sc = lam + (size_t)B * n;
+  proj_kl_cov_fwd_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, eps_cov, proj_L, Q, lam, sc, info, n);
+  TCE_CHECK_LAUNCH("proj_kl_cov_fwd_kernel");
+  return TCE_OK;
+}
+
+extern "C" int tce_proj_kl_cov_bwd(const float *L, const float *L_o, const float *proj_L, const float *grad_out,
+                                   const double *save, float *grad_L, int64_t B, int n, void *stream) {
+  if (!L || !L_o || !proj_L || !grad_out || !save || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
+  PJ_CHECK_N(n);
+  if (B == 0) return TCE_OK;
+  const size_t smem = pj_smem(n, 4);
+  int rc = set_smem(proj_kl_cov_bwd_kernel, smem);
+  if (rc) return rc;
+  const double *Q = save, *lam = Q + (size_t)B * n * n, *sc = lam + (size_t)B * n;
+  proj_kl_cov_bwd_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, proj_L, grad_out, Q, lam, sc, grad_L, n);
+  TCE_CHECK_LAUNCH("proj_kl_cov_bwd_kernel");
+  return TCE_OK;
+}
+
+extern "C" int tce_proj_frob_cov_fwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov, float *proj_L,
+                                     double *save_sc, int32_t *info, int64_t B, int n, void *stream) {
+  if (!L || !L_o || !proj_L || !save_sc || B < 0 || !(eps_cov > 0)) return TCE_ERR_INVALID_ARGUMENT;
+  PJ_CHECK_N(n);
+  if (B == 0) return TCE_OK;
+  const size_t smem = pj_smem(n, 3);
+  int rc = set_smem(proj_frob_cov_fwd_kernel, smem);
+  if (rc) return rc;
+  proj_frob_cov_fwd_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, ldb_Lo, eps_cov, proj_L, save_sc, info, n);
+  TCE_CHECK_LAUNCH("proj_frob_cov_fwd_kernel");
+  return TCE_OK;
+}
+
+extern "C" int tce_proj_frob_cov_bwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov,
+                                     const float *proj_L, const float *grad_out, const double *save_sc, float *grad_L,
+                                     int64_t B, int n, void *stream) {
+  if (!L || !L_o || !proj_L || !grad_out || !save_sc || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
+  PJ_CHECK_N(n);
+  if (B == 0) return TCE_OK;
+  const size_t smem = pj_smem(n, 4);
+  int rc = set_smem(proj_frob_cov_bwd_kernel, smem);
+  if (rc) return rc;
+  proj_frob_cov_bwd_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, ldb_Lo, eps_cov, proj_L, grad_out, save_sc, grad_L, n);
+  TCE_CHECK_LAUNCH("proj_frob_cov_bwd_kernel");
+  return TCE_OK;
+}
+
+extern "C" int tce_proj_w2_cov_fwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov, int scale_prec,
+                                   float *proj_L, double *save_sc, int64_t B, int n, void *stream) {
+  if (!L || !L_o || !proj_L || !save_sc || B < 0 || !(eps_cov > 0)) return TCE_ERR_INVALID_ARGUMENT;
+  PJ_CHECK_N(n);
+  if (B == 0) return TCE_OK;
+  const size_t smem = pj_smem(n, 5);
+  int rc = set_smem(proj_w2_cov_kernel, smem);
+  if (rc) return rc;
+  proj_w2_cov_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, ldb_Lo, eps_cov, scale_prec, nullptr, proj_L, save_sc, n);
+  TCE_CHECK_LAUNCH("proj_w2_cov_kernel");
+  return TCE_OK;
+}
+
+extern "C" int tce_proj_w2_cov_bwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov, int scale_prec,
+                                   const float *grad_out, float *grad_L, int64_t B, int n, void *stream) {
+  if (!L || !L_o || !grad_out || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
+  PJ_CHECK_N(n);
+  if (B == 0) return TCE_OK;
+  const size_t smem = pj_smem(n, 5);
+  int rc = set_smem(proj_w2_cov_kernel, smem);
+  if (rc) return rc;
+  proj_w2_cov_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, ldb_Lo, eps_cov, scale_prec, grad_out, grad_L, nullptr, n);
+  TCE_CHECK_LAUNCH("proj_w2_cov_kernel(bwd)");
+  return TCE_OK;
+}
+
+extern "C" int tce_cov_distance(int kind, const float *L, const float *L_o, int64_t ldb_Lo, int scale_prec,
+                                const double *grad_val, double *val, float *grad_L, int64_t B, int n, void *stream) {
+  if (kind < 0 || kind > 1 || !L || !L_o || B < 0 || (grad_val && !grad_L) || (!grad_val && !val))
+    return TCE_ERR_INVALID_ARGUMENT;
+  PJ_CHECK_N(n);
+  if (B == 0) return TCE_OK;
+  const size_t smem = pj_smem(n, 5);
+  int rc = set_smem(cov_distance_kernel, smem);
+  if (rc) return rc;
+  cov_distance_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(kind, L, L_o, ldb_Lo, scale_prec, grad_val, val, grad_L, n);
+  TCE_CHECK_LAUNCH("cov_distance_kernel");
+  return TCE_OK;
+}

@@ -449,3 +449,363 @@ def normalize(x: Tensor) -> Tensor:
 @normalize.register_fake
 def _(x):
     return torch.empty_like(x)
+
+
+@torch.library.custom_op("tce::gauss_maha", mutates_args=())
+def gauss_maha(mean: Tensor, mean_o: Tensor, L_o: Tensor) -> Tensor:
+    """|L_o^-1 (mean - mean_o)|^2  [B] fp64 (``policy.maha``); differentiable w.r.t. ``mean``."""
+    mean, mean_o = _chk(mean), _chk(mean_o)
+    L_o, ldbo = _batched_matrix(L_o, "L_o")
+    B, n = mean.shape
+    out = torch.empty(B, 5, device=mean.device, dtype=torch.float64)
+    _lib.call("tce_gauss_stats", _p(mean), None, 0, _p(mean_o), _p(L_o), ldbo, _p(out), B, n, _stream())
+    return out[:, 0].contiguous()
+
+
+@gauss_maha.register_fake
+def _(mean, mean_o, L_o):
+    return mean.new_empty(mean.shape[0], dtype=torch.float64)
+
+
+@torch.library.custom_op("tce::gauss_maha_bwd", mutates_args=())
+def gauss_maha_bwd(grad: Tensor, mean: Tensor, mean_o: Tensor, L_o: Tensor) -> Tensor:
+    mean, mean_o = _chk(mean), _chk(mean_o)
+    L_o, ldbo = _batched_matrix(L_o, "L_o")
+    B, n = mean.shape
+    g5 = torch.zeros(B, 5, device=mean.device, dtype=torch.float64)
+    g5[:, 0] = grad
+    g_mean = torch.empty_like(mean)
+    _lib.call("tce_gauss_stats_bwd", _p(mean), None, 0, _p(mean_o), _p(L_o), ldbo, _p(g5), _p(g_mean), None, B, n,
+              _stream())
+    return g_mean
+
+
+@gauss_maha_bwd.register_fake
+def _(grad, mean, mean_o, L_o):
+    return torch.empty_like(mean)
+
+
+def _gm_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _gm_backward(ctx, g):
+    mean, mean_o, L_o = ctx.saved_tensors
+    return gauss_maha_bwd(g, mean, mean_o, L_o), None, None
+
+
+gauss_maha.register_autograd(_gm_backward, setup_context=_gm_setup)
+
+
+# --------------------------------------------------------------------------------------------------
+# (4a) trust-region projection building blocks (each: hand-written forward + backward kernels)
+# --------------------------------------------------------------------------------------------------
+@torch.library.custom_op("tce::gauss_stats_bwd", mutates_args=())
+def gauss_stats_bwd(grad_out: Tensor, mean: Tensor, L: Tensor, mean_o: Tensor, L_o: Tensor,
+                    need_L: bool) -> Tuple[Tensor, Tensor]:
+    mean, mean_o = _chk(mean), _chk(mean_o)
+    g = _chk(grad_out, torch.float64, "grad_out")
+    Lc, ldb = _batched_matrix(L)
+    L_oc, ldbo = _batched_matrix(L_o, "L_o")
+    B, n = mean.shape
+    g_mean = torch.empty_like(mean)
+    g_L = torch.empty(B, n, n, device=mean.device, dtype=torch.float32) if need_L else mean.new_empty(0)
+    _lib.call("tce_gauss_stats_bwd", _p(mean), _p(Lc), ldb, _p(mean_o), _p(L_oc), ldbo, _p(g), _p(g_mean),
+              _p(g_L) if need_L else None, B, n, _stream())
+    return g_mean, g_L
+
+
+@gauss_stats_bwd.register_fake
+def _(grad_out, mean, L, mean_o, L_o, need_L):
+    B, n = mean.shape
+    return torch.empty_like(mean), (mean.new_empty(B, n, n) if need_L else mean.new_empty(0))
+
+
+def _gs_setup(ctx, inputs, output):
+    mean, L, mean_o, L_o = inputs
+    ctx.save_for_backward(mean, L, mean_o, L_o)
+    ctx.need_L = L.requires_grad
+
+
+def _gs_backward(ctx, g):
+    mean, L, mean_o, L_o = ctx.saved_tensors
+    g_mean, g_L = gauss_stats_bwd(g.contiguous(), mean, L, mean_o, L_o, ctx.need_L)
+    return g_mean, (g_L if ctx.need_L else None), None, None
+
+
+gauss_stats.register_autograd(_gs_backward, setup_context=_gs_setup)
+
+
+@torch.library.custom_op("tce::proj_mean", mutates_args=())
+def proj_mean(mean: Tensor, mean_o: Tensor, mean_part: Tensor, eps: float) -> Tensor:
+    mean, mean_o = _chk(mean), _chk(mean_o)
+    mp = _chk(mean_part, torch.float64, "mean_part")
+    out = torch.empty_like(mean)
+    _lib.call("tce_proj_mean_fwd", _p(mean), _p(mean_o), _p(mp), float(eps), _p(out), mean.shape[0], mean.shape[1],
+              _stream())
+    return out
+
+
+@proj_mean.register_fake
+def _(mean, mean_o, mean_part, eps):
+    return torch.empty_like(mean)
+
+
+@torch.library.custom_op("tce::proj_mean_bwd", mutates_args=())
+def proj_mean_bwd(grad_out: Tensor, mean: Tensor, mean_o: Tensor, mean_part: Tensor, eps: float) -> Tuple[Tensor, Tensor]:
+    g, mean, mean_o = _chk(grad_out), _chk(mean), _chk(mean_o)
+    mp = _chk(mean_part, torch.float64)
+    g_mean, g_part = torch.empty_like(mean), torch.empty_like(mp)
+    _lib.call("tce_proj_mean_bwd", _p(mean), _p(mean_o), _p(mp), float(eps), _p(g), _p(g_mean), _p(g_part),
+              mean.shape[0], mean.shape[1], _stream())
+    return g_mean, g_part
+
+
+@proj_mean_bwd.register_fake
+def _(grad_out, mean, mean_o, mean_part, eps):
+    return torch.empty_like(mean), torch.empty_like(mean_part)
+
+
+def _pm_setup(ctx, inputs, output):
+    mean, mean_o, mean_part, eps = inputs
+    ctx.save_for_backward(mean, mean_o, mean_part)
+    ctx.eps = eps
+
+
+def _pm_backward(ctx, g):
+    mean, mean_o, mean_part = ctx.saved_tensors
+    g_mean, g_part = proj_mean_bwd(g, mean, mean_o, mean_part, ctx.eps)
+    return g_mean, None, g_part, None
+
+
+proj_mean.register_autograd(_pm_backward, setup_context=_pm_setup)
+
+
+@torch.library.custom_op("tce::proj_entropy", mutates_args=())
+def proj_entropy(L: Tensor, beta: Tensor, equality: bool) -> Tuple[Tensor, Tensor]:
+    """-> (projected L [Bc,n,n], entropy before projection [Bc] fp64); beta [Bc] or [1] fp64."""
+    L = _chk(L, name="L")
+    beta = _chk(beta, torch.float64, "beta")
+    Bc, n = L.shape[0], L.shape[-1]
+    out = torch.empty_like(L)
+    ent = torch.empty(Bc, device=L.device, dtype=torch.float64)
+    _lib.call("tce_proj_entropy_fwd", _p(L), _p(beta), 0 if beta.numel() == 1 else 1, int(equality), _p(out), _p(ent),
+              Bc, n, _stream())
+    return out, ent
+
+
+@proj_entropy.register_fake
+def _(L, beta, equality):
+    return torch.empty_like(L), L.new_empty(L.shape[0], dtype=torch.float64)
+
+
+@torch.library.custom_op("tce::proj_entropy_bwd", mutates_args=())
+def proj_entropy_bwd(grad_out: Tensor, L: Tensor, beta: Tensor, equality: bool) -> Tensor:
+    g, L = _chk(grad_out), _chk(L)
+    beta = _chk(beta, torch.float64)
+    out = torch.empty_like(L)
+    _lib.call("tce_proj_entropy_bwd", _p(L), _p(beta), 0 if beta.numel() == 1 else 1, int(equality), _p(g), _p(out),
+              L.shape[0], L.shape[-1], _stream())
+    return out
+
+
+@proj_entropy_bwd.register_fake
+def _(grad_out, L, beta, equality):
+    return torch.empty_like(L)
+
+
+def _pe_setup(ctx, inputs, output):
+    L, beta, equality = inputs
+    ctx.save_for_backward(L, beta)
+    ctx.equality = equality
+
+
+def _pe_backward(ctx, g, g_ent):
+    L, beta = ctx.saved_tensors
+    return proj_entropy_bwd(g, L, beta, ctx.equality), None, None
+
+
+proj_entropy.register_autograd(_pe_backward, setup_context=_pe_setup)
+
+
+@torch.library.custom_op("tce::proj_kl_cov", mutates_args=())
+def proj_kl_cov(L: Tensor, L_o: Tensor, eps_cov: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (proj_L [Bc,n,n], save (fp64: Q, lambda, eta/active/kl0), info [Bc])."""
+    L, L_o = _chk(L, name="L"), _chk(L_o, name="L_o")
+    Bc, n = L.shape[0], L.shape[-1]
+    out = torch.empty_like(L)
+    save = torch.empty(_lib.load().tce_proj_kl_save_doubles(Bc, n), device=L.device, dtype=torch.float64)
+    info = torch.empty(Bc, device=L.device, dtype=torch.int32)
+    _lib.call("tce_proj_kl_cov_fwd", _p(L), _p(L_o), float(eps_cov), _p(out), _p(save), _p(info), Bc, n, _stream())
+    return out, save, info
+
+
+@proj_kl_cov.register_fake
+def _(L, L_o, eps_cov):
+    Bc, n = L.shape[0], L.shape[-1]
+    return torch.empty_like(L), L.new_empty(Bc * (n * n + n + 4), dtype=torch.float64), L.new_empty(Bc, dtype=torch.int32)
+
+
+@torch.library.custom_op("tce::proj_kl_cov_bwd", mutates_args=())
+def proj_kl_cov_bwd(grad_out: Tensor, L: Tensor, L_o: Tensor, proj_L: Tensor, save: Tensor) -> Tensor:
+    g, L, L_o, proj_L = _chk(grad_out), _chk(L), _chk(L_o), _chk(proj_L)
+    out = torch.empty_like(L)
+    _lib.call("tce_proj_kl_cov_bwd", _p(L), _p(L_o), _p(proj_L), _p(g), _p(save), _p(out), L.shape[0], L.shape[-1],
+              _stream())
+    return out
+
+
+@proj_kl_cov_bwd.register_fake
+def _(grad_out, L, L_o, proj_L, save):
+    return torch.empty_like(L)
+
+
+def _pk_setup(ctx, inputs, output):
+    L, L_o, eps_cov = inputs
+    ctx.save_for_backward(L, L_o, output[0], output[1])
+
+
+def _pk_backward(ctx, g, g_save, g_info):
+    L, L_o, proj_L, save = ctx.saved_tensors
+    return proj_kl_cov_bwd(g, L, L_o, proj_L, save), None, None
+
+
+proj_kl_cov.register_autograd(_pk_backward, setup_context=_pk_setup)
+
+
+@torch.library.custom_op("tce::proj_frob_cov", mutates_args=())
+def proj_frob_cov(L: Tensor, L_o: Tensor, eps_cov: float) -> Tuple[Tensor, Tensor, Tensor]:
+    L = _chk(L, name="L")
+    L_o, ldbo = _batched_matrix(L_o, "L_o")
+    Bc, n = L.shape[0], L.shape[-1]
+    out = torch.empty_like(L)
+    sc = torch.empty(Bc, 4, device=L.device, dtype=torch.float64)
+    info = torch.empty(Bc, device=L.device, dtype=torch.int32)
+    _lib.call("tce_proj_frob_cov_fwd", _p(L), _p(L_o), ldbo, float(eps_cov), _p(out), _p(sc), _p(info), Bc, n, _stream())
+    return out, sc, info
+
+
+@proj_frob_cov.register_fake
+def _(L, L_o, eps_cov):
+    return torch.empty_like(L), L.new_empty(L.shape[0], 4, dtype=torch.float64), L.new_empty(L.shape[0], dtype=torch.int32)
+
+
+@torch.library.custom_op("tce::proj_frob_cov_bwd", mutates_args=())
+def proj_frob_cov_bwd(grad_out: Tensor, L: Tensor, L_o: Tensor, proj_L: Tensor, sc: Tensor, eps_cov: float) -> Tensor:
+    g, L, proj_L = _chk(grad_out), _chk(L), _chk(proj_L)
+    L_o, ldbo = _batched_matrix(L_o, "L_o")
+    out = torch.empty_like(L)
+    _lib.call("tce_proj_frob_cov_bwd", _p(L), _p(L_o), ldbo, float(eps_cov), _p(proj_L), _p(g), _p(sc), _p(out),
+              L.shape[0], L.shape[-1], _stream())
+    return out
+
+
+@proj_frob_cov_bwd.register_fake
+def _(grad_out, L, L_o, proj_L, sc, eps_cov):
+    return torch.empty_like(L)
+
+
+def _pf_setup(ctx, inputs, output):
+    L, L_o, eps_cov = inputs
+    ctx.save_for_backward(L, L_o, output[0], output[1])
+    ctx.eps_cov = eps_cov
+
+
+def _pf_backward(ctx, g, g_sc, g_info):
+    L, L_o, proj_L, sc = ctx.saved_tensors
+    return proj_frob_cov_bwd(g, L, L_o, proj_L, sc, ctx.eps_cov), None, None
+
+
+proj_frob_cov.register_autograd(_pf_backward, setup_context=_pf_setup)
+
+
+@torch.library.custom_op("tce::proj_w2_cov", mutates_args=())
+def proj_w2_cov(L: Tensor, L_o: Tensor, eps_cov: float, scale_prec: bool) -> Tuple[Tensor, Tensor]:
+    L = _chk(L, name="L")
+    L_o, ldbo = _batched_matrix(L_o, "L_o")
+    Bc, n = L.shape[0], L.shape[-1]
+    out = torch.empty_like(L)
+    sc = torch.empty(Bc, 4, device=L.device, dtype=torch.float64)
+    _lib.call("tce_proj_w2_cov_fwd", _p(L), _p(L_o), ldbo, float(eps_cov), int(scale_prec), _p(out), _p(sc), Bc, n,
+              _stream())
+    return out, sc
+
+
+@proj_w2_cov.register_fake
+def _(L, L_o, eps_cov, scale_prec):
+    return torch.empty_like(L), L.new_empty(L.shape[0], 4, dtype=torch.float64)
+
+
+@torch.library.custom_op("tce::proj_w2_cov_bwd", mutates_args=())
+def proj_w2_cov_bwd(grad_out: Tensor, L: Tensor, L_o: Tensor, eps_cov: float, scale_prec: bool) -> Tensor:
+    g, L = _chk(grad_out), _chk(L)
+    L_o, ldbo = _batched_matrix(L_o, "L_o")
+    out = torch.empty_like(L)
+    _lib.call("tce_proj_w2_cov_bwd", _p(L), _p(L_o), ldbo, float(eps_cov), int(scale_prec), _p(g), _p(out), L.shape[0],
+              L.shape[-1], _stream())
+    return out
+
+
+@proj_w2_cov_bwd.register_fake
+def _(grad_out, L, L_o, eps_cov, scale_prec):
+    return torch.empty_like(L)
+
+
+def _pw_setup(ctx, inputs, output):
+    L, L_o, eps_cov, scale_prec = inputs
+    ctx.save_for_backward(L, L_o)
+    ctx.eps_cov, ctx.scale_prec = eps_cov, scale_prec
+
+
+def _pw_backward(ctx, g, g_sc):
+    L, L_o = ctx.saved_tensors
+    return proj_w2_cov_bwd(g, L, L_o, ctx.eps_cov, ctx.scale_prec), None, None, None
+
+
+proj_w2_cov.register_autograd(_pw_backward, setup_context=_pw_setup)
+
+
+@torch.library.custom_op("tce::cov_distance", mutates_args=())
+def cov_distance(kind: int, L: Tensor, L_o: Tensor, scale_prec: bool) -> Tensor:
+    """Frobenius (kind 0) / commutative W2 (kind 1) covariance distance [Bc] fp64, differentiable w.r.t. L."""
+    L = _chk(L, name="L")
+    L_o, ldbo = _batched_matrix(L_o, "L_o")
+    val = torch.empty(L.shape[0], device=L.device, dtype=torch.float64)
+    _lib.call("tce_cov_distance", int(kind), _p(L), _p(L_o), ldbo, int(scale_prec), None, _p(val), None, L.shape[0],
+              L.shape[-1], _stream())
+    return val
+
+
+@cov_distance.register_fake
+def _(kind, L, L_o, scale_prec):
+    return L.new_empty(L.shape[0], dtype=torch.float64)
+
+
+@torch.library.custom_op("tce::cov_distance_bwd", mutates_args=())
+def cov_distance_bwd(grad_val: Tensor, kind: int, L: Tensor, L_o: Tensor, scale_prec: bool) -> Tensor:
+    L = _chk(L)
+    g = _chk(grad_val, torch.float64)
+    L_o, ldbo = _batched_matrix(L_o, "L_o")
+    out = torch.empty_like(L)
+    _lib.call("tce_cov_distance", int(kind), _p(L), _p(L_o), ldbo, int(scale_prec), _p(g), None, _p(out), L.shape[0],
+              L.shape[-1], _stream())
+    return out
+
+
+@cov_distance_bwd.register_fake
+def _(grad_val, kind, L, L_o, scale_prec):
+    return torch.empty_like(L)
+
+
+def _cd_setup(ctx, inputs, output):
+    kind, L, L_o, scale_prec = inputs
+    ctx.save_for_backward(L, L_o)
+    ctx.kind, ctx.scale_prec = kind, scale_prec
+
+
+def _cd_backward(ctx, g):
+    L, L_o = ctx.saved_tensors
+    return None, cov_distance_bwd(g.contiguous(), ctx.kind, L, L_o, ctx.scale_prec), None, None
+
+
+cov_distance.register_autograd(_cd_backward, setup_context=_cd_setup)

@@ -1,0 +1,321 @@
+"""TCE agent (policy-update side) with the reference's method surface.
+
+Reference: mprl/rl/agent/abstract_agent.py:12-107 (optimisers, LR schedulers),
+mprl/rl/agent/temporal_correlated_agent.py: process_dataset :102-116, get_advantage_return :118-181,
+get_segment_advantage :183-321, update_critic :323-379, update_policy :381-639, kl_old_new_proj :641-686,
+value_loss :688-716, surrogate_loss :718-739, entropy_loss :741-745.
+
+Differences that do not change results: all per-epoch logging scalars are accumulated in ONE device
+buffer and read back once per update (the reference issues >= 20 host synchronisations per epoch, SURVEY
+3.3); the epoch can be captured in a CUDA graph (``use_cuda_graph=True``); at >1 GPU the gradients are
+all-reduced (SUM of per-rank means scaled by 1/world) in one flat NCCL call per optimiser step.
+Environment rollout (``sampler.run``) is out of scope: ``step()`` needs a sampler that provides it.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch.optim.lr_scheduler import LinearLR
+
+from .. import ops, util
+from .projection import gaussian_kl_details
+
+_KL_KEYS = ["new_old_mean_diff", "new_old_cov_diff", "new_old_shape_diff", "new_old_volume_diff",
+            "new_proj_mean_diff", "new_proj_cov_diff", "new_proj_shape_diff", "new_proj_volume_diff",
+            "proj_old_mean_diff", "proj_old_cov_diff", "proj_old_shape_diff", "proj_old_volume_diff"]
+_LOSS_KEYS = ["surrogate_loss", "entropy_loss", "trust_region_loss", "policy_loss", "entropy", "imp_smp_ratio",
+              "policy_grad_norm"]
+
+
+class SegmentTimeSampler:
+    """The two sampler methods the update path needs (temporal_correlated_sampler.py:64-85).
+    Time-pair selection draws from the HOST torch generator exactly like the reference."""
+
+    def __init__(self, dt: float, num_times: int, time_pairs_config: dict, device="cuda", dtype=torch.float32):
+        self.dt, self.num_times = float(dt), int(num_times)
+        self.time_pairs_config = dict(time_pairs_config)
+        self.device, self.dtype = torch.device(device), dtype
+        self.pred_pairs = None
+
+    def get_times(self, init_time, num_times):
+        return util.tensor_linspace(start=init_time + self.dt, end=init_time + num_times * self.dt,
+                                    steps=num_times).T.contiguous()
+
+    def get_time_pairs(self):
+        pairs = util.select_pred_pairs(num_all=self.num_times, **self.time_pairs_config)
+        self.pred_pairs = pairs.to(torch.long).to(self.device)
+        return self.pred_pairs
+
+
+def _stats(values, name):
+    a = np.asarray(values, dtype=np.float64)
+    return {f"{name}_mean": a.mean(), f"{name}_max": a.max(), f"{name}_min": a.min(), f"{name}_std": a.std(),
+            f"{name}_median": np.median(a)}
+
+
+class TemporalCorrelatedAgent:
+    def __init__(self, policy, critic, sampler, projection, dtype=torch.float32, device="cuda", **kwargs):
+        self.policy, self.critic, self.sampler, self.projection = policy, critic, sampler, projection
+        self.dtype, self.device = util.parse_dtype_device(dtype, device)
+        self.lr_policy, self.lr_critic = float(kwargs["lr_policy"]), float(kwargs["lr_critic"])
+        self.wd_policy, self.wd_critic = float(kwargs["wd_policy"]), float(kwargs["wd_critic"])
+        self.schedule_lr_policy = kwargs.get("schedule_lr_policy", False)
+        self.schedule_lr_critic = kwargs.get("schedule_lr_critic", False)
+        self.total_iterations = kwargs.get("total_iterations", 10000)
+        self.discount_factor = torch.tensor(float(kwargs["discount_factor"]), dtype=self.dtype, device=self.device)
+        self._gamma = float(kwargs["discount_factor"])
+        self.epochs_policy, self.epochs_critic = kwargs["epochs_policy"], kwargs["epochs_critic"]
+        self.clip_critic = float(kwargs.get("clip_critic", 0.0))
+        self.clip_grad_norm = float(kwargs.get("clip_grad_norm", 0.0))
+        self.num_minibatchs = kwargs.get("num_minibatchs", 10)
+        self.norm_advantages = kwargs.get("norm_advantages", False)
+        self.clip_advantages = kwargs.get("clip_advantages", False)
+        self.entropy_penalty_coef = float(kwargs.get("entropy_penalty_coef", 0.0))
+        self.use_gae = kwargs.get("use_gae", True)
+        self.gae_scaling = float(kwargs.get("gae_scaling", 0.95))
+        self.segment_advantage = kwargs.get("segment_advantage", "accumulate")
+        self.set_variance = kwargs.get("set_variance", False)
+        self.balance_check = kwargs.get("balance_check", 10)
+        self.evaluation_interval = kwargs.get("evaluation_interval", 1)
+        self.use_cuda_graph = bool(kwargs.get("use_cuda_graph", False))
+        self.process_group = kwargs.get("process_group", None)      # torch.distributed group (None = single GPU)
+        self.policy_net_params = policy.parameters
+        self.critic_net_params = critic.parameters if critic is not None else []
+        capt = dict(capturable=True) if self.device.type == "cuda" else {}
+        self.policy_optimizer = torch.optim.Adam(self.policy_net_params, lr=self.lr_policy,
+                                                 weight_decay=self.wd_policy, **capt)
+        self.critic_optimizer = (torch.optim.Adam(self.critic_net_params, lr=self.lr_critic,
+                                                  weight_decay=self.wd_critic, **capt)
+                                 if self.critic_net_params else None)
+        mk = lambda opt: LinearLR(opt, start_factor=1, end_factor=0.01, total_iters=self.total_iterations)
+        self.policy_lr_scheduler = mk(self.policy_optimizer) if self.schedule_lr_policy else None
+        self.critic_lr_scheduler = (mk(self.critic_optimizer)
+                                    if self.schedule_lr_critic and self.critic_optimizer else None)
+        self.num_iterations = 0
+        self.num_global_steps = 0
+        self._graph = None
+
+    # ---- distributed helpers ---------------------------------------------------------------------------
+    @property
+    def world_size(self):
+        return dist.get_world_size(self.process_group) if self._distributed else 1
+
+    @property
+    def _distributed(self):
+        return self.process_group is not None and dist.is_available() and dist.is_initialized()
+
+    def _group(self):
+        return None if self.process_group is True else self.process_group
+
+    def _allreduce_grads(self, params):
+        """One flat all-reduce(SUM) of the gradients; losses are local means, so divide by the world size."""
+        if not self._distributed:
+            return
+        grads = [p.grad for p in params if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self._group())
+        flat.div_(self.world_size)
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+
+    def _global_mean(self, x):
+        """Mean over the global batch (equal shard sizes)."""
+        m = x.mean()
+        if self._distributed:
+            dist.all_reduce(m, op=dist.ReduceOp.SUM, group=self._group())
+            m = m / self.world_size
+        return m
+
+    # ---- dataset processing -----------------------------------------------------------------------------
+    def process_dataset(self, dataset):
+        adv, ret = self.get_advantage_return(dataset["step_rewards"], dataset["step_values"], dataset["step_dones"],
+                                             dataset["step_time_limit_dones"])
+        dataset["step_advantages"], dataset["step_returns"] = adv, ret
+        dataset["segment_advantage"] = self.get_segment_advantage(dataset["step_rewards"], dataset["step_values"],
+                                                                  adv, self.sampler.pred_pairs)
+        return dataset
+
+    def get_advantage_return(self, rewards, values, dones, time_limit_dones):
+        """GAE(gamma, lambda) in one launch (``tce::gae``)."""
+        return ops.gae(rewards, values, dones, time_limit_dones, self._gamma, self.gae_scaling, bool(self.use_gae))
+
+    def get_segment_advantage(self, rewards, values, advantages, pred_pairs, **kwargs):
+        norm = bool(self.norm_advantages)
+        if self.segment_advantage == "accumulate":
+            if norm:
+                advantages = ops.normalize(advantages)
+            if self.clip_advantages > 0:
+                advantages = torch.clamp(advantages, -self.clip_advantages, self.clip_advantages)
+            return ops.segment_advantage(0, rewards, values, advantages.contiguous(), pred_pairs, self._gamma, norm)
+        if self.segment_advantage == "value_subtraction":
+            return ops.segment_advantage(1, rewards, values, advantages, pred_pairs, self._gamma, norm)
+        if self.segment_advantage == "accumulated_rewards":
+            acc = ops.segment_advantage(2, rewards, values, advantages, pred_pairs, self._gamma, False)
+            mean = acc.mean(dim=0)
+            if self._distributed:
+                dist.all_reduce(mean, op=dist.ReduceOp.SUM, group=self._group())
+                mean = mean / self.world_size
+            return acc - mean        # gamma^start cancels: (acc - mean) / gamma^start with acc already divided
+        raise NotImplementedError
+
+    # ---- losses ---------------------------------------------------------------------------------------------
+    def value_loss(self, values, returns, old_vs):
+        vf_loss = (returns - values).pow(2)
+        if self.clip_critic > 0:
+            vs_clipped = old_vs + (values - old_vs).clamp(-self.clip_critic, self.clip_critic)
+            vf_loss = torch.max(vf_loss, (vs_clipped - returns).pow(2))
+        return vf_loss.mean()
+
+    @staticmethod
+    def surrogate_loss(advantages, log_prob_new, log_prob_old):
+        ratio = (log_prob_new - log_prob_old).exp()
+        return -(ratio * advantages).mean(), {"imp_smp_ratio": ratio.mean()}
+
+    def entropy_loss(self, params_mean, params_L):
+        entropy = self.policy.entropy([params_mean, params_L]).mean()
+        return -self.entropy_penalty_coef * entropy, {"entropy": entropy}
+
+    def kl_old_new_proj(self, new, old, proj):
+        """The 12 logging means of temporal_correlated_agent.py:641-686 as one device vector."""
+        out = []
+        with torch.no_grad():
+            for p, q in ((new, old), (new, proj), (proj, old)):
+                out += [x.mean() for x in gaussian_kl_details(self.policy, p, q)]
+        return torch.stack(out)
+
+    # ---- critic ---------------------------------------------------------------------------------------------
+    def update_critic(self, dataset):
+        D2 = self.policy.num_dof * 2
+        states = dataset["step_states"].flatten(0, 1)
+        old_values = dataset["step_values"][:, :-1].flatten(0, 1)
+        returns = dataset["step_returns"].flatten(0, 1)
+        losses, norms = [], []
+        for _ in range(self.epochs_critic):
+            perm = np.random.permutation(states.shape[0])          # util_data_structure.py:378-391 (numpy RNG)
+            for idx in np.array_split(perm, self.num_minibatchs):
+                sel = torch.as_tensor(idx, device=states.device)
+                values_new = self.critic.critic(states[sel][..., :-D2]).squeeze(-1)
+                loss = self.value_loss(values_new, returns[sel], old_values[sel])
+                self.critic_optimizer.zero_grad(set_to_none=True)
+                loss.backward()
+                self._allreduce_grads(self.critic_net_params)
+                norms.append(self._grad_norm_clip(self.critic_net_params))
+                self.critic_optimizer.step()
+                losses.append(loss.detach())
+        losses = torch.stack(losses).cpu().numpy()
+        norms = torch.stack(norms).cpu().numpy()
+        return {**_stats(losses, "critic_loss"), **_stats(norms, "critic_grad_norm")}
+
+    def _grad_norm_clip(self, params):
+        """util_numerical.py:244-275 without the per-parameter .item(): norm on the device."""
+        norm = torch.sqrt(sum((p.grad.detach() ** 2).sum() for p in params))
+        if self.clip_grad_norm > 0:
+            torch.nn.utils.clip_grad_norm_(params, self.clip_grad_norm)
+        return norm
+
+    # ---- policy -----------------------------------------------------------------------------------------------
+    def policy_epoch(self, dataset, times, pred_pairs):
+        """One epoch body of ``update_policy`` (temporal_correlated_agent.py:524-589): returns the metrics
+        vector [7 + 12] (``_LOSS_KEYS`` then ``_KL_KEYS``) living on the device."""
+        D2 = self.policy.num_dof * 2
+        old = (dataset["segment_params_mean"], dataset["segment_params_L"])
+        new = self.policy.policy(dataset["segment_state"][..., :-D2])
+        proj = self.projection(self.policy, new, old, self.num_iterations)
+        log_prob_new = self.policy.log_prob(dataset["step_actions"], params_mean=proj[0], params_L=proj[1],
+                                            times=times, init_time=dataset["segment_init_time"],
+                                            init_pos=dataset["segment_init_pos"],
+                                            init_vel=dataset["segment_init_vel"], pred_pairs=pred_pairs)
+        surrogate, sur_stats = self.surrogate_loss(dataset["segment_advantage"], log_prob_new,
+                                                   dataset["segment_log_prob_estimate"])
+        kl = self.kl_old_new_proj(new, old, proj)
+        if self.entropy_penalty_coef != 0.0:
+            ent_loss, ent_stats = self.entropy_loss(proj[0], proj[1])
+        else:                                             # coefficient 0 in every config: logging value only
+            with torch.no_grad():
+                ent_loss, ent_stats = self.entropy_loss(proj[0], proj[1])
+        tr_loss = self.projection.get_trust_region_loss(self.policy, new, proj, set_variance=self.set_variance)
+        policy_loss = surrogate + ent_loss + tr_loss
+        self.policy_optimizer.zero_grad(set_to_none=False)
+        policy_loss.backward()
+        self._allreduce_grads(self.policy_net_params)
+        grad_norm = self._grad_norm_clip(self.policy_net_params)
+        self.policy_optimizer.step()
+        head = torch.stack([surrogate.detach(), ent_loss.detach().to(surrogate.dtype), tr_loss.detach(),
+                            policy_loss.detach(), ent_stats["entropy"].detach().to(surrogate.dtype),
+                            sur_stats["imp_smp_ratio"].detach(), grad_norm.detach()])
+        return torch.cat([head.double(), kl.double()])
+
+    def update_policy(self, dataset):
+        init_time = dataset["segment_init_time"]
+        times = self.sampler.get_times(init_time, self.sampler.num_times)
+        pred_pairs = self.sampler.pred_pairs
+        old = (dataset["segment_params_mean"], dataset["segment_params_L"])
+        if self.projection.initial_entropy is None:
+            self.projection.initial_entropy = self._global_mean(self.policy.entropy(list(old)))
+        for p in self.policy_net_params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        rows = []
+        if self.use_cuda_graph and not self._distributed:
+            metrics = self._graphed_epochs(dataset, times, pred_pairs, rows)
+        else:
+            for _ in range(self.epochs_policy):
+                rows.append(self.policy_epoch(dataset, times, pred_pairs))
+            metrics = torch.stack(rows)
+        metrics = metrics.cpu().numpy()                      # the ONE synchronisation of the update
+        if not np.isfinite(metrics[:, :4]).all():
+            raise Exception("NAN loss detected")           # temporal_correlated_agent.py:569-577
+        out = {}
+        for i, k in enumerate(_LOSS_KEYS):
+            out.update(_stats(metrics[:, i], k))
+        for i, k in enumerate(_KL_KEYS):
+            out.update(_stats(metrics[:, len(_LOSS_KEYS) + i], "projection_" + k))
+        if self.set_variance and not self.policy.contextual_cov:
+            D2 = self.policy.num_dof * 2
+            with torch.no_grad():
+                new = self.policy.policy(dataset["segment_state"][..., :-D2])
+                proj = self.projection(self.policy, new, old, self.num_iterations)
+            self.policy.set_cov_variable(proj[1][0].detach())
+        return out
+
+    def _graphed_epochs(self, dataset, times, pred_pairs, rows):
+        """Capture one epoch (forward, backward, Adam) in a CUDA graph and replay it ``epochs_policy`` times."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                        # warm-up outside the capture (lazy inits)
+            rows.append(self.policy_epoch(dataset, times, pred_pairs).clone())
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_metrics = self.policy_epoch(dataset, times, pred_pairs)
+        for _ in range(self.epochs_policy - 1):
+            graph.replay()
+            rows.append(static_metrics.clone())
+        self._graph = graph
+        return torch.stack(rows)
+
+    def step(self):
+        if not hasattr(self.sampler, "run"):
+            raise NotImplementedError("environment rollout is outside the B200 hot path: provide a sampler with "
+                                      "run() (temporal_correlated_sampler.py:91-344) or call update_* directly")
+        self.num_iterations += 1
+        dataset, n = self.sampler.run(training=True, policy=self.policy, critic=self.critic)
+        self.num_global_steps += n
+        dataset = self.process_dataset(dataset)
+        out = {**self.update_critic(dataset)}
+        if self.critic_lr_scheduler:
+            self.critic_lr_scheduler.step()
+        out.update(self.update_policy(dataset))
+        if self.policy_lr_scheduler:
+            self.policy_lr_scheduler.step()
+        return out
+
+
+def agent_factory(typ: str, **kwargs):
+    """mprl/rl/agent/__init__.py:8-19 (only the TCE agent is on the B200 path)."""
+    if typ != "TemporalCorrelatedAgent":
+        raise NotImplementedError(f"{typ}: only TemporalCorrelatedAgent is built (SURVEY section 8(f))")
+    return TemporalCorrelatedAgent(**kwargs)

@@ -1,0 +1,210 @@
+"""Differentiable trust-region projection layers with the API of ``trust_region_projections``.
+
+Reference: factory mprl/rl/projection/__init__.py:19-40; call sites
+mprl/rl/agent/temporal_correlated_agent.py:439-441 (initial_entropy), :530-533 (projection),
+:561-567 (get_trust_region_loss), black_box_agent.py:359-363 (compute_metrics).  The layer classes
+themselves live in the unvendored BruceGeLi/trust-region-layers@TCE_ICLR24 (+ C++ cpp_projection); their
+behaviour follows SURVEY App. B.  All arithmetic runs in the hand-written kernels of csrc/tce_proj.cu; the
+Python below only routes tensors (per-episode scalars stay on the device, no host synchronisation).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from .. import ops, util
+
+
+def _expand_first(t, batch):
+    return t.expand(batch, -1, -1)
+
+
+def _shared(policy, L):
+    """A non-contextual policy carries ONE covariance (every batch entry equal): evaluate the covariance
+    terms once and broadcast, as the KL layer of the reference does for the projection itself."""
+    return not policy.contextual_std and L.dim() == 3 and L.shape[0] > 1
+
+
+def _cov_stats(policy, L, L_o):
+    """gauss_stats on the covariance factors only (zero mean difference), broadcast when shared."""
+    B = L.shape[0]
+    if _shared(policy, L):
+        L, L_o = L[:1], L_o[:1]
+    zeros = torch.zeros(L.shape[0], L.shape[-1], device=L.device)
+    st = ops.gauss_stats(zeros, L.contiguous(), zeros, L_o)
+    return st.expand(B, -1) if st.shape[0] != B else st
+
+
+def gaussian_kl(policy, p, q):
+    """(mean part, covariance part) of KL(p || q), each [B] fp64 (projection_utils.gaussian_kl)."""
+    st = _cov_stats(policy, p[1], q[1])
+    k = p[0].shape[-1]
+    return 0.5 * ops.gauss_maha(p[0], q[0], q[1]), 0.5 * (st[:, 1] - k + st[:, 3] - st[:, 2])
+
+
+def gaussian_kl_details(policy, p, q):
+    """(mean, cov, shape, volume) parts used for logging at temporal_correlated_agent.py:641-686."""
+    st = _cov_stats(policy, p[1], q[1])
+    k = p[0].shape[-1]
+    shape, volume = 0.5 * (st[:, 1] - k), 0.5 * (st[:, 3] - st[:, 2])
+    return 0.5 * ops.gauss_maha(p[0], q[0], q[1]), shape + volume, shape, volume
+
+
+def _entropy_schedule(kind, total_train_steps, dim):
+    if kind == "linear":
+        return lambda init, target, temp, step: step * (target * dim - init) / total_train_steps + init
+    if kind == "exp":
+        return lambda init, target, temp, step: dim * target + (init - dim * target) * temp ** (
+            10 * step / total_train_steps)
+    return None
+
+
+class BaseProjectionLayer:
+    def __init__(self, proj_type="", mean_bound=0.03, cov_bound=1e-3, trust_region_coeff=0.0, scale_prec=True,
+                 entropy_schedule=None, action_dim=None, total_train_steps=None, target_entropy=0.0,
+                 temperature=0.5, entropy_eq=False, entropy_first=False, do_regression=False, cpu=False,
+                 dtype=torch.float32, **kwargs):
+        if cpu:
+            raise NotImplementedError("tce_rl_b200 projections run on the GPU only (no CPU path)")
+        if do_regression:
+            raise NotImplementedError("do_regression is false in every TCE config and is not built")
+        self.proj_type = proj_type
+        self.mean_bound, self.cov_bound = float(mean_bound), float(cov_bound)
+        self.trust_region_coeff = trust_region_coeff
+        self.scale_prec = bool(scale_prec)
+        assert (action_dim and total_train_steps) if entropy_schedule else True
+        self.entropy_eq, self.entropy_first = bool(entropy_eq), bool(entropy_first)
+        self.entropy_schedule = _entropy_schedule(entropy_schedule, total_train_steps, action_dim)
+        self.target_entropy, self.temperature = float(target_entropy), temperature
+        self._initial_entropy = None
+
+    @property
+    def initial_entropy(self):
+        return self._initial_entropy
+
+    @initial_entropy.setter
+    def initial_entropy(self, entropy):
+        if self._initial_entropy is None:                     # write once
+            self._initial_entropy = entropy
+
+    # ---- pieces ---------------------------------------------------------------------------------------
+    def _entropy_bound(self, step, device):
+        if self.entropy_schedule is None:
+            return None                                        # bound -inf: the projection is the identity
+        beta = self.entropy_schedule(self.initial_entropy, self.target_entropy, self.temperature, step)
+        return torch.as_tensor(beta, device=device).to(torch.float64).reshape(1)
+
+    def _entropy_projection(self, policy, p, beta):
+        if beta is None:
+            return p
+        mean, L = p
+        shared = L.dim() == 3 and L.stride(0) == 0
+        L_in = L[:1] if shared else L
+        out, _ = ops.proj_entropy(L_in.contiguous(), beta, self.entropy_eq)
+        return mean, (_expand_first(out, mean.shape[0]) if shared else out)
+
+    def _mean_part(self, policy, p, q):
+        raise NotImplementedError
+
+    def _cov_projection(self, policy, L, L_old):
+        return L
+
+    def _trust_region_projection(self, policy, p, q):
+        mean, L = p
+        old_mean, old_L = q
+        proj_mean = ops.proj_mean(mean, old_mean, self._mean_part(policy, p, q), self.mean_bound)
+        if not policy.contextual_std:                          # one shared covariance: project the first only
+            proj_L = _expand_first(self._cov_projection(policy, L[:1], old_L[:1]), mean.shape[0])
+        else:
+            proj_L = self._cov_projection(policy, L, old_L)
+        return proj_mean, proj_L
+
+    def __call__(self, policy, p, q, step, *args, **kwargs):
+        beta = self._entropy_bound(step, p[0].device)
+        if self.entropy_first:
+            p = self._entropy_projection(policy, p, beta)
+        proj = self._trust_region_projection(policy, p, q)
+        return proj if self.entropy_first else self._entropy_projection(policy, proj, beta)
+
+    def trust_region_value(self, policy, p, q):
+        return gaussian_kl(policy, p, q)
+
+    def _with_cov(self, policy, set_variance):
+        return policy.contextual_std or (set_variance is not None and not set_variance)
+
+    def get_trust_region_loss(self, policy, p, proj_p, set_variance=None):
+        """coeff * mean(mean_diff [+ cov_diff]) between p and the DETACHED projection."""
+        target = (proj_p[0].detach(), proj_p[1].detach())
+        mean_diff, cov_diff = self.trust_region_value(policy, p, target)
+        loss = (mean_diff + cov_diff if self._with_cov(policy, set_variance) else mean_diff).mean()
+        return (loss * self.trust_region_coeff).to(p[0].dtype)
+
+    def compute_metrics(self, policy, p, q, step=None):
+        with torch.no_grad():
+            ent, ent_q = policy.entropy(p), policy.entropy(q)
+            mean_kl, cov_kl = gaussian_kl(policy, p, q)
+            mean_diff, cov_diff = self.trust_region_value(policy, p, q)
+            kl, con = mean_kl + cov_kl, mean_diff + cov_diff
+            return {"kl": kl.mean(), "constraint": con.mean(), "mean_constraint": mean_diff.mean(),
+                    "cov_constraint": cov_diff.mean(), "entropy": ent.mean(), "entropy_diff": (ent_q - ent).mean(),
+                    "kl_max": kl.max(), "constraint_max": con.max(), "mean_constraint_max": mean_diff.max(),
+                    "cov_constraint_max": cov_diff.max(), "entropy_max": ent.max()}
+
+
+class KLProjectionLayer(BaseProjectionLayer):
+    def _mean_part(self, policy, p, q):
+        return 0.5 * ops.gauss_maha(p[0], q[0], q[1])
+
+    def _cov_projection(self, policy, L, L_old):
+        if policy.is_diag:
+            raise NotImplementedError("diagonal KL projection is outside the TCE configs")
+        return ops.proj_kl_cov(L.contiguous(), L_old.contiguous(), self.cov_bound)[0]
+
+
+class FrobeniusProjectionLayer(BaseProjectionLayer):
+    def _mean_dist(self, p, q):
+        if self.scale_prec:
+            return ops.gauss_maha(p[0], q[0], q[1])
+        return ((q[0] - p[0]) ** 2).sum(-1).to(torch.float64)
+
+    def _mean_part(self, policy, p, q):
+        return self._mean_dist(p, q)
+
+    def _cov_projection(self, policy, L, L_old):
+        return ops.proj_frob_cov(L.contiguous(), L_old, self.cov_bound)[0]
+
+    def trust_region_value(self, policy, p, q):
+        return self._mean_dist(p, q), ops.cov_distance(0, p[1].contiguous(), q[1], False)
+
+    def get_trust_region_loss(self, policy, p, proj_p, set_variance=None):
+        target = (proj_p[0].detach(), proj_p[1].detach())
+        diff = self._mean_dist(p, target)
+        if self._with_cov(policy, set_variance):               # squared L difference instead of the Frobenius metric
+            diff = diff + (p[1] - target[1]).pow(2).sum([-1, -2]).to(torch.float64)
+        return (diff.mean() * self.trust_region_coeff).to(p[0].dtype)
+
+
+class WassersteinProjectionLayer(FrobeniusProjectionLayer):
+    def _cov_projection(self, policy, L, L_old):
+        return ops.proj_w2_cov(L.contiguous(), L_old, self.cov_bound, self.scale_prec)[0]
+
+    def trust_region_value(self, policy, p, q):
+        return self._mean_dist(p, q), ops.cov_distance(1, p[1].contiguous(), q[1], self.scale_prec)
+
+    def get_trust_region_loss(self, policy, p, proj_p, set_variance=None):
+        return BaseProjectionLayer.get_trust_region_loss(self, policy, p, proj_p, set_variance)
+
+
+def projection_factory(typ: str, **kwargs):
+    """mprl/rl/projection/__init__.py:19-40 (device -> ``cpu`` flag, dtype parsing)."""
+    kwargs = dict(kwargs)
+    dtype, device = util.parse_dtype_device(kwargs.get("dtype", "float32"), kwargs.pop("device", "cuda"))
+    kwargs["cpu"] = device == torch.device("cpu")
+    kwargs["dtype"] = dtype
+    layers = {"BaseProjectionLayer": BaseProjectionLayer, "KLProjectionLayer": KLProjectionLayer,
+              "FrobeniusProjectionLayer": FrobeniusProjectionLayer,
+              "WassersteinProjectionLayer": WassersteinProjectionLayer}
+    if typ not in layers:
+        raise NotImplementedError(f"{typ} is not on the TCE policy-update path (SURVEY section 2, row 7)")
+    return layers[typ](**kwargs)
