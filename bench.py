@@ -1,0 +1,512 @@
+#!/usr/bin/env python
+"""bench.py -- TCE policy-update throughput on B200 (BASELINE.json: "TCE policy-update episodes/sec").
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A *step* is ONE policy epoch of ``TemporalCorrelatedAgent.update_policy``
+(mprl/rl/agent/temporal_correlated_agent.py:524-589) on the headline workload (BASELINE.json configs[1]):
+box-pushing shape (7 DoF, 8 basis + goal, Dp = 63, T = 100), 1024 episodes x 24 segments per GPU
+(``num_select: 25`` yields 24 pairs), KL projection, non-contextual full covariance, fp32:
+policy MLP forward -> vector->Cholesky head -> KL trust-region projection (+ entropy projection) ->
+segment-wise likelihood -> surrogate + trust-region loss -> backward -> (gradient all-reduce) -> Adam step.
+Nothing is skipped inside the timed region.  Weak scaling: every rank owns 1024 episodes.
+
+One JSON line is printed by rank 0 (see the contract in the task description): ``value`` is the whole-job
+episodes/s with inputs resident in HBM (CUDA-graph replay, CUDA events, L2 flushed between steps, max
+over ranks); ``e2e`` re-measures it through the public agent API with the dataset coming from pinned host
+memory every step and the loss vector read back; ``roofline`` describes the dominant kernel;
+``cpu_baseline`` times the CPU oracle (a port of the reference path) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# ---- headline workload (mprl/config/box_push_random_init/tcp/entire/shared.yaml) ---------------------------
+MP_BOX = dict(num_dof=7, tau=2.0, alpha_phase=3, num_basis=8, basis_bandwidth_factor=3, num_basis_outside=0,
+              alpha=10, relative_goal=False, auto_scale_basis=True, weights_scale=0.3, goal_scale=0.3, dt=0.02)
+T_STEPS, OBS_DIM, B_PER_GPU = 100, 20, 1024
+PROJ = dict(proj_type="kl", mean_bound=0.05, cov_bound=5e-4, trust_region_coeff=1.0, scale_prec=True,
+            entropy_schedule="linear", total_train_steps=7500, target_entropy=0.0, temperature=0.7,
+            entropy_eq=False, entropy_first=False, do_regression=False)
+AGENT = dict(lr_policy=1e-4, lr_critic=1e-3, wd_policy=5e-5, wd_critic=5e-5, discount_factor=1.0, epochs_policy=50,
+             epochs_critic=50, num_minibatchs=1, norm_advantages=True, segment_advantage="value_subtraction",
+             set_variance=False, gae_scaling=0.95)
+POLICY = dict(mean_net_args=dict(avg_neuron=128, num_hidden=2, shape=0.0),
+              variance_net_args=dict(std_only=False, contextual=False), init_method="orthogonal",
+              out_layer_gain=0.01, act_func_hidden="leaky_relu", act_func_last=None, min_std=1e-4)
+D, K1 = MP_BOX["num_dof"], MP_BOX["num_basis"] + 1
+DP = D * K1
+
+
+def synthetic_host_data(B, seed):
+    """Synthetic rollout data of SURVEY 8(d) (CPU tensors, fp32)."""
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    out = dict(obs=rn(B, OBS_DIM + 2 * D), mean_noise=0.05 * rn(B, DP), L_noise=torch.tril(0.01 * rn(DP, DP), -1),
+               init_time=torch.zeros(B), init_pos=torch.rand(B, D, generator=g) * 2 - 1, init_vel=0.1 * rn(B, D),
+               eps=rn(B, DP), rewards=rn(B, T_STEPS), values=rn(B, T_STEPS + 1))
+    out["dones"] = torch.zeros(B, T_STEPS, dtype=torch.bool)
+    out["dones"][:, -1] = True
+    out["time_limit_dones"] = torch.zeros(B, T_STEPS, dtype=torch.bool)
+    return out
+
+
+# =============================================================================================================
+# clocks
+# =============================================================================================================
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.rows[0][2]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+# =============================================================================================================
+# GPU arm
+# =============================================================================================================
+def build_gpu_workload(device, rank, world):
+    from tce_rl_b200 import ops
+    from tce_rl_b200.rl import TemporalCorrelatedAgent, policy_factory, projection_factory
+    from tce_rl_b200.rl.agent import SegmentTimeSampler
+
+    torch.manual_seed(0)                                        # identical initial weights on every rank
+    policy = policy_factory("TemporalCorrelatedPolicy", dim_in=OBS_DIM, dim_out=DP, dtype="float32", device=device,
+                            mp=dict(type="prodmp", args=dict(MP_BOX)), **POLICY)
+    projection = projection_factory("KLProjectionLayer", device=device, dtype="float32", action_dim=DP, **PROJ)
+    sampler = SegmentTimeSampler(MP_BOX["dt"], T_STEPS, dict(num_select=25, fixed_interval=True), device=device)
+    torch.manual_seed(0)
+    pairs = sampler.get_time_pairs()                            # seed 0 -> indices 0, 4, ..., 96 (P = 24)
+    dist_on = world > 1
+    agent = TemporalCorrelatedAgent(policy, None, sampler, projection, dtype="float32", device=device,
+                                    process_group=True if dist_on else None, **AGENT)
+    if dist_on:
+        ops.set_regulariser_group(True)
+        ops.set_stats_group(True)
+    host = synthetic_host_data(B_PER_GPU, seed=1234 + rank)
+    c = lambda t: t.to(device)
+    with torch.no_grad():
+        times = sampler.get_times(c(host["init_time"]), T_STEPS)
+        mean0, L0 = policy.policy(c(host["obs"])[..., :-2 * D])
+        mean_old = mean0 + c(host["mean_noise"])
+        L_old = (1.05 * L0[:1] + c(host["L_noise"])).expand(B_PER_GPU, -1, -1).contiguous()
+        smp = policy.sample(False, mean_old, L_old, times, c(host["init_time"]), c(host["init_pos"]),
+                            c(host["init_vel"]), eps=c(host["eps"]))
+        lp_old = policy.log_prob(smp, mean_old, L_old, times, c(host["init_time"]), c(host["init_pos"]),
+                                 c(host["init_vel"]), pred_pairs=pairs)
+        adv, ret = agent.get_advantage_return(c(host["rewards"]), c(host["values"]), c(host["dones"]),
+                                              c(host["time_limit_dones"]))
+        seg_adv = agent.get_segment_advantage(c(host["rewards"]), c(host["values"]), adv, pairs)
+        # the new policy starts away from the old one so that both projection branches are active
+        for p in policy.mean_net.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+        policy.variance_net.variable.add_(0.02 * torch.randn_like(policy.variance_net.variable))
+    dataset = dict(segment_state=c(host["obs"]), step_actions=smp, segment_log_prob_estimate=lp_old,
+                   segment_params_mean=mean_old, segment_params_L=L_old, segment_advantage=seg_adv,
+                   segment_init_time=c(host["init_time"]), segment_init_pos=c(host["init_pos"]),
+                   segment_init_vel=c(host["init_vel"]))
+    projection.initial_entropy = agent._global_mean(policy.entropy([mean_old, L_old]))
+    agent.num_iterations = 100
+    for p in policy.parameters:
+        p.grad = torch.zeros_like(p)
+    return agent, dataset, times, pairs
+
+
+def roofline_numbers(agent, dataset, times, pairs, device, peaks):
+    """Time the three stages of the segment likelihood alone (CUDA events, L2 flushed) and the FMA pipes."""
+    import ctypes
+    from tce_rl_b200 import _lib, ops
+    tabs = agent.policy.mp.tables
+    B, P = B_PER_GPU, pairs.shape[0]
+    with torch.no_grad():
+        new = agent.policy.policy(dataset["segment_state"][..., :-2 * D])
+    mean, L = new[0].contiguous(), new[1].contiguous()
+    work = ops._work(tabs.handle, B, P, device)
+    adj = torch.empty_like(work)
+    dmax = torch.zeros(1, device=device, dtype=torch.float64)
+    logp = torch.empty(B, P, device=device)
+    info = torch.empty(B, P, device=device, dtype=torch.int32)
+    glp = torch.full((B, P), 1.0 / (B * P), device=device)
+    gm, gL = torch.empty_like(mean), torch.empty_like(L)
+    flush = torch.empty(192 * 1024 * 1024, device=device, dtype=torch.int32)     # 768 MB > 126 MB L2
+    st = torch.cuda.current_stream().cuda_stream
+    p = lambda t: t.data_ptr()
+    ds = dataset
+
+    def gram():
+        _lib.call("tce_seglik_gram", tabs.handle, p(ds["step_actions"]), p(mean), p(L), DP * DP, p(times),
+                  p(ds["segment_init_time"]), p(ds["segment_init_pos"]), p(ds["segment_init_vel"]), p(pairs), p(work),
+                  p(dmax), B, T_STEPS, P, st)
+
+    def chol():
+        _lib.call("tce_seglik_chol", tabs.handle, p(work), p(adj), p(dmax), 1e-4, p(glp), None, None, 0.0, None, p(logp),
+                  p(info), B, P, st)
+
+    def bwd():
+        _lib.call("tce_seglik_bwd", tabs.handle, p(adj), p(L), DP * DP, p(times), p(ds["segment_init_time"]), p(pairs),
+                  p(gm), p(gL), B, T_STEPS, P, st)
+
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        total = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            total += a.elapsed_time(b)
+        return total / reps * 1e-3                     # seconds
+
+    gram(); chol()
+    t = {"seglik_gram": timed(gram), "seglik_chol": timed(chol), "seglik_bwd": timed(bwd)}
+    scratch = torch.empty(16, device=device, dtype=torch.float64)
+    pipes = {}
+    for name, fp64 in (("fp32", 0), ("fp64", 1)):
+        fl = ctypes.c_double()
+        run = lambda: _lib.call("tce_bench_fma", fp64, 4096, p(scratch), ctypes.byref(fl), st)
+        pipes[name] = 0.0
+        for _ in range(3):
+            pipes[name] = max(pipes[name], 1.0 / timed(run, reps=3))
+        pipes[name] *= fl.value / 1e12                  # TFLOP/s
+    # algorithmic bytes / FLOPs per episode (fp32 = 4 B, L counted as its lower triangle)
+    tri = DP * (DP + 1) // 2
+    fwd_bytes = 4 * (tri + DP + (P + 1) * D + (1 + 2 * D) + P)
+    bwd_bytes = fwd_bytes + 4 * (P + DP + tri)
+    n = 2 * D
+    mac_seg = DP * (DP + 1) + K1 * (4 * sum(d * (d + 1) // 2 for d in range(D)) + 3 * D * (D + 1) // 2) \
+        + n ** 3 // 6 + n * n // 2 + n * K1
+    fwd_flops = P * 2 * mac_seg
+    dom = max(t, key=t.get)
+    alg = {"seglik_gram": (fwd_bytes, fwd_flops), "seglik_chol": (8 * P * (n * (n + 1) // 2 + n), P * 2 * (n ** 3 // 2)),
+           "seglik_bwd": (bwd_bytes, 2 * fwd_flops)}[dom]
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg[0] * B / t[dom] / 1e9
+    roof = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
+            "frac": round(achieved / hbm_peak, 5), "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst, kernel timed alone)" if "hbm_gbs" in peaks
+            else "fallback 6650 GB/s (B200_PROFILING.md)",
+            "algorithmic_bytes_per_launch": alg[0] * B, "kernel_us": {k: round(v * 1e6, 2) for k, v in t.items()},
+            "compute": {"note": "this kernel is FMA-pipe bound (SURVEY 8(d)): mixed fp32 FFMA + fp64 DFMA",
+                        "achieved_tflops": round(alg[1] * B / t[dom] / 1e12, 3),
+                        "measured_fp32_fma_tflops": round(pipes["fp32"], 2),
+                        "measured_fp64_fma_tflops": round(pipes["fp64"], 2),
+                        "frac_of_fp32_fma": round(alg[1] * B / t[dom] / 1e12 / pipes["fp32"], 4),
+                        "algorithmic_flops_per_launch": alg[1] * B}}
+    return roof
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE {world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (GPU arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    from tce_rl_b200 import _lib
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
+    agent, dataset, times, pairs = build_gpu_workload(device, rank, world)
+    K, W = args.steps, max(args.warmup, 3)
+    flush = torch.empty(192 * 1024 * 1024, device=device, dtype=torch.int32)
+
+    # ---- capture one epoch in a CUDA graph (falls back to eager replay when NCCL refuses capture) ------------
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            agent.policy_epoch(dataset, times, pairs)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph, metrics, launches_per_step = None, None, 0
+    try:
+        l0 = _lib.LAUNCHES
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            metrics = agent.policy_epoch(dataset, times, pairs)
+        launches_per_step = _lib.LAUNCHES - l0
+        step_fn = graph.replay
+        mode = "cuda_graph"
+    except Exception as exc:                                     # pragma: no cover
+        if rank == 0:
+            print(f"[bench] CUDA-graph capture failed ({exc!r}); timing eager steps", file=sys.stderr)
+        graph, mode = None, "eager"
+        torch.cuda.synchronize()
+        l0 = _lib.LAUNCHES
+        metrics = agent.policy_epoch(dataset, times, pairs)
+        launches_per_step = _lib.LAUNCHES - l0
+
+        def step_fn():
+            nonlocal metrics
+            metrics = agent.policy_epoch(dataset, times, pairs)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------------------------------------
+    for _ in range(W):
+        flush.zero_()
+        step_fn()
+    barrier()
+    events = []
+    with ClockSampler(local) as clocks:
+        t_wall0 = time.perf_counter()
+        for _ in range(K):
+            flush.zero_()                                        # L2 flush, outside the timed events
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_fn()
+            b.record()
+            events.append((a, b))
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    total_ms = sum(a.elapsed_time(b) for a, b in events)
+    tt = torch.tensor([total_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = tt.item()
+    ms_per_step = total_ms / K
+    value = world * B_PER_GPU / (ms_per_step * 1e-3)
+    final = metrics.cpu()
+    if not torch.isfinite(final).all():
+        raise SystemExit("non-finite loss in the timed region")
+
+    # ---- end to end: host-resident dataset in, loss vector out, every step -------------------------------------------
+    keys = ["segment_state", "step_actions", "segment_log_prob_estimate", "segment_params_mean", "segment_params_L",
+            "segment_advantage", "segment_init_time", "segment_init_pos", "segment_init_vel"]
+    pinned = {k: dataset[k].cpu().pin_memory() for k in keys}
+    out_host = torch.empty_like(final).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    d2h = out_host.numel() * out_host.element_size()
+
+    def e2e_step():
+        for k in keys:
+            dataset[k].copy_(pinned[k], non_blocking=True)
+        step_fn()
+        out_host.copy_(metrics, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    ev = []
+    for _ in range(K):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        e2e_step()
+        b.record()
+        b.synchronize()                                          # the caller owns the loss before the next step
+        ev.append((a, b))
+    barrier()
+    e2e_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / K], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * B_PER_GPU / (e2e_ms.item() * 1e-3)
+
+    roof = roofline_numbers(agent, dataset, times, pairs, device, peaks) if rank == 0 else None
+    cpu = cpu_baseline(budget_s=12.0) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        P = int(pairs.shape[0])
+        line = {
+            "metric": "TCE policy-update episodes/sec", "value": round(value, 1), "unit": "episodes/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"boxpush_tce_policy_epoch_B{B_PER_GPU}_P{P}", "episodes_per_gpu": B_PER_GPU,
+                       "global_episodes": world * B_PER_GPU, "segments": P, "num_dof": D, "num_basis_g": K1,
+                       "dim_params": DP, "num_times": T_STEPS, "projection": "KLProjectionLayer",
+                       "contextual_cov": False, "L_layout": "per-episode [B,63,63] into the likelihood",
+                       "step": "policy MLP + head + KL/entropy projection + segment likelihood + losses + backward "
+                               "+ grad all-reduce + Adam", "replay": mode, "l2": "flushed between timed steps",
+                       "segment_logprobs_per_s_fwd_bwd": round(value * P, 1)},
+            "clocks": clocks.summary(),
+            "e2e": {"value": round(e2e_value, 1), "unit": "episodes/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms.item(), 5)},
+            "gpu_launches": launches_per_step * K,
+            "gpu_launches_per_step": launches_per_step,
+            "roofline": roof,
+            "wall_s_timed_region": round(t_wall, 3),
+            "loss": {"surrogate": round(final[0].item(), 6), "trust_region": round(final[2].item(), 6)},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# =============================================================================================================
+# CPU arm: the oracle (a port of the reference's path: mprl.rl + restated mp_pytorch / trust_region_projections)
+# =============================================================================================================
+def make_oracle_workload(B, dtype=torch.float32, seed=1234):
+    from oracle import agent as oa, policy as opol, projection as oproj, util as ou
+    torch.manual_seed(0)
+    dims = [OBS_DIM, 128, 128, DP]
+    layers = []
+    for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+        lin = torch.nn.Linear(a, b, dtype=dtype)
+        torch.nn.init.orthogonal_(lin.weight, gain=0.01 if i == 2 else math.sqrt(2))
+        torch.nn.init.zeros_(lin.bias)
+        layers += [lin] + ([torch.nn.LeakyReLU()] if i < 2 else [])
+    mean_net = torch.nn.Sequential(*layers)
+    policy = opol.TemporalCorrelatedPolicy(DP, mp=dict(type="prodmp", args=dict(MP_BOX, dtype=dtype)), mean_net=mean_net,
+                                           contextual=False, min_std=1e-4, dtype=dtype)
+    policy.cov_vector = policy.cov_vector.clone().requires_grad_(True)
+    layer = oproj.projection_factory("KLProjectionLayer", dtype=dtype, action_dim=DP, **PROJ)
+    host = synthetic_host_data(B, seed)
+    c = lambda t: t.to(dtype) if t.is_floating_point() else t
+    torch.manual_seed(0)
+    pairs = ou.get_time_pairs(T_STEPS, dict(num_select=25, fixed_interval=True))
+    with torch.no_grad():
+        times = ou.get_times(c(host["init_time"]), T_STEPS, MP_BOX["dt"])
+        mean0, L0 = policy.policy(c(host["obs"])[..., :-2 * D])
+        mean_old = mean0 + c(host["mean_noise"])
+        L_old = (1.05 * L0[:1] + c(host["L_noise"])).expand(B, -1, -1).contiguous()
+        smp = policy.sample(False, mean_old, L_old, times, c(host["init_time"]), c(host["init_pos"]), c(host["init_vel"]),
+                            eps=c(host["eps"]))
+        lp_old = policy.log_prob(smp, mean_old, L_old, times, c(host["init_time"]), c(host["init_pos"]),
+                                 c(host["init_vel"]), pred_pairs=pairs)
+        adv, _ = oa.get_advantage_return(c(host["rewards"]), c(host["values"]), host["dones"], host["time_limit_dones"],
+                                         1.0, 0.95)
+        seg = oa.get_segment_advantage(c(host["rewards"]), c(host["values"]), adv, pairs, 1.0, "value_subtraction", True)
+        for p in mean_net.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    data = dict(segment_state=c(host["obs"]), step_actions=smp, segment_log_prob_estimate=lp_old,
+                segment_params_mean=mean_old, segment_params_L=L_old, segment_advantage=seg,
+                segment_init_time=c(host["init_time"]), segment_init_pos=c(host["init_pos"]),
+                segment_init_vel=c(host["init_vel"]))
+    layer.initial_entropy = policy.entropy([mean_old, L_old]).mean()
+    params = list(mean_net.parameters()) + [policy.cov_vector]
+    opt = torch.optim.Adam(params, lr=1e-4, weight_decay=5e-5)
+
+    def epoch():
+        loss, _ = oa.policy_epoch(policy, layer, data, times, pairs, 100, set_variance=False)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+    return epoch
+
+
+def cpu_baseline(budget_s=12.0, sample_B=256):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    epoch = make_oracle_workload(sample_B)
+    epoch()                                                      # warm-up
+    t0, n = time.perf_counter(), 0
+    while True:
+        epoch()
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or n >= 50:
+            break
+    return {"value": round(sample_B * n / dt, 2), "unit": "episodes/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} policy epochs of {sample_B} episodes x 24 segments (same shapes, fp32, torch CPU oracle "
+                      f"= reference mprl.rl path + restated mp_pytorch / trust-region layers), {dt:.1f} s",
+            "note": "the restated KL projection solves the dual exactly (cheaper than the reference's ITPAL/NLopt "
+                    "C++ path), so this is a lower bound on the reference's CPU cost"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_B = 256
+    epoch = make_oracle_workload(sample_B)
+    for _ in range(max(1, min(args.warmup, 3))):
+        epoch()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        epoch()
+    dt = time.perf_counter() - t0
+    value = sample_B * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "TCE policy-update episodes/sec", "value": round(value, 2),
+        "unit": "episodes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"boxpush_tce_policy_epoch_B{B_PER_GPU}_P24",
+                   "sample": f"each step = one policy epoch over a {sample_B}-episode sample of the workload"},
+        "cpu_baseline": {"value": round(value, 2), "unit": "episodes/s", "cores": torch.get_num_threads(),
+                         "kind": "port", "sample": f"{args.steps} epochs x {sample_B} episodes x 24 segments"},
+        "e2e": {"value": round(value, 2), "unit": "episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

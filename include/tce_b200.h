@@ -209,6 +209,11 @@ int tce_sum_stats(const float *x, double *stats, int64_t N, void *stream);
 /* (x - mean) / (std_unbiased + 1e-8) with mean/std from stats[3] (temporal_correlated_agent.py:281-284) */
 int tce_normalize_by_stats(float *x, const double *stats, int64_t N, void *stream);
 
+/* ---- measurement helper ---------------------------------------------------------------------------------
+ * One register-resident FMA-chain kernel (fp32 or fp64) over the whole chip; *flops (host) receives the
+ * FLOPs executed.  bench.py times it to obtain the FMA-pipe roofline denominators.                      */
+int tce_bench_fma(int fp64, int iters, void *scratch, double *flops, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

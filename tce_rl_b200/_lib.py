@@ -66,6 +66,7 @@ SIGNATURES = {
     "tce_segment_advantage_raw": (C.c_int, [_I32, _P, _P, _P, _P, _F, _P, _P, _I64, _I64, _I64, _P]),
     "tce_sum_stats": (C.c_int, [_P, _P, _I64, _P]),
     "tce_normalize_by_stats": (C.c_int, [_P, _P, _I64, _P]),
+    "tce_bench_fma": (C.c_int, [_I32, _I32, _P, C.POINTER(C.c_double), _P]),
 }
 
 _lib = None
@@ -95,5 +96,12 @@ def check(status: int, what: str = "") -> None:
         raise TceError(f"{what}: {msg} (status {status})")
 
 
+LAUNCHES = 0          # kernel launches issued through the C ABI (bench.py reports them as gpu_launches)
+_NO_KERNEL = {"tce_prodmp_tables_export", "tce_prodmp_tables_create"}
+
+
 def call(name: str, *args) -> None:
+    global LAUNCHES
     check(getattr(load(), name)(*args), name)
+    if name not in _NO_KERNEL:
+        LAUNCHES += 1
