@@ -187,7 +187,7 @@ def roofline_numbers(agent, dataset, times, pairs, device, peaks):
 
     def bwd():
         _lib.call("tce_seglik_bwd", tabs.handle, p(adj), p(L), DP * DP, p(times), p(ds["segment_init_time"]), p(pairs),
-                  p(gm), p(gL), B, T_STEPS, P, st)
+                  None, p(gm), p(gL), B, T_STEPS, P, st)
 
     def timed(fn, reps=20):
         for _ in range(3):

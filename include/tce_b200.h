@@ -115,6 +115,11 @@ int tce_gauss_stats_bwd(const float *mean, const float *L, int64_t ldb_L, const 
                         const float *L_o, int64_t ldb_Lo, const double *grad_out, float *grad_mean,
                         float *grad_L, int64_t B, int n, void *stream);
 
+/* maha [B] = |L_o^-1 (mean - mean_o)|^2 (policy.maha, black_box_policy.py:205-224) when grad_out == NULL;
+ * otherwise grad_mean [B,n] = grad_out[b] * 2 Sigma_o^-1 (mean - mean_o) (maha may also be written).      */
+int tce_gauss_maha(const float *mean, const float *mean_o, const float *L_o, int64_t ldb_Lo,
+                   const double *grad_out, double *maha, float *grad_mean, int64_t B, int n, void *stream);
+
 /* ---- (4a) differentiable trust-region projections ------------------------------------------------------
  * Replace the trust_region_projections layers (BruceGeLi/trust-region-layers@TCE_ICLR24) created by
  * projection_factory (mprl/rl/projection/__init__.py:19-40) and called at
@@ -172,9 +177,11 @@ int tce_cov_distance(int kind, const float *L, const float *L_o, int64_t ldb_Lo,
  *                  size as `work`; may alias it).
  *                  With logp_old/advantage [B,P] != NULL instead, the surrogate loss of
  *                  temporal_correlated_agent.py:718-739 is fused: the upstream gradient is
- *                  -exp(lp - lp_old) * adv * grad_scale and its sum is added to *loss_acc
- *                  (grad_scale = 1 / (B_global * P) gives loss = -mean(ratio * adv)).
- * Stage 3 (bwd):   per episode, from `adj`: grad_mean [B, Dp] and grad_L [B, Dp, Dp] (lower triangle).
+ *                  -exp(lp - lp_old) * adv * grad_scale; its sum is added to loss_acc[0] and the sum of
+ *                  ratio * grad_scale to loss_acc[1] (grad_scale = 1 / (B * P) gives loss = -mean(ratio *
+ *                  adv) and the mean importance ratio).  loss_acc: 2 device doubles, caller zeroes.
+ * Stage 3 (bwd):   per episode, from `adj`: grad_mean [B, Dp] and grad_L [B, Dp, Dp] (lower triangle),
+ *                  both multiplied by *upstream (device float) when upstream != NULL.
  *
  * smp_traj [B, T, 2D] (only [:, pairs, :D] is read), mean [B, Dp], L [B, Dp, Dp] (batch stride
  * ldb_L, 0 = shared), times [B, T], init_* as above, pred_pairs [P, 2] int64.                       */
@@ -189,7 +196,8 @@ int tce_seglik_chol(const tce_tables_t *tables, const void *work, void *adj, con
                     int64_t P, void *stream);
 int tce_seglik_bwd(const tce_tables_t *tables, const void *work, const float *L, int64_t ldb_L,
                    const float *times, const float *init_time, const int64_t *pred_pairs,
-                   float *grad_mean, float *grad_L, int64_t B, int64_t T, int64_t P, void *stream);
+                   const float *upstream, float *grad_mean, float *grad_L, int64_t B, int64_t T, int64_t P,
+                   void *stream);
 
 /* ---- (4b) GAE and segment advantages ------------------------------------------------------------------
  * TemporalCorrelatedAgent.get_advantage_return (temporal_correlated_agent.py:118-181).

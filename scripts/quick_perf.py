@@ -49,7 +49,7 @@ for B in [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["10
     res["gram_us"] = timeit(lambda: _lib.call("tce_seglik_gram", tabs.handle, p(traj), p(g["mean"]), p(g["L"]), Dp*Dp, p(times_g), p(g["init_time"]), p(g["init_pos"]), p(g["init_vel"]), p(pairs_g), p(work), p(dmax), B, T, P, st))
     res["chol_fwd_us"] = timeit(lambda: _lib.call("tce_seglik_chol", tabs.handle, p(work), None, p(dmax), 1e-4, None, None, None, 0.0, None, p(logp), p(info), B, P, st))
     res["chol_grad_us"] = timeit(lambda: _lib.call("tce_seglik_chol", tabs.handle, p(work), p(adj), p(dmax), 1e-4, p(glp), None, None, 0.0, None, p(logp), p(info), B, P, st))
-    res["bwd_us"] = timeit(lambda: _lib.call("tce_seglik_bwd", tabs.handle, p(adj), p(g["L"]), Dp*Dp, p(times_g), p(g["init_time"]), p(pairs_g), p(gm), p(gL), B, T, P, st))
+    res["bwd_us"] = timeit(lambda: _lib.call("tce_seglik_bwd", tabs.handle, p(adj), p(g["L"]), Dp*Dp, p(times_g), p(g["init_time"]), p(pairs_g), None, p(gm), p(gL), B, T, P, st))
     res["gauss_stats_us"] = timeit(lambda: ops.gauss_stats(g["mean"], g["L"], g["mean_old"], g["L_old"]))
     res["gae_us"] = timeit(lambda: ops.gae(g["rewards"], g["values"], g["dones"], g["time_limit_dones"], 1.0, 0.95, True))
     res["segadv_us"] = timeit(lambda: ops.segment_advantage(1, g["rewards"], g["values"], g["rewards"], pairs_g, 1.0, True))

@@ -11,6 +11,7 @@
 namespace {
 
 constexpr int PJ_THREADS = 512;
+constexpr int KL_THREADS = 1024;  // one warp per Jacobi column pair (n <= 64 -> 32 pairs)
 constexpr double LOG_2PI = 1.8378770664093453;
 
 __device__ inline int pad_even(int n) { return (n + 1) & ~1; }
@@ -143,6 +144,55 @@ gauss_kl_kernel(const float *__restrict__ mean, const float *__restrict__ L, lon
 }
 
 // =====================================================================================================
+// Mahalanobis distance |L_o^-1 (mean - mean_o)|^2 and its gradient 2 g Sigma_o^-1 (mean - mean_o).
+// Called several times per epoch on the whole batch: light kernel, one 128-thread CTA per episode, L_o staged
+// as fp32 (odd row stride -> conflict-free column access), the two triangular vector solves run in fp64 on
+// warp 0 (column oriented: after z_j is known every lane updates its rows).
+// =====================================================================================================
+__global__ void __launch_bounds__(128)
+maha_kernel(const float *__restrict__ mean, const float *__restrict__ mean_o, const float *__restrict__ L_o,
+            long long ldb_Lo, const double *__restrict__ gout, double *__restrict__ out,
+            float *__restrict__ grad_mean, int n) {
+  extern __shared__ double smd[];
+  const int LD = n | 1;
+  double *bv = smd, *inv = smd + n;
+  float *sL = reinterpret_cast<float *>(smd + 2 * n);
+  const long long b = blockIdx.x;
+  const float *Lo = L_o + b * ldb_Lo;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    if (j <= i) sL[i * LD + j] = Lo[e];
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    bv[i] = (double)mean[b * n + i] - (double)mean_o[b * n + i];
+    inv[i] = 1.0 / (double)Lo[(size_t)i * n + i];
+  }
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  double maha = 0.0;
+  for (int j = 0; j < n; ++j) {                       // z = L_o^-1 diff
+    const double zj = bv[j] * inv[j];
+    __syncwarp();
+    for (int i = j + 1 + lane; i < n; i += 32) bv[i] = fma(-(double)sL[i * LD + j], zj, bv[i]);
+    if (lane == 0) bv[j] = zj;
+    maha = fma(zj, zj, maha);
+    __syncwarp();
+  }
+  if (out && lane == 0) out[b] = maha;
+  if (!gout) return;
+  const double g2 = 2.0 * gout[b];
+  for (int i = n - 1; i >= 0; --i) {                  // u = L_o^-T z
+    const double ui = bv[i] * inv[i];
+    __syncwarp();
+    for (int k = lane; k < i; k += 32) bv[k] = fma(-(double)sL[i * LD + k], ui, bv[k]);
+    if (lane == 0) bv[i] = ui;
+    __syncwarp();
+  }
+  for (int i = lane; i < n; i += 32) grad_mean[b * n + i] = (float)(g2 * bv[i]);
+}
+
+// =====================================================================================================
 // mean projection (closed form) -- elementwise, one warp per episode
 // =====================================================================================================
 __global__ void proj_mean_fwd_kernel(const float *__restrict__ mean, const float *__restrict__ mean_o,
@@ -242,7 +292,7 @@ __device__ inline double kl_of_eta(const double *lam, int n, double eta, double 
   return 0.5 * f;
 }
 
-__global__ void __launch_bounds__(PJ_THREADS)
+__global__ void __launch_bounds__(KL_THREADS)
 proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_o, double eps_cov,
                        float *__restrict__ proj_L, double *__restrict__ save_Q, double *__restrict__ save_lam,
                        double *__restrict__ save_sc, int32_t *__restrict__ info, int n) {
@@ -259,10 +309,9 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   load_lower_d(b1, Lo, n, m);
   la_inv_diag(b0, inv_diag, n);
   la_trsm_lower(b0, inv_diag, b1, n, n, true);                                   // W = Lt^-1 Lo (lower)
-  la_gemm(b2, b1.T(), b1, n, n, n, TRI_UPPER, TRI_LOWER, TRI_FULL, 1.0, 0.0);     // N = W^T W
   for (int e = threadIdx.x; e < m * m; e += blockDim.x) b3(e / m, e % m) = (e / m == e % m) ? 1.0 : 0.0;
   __syncthreads();
-  la_jacobi(b2, b3, lam, n, rot, red);                                            // N = Q diag(lam) Q^T
+  la_jacobi_onesided(b1, b3, lam, rot, n);                                             // W^T W = Q diag(lam) Q^T
   if (threadIdx.x < 32) {
     const double kl0 = kl_of_eta(lam, n, 0.0, nullptr);
     double eta = 0.0;
@@ -651,6 +700,19 @@ extern "C" int tce_gauss_stats_bwd(const float *mean, const float *L, int64_t ld
   return TCE_OK;
 }
 
+extern "C" int tce_gauss_maha(const float *mean, const float *mean_o, const float *L_o, int64_t ldb_Lo,
+                              const double *grad_out, double *maha, float *grad_mean, int64_t B, int n, void *stream) {
+  if (!mean || !mean_o || !L_o || B < 0 || n < 1 || n > 128 || (grad_out && !grad_mean) || (!grad_out && !maha))
+    return TCE_ERR_INVALID_ARGUMENT;
+  if (B == 0) return TCE_OK;
+  const size_t smem = 2 * (size_t)n * sizeof(double) + (size_t)n * (n | 1) * sizeof(float);
+  if (smem > 48 * 1024)
+    TCE_CUDA(cudaFuncSetAttribute(maha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "maha attr");
+  maha_kernel<<<(unsigned)B, 128, smem, (cudaStream_t)stream>>>(mean, mean_o, L_o, ldb_Lo, grad_out, maha, grad_mean, n);
+  TCE_CHECK_LAUNCH("maha_kernel");
+  return TCE_OK;
+}
+
 extern "C" int tce_proj_mean_fwd(const float *mean, const float *mean_o, const double *mean_part, double eps,
                                  float *proj_mean, int64_t B, int n, void *stream) {
   if (!mean || !mean_o || !mean_part || !proj_mean || B < 0 || n < 1 || !(eps > 0)) return TCE_ERR_INVALID_ARGUMENT;
@@ -702,7 +764,7 @@ extern "C" int tce_proj_kl_cov_fwd(const float *L, const float *L_o, double eps_
   int rc = set_smem(proj_kl_cov_fwd_kernel, smem);
   if (rc) return rc;
   double *Q = save, *lam = Q + (size_t)B * n * n, *sc = lam + (size_t)B * n;
-  proj_kl_cov_fwd_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, eps_cov, proj_L, Q, lam, sc, info, n);
+  proj_kl_cov_fwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, eps_cov, proj_L, Q, lam, sc, info, n);
   TCE_CHECK_LAUNCH("proj_kl_cov_fwd_kernel");
   return TCE_OK;
 }

@@ -219,7 +219,7 @@ seglik_chol_kernel(const double *Cmat, const double *Rres, double *Gout, double 
   __shared__ double sm[NT * CH_THREADS];
   const long long gid = (long long)blockIdx.x * CH_THREADS + threadIdx.x;
   const bool active = gid < BP;
-  double loss_part = 0.0;
+  double loss_part = 0.0, ratio_part = 0.0;
   if (active) {
     const long long b = gid / P;
     const int p = (int)(gid % P);
@@ -270,6 +270,7 @@ seglik_chol_kernel(const double *Cmat, const double *Rres, double *Gout, double 
         const double ratio = exp(lp - (double)logp_old[gid]);
         g = -ratio * (double)advantage[gid] * grad_scale;
         loss_part = g;
+        ratio_part = ratio * grad_scale;
       } else {
         g = (double)grad_logp[gid];
       }
@@ -316,7 +317,11 @@ seglik_chol_kernel(const double *Cmat, const double *Rres, double *Gout, double 
   }
   if (loss_acc) {
     loss_part = warp_sum(loss_part);
-    if ((threadIdx.x & 31) == 0 && loss_part != 0.0) atomicAdd(loss_acc, loss_part);
+    ratio_part = warp_sum(ratio_part);
+    if ((threadIdx.x & 31) == 0 && ratio_part != 0.0) {
+      atomicAdd(loss_acc, loss_part);
+      atomicAdd(loss_acc + 1, ratio_part);
+    }
   }
 }
 
@@ -328,7 +333,8 @@ __global__ void __launch_bounds__(SL_THREADS)
 seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__restrict__ Alpha,
                   const float *__restrict__ L, long long ldb_L, const float *__restrict__ times,
                   const float *__restrict__ init_time, const int64_t *__restrict__ pairs,
-                  float *__restrict__ grad_mean, float *__restrict__ grad_L, int T, int P) {
+                  const float *__restrict__ upstream, float *__restrict__ grad_mean, float *__restrict__ grad_L,
+                  int T, int P) {
   constexpr int Dp = D * K1, N = 2 * D, NT = tri(N);
   constexpr int NR = (Dp + 1) & ~1;
   constexpr int LD = NR + 1;
@@ -344,6 +350,7 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
   const long long b = blockIdx.x;
   const double *Gb = Gmat + (size_t)b * NT * P;
   const double *Ab = Alpha + (size_t)b * N * P;
+  const float up = upstream ? *upstream : 1.0f;       // scalar gradient of the fused surrogate loss
 
   load_lower(L + b * ldb_L, Ls, Dp, NR, LD);
   for (int e = threadIdx.x; e < NT * P; e += blockDim.x) Gs[e] = Gb[e];
@@ -356,7 +363,7 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
       const int d = o / K1, j = o % K1;
       double acc = 0.0;
       for (int q = 0; q < 2 * P; ++q) acc = fma(hs[q * K1 + j], Ab[(size_t)(2 * d + (q & 1)) * P + (q >> 1)], acc);
-      grad_mean[b * Dp + o] = (float)acc;
+      grad_mean[b * Dp + o] = up * (float)acc;
     }
   }
   if (!grad_L) return;
@@ -409,12 +416,12 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
       }
       const int i0 = 2 * I, j0 = 2 * J;
       if (i0 < Dp) {
-        out[i0 * Dp + j0] = 2.f * c00;
-        if (j0 + 1 <= i0) out[i0 * Dp + j0 + 1] = 2.f * c01;
+        out[i0 * Dp + j0] = 2.f * up * c00;
+        if (j0 + 1 <= i0) out[i0 * Dp + j0 + 1] = 2.f * up * c01;
       }
       if (i0 + 1 < Dp) {
-        out[(i0 + 1) * Dp + j0] = 2.f * c10;
-        if (j0 + 1 < Dp) out[(i0 + 1) * Dp + j0 + 1] = 2.f * c11;
+        out[(i0 + 1) * Dp + j0] = 2.f * up * c10;
+        if (j0 + 1 < Dp) out[(i0 + 1) * Dp + j0 + 1] = 2.f * up * c11;
       }
     }
   }
@@ -511,7 +518,8 @@ extern "C" int tce_seglik_chol(const tce_tables_t *t, const void *work, void *ad
 
 extern "C" int tce_seglik_bwd(const tce_tables_t *t, const void *work, const float *L, int64_t ldb_L,
                               const float *times, const float *init_time, const int64_t *pred_pairs,
-                              float *grad_mean, float *grad_L, int64_t B, int64_t T, int64_t P, void *stream) {
+                              const float *upstream, float *grad_mean, float *grad_L, int64_t B, int64_t T,
+                              int64_t P, void *stream) {
   if (!t || !work || !L || !times || !init_time || !pred_pairs || B < 0 || T < 1 || P < 1)
     return TCE_ERR_INVALID_ARGUMENT;
   if (B == 0) return TCE_OK;
@@ -524,7 +532,7 @@ extern "C" int tce_seglik_bwd(const tce_tables_t *t, const void *work, const flo
     TCE_CUDA(cudaFuncSetAttribute(seglik_bwd_kernel<Dv, Kv>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                   (int)smem), "bwd smem attr");                                                  \
     seglik_bwd_kernel<Dv, Kv><<<(unsigned)B, SL_THREADS, smem, st>>>(tab_dev(t), G, A, L, ldb_L, times, init_time, \
-                                                                    pred_pairs, grad_mean, grad_L, (int)T, (int)P); \
+                                                                    pred_pairs, upstream, grad_mean, grad_L, (int)T, (int)P); \
     TCE_CHECK_LAUNCH("seglik_bwd_kernel");                                                                       \
     return TCE_OK;                                                                                               \
   }

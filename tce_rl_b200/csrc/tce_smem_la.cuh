@@ -197,3 +197,74 @@ __device__ inline void la_jacobi(Mat A, Mat Q, double *lam, int n, double *rot, 
   for (int i = threadIdx.x; i < n; i += blockDim.x) lam[i] = A(i, i);
   __syncthreads();
 }
+
+// One-sided (Hestenes) Jacobi SVD of W (n x n, destroyed): W V = U diag(sigma), i.e. W^T W = V diag(sigma^2) V^T.
+// V must hold the identity on entry; on exit lam[i] = sigma_i^2.  Round-robin ordering, ONE WARP PER COLUMN
+// PAIR (needs blockDim.x >= 32 * ceil(n/2)), one barrier per step.  Works on W directly (no W^T W), which
+// keeps the small generalised eigenvalues accurate.  Latency matters (a single matrix sits on the critical
+// path of every policy epoch): squared column norms are cached in `nrm` (>= n doubles) and updated in closed
+// form, so a step needs ONE warp reduction; the rotation angle is evaluated in fp32 (it only steers
+// convergence) while (c, s) are normalised in fp64 so every rotation stays orthogonal to 1e-16.
+__device__ inline void la_jacobi_onesided(Mat W, Mat V, double *lam, double *nrm, int n) {
+  const int m = (n + 1) & ~1, half = m / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = (int)(blockDim.x >> 5);
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    // (re)compute the squared column norms once per sweep (also bounds the drift of the closed-form update)
+    for (int j = warp; j < n; j += nwarp) {
+      double a = 0.0;
+      for (int r = lane; r < n; r += 32) a = fma(W(r, j), W(r, j), a);
+      a = warp_sum(a);
+      if (lane == 0) nrm[j] = a;
+    }
+    __syncthreads();
+    int rotated = 0;
+    for (int step = 0; step < m - 1; ++step) {
+      if (warp < half) {
+        int p, q;
+        if (warp == 0) { p = m - 1; q = step % (m - 1); }
+        else { p = (step + warp) % (m - 1); q = (step - warp + (m - 1)) % (m - 1); }
+        if (p > q) { const int t = p; p = q; q = t; }
+        if (q < n) {
+          const int r0 = lane, r1 = lane + 32;
+          const double x0 = r0 < n ? W(r0, p) : 0.0, y0 = r0 < n ? W(r0, q) : 0.0;
+          const double x1 = r1 < n ? W(r1, p) : 0.0, y1 = r1 < n ? W(r1, q) : 0.0;
+          double g = fma(x0, y0, x1 * y1);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+          const double a = nrm[p], b = nrm[q];
+          if (g * g > 1e-22 * a * b) {
+            rotated = 1;
+            const float zeta = (float)((b - a) / (2.0 * g));
+            const float tf = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
+            const double t = (double)tf;
+            const double c = rsqrt(fma(t, t, 1.0)), s = c * t;
+            if (r0 < n) {
+              W(r0, p) = c * x0 - s * y0; W(r0, q) = s * x0 + c * y0;
+              const double u = V(r0, p), v = V(r0, q);
+              V(r0, p) = c * u - s * v; V(r0, q) = s * u + c * v;
+            }
+            if (r1 < n) {
+              W(r1, p) = c * x1 - s * y1; W(r1, q) = s * x1 + c * y1;
+              const double u = V(r1, p), v = V(r1, q);
+              V(r1, p) = c * u - s * v; V(r1, q) = s * u + c * v;
+            }
+            if (lane == 0) {                       // |c x - s y|^2 and |s x + c y|^2
+              const double c2 = c * c, s2 = s * s, cs2 = 2.0 * c * s * g;
+              nrm[p] = c2 * a + s2 * b - cs2;
+              nrm[q] = s2 * a + c2 * b + cs2;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (!__syncthreads_or(rotated)) break;
+  }
+  for (int j = warp; j < n; j += nwarp) {
+    double a = 0.0;
+    for (int r = lane; r < n; r += 32) a = fma(W(r, j), W(r, j), a);
+    a = warp_sum(a);
+    if (lane == 0) lam[j] = a;
+  }
+  __syncthreads();
+}

@@ -333,7 +333,7 @@ def seglik_bwd(grad_logp: Tensor, work: Tensor, diag_max: Tensor, L: Tensor, tim
     st = _stream()
     _lib.call("tce_seglik_chol", tables, _p(work), _p(adj), _p(diag_max), float(reg_rel), _p(grad_logp), None, None,
               0.0, None, None, None, B, P, st)
-    _lib.call("tce_seglik_bwd", tables, _p(adj), _p(L), ldb, _p(times), _p(init_time), _p(pairs), _p(g_mean),
+    _lib.call("tce_seglik_bwd", tables, _p(adj), _p(L), ldb, _p(times), _p(init_time), _p(pairs), None, _p(g_mean),
               _p(g_L), B, T, P, st)
     return g_mean, g_L
 
@@ -371,6 +371,95 @@ def seg_logprob(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pa
     logp, _work_, diag_max, info = seglik_fwd(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs,
                                               tables.handle, reg_rel)
     return (logp, info, diag_max) if return_info else logp
+
+
+@torch.library.custom_op("tce::seglik_surrogate_fwd", mutates_args=())
+def seglik_surrogate_fwd(smp_traj: Tensor, mean: Tensor, L: Tensor, times: Tensor, init_time: Tensor,
+                         init_pos: Tensor, init_vel: Tensor, pred_pairs: Tensor, logp_old: Tensor, advantage: Tensor,
+                         tables: int, reg_rel: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Fused segment likelihood + importance-sampling surrogate (temporal_correlated_agent.py:718-739).
+
+    -> (stats [2] fp64 = {-mean(ratio * adv), mean(ratio)}, logp [B,P], adj (per-segment adjoints for the
+    backward stage, already scaled by d loss / d logp), info [B,P]).
+    """
+    smp_traj, mean, times = _chk(smp_traj, name="smp_traj"), _chk(mean, name="mean"), _chk(times, name="times")
+    init_time, init_pos, init_vel = _chk(init_time), _chk(init_pos), _chk(init_vel)
+    logp_old, advantage = _chk(logp_old, name="logp_old"), _chk(advantage, name="advantage")
+    pairs = _chk(pred_pairs, torch.int64, "pred_pairs")
+    L, ldb = _batched_matrix(L)
+    B, T = times.shape
+    P = pairs.shape[0]
+    dev = mean.device
+    work = _work(tables, B, P, dev)
+    diag_max = torch.zeros(1, device=dev, dtype=torch.float64)
+    stats = torch.zeros(2, device=dev, dtype=torch.float64)
+    logp = torch.empty(B, P, device=dev, dtype=torch.float32)
+    info = torch.empty(B, P, device=dev, dtype=torch.int32)
+    st = _stream()
+    _lib.call("tce_seglik_gram", tables, _p(smp_traj), _p(mean), _p(L), ldb, _p(times), _p(init_time), _p(init_pos),
+              _p(init_vel), _p(pairs), _p(work), _p(diag_max), B, T, P, st)
+    _reduce_diag_max(diag_max)
+    _lib.call("tce_seglik_chol", tables, _p(work), _p(work), _p(diag_max), float(reg_rel), None, _p(logp_old),
+              _p(advantage), 1.0 / (B * P), _p(stats), _p(logp), _p(info), B, P, st)
+    return stats, logp, work, info
+
+
+@seglik_surrogate_fwd.register_fake
+def _(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, logp_old, advantage, tables, reg_rel):
+    B, P = times.shape[0], pred_pairs.shape[0]
+    n = smp_traj.shape[-1]
+    return (mean.new_empty(2, dtype=torch.float64), mean.new_empty(B, P),
+            mean.new_empty(B * P * (n * (n + 1) // 2 + n), dtype=torch.float64), mean.new_empty(B, P, dtype=torch.int32))
+
+
+@torch.library.custom_op("tce::seglik_surrogate_bwd", mutates_args=())
+def seglik_surrogate_bwd(upstream: Tensor, adj: Tensor, L: Tensor, times: Tensor, init_time: Tensor,
+                         pred_pairs: Tensor, tables: int, dim_params: int) -> Tuple[Tensor, Tensor]:
+    times, init_time = _chk(times), _chk(init_time)
+    pairs = _chk(pred_pairs, torch.int64)
+    up = _chk(upstream, torch.float32, "upstream")
+    L, ldb = _batched_matrix(L)
+    B, T = times.shape
+    P = pairs.shape[0]
+    g_mean = torch.empty(B, dim_params, device=times.device, dtype=torch.float32)
+    g_L = torch.empty(B, dim_params, dim_params, device=times.device, dtype=torch.float32)
+    _lib.call("tce_seglik_bwd", tables, _p(adj), _p(L), ldb, _p(times), _p(init_time), _p(pairs), _p(up), _p(g_mean),
+              _p(g_L), B, T, P, _stream())
+    return g_mean, g_L
+
+
+@seglik_surrogate_bwd.register_fake
+def _(upstream, adj, L, times, init_time, pred_pairs, tables, dim_params):
+    B = times.shape[0]
+    return times.new_empty(B, dim_params), times.new_empty(B, dim_params, dim_params)
+
+
+def _sur_setup(ctx, inputs, output):
+    (smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, logp_old, advantage, tables, reg_rel) = inputs
+    ctx.save_for_backward(output[2], L, times, init_time, pred_pairs)
+    ctx.tables, ctx.dim_params = tables, mean.shape[-1]
+    ctx.set_materialize_grads(False)
+
+
+def _sur_backward(ctx, g_stats, g_logp, g_adj, g_info):
+    adj, L, times, init_time, pred_pairs = ctx.saved_tensors
+    none = (None,) * 12
+    if g_stats is None:
+        return none
+    up = g_stats[0].to(torch.float32).reshape(1)           # d total / d surrogate loss (device scalar, no sync)
+    g_mean, g_L = seglik_surrogate_bwd(up, adj, L, times, init_time, pred_pairs, ctx.tables, ctx.dim_params)
+    return None, g_mean, g_L, None, None, None, None, None, None, None, None, None
+
+
+seglik_surrogate_fwd.register_autograd(_sur_backward, setup_context=_sur_setup)
+
+
+def seg_surrogate(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, logp_old, advantage,
+                  tables: Tables, reg_rel: float = 1e-4):
+    """-> (surrogate loss = -mean(exp(lp - lp_old) * adv) [fp32 scalar, differentiable], mean ratio, logp)."""
+    stats, logp, _adj, _info = seglik_surrogate_fwd(smp_traj, mean, L, times, init_time, init_pos, init_vel,
+                                                    pred_pairs, logp_old, advantage, tables.handle, reg_rel)
+    return stats[0].to(torch.float32), stats[1].detach().to(torch.float32), logp.detach()
 
 
 # --------------------------------------------------------------------------------------------------
@@ -457,9 +546,9 @@ def gauss_maha(mean: Tensor, mean_o: Tensor, L_o: Tensor) -> Tensor:
     mean, mean_o = _chk(mean), _chk(mean_o)
     L_o, ldbo = _batched_matrix(L_o, "L_o")
     B, n = mean.shape
-    out = torch.empty(B, 5, device=mean.device, dtype=torch.float64)
-    _lib.call("tce_gauss_stats", _p(mean), None, 0, _p(mean_o), _p(L_o), ldbo, _p(out), B, n, _stream())
-    return out[:, 0].contiguous()
+    out = torch.empty(B, device=mean.device, dtype=torch.float64)
+    _lib.call("tce_gauss_maha", _p(mean), _p(mean_o), _p(L_o), ldbo, None, _p(out), None, B, n, _stream())
+    return out
 
 
 @gauss_maha.register_fake
@@ -472,11 +561,9 @@ def gauss_maha_bwd(grad: Tensor, mean: Tensor, mean_o: Tensor, L_o: Tensor) -> T
     mean, mean_o = _chk(mean), _chk(mean_o)
     L_o, ldbo = _batched_matrix(L_o, "L_o")
     B, n = mean.shape
-    g5 = torch.zeros(B, 5, device=mean.device, dtype=torch.float64)
-    g5[:, 0] = grad
+    g = _chk(grad, torch.float64, "grad")
     g_mean = torch.empty_like(mean)
-    _lib.call("tce_gauss_stats_bwd", _p(mean), None, 0, _p(mean_o), _p(L_o), ldbo, _p(g5), _p(g_mean), None, B, n,
-              _stream())
+    _lib.call("tce_gauss_maha", _p(mean), _p(mean_o), _p(L_o), ldbo, _p(g), None, _p(g_mean), B, n, _stream())
     return g_mean
 
 

@@ -19,7 +19,7 @@ import torch.distributed as dist
 from torch.optim.lr_scheduler import LinearLR
 
 from .. import ops, util
-from .projection import gaussian_kl_details
+from .projection import KLProjectionLayer, gaussian_kl_details
 
 _KL_KEYS = ["new_old_mean_diff", "new_old_cov_diff", "new_old_shape_diff", "new_old_volume_diff",
             "new_proj_mean_diff", "new_proj_cov_diff", "new_proj_shape_diff", "new_proj_volume_diff",
@@ -79,6 +79,7 @@ class TemporalCorrelatedAgent:
         self.balance_check = kwargs.get("balance_check", 10)
         self.evaluation_interval = kwargs.get("evaluation_interval", 1)
         self.use_cuda_graph = bool(kwargs.get("use_cuda_graph", False))
+        self.fused_surrogate = bool(kwargs.get("fused_surrogate", True))
         self.process_group = kwargs.get("process_group", None)      # torch.distributed group (None = single GPU)
         self.policy_net_params = policy.parameters
         self.critic_net_params = critic.parameters if critic is not None else []
@@ -179,11 +180,19 @@ class TemporalCorrelatedAgent:
         return -self.entropy_penalty_coef * entropy, {"entropy": entropy}
 
     def kl_old_new_proj(self, new, old, proj):
-        """The 12 logging means of temporal_correlated_agent.py:641-686 as one device vector."""
+        """The 12 logging means of temporal_correlated_agent.py:641-686 as one device vector.  Parts that the
+        projection / trust-region loss of this epoch already evaluated (``projection.cache``) are reused."""
+        cache = getattr(self.projection, "cache", {})
+        kl_metric = isinstance(self.projection, KLProjectionLayer)
         out = []
         with torch.no_grad():
-            for p, q in ((new, old), (new, proj), (proj, old)):
-                out += [x.mean() for x in gaussian_kl_details(self.policy, p, q)]
+            mp = cache.get("new_old_mean") if kl_metric else None
+            out += [x.mean() for x in gaussian_kl_details(self.policy, new, old, mean_part=mp)]
+            if "new_proj" in cache:
+                out += [x.mean() for x in cache["new_proj"]]
+            else:
+                out += [x.mean() for x in gaussian_kl_details(self.policy, new, proj)]
+            out += [x.mean() for x in gaussian_kl_details(self.policy, proj, old)]
         return torch.stack(out)
 
     # ---- critic ---------------------------------------------------------------------------------------------
@@ -224,19 +233,26 @@ class TemporalCorrelatedAgent:
         old = (dataset["segment_params_mean"], dataset["segment_params_L"])
         new = self.policy.policy(dataset["segment_state"][..., :-D2])
         proj = self.projection(self.policy, new, old, self.num_iterations)
-        log_prob_new = self.policy.log_prob(dataset["step_actions"], params_mean=proj[0], params_L=proj[1],
-                                            times=times, init_time=dataset["segment_init_time"],
-                                            init_pos=dataset["segment_init_pos"],
-                                            init_vel=dataset["segment_init_vel"], pred_pairs=pred_pairs)
-        surrogate, sur_stats = self.surrogate_loss(dataset["segment_advantage"], log_prob_new,
-                                                   dataset["segment_log_prob_estimate"])
-        kl = self.kl_old_new_proj(new, old, proj)
+        if self.fused_surrogate and hasattr(self.policy, "segment_surrogate"):
+            surrogate, ratio, _ = self.policy.segment_surrogate(
+                dataset["step_actions"], proj[0], proj[1], times, dataset["segment_init_time"],
+                dataset["segment_init_pos"], dataset["segment_init_vel"], pred_pairs,
+                dataset["segment_log_prob_estimate"], dataset["segment_advantage"])
+            sur_stats = {"imp_smp_ratio": ratio}
+        else:
+            log_prob_new = self.policy.log_prob(dataset["step_actions"], params_mean=proj[0], params_L=proj[1],
+                                                times=times, init_time=dataset["segment_init_time"],
+                                                init_pos=dataset["segment_init_pos"],
+                                                init_vel=dataset["segment_init_vel"], pred_pairs=pred_pairs)
+            surrogate, sur_stats = self.surrogate_loss(dataset["segment_advantage"], log_prob_new,
+                                                       dataset["segment_log_prob_estimate"])
         if self.entropy_penalty_coef != 0.0:
             ent_loss, ent_stats = self.entropy_loss(proj[0], proj[1])
         else:                                             # coefficient 0 in every config: logging value only
             with torch.no_grad():
                 ent_loss, ent_stats = self.entropy_loss(proj[0], proj[1])
         tr_loss = self.projection.get_trust_region_loss(self.policy, new, proj, set_variance=self.set_variance)
+        kl = self.kl_old_new_proj(new, old, proj)
         policy_loss = surrogate + ent_loss + tr_loss
         self.policy_optimizer.zero_grad(set_to_none=False)
         policy_loss.backward()

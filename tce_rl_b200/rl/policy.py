@@ -104,33 +104,30 @@ class BlackBoxPolicy(AbstractGaussianPolicy):
             smp = ops.mvn_rsample(params_mean, params_L, eps, seed, 0)
         return smp if require_grad else smp.detach()
 
-    def _stats(self, mean, L, mean_o=None, L_o=None):
-        return ops.gauss_stats(mean, L, mean if mean_o is None else mean_o, L if L_o is None else L_o)
-
     def log_prob(self, smp_params, params_mean, params_L, **kwargs):
         """MVN(loc, scale_tril).log_prob (black_box_policy.py:95-128) = -1/2 (k ln 2pi + maha) - 1/2 logdet."""
-        st = ops.gauss_stats(smp_params, params_L, params_mean, params_L)
         k = params_mean.shape[-1]
-        return (-0.5 * (k * 1.8378770664093453 + st[:, 0]) - 0.5 * st[:, 3]).to(params_mean.dtype)
+        maha = ops.gauss_maha(smp_params, params_mean, params_L)
+        return (-0.5 * (k * 1.8378770664093453 + maha) - 0.5 * self.log_determinant(params_L)).to(params_mean.dtype)
 
     def entropy(self, params):
-        mean, L = params
-        return self._stats(mean, L)[:, 4].to(mean.dtype)
+        """1/2 k (1 + ln 2 pi) + sum log L_ii (MultivariateNormal.entropy, black_box_policy.py:130-154)."""
+        L = params[1]
+        k = L.shape[-1]
+        return 0.5 * k * (1.0 + 1.8378770664093453) + torch.diagonal(L, dim1=-2, dim2=-1).log().sum(-1)
 
     def covariance(self, params_L):
         return torch.einsum('...ij,...kj->...ik', params_L, params_L)
 
     def log_determinant(self, params_L):
-        B = params_L.shape[0]
-        zeros = torch.zeros(B, params_L.shape[-1], device=params_L.device)
-        return self._stats(zeros, params_L)[:, 2].to(params_L.dtype)
+        return 2 * torch.diagonal(params_L, dim1=-2, dim2=-1).log().sum(-1)
 
     def precision(self, params_L):
         eye = torch.eye(params_L.shape[-1], dtype=params_L.dtype, device=params_L.device)
         return torch.cholesky_solve(eye, params_L, upper=False)
 
     def maha(self, params, params_other, params_L):
-        return ops.gauss_stats(params, params_L, params_other, params_L)[:, 0].to(params.dtype)
+        return ops.gauss_maha(params, params_other, params_L).to(params.dtype)
 
 
 class TemporalCorrelatedPolicy(BlackBoxPolicy):
@@ -156,6 +153,13 @@ class TemporalCorrelatedPolicy(BlackBoxPolicy):
         pred_pairs = kwargs["pred_pairs"]
         return ops.seg_logprob(smp_traj, params_mean, params_L, times, init_time, init_pos, init_vel, pred_pairs,
                                self.mp.tables)
+
+    def segment_surrogate(self, smp_traj, params_mean, params_L, times, init_time, init_pos, init_vel, pred_pairs,
+                          log_prob_old, advantages):
+        """Fused ``log_prob`` + ``surrogate_loss`` (temporal_correlated_agent.py:538-550,718-739): returns
+        (-mean(exp(lp_new - lp_old) * adv), mean importance ratio, lp_new) from two kernels, backward = one."""
+        return ops.seg_surrogate(smp_traj, params_mean, params_L, times, init_time, init_pos, init_vel, pred_pairs,
+                                 log_prob_old, advantages, self.mp.tables)
 
 
 def policy_factory(typ: str, **kwargs):

@@ -36,19 +36,22 @@ def _cov_stats(policy, L, L_o):
     return st.expand(B, -1) if st.shape[0] != B else st
 
 
-def gaussian_kl(policy, p, q):
-    """(mean part, covariance part) of KL(p || q), each [B] fp64 (projection_utils.gaussian_kl)."""
-    st = _cov_stats(policy, p[1], q[1])
-    k = p[0].shape[-1]
-    return 0.5 * ops.gauss_maha(p[0], q[0], q[1]), 0.5 * (st[:, 1] - k + st[:, 3] - st[:, 2])
-
-
-def gaussian_kl_details(policy, p, q):
-    """(mean, cov, shape, volume) parts used for logging at temporal_correlated_agent.py:641-686."""
+def gaussian_kl_details(policy, p, q, mean_part=None):
+    """(mean, cov, shape, volume) parts of KL(p || q), each [B] fp64, cov = shape + volume
+    (gaussian_kl_details of the fork, used for logging at temporal_correlated_agent.py:641-686).
+    ``mean_part`` may carry an already computed 1/2 maha (avoids a second batch-sized launch)."""
     st = _cov_stats(policy, p[1], q[1])
     k = p[0].shape[-1]
     shape, volume = 0.5 * (st[:, 1] - k), 0.5 * (st[:, 3] - st[:, 2])
-    return 0.5 * ops.gauss_maha(p[0], q[0], q[1]), shape + volume, shape, volume
+    if mean_part is None:
+        mean_part = 0.5 * ops.gauss_maha(p[0], q[0], q[1])
+    return mean_part, shape + volume, shape, volume
+
+
+def gaussian_kl(policy, p, q):
+    """(mean part, covariance part) of KL(p || q), each [B] fp64 (projection_utils.gaussian_kl)."""
+    mean_part, cov_part, _, _ = gaussian_kl_details(policy, p, q)
+    return mean_part, cov_part
 
 
 def _entropy_schedule(kind, total_train_steps, dim):
@@ -78,6 +81,9 @@ class BaseProjectionLayer:
         self.entropy_schedule = _entropy_schedule(entropy_schedule, total_train_steps, action_dim)
         self.target_entropy, self.temperature = float(target_entropy), temperature
         self._initial_entropy = None
+        # detached by-products of the last projection / trust-region-loss call, reused by the agent's logging
+        # (temporal_correlated_agent.py:641-686 recomputes them): {"new_old_mean": [B], "new_proj": 4 x [B]}
+        self.cache = {}
 
     @property
     def initial_entropy(self):
@@ -113,7 +119,9 @@ class BaseProjectionLayer:
     def _trust_region_projection(self, policy, p, q):
         mean, L = p
         old_mean, old_L = q
-        proj_mean = ops.proj_mean(mean, old_mean, self._mean_part(policy, p, q), self.mean_bound)
+        mean_part = self._mean_part(policy, p, q)
+        self.cache = {"new_old_mean": mean_part.detach()}
+        proj_mean = ops.proj_mean(mean, old_mean, mean_part, self.mean_bound)
         if not policy.contextual_std:                          # one shared covariance: project the first only
             proj_L = _expand_first(self._cov_projection(policy, L[:1], old_L[:1]), mean.shape[0])
         else:
@@ -136,7 +144,11 @@ class BaseProjectionLayer:
     def get_trust_region_loss(self, policy, p, proj_p, set_variance=None):
         """coeff * mean(mean_diff [+ cov_diff]) between p and the DETACHED projection."""
         target = (proj_p[0].detach(), proj_p[1].detach())
-        mean_diff, cov_diff = self.trust_region_value(policy, p, target)
+        if type(self).trust_region_value is BaseProjectionLayer.trust_region_value:      # KL metric
+            mean_diff, cov_diff, shape, volume = gaussian_kl_details(policy, p, target)
+            self.cache["new_proj"] = tuple(x.detach() for x in (mean_diff, cov_diff, shape, volume))
+        else:
+            mean_diff, cov_diff = self.trust_region_value(policy, p, target)
         loss = (mean_diff + cov_diff if self._with_cov(policy, set_variance) else mean_diff).mean()
         return (loss * self.trust_region_coeff).to(p[0].dtype)
 

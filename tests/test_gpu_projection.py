@@ -148,7 +148,8 @@ def test_policy_epoch_matches_oracle(name, typ, contextual):
     agent = TemporalCorrelatedAgent(policy, None, sampler, layer, dtype="float32", device=DEV, lr_policy=1e-4,
                                     lr_critic=1e-3, wd_policy=5e-5, wd_critic=5e-5, discount_factor=1.0,
                                     epochs_policy=1, epochs_critic=1, norm_advantages=True,
-                                    segment_advantage="value_subtraction", set_variance=False)
+                                    segment_advantage="value_subtraction", set_variance=False,
+                                    fused_surrogate=(name != "metaworld"))
     obs = torch.randn(B, obs_dim + 2 * D)
     c = lambda t: t.to(DEV)
     init_time = inp["init_time"]
