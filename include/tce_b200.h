@@ -220,6 +220,8 @@ int tce_normalize_by_stats(float *x, const double *stats, int64_t N, void *strea
 /* ---- measurement helper ---------------------------------------------------------------------------------
  * One register-resident FMA-chain kernel (fp32 or fp64) over the whole chip; *flops (host) receives the
  * FLOPs executed.  bench.py times it to obtain the FMA-pipe roofline denominators.                      */
+/* debugging aid: SM-clock stamps taken between the phases of the last tce_proj_kl_cov_fwd launch */
+int tce_debug_kl_phase_cycles(long long *out16);
 int tce_bench_fma(int fp64, int iters, void *scratch, double *flops, void *stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,24 @@
+import sys, os, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from tce_rl_b200 import ops, _lib
+from oracle.gen_golden import synthetic_inputs
+inp = synthetic_inputs("box", 4, dtype=torch.float32)
+L, Lo = inp["L"][:1].cuda(), inp["L_old"][:1].cuda()
+for _ in range(3):
+    out = ops.proj_kl_cov(L, Lo, 5e-4)
+torch.cuda.synchronize()
+buf = (ctypes.c_longlong * 16)()
+_lib.call("tce_debug_kl_phase_cycles", buf)
+st = list(buf)[:10]
+names = ["load", "trsm W", "jacobi", "eta solve", "save", "load+gemm M", "gemm Sigma", "chol", "store"]
+print("active", out[1][-4:].tolist())
+for i, n in enumerate(names):
+    print(f"{n:14s} {st[i+1]-st[i]:9d} cycles")
+print("total", st[9]-st[0])
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(10):
+    ops.proj_kl_cov(L, Lo, 5e-4)
+b.record(); torch.cuda.synchronize()
+print("us per call (incl. python)", a.elapsed_time(b) * 100)

@@ -8,6 +8,9 @@
 
 #include "tce_smem_la.cuh"
 
+__device__ long long g_kl_prof[16];   // SM-clock stamps of the last KL forward kernel (block 0, thread 0)
+#define KL_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_kl_prof[i] = clock64(); } while (0)
+
 namespace {
 
 constexpr int PJ_THREADS = 512;
@@ -305,13 +308,17 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   const long long b = blockIdx.x;
   const float *Lt = L + (size_t)b * n * n, *Lo = L_o + (size_t)b * n * n;
   if (threadIdx.x == 0) s_bad = 0;
+  KL_STAMP(0);
   load_lower_d(b0, Lt, n, m);
   load_lower_d(b1, Lo, n, m);
   la_inv_diag(b0, inv_diag, n);
+  KL_STAMP(1);
   la_trsm_lower(b0, inv_diag, b1, n, n, true);                                   // W = Lt^-1 Lo (lower)
   for (int e = threadIdx.x; e < m * m; e += blockDim.x) b3(e / m, e % m) = (e / m == e % m) ? 1.0 : 0.0;
   __syncthreads();
+  KL_STAMP(2);
   la_jacobi_onesided(b1, b3, lam, rot, n);                                             // W^T W = Q diag(lam) Q^T
+  KL_STAMP(3);
   if (threadIdx.x < 32) {
     const double kl0 = kl_of_eta(lam, n, 0.0, nullptr);
     double eta = 0.0;
@@ -333,6 +340,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
     if (threadIdx.x == 0) { s_eta = eta; s_active = active ? 1.0 : 0.0; s_kl0 = kl0; }
   }
   __syncthreads();
+  KL_STAMP(4);
   const double eta = s_eta;
   const bool active = s_active != 0.0;
   if (save_sc && threadIdx.x == 0) {
@@ -346,6 +354,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
     if (info && threadIdx.x == 0) info[b] = 0;
     return;
   }
+  KL_STAMP(5);
   load_lower_d(b0, Lo, n, m);
   la_gemm(b1, b0, b3, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);          // M = Lo Q
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
@@ -353,9 +362,13 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
     b1(e / n, j) *= sqrt((1.0 + eta) / (lam[j] + eta));
   }
   __syncthreads();
+  KL_STAMP(6);
   la_gemm(b2, b1, b1.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_LOWER, 1.0, 0.0);      // Sigma_proj (lower)
+  KL_STAMP(7);
   la_chol(b2, n, &s_bad);
+  KL_STAMP(8);
   store_lower_f(out, b2, n, 1.0);
+  KL_STAMP(9);
   if (info && threadIdx.x == 0) info[b] = s_bad;
 }
 
@@ -750,6 +763,14 @@ extern "C" int tce_proj_entropy_bwd(const float *L, const double *beta, int64_t 
   if (B == 0) return TCE_OK;
   proj_entropy_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(L, beta, ldb_beta, equality, grad_out, grad_L, nullptr, n);
   TCE_CHECK_LAUNCH("proj_entropy_kernel(bwd)");
+  return TCE_OK;
+}
+
+// debugging aid: SM-clock stamps of the phases of the last KL forward kernel (synchronises)
+extern "C" int tce_debug_kl_phase_cycles(long long *out16) {
+  if (!out16) return TCE_ERR_INVALID_ARGUMENT;
+  TCE_CUDA(cudaDeviceSynchronize(), "kl prof sync");
+  TCE_CUDA(cudaMemcpyFromSymbol(out16, g_kl_prof, 16 * sizeof(long long)), "kl prof copy");
   return TCE_OK;
 }
 

@@ -100,7 +100,7 @@ class TemporalCorrelatedAgent:
     # ---- distributed helpers ---------------------------------------------------------------------------
     @property
     def world_size(self):
-        return dist.get_world_size(self.process_group) if self._distributed else 1
+        return dist.get_world_size(self._group()) if self._distributed else 1
 
     @property
     def _distributed(self):
