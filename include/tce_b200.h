@@ -140,14 +140,16 @@ int tce_proj_entropy_fwd(const float *L, const double *beta, int64_t ldb_beta, i
 int tce_proj_entropy_bwd(const float *L, const double *beta, int64_t ldb_beta, int equality,
                          const float *grad_out, float *grad_L, int64_t B, int n, void *stream);
 /* KL covariance projection: min KL(N(.,S)||N(.,S~)) s.t. KL_cov(S||S_old) <= eps_cov, solved exactly on
- * the generalised eigenvalues (CTA-per-matrix Jacobi + safeguarded Newton); proj_L = chol(S_proj).
- * `save` (tce_proj_kl_save_doubles(B, n) doubles) carries Q, lambda, eta to the backward (implicit
- * differentiation of eta*).  info [B]: non positive pivot of the final Cholesky (0 = ok).               */
+ * the generalised eigenvalues (CTA-per-matrix one-sided Jacobi + Newton for eta); proj_L = chol(S_proj).
+ * `save` (tce_proj_kl_save_doubles(B, n) doubles) carries M = L_old Q, lambda, eta to the backward
+ * (implicit differentiation of eta*).  warm_start != 0: `save` still holds the state of a previous call;
+ * it is used to start the eigen-solve when it was produced with the same L_o (checked by a fingerprint),
+ * e.g. across the epochs of one update_policy.  info [B]: non positive pivot of the final Cholesky.     */
 size_t tce_proj_kl_save_doubles(int64_t B, int n);
 int tce_proj_kl_cov_fwd(const float *L, const float *L_o, double eps_cov, float *proj_L, double *save,
-                        int32_t *info, int64_t B, int n, void *stream);
-int tce_proj_kl_cov_bwd(const float *L, const float *L_o, const float *proj_L, const float *grad_out,
-                        const double *save, float *grad_L, int64_t B, int n, void *stream);
+                        int32_t *info, int warm_start, int64_t B, int n, void *stream);
+int tce_proj_kl_cov_bwd(const float *L, const float *proj_L, const float *grad_out, const double *save,
+                        float *grad_L, int64_t B, int n, void *stream);
 /* Frobenius: S_new = (S + eta S_old) / (1 + eta), eta = sqrt(|S_old - S|_F^2 / eps_cov) - 1; save_sc [B,4] */
 int tce_proj_frob_cov_fwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov, float *proj_L,
                           double *save_sc, int32_t *info, int64_t B, int n, void *stream);

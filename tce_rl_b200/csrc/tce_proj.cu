@@ -61,7 +61,7 @@ __device__ inline void chol_backward(Mat bP, Mat bG, Mat bM, double *inv_diag, i
     if (j > i) bM(i, j) = 0.0; else if (i == j) bM(i, j) *= 0.5;
   }
   __syncthreads();
-  la_inv_diag(bP, inv_diag, n);
+  la_diag_block_inverses(bP, inv_diag, n);
   la_trsm_lower_t(bP, inv_diag, bM, n, n);            // Y = P^-T M
   la_trsm_lower_t(bP, inv_diag, bM.T(), n, n);        // X^T = P^-T Y^T  -> bM = X
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
@@ -91,7 +91,7 @@ gauss_kl_kernel(const float *__restrict__ mean, const float *__restrict__ L, lon
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1;
   Mat Lo{sd, LD, 1}, W{sd + m * LD, LD, 1};
-  double *inv_diag = sd + 2 * m * LD, *red = inv_diag + m;
+  double *inv_diag = sd + 2 * m * LD, *red = inv_diag + LA_DINV_DOUBLES;
   const long long b = blockIdx.x;
   load_lower_d(Lo, L_o + b * ldb_Lo, n, m);
   // W = [L | diff] : n x (n+1)
@@ -105,7 +105,7 @@ gauss_kl_kernel(const float *__restrict__ mean, const float *__restrict__ L, lon
   for (int i = threadIdx.x; i < n; i += blockDim.x) { ld += mean_only ? 0.0 : log(W(i, i)); ldo += log(Lo(i, i)); }
   ld = block_sum(ld, red);
   ldo = block_sum(ldo, red);
-  la_inv_diag(Lo, inv_diag, n);
+  la_diag_block_inverses(Lo, inv_diag, n);
   const bool backward = gout != nullptr;
   double g_tr = 0.0, g_ld = 0.0, g_ent = 0.0, g_maha = 0.0;
   if (backward) {
@@ -280,107 +280,152 @@ proj_entropy_kernel(const float *__restrict__ L, const double *__restrict__ beta
 // =====================================================================================================
 // KL covariance projection (exact dual solve on the generalised eigenvalues)
 // =====================================================================================================
-struct KlScalars { double eta; double active; double kl0; double pad; };
-
+// Warp-cooperative evaluation of KL_cov(eta) = 1/2 sum_i g((lam_i + eta) / (1 + eta)), g(r) = 1/r - 1 + ln r,
+// and of d/d eta (every lane of the calling warp participates).
 __device__ inline double kl_of_eta(const double *lam, int n, double eta, double *dfd_eta) {
-  // warp-cooperative: every lane of warp 0 calls this
   double f = 0.0, df = 0.0;
+  const double ope = 1.0 + eta;
   for (int i = threadIdx.x & 31; i < n; i += 32) {
-    const double r = (lam[i] + eta) / (1.0 + eta);
+    const double r = (lam[i] + eta) / ope;
     f += 1.0 / r - 1.0 + log(r);
-    df += ((r - 1.0) / (r * r)) * ((1.0 - lam[i]) / ((1.0 + eta) * (1.0 + eta)));
+    df += ((r - 1.0) / (r * r)) * ((1.0 - lam[i]) / (ope * ope));
   }
   f = warp_sum(f); df = warp_sum(df);
   if (dfd_eta) *dfd_eta = 0.5 * df;
   return 0.5 * f;
 }
 
+// Root of KL_cov(eta) = eps (monotone decreasing in eta).  All warps of the CTA evaluate candidates in
+// parallel (two grid-refinement rounds), warp 0 polishes with safeguarded Newton steps.  cand: >= 34 doubles.
+__device__ inline double kl_solve_eta(const double *lam, int n, double eps, double *cand) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = (int)(blockDim.x >> 5);
+  // round 1: geometric grid eta_w = 2^(w - 10), w = 0..nwarp-1  (1e-3 .. 2e6 for 32 warps)
+  double lo = 0.0, hi = ldexp(1.0, nwarp - 10);
+  for (int round = 0; round < 3; ++round) {
+    for (int w = warp; w < 32; w += nwarp) {
+      const double e = round == 0 ? ldexp(1.0, w - 10) : lo + (hi - lo) * (double)(w + 1) / 33.0;
+      const double f = kl_of_eta(lam, n, e, nullptr);
+      if (lane == 0) cand[w] = f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {            // f decreasing: last candidate with f > eps brackets from below
+      double nlo = lo, nhi = hi;
+      for (int w = 0; w < 32; ++w) {
+        const double e = round == 0 ? ldexp(1.0, w - 10) : lo + (hi - lo) * (double)(w + 1) / 33.0;
+        if (cand[w] > eps) nlo = e; else { nhi = e; break; }
+      }
+      cand[32] = nlo; cand[33] = nhi;
+    }
+    __syncthreads();
+    lo = cand[32]; hi = cand[33];
+    __syncthreads();
+  }
+  if (warp == 0) {
+    double eta = 0.5 * (lo + hi);
+    for (int it = 0; it < 8; ++it) {              // bracket is ~1e-3 wide: Newton converges in 3-4 steps
+      double df;
+      const double f = kl_of_eta(lam, n, eta, &df) - eps;
+      if (f > 0.0) lo = eta; else hi = eta;
+      double nxt = (df != 0.0) ? eta - f / df : 0.5 * (lo + hi);
+      if (!(nxt > lo && nxt < hi)) nxt = 0.5 * (lo + hi);
+      const bool done = fabs(nxt - eta) <= 4e-16 * fmax(1.0, fabs(eta)) || hi - lo <= 4e-16 * fmax(1.0, hi);
+      eta = nxt;
+      if (done) break;
+    }
+    if (lane == 0) cand[32] = eta;
+  }
+  __syncthreads();
+  const double eta = cand[32];
+  __syncthreads();
+  return eta;
+}
+
+// Forward.  With W = Lt^-1 Lo, one-sided Jacobi rotates the columns of W into U~ = W Q (orthogonal columns,
+// |U~_j|^2 = lam_j = eigenvalues of W^T W); then M := Lo Q = Lt U~ and
+//   Sigma_proj = Lo Q diag((1+eta)/(lam+eta)) Q^T Lo^T = M D M^T ,   proj_L = chol(Sigma_proj).
+// `save` = { M [n,n], lam [n], {eta, active, kl0, fingerprint(Lo)} } per matrix: state for the backward AND a
+// warm start for the next call with the same Lo (the 50 epochs of one update_policy): starting Jacobi from
+// Lt^-1 M_prev = W Q_prev is an orthogonal change of basis of the same problem, so 2-3 sweeps suffice.
 __global__ void __launch_bounds__(KL_THREADS)
 proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_o, double eps_cov,
-                       float *__restrict__ proj_L, double *__restrict__ save_Q, double *__restrict__ save_lam,
-                       double *__restrict__ save_sc, int32_t *__restrict__ info, int n) {
+                       float *__restrict__ proj_L, double *__restrict__ save_M, double *__restrict__ save_lam,
+                       double *__restrict__ save_sc, int32_t *__restrict__ info, int n, int warm_start) {
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
-  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
-  double *inv_diag = sd + 4 * MS, *lam = inv_diag + m, *rot = lam + m, *red = rot + 4 * m;   // red: 80 doubles
-  __shared__ double s_eta, s_active, s_kl0;
+  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1};
+  double *dinv = sd + 3 * MS, *lam = dinv + LA_DINV_DOUBLES, *nrm = lam + m, *red = nrm + m + 96;   // red: >= 48
   __shared__ int s_bad;
   const long long b = blockIdx.x;
-  const float *Lt = L + (size_t)b * n * n, *Lo = L_o + (size_t)b * n * n;
+  const size_t off = (size_t)b * n * n;
+  const float *Lt = L + off, *Lo = L_o + off;
   if (threadIdx.x == 0) s_bad = 0;
   KL_STAMP(0);
   load_lower_d(b0, Lt, n, m);
-  load_lower_d(b1, Lo, n, m);
-  la_inv_diag(b0, inv_diag, n);
+  // fingerprint of Lo (position weighted sum, deterministic order): guards the warm start
+  double fp = 0.0;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) fp = fma((double)(e % 251 + 1), (double)Lo[e], fp);
+  fp = block_sum(fp, red);
+  const bool warm = warm_start && save_sc[b * 4 + 3] == fp;
+  if (warm) load_full_d(b1, save_M + off, n, m); else load_lower_d(b1, Lo, n, m);
+  la_diag_block_inverses(b0, dinv, n);
   KL_STAMP(1);
-  la_trsm_lower(b0, inv_diag, b1, n, n, true);                                   // W = Lt^-1 Lo (lower)
-  for (int e = threadIdx.x; e < m * m; e += blockDim.x) b3(e / m, e % m) = (e / m == e % m) ? 1.0 : 0.0;
-  __syncthreads();
+  la_trsm_lower(b0, dinv, b1, n, n, !warm);                                        // W (or W Q_prev)
   KL_STAMP(2);
-  la_jacobi_onesided(b1, b3, lam, rot, n);                                             // W^T W = Q diag(lam) Q^T
+  const int sweeps = la_jacobi_onesided(b1, lam, nrm, n);                          // b1 = U~
   KL_STAMP(3);
-  if (threadIdx.x < 32) {
-    const double kl0 = kl_of_eta(lam, n, 0.0, nullptr);
-    double eta = 0.0;
-    const bool active = kl0 > eps_cov;
-    if (active) {
-      double lo = 0.0, hi = 1.0;
-      while (kl_of_eta(lam, n, hi, nullptr) > eps_cov && hi < 1e30) { lo = hi; hi *= 2.0; }
-      eta = 0.5 * (lo + hi);
-      for (int it = 0; it < 200; ++it) {
-        double df;
-        const double f = kl_of_eta(lam, n, eta, &df) - eps_cov;
-        if (f > 0.0) lo = eta; else hi = eta;
-        double nxt = (df != 0.0) ? eta - f / df : 0.5 * (lo + hi);
-        if (!(nxt > lo && nxt < hi)) nxt = 0.5 * (lo + hi);
-        if (fabs(nxt - eta) <= 1e-15 * fmax(1.0, fabs(eta)) || hi - lo <= 1e-15 * fmax(1.0, hi)) { eta = nxt; break; }
-        eta = nxt;
-      }
-    }
-    if (threadIdx.x == 0) { s_eta = eta; s_active = active ? 1.0 : 0.0; s_kl0 = kl0; }
-  }
-  __syncthreads();
+  const double kl0 = [&] {
+    double v = 0.0;
+    if (threadIdx.x < 32) v = kl_of_eta(lam, n, 0.0, nullptr);
+    if (threadIdx.x == 0) red[40] = v;
+    __syncthreads();
+    v = red[40];
+    __syncthreads();
+    return v;
+  }();
+  const bool active = kl0 > eps_cov;
+  const double eta = active ? kl_solve_eta(lam, n, eps_cov, red) : 0.0;
   KL_STAMP(4);
-  const double eta = s_eta;
-  const bool active = s_active != 0.0;
-  if (save_sc && threadIdx.x == 0) {
-    save_sc[b * 4 + 0] = eta; save_sc[b * 4 + 1] = s_active; save_sc[b * 4 + 2] = s_kl0; save_sc[b * 4 + 3] = 0.0;
+  la_gemm(b2, b0, b1, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // M = Lt U~
+  if (threadIdx.x == 0) {
+    save_sc[b * 4 + 0] = eta; save_sc[b * 4 + 1] = active ? 1.0 : 0.0; save_sc[b * 4 + 2] = kl0; save_sc[b * 4 + 3] = fp;
+    if (blockIdx.x == 0) g_kl_prof[15] = sweeps;
   }
-  if (save_lam) for (int i = threadIdx.x; i < n; i += blockDim.x) save_lam[b * n + i] = lam[i];
-  if (save_Q) for (int e = threadIdx.x; e < n * n; e += blockDim.x) save_Q[(size_t)b * n * n + e] = b3(e / n, e % n);
-  float *out = proj_L + (size_t)b * n * n;
-  if (!active) {                                                                   // identity
+  for (int i = threadIdx.x; i < n; i += blockDim.x) save_lam[b * n + i] = lam[i];
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) save_M[off + e] = b2(e / n, e % n);
+  KL_STAMP(5);
+  float *out = proj_L + off;
+  if (!active) {                                                                    // identity
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) out[e] = (e % n <= e / n) ? Lt[e] : 0.f;
     if (info && threadIdx.x == 0) info[b] = 0;
     return;
   }
-  KL_STAMP(5);
-  load_lower_d(b0, Lo, n, m);
-  la_gemm(b1, b0, b3, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);          // M = Lo Q
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     const int j = e % n;
-    b1(e / n, j) *= sqrt((1.0 + eta) / (lam[j] + eta));
+    b2(e / n, j) *= sqrt((1.0 + eta) / (lam[j] + eta));
   }
   __syncthreads();
   KL_STAMP(6);
-  la_gemm(b2, b1, b1.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_LOWER, 1.0, 0.0);      // Sigma_proj (lower)
+  la_gemm(b1, b2, b2.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_LOWER, 1.0, 0.0);       // Sigma_proj (lower)
   KL_STAMP(7);
-  la_chol(b2, n, &s_bad);
+  la_chol(b1, n, &s_bad);
   KL_STAMP(8);
-  store_lower_f(out, b2, n, 1.0);
-  KL_STAMP(9);
+  store_lower_f(out, b1, n, 1.0);
   if (info && threadIdx.x == 0) info[b] = s_bad;
+  KL_STAMP(9);
 }
 
+// Backward (implicit differentiation of eta*, no eigen-derivative singularities).  With U~ = Lt^-1 M,
+// rho_i = 1/(lam_i + eta), Sbar = d/dSigma_proj (from the Cholesky adjoint):
+//   Ft = M^T Sbar M ;  Nt_ij = -(1+eta) rho_i rho_j Ft_ij - delta_ij etabar (df/dlam_i) / (df/deta) ,
+//   etabar = sum_i Ft_ii (rho_i - (1+eta) rho_i^2) ;  grad_Lt = -2 tril(Lt^-T U~ Nt U~^T).
 __global__ void __launch_bounds__(PJ_THREADS)
-proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ L_o, const float *__restrict__ proj_L,
-                       const float *__restrict__ gout, const double *__restrict__ save_Q,
-                       const double *__restrict__ save_lam, const double *__restrict__ save_sc,
-                       float *__restrict__ grad_L, int n) {
+proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ proj_L, const float *__restrict__ gout,
+                       const double *__restrict__ save_M, const double *__restrict__ save_lam,
+                       const double *__restrict__ save_sc, float *__restrict__ grad_L, int n) {
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
   Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
-  double *inv_diag = sd + 4 * MS, *lam = inv_diag + m, *rho = lam + m, *red = rho + m;
+  double *dinv = sd + 4 * MS, *lam = dinv + LA_DINV_DOUBLES, *rho = lam + m, *red = rho + m;
   const long long b = blockIdx.x;
   const size_t off = (size_t)b * n * n;
   float *gl = grad_L + off;
@@ -392,19 +437,10 @@ proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   for (int i = threadIdx.x; i < n; i += blockDim.x) { lam[i] = save_lam[b * n + i]; rho[i] = 1.0 / (lam[i] + eta); }
   load_lower_d(b0, proj_L + off, n, m);
   load_lower_d(b1, gout + off, n, m);
-  chol_backward(b0, b1, b2, inv_diag, n);                                          // b2 = Sbar (sym)
-  load_lower_d(b0, L_o + off, n, m);
-  la_gemm(b1, b2, b0, n, n, n, TRI_FULL, TRI_LOWER, TRI_FULL, 1.0, 0.0);          // T1 = Sbar Lo
-  la_gemm(b2, b0.T(), b1, n, n, n, TRI_UPPER, TRI_FULL, TRI_FULL, 1.0, 0.0);      // Fbar = Lo^T T1
-  // W = Lt^-1 Lo -> b3
-  load_lower_d(b1, L + off, n, m);
-  load_lower_d(b3, L_o + off, n, m);
-  la_inv_diag(b1, inv_diag, n);
-  la_trsm_lower(b1, inv_diag, b3, n, n, true);
-  load_full_d(b0, save_Q + off, n, m);                                             // Q
-  la_gemm(b1, b2, b0, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);           // Fbar Q
-  la_gemm(b2, b0.T(), b1, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);       // Ft = Q^T Fbar Q
-  // eigenbasis: Nt_ij = -(1+eta) rho_i rho_j Ft_ij ; implicit eta term on the diagonal
+  chol_backward(b0, b1, b2, dinv, n);                                              // b2 = Sbar (sym)
+  load_full_d(b0, save_M + off, n, m);                                             // M
+  la_gemm(b1, b2, b0, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);            // Sbar M
+  la_gemm(b2, b0.T(), b1, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // Ft = M^T Sbar M
   double eb = 0.0, dfe = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     eb += b2(i, i) * (rho[i] - (1.0 + eta) * rho[i] * rho[i]);
@@ -416,17 +452,16 @@ proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
     const int i = e / n, j = e % n;
     double v = -(1.0 + eta) * rho[i] * rho[j] * b2(i, j);
     if (i == j) v -= eb * (0.5 * (rho[i] - (1.0 + eta) * rho[i] * rho[i])) / dfe;
-    b2(i, j) = v;
+    b2(i, j) = v;                                                                  // Nt
   }
   __syncthreads();
-  la_gemm(b1, b0, b2, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);           // Q Nt
-  la_gemm(b2, b1, b0.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);       // Nbar = Q Nt Q^T
-  la_gemm(b0, b3, b2, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 2.0, 0.0);          // Wbar = 2 W Nbar
-  la_gemm(b1, b0, b3.T(), n, n, n, TRI_FULL, TRI_UPPER, TRI_FULL, 1.0, 0.0);      // T2 = Wbar W^T
-  load_lower_d(b0, L + off, n, m);
-  la_inv_diag(b0, inv_diag, n);
-  la_trsm_lower_t(b0, inv_diag, b1, n, n);                                         // Z = Lt^-T T2
-  store_lower_f(gl, b1, n, -1.0);
+  load_lower_d(b1, L + off, n, m);                                                 // Lt
+  la_diag_block_inverses(b1, dinv, n);
+  la_trsm_lower(b1, dinv, b0, n, n, false);                                        // U~ = Lt^-1 M   (in b0)
+  la_gemm(b3, b0, b2, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);            // U~ Nt
+  la_gemm(b2, b3, b0.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // U~ Nt U~^T
+  la_trsm_lower_t(b1, dinv, b2, n, n);                                             // Lt^-T (.)
+  store_lower_f(gl, b2, n, -2.0);
 }
 
 // =====================================================================================================
@@ -474,7 +509,7 @@ proj_frob_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ 
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
   Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
-  double *inv_diag = sd + 4 * MS, *red = inv_diag + m;
+  double *inv_diag = sd + 4 * MS, *red = inv_diag + LA_DINV_DOUBLES;
   const long long b = blockIdx.x;
   const size_t off = (size_t)b * n * n;
   float *gl = grad_L + off;
@@ -523,7 +558,7 @@ proj_w2_cov_kernel(const float *__restrict__ L, const float *__restrict__ L_o, l
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
   Mat R{sd, LD, 1}, S{sd + MS, LD, 1}, A{sd + 2 * MS, LD, 1}, T{sd + 3 * MS, LD, 1}, U{sd + 4 * MS, LD, 1};
-  double *inv_diag = sd + 5 * MS, *red = inv_diag + m;
+  double *inv_diag = sd + 5 * MS, *red = inv_diag + LA_DINV_DOUBLES;
   const long long b = blockIdx.x;
   const size_t off = (size_t)b * n * n;
   load_lower_d(R, L + off, n, m);
@@ -532,7 +567,7 @@ proj_w2_cov_kernel(const float *__restrict__ L, const float *__restrict__ L_o, l
   if (scale_prec) {
     for (int e = threadIdx.x; e < m * m; e += blockDim.x) A(e / m, e % m) = (e / m == e % m && e / m < n) ? 1.0 : 0.0;
     __syncthreads();
-    la_inv_diag(S, inv_diag, n);
+    la_diag_block_inverses(S, inv_diag, n);
     la_trsm_lower(S, inv_diag, A, n, n, true);                                     // A = S^-1 (lower)
     la_gemm(T, A, R, n, n, n, TRI_LOWER, TRI_LOWER, TRI_FULL, 1.0, 0.0);           // T = A R (lower)
     la_gemm(U, A.T(), R, n, n, n, TRI_UPPER, TRI_LOWER, TRI_FULL, 1.0, 0.0);       // U = A^T R
@@ -607,7 +642,7 @@ cov_distance_kernel(int kind /*0 frob, 1 w2*/, const float *__restrict__ L, cons
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
   Mat R{sd, LD, 1}, S{sd + MS, LD, 1}, A{sd + 2 * MS, LD, 1}, T{sd + 3 * MS, LD, 1}, U{sd + 4 * MS, LD, 1};
-  double *inv_diag = sd + 5 * MS, *red = inv_diag + m;
+  double *inv_diag = sd + 5 * MS, *red = inv_diag + LA_DINV_DOUBLES;
   const long long b = blockIdx.x;
   const size_t off = (size_t)b * n * n;
   load_lower_d(R, L + off, n, m);
@@ -630,7 +665,7 @@ cov_distance_kernel(int kind /*0 frob, 1 w2*/, const float *__restrict__ L, cons
   } else if (scale_prec) {
     for (int e = threadIdx.x; e < m * m; e += blockDim.x) A(e / m, e % m) = (e / m == e % m && e / m < n) ? 1.0 : 0.0;
     __syncthreads();
-    la_inv_diag(S, inv_diag, n);
+    la_diag_block_inverses(S, inv_diag, n);
     la_trsm_lower(S, inv_diag, A, n, n, true);
     la_gemm(T, A, R, n, n, n, TRI_LOWER, TRI_LOWER, TRI_FULL, 1.0, 0.0);
     la_gemm(U, A.T(), R, n, n, n, TRI_UPPER, TRI_LOWER, TRI_FULL, 1.0, 0.0);
@@ -670,7 +705,7 @@ cov_distance_kernel(int kind /*0 frob, 1 w2*/, const float *__restrict__ L, cons
 
 size_t pj_smem(int n, int nbuf) {
   const int m = (n + 1) & ~1;
-  return sizeof(double) * ((size_t)nbuf * m * (m + 1) + 8 * m + 160);
+  return sizeof(double) * ((size_t)nbuf * m * (m + 1) + LA_DINV_DOUBLES + 8 * m + 256);
 }
 
 template <typename K>
@@ -777,29 +812,30 @@ extern "C" int tce_debug_kl_phase_cycles(long long *out16) {
 extern "C" size_t tce_proj_kl_save_doubles(int64_t B, int n) { return (size_t)B * ((size_t)n * n + n + 4); }
 
 extern "C" int tce_proj_kl_cov_fwd(const float *L, const float *L_o, double eps_cov, float *proj_L, double *save,
-                                   int32_t *info, int64_t B, int n, void *stream) {
+                                   int32_t *info, int warm_start, int64_t B, int n, void *stream) {
   if (!L || !L_o || !proj_L || !save || B < 0 || !(eps_cov > 0)) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
   if (B == 0) return TCE_OK;
-  const size_t smem = pj_smem(n, 4);
+  const size_t smem = pj_smem(n, 3);
   int rc = set_smem(proj_kl_cov_fwd_kernel, smem);
   if (rc) return rc;
-  double *Q = save, *lam = Q + (size_t)B * n * n, *sc = lam + (size_t)B * n;
-  proj_kl_cov_fwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, eps_cov, proj_L, Q, lam, sc, info, n);
+  double *M = save, *lam = M + (size_t)B * n * n, *sc = lam + (size_t)B * n;
+  proj_kl_cov_fwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, eps_cov, proj_L, M, lam, sc, info, n,
+                                                                                 warm_start);
   TCE_CHECK_LAUNCH("proj_kl_cov_fwd_kernel");
   return TCE_OK;
 }
 
-extern "C" int tce_proj_kl_cov_bwd(const float *L, const float *L_o, const float *proj_L, const float *grad_out,
-                                   const double *save, float *grad_L, int64_t B, int n, void *stream) {
-  if (!L || !L_o || !proj_L || !grad_out || !save || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
+extern "C" int tce_proj_kl_cov_bwd(const float *L, const float *proj_L, const float *grad_out, const double *save,
+                                   float *grad_L, int64_t B, int n, void *stream) {
+  if (!L || !proj_L || !grad_out || !save || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
   if (B == 0) return TCE_OK;
   const size_t smem = pj_smem(n, 4);
   int rc = set_smem(proj_kl_cov_bwd_kernel, smem);
   if (rc) return rc;
-  const double *Q = save, *lam = Q + (size_t)B * n * n, *sc = lam + (size_t)B * n;
-  proj_kl_cov_bwd_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, proj_L, grad_out, Q, lam, sc, grad_L, n);
+  const double *M = save, *lam = M + (size_t)B * n * n, *sc = lam + (size_t)B * n;
+  proj_kl_cov_bwd_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(L, proj_L, grad_out, M, lam, sc, grad_L, n);
   TCE_CHECK_LAUNCH("proj_kl_cov_bwd_kernel");
   return TCE_OK;
 }

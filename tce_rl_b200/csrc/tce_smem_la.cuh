@@ -13,252 +13,312 @@ struct Mat {            // strided view; a transpose is a stride swap
 
 enum { TRI_FULL = 0, TRI_LOWER = 1, TRI_UPPER = 2 };
 
-// C = beta * C + alpha * A B over the index ranges allowed by the triangular structure of A (m x k) and
-// B (k x n); c_tri restricts which entries of C are written (others untouched).
+// C = beta * C + alpha * A B (m x n x k) with 2x2 register tiles (halves the shared-memory traffic per DFMA).
+// a_tri / b_tri describe the structure of A and B and only clip the k range of a tile: the unused triangle
+// of a triangular operand MUST hold zeros.  c_tri = TRI_LOWER / TRI_UPPER: tiles entirely on the other side
+// of the diagonal are skipped; inside diagonal tiles both triangles are written (callers read one only).
 __device__ inline void la_gemm(Mat C, Mat A, Mat B, int m, int n, int k, int a_tri, int b_tri, int c_tri,
                                double alpha, double beta) {
-  for (int e = threadIdx.x; e < m * n; e += blockDim.x) {
-    const int i = e / n, j = e % n;
-    if ((c_tri == TRI_LOWER && j > i) || (c_tri == TRI_UPPER && j < i)) continue;
+  const int tm = (m + 1) >> 1, tn = (n + 1) >> 1;
+  for (int t = threadIdx.x; t < tm * tn; t += blockDim.x) {
+    const int I = t / tn, J = t - I * tn;
+    const int i0 = 2 * I, j0 = 2 * J;
+    const int i1 = i0 + 1 < m ? i0 + 1 : i0, j1 = j0 + 1 < n ? j0 + 1 : j0;     // clamped (odd sizes)
+    if ((c_tri == TRI_LOWER && j0 > i1) || (c_tri == TRI_UPPER && j1 < i0)) continue;
     int lo = 0, hi = k;
-    if (a_tri == TRI_LOWER) hi = min(hi, i + 1);
-    if (a_tri == TRI_UPPER) lo = max(lo, i);
-    if (b_tri == TRI_LOWER) lo = max(lo, j);
-    if (b_tri == TRI_UPPER) hi = min(hi, j + 1);
-    double s0 = 0.0, s1 = 0.0;
-    int q = lo;
-    for (; q + 1 < hi; q += 2) {
-      s0 = fma(A(i, q), B(q, j), s0);
-      s1 = fma(A(i, q + 1), B(q + 1, j), s1);
+    if (a_tri == TRI_LOWER) hi = min(hi, i1 + 1);
+    if (a_tri == TRI_UPPER) lo = max(lo, i0);
+    if (b_tri == TRI_LOWER) lo = max(lo, j0);
+    if (b_tri == TRI_UPPER) hi = min(hi, j1 + 1);
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+    for (int q = lo; q < hi; ++q) {
+      const double a0 = A(i0, q), a1 = A(i1, q), b0 = B(q, j0), b1 = B(q, j1);
+      c00 = fma(a0, b0, c00); c01 = fma(a0, b1, c01);
+      c10 = fma(a1, b0, c10); c11 = fma(a1, b1, c11);
     }
-    if (q < hi) s0 = fma(A(i, q), B(q, j), s0);
-    const double v = alpha * (s0 + s1);
-    C(i, j) = beta == 0.0 ? v : fma(beta, C(i, j), v);
+    if (beta == 0.0) {
+      C(i0, j0) = alpha * c00;
+      if (j1 != j0) C(i0, j1) = alpha * c01;
+      if (i1 != i0) { C(i1, j0) = alpha * c10; if (j1 != j0) C(i1, j1) = alpha * c11; }
+    } else {
+      C(i0, j0) = fma(beta, C(i0, j0), alpha * c00);
+      if (j1 != j0) C(i0, j1) = fma(beta, C(i0, j1), alpha * c01);
+      if (i1 != i0) {
+        C(i1, j0) = fma(beta, C(i1, j0), alpha * c10);
+        if (j1 != j0) C(i1, j1) = fma(beta, C(i1, j1), alpha * c11);
+      }
+    }
   }
   __syncthreads();
 }
 
-// X <- L^-1 X, L lower triangular n x n (inv_diag[i] = 1 / L(i,i)), X n x ncols.  Blocked forward
-// substitution (block 8): parallel GEMM update + short per-column solve.  x_lower: X(i,c) = 0 for i < c.
-__device__ inline void la_trsm_lower(Mat L, const double *inv_diag, Mat X, int n, int ncols, bool x_lower) {
-  constexpr int NB = 8;
-  for (int r0 = 0; r0 < n; r0 += NB) {
-    const int nb = min(NB, n - r0);
-    if (r0 > 0) {
-      for (int e = threadIdx.x; e < nb * ncols; e += blockDim.x) {
-        const int c = e % ncols, i = r0 + e / ncols;
-        if (x_lower && i < c) continue;
-        const int lo = x_lower ? c : 0;
-        double s0 = 0.0, s1 = 0.0;
-        int q = lo;
-        for (; q + 1 < r0; q += 2) {
-          s0 = fma(L(i, q), X(q, c), s0);
-          s1 = fma(L(i, q + 1), X(q + 1, c), s1);
-        }
-        if (q < r0) s0 = fma(L(i, q), X(q, c), s0);
-        X(i, c) -= s0 + s1;
-      }
-      __syncthreads();
-    }
-    for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
-      for (int ii = 0; ii < nb; ++ii) {
-        const int i = r0 + ii;
-        if (x_lower && i < c) continue;
-        double v = X(i, c);
-        for (int kk = 0; kk < ii; ++kk) v = fma(-L(i, r0 + kk), X(r0 + kk, c), v);
-        X(i, c) = v * inv_diag[i];
-      }
-    }
-    __syncthreads();
-  }
-}
+constexpr int LA_NB = 8;                              // block size of the blocked triangular routines
+constexpr int LA_DINV_DOUBLES = 8 * LA_NB * LA_NB;    // scratch for the inverted diagonal blocks (n <= 64)
 
-// X <- L^-T X (back substitution with the transpose of a lower-triangular L)
-__device__ inline void la_trsm_lower_t(Mat L, const double *inv_diag, Mat X, int n, int ncols) {
-  constexpr int NB = 8;
-  for (int r1 = n; r1 > 0; r1 -= NB) {
-    const int r0 = max(r1 - NB, 0), nb = r1 - r0;
-    if (r1 < n) {
-      for (int e = threadIdx.x; e < nb * ncols; e += blockDim.x) {
-        const int c = e % ncols, i = r0 + e / ncols;
-        double s0 = 0.0, s1 = 0.0;
-        int q = r1;
-        for (; q + 1 < n; q += 2) {
-          s0 = fma(L(q, i), X(q, c), s0);
-          s1 = fma(L(q + 1, i), X(q + 1, c), s1);
+// dinv[bk][i][j] = inverse of the bk-th LA_NB x LA_NB diagonal block of the lower-triangular L (zeros above
+// the diagonal).  One warp per block, lane j < 8 builds column j.
+__device__ inline void la_diag_block_inverses(Mat L, double *dinv, int n) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = (int)(blockDim.x >> 5);
+  const int nblk = (n + LA_NB - 1) / LA_NB;
+  for (int bk = warp; bk < nblk; bk += nwarp) {
+    if (lane < LA_NB) {
+      const int r0 = bk * LA_NB, j = lane;
+      double x[LA_NB];
+#pragma unroll
+      for (int i = 0; i < LA_NB; ++i) {
+        const int gi = r0 + i;
+        double v = (i == j) ? 1.0 : 0.0;
+        if (gi < n) {
+#pragma unroll
+          for (int q = 0; q < i; ++q) v = fma(-L(gi, r0 + q), x[q], v);     // x[q] = 0 for q < j
+          v = (i >= j) ? v / L(gi, gi) : 0.0;
+        } else {
+          v = 0.0;
         }
-        if (q < n) s0 = fma(L(q, i), X(q, c), s0);
-        X(i, c) -= s0 + s1;
-      }
-      __syncthreads();
-    }
-    for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
-      for (int i = r1 - 1; i >= r0; --i) {
-        double v = X(i, c);
-        for (int q = i + 1; q < r1; ++q) v = fma(-L(q, i), X(q, c), v);
-        X(i, c) = v * inv_diag[i];
+        x[i] = v;
+        dinv[(bk * LA_NB + i) * LA_NB + j] = v;
       }
     }
-    __syncthreads();
   }
-}
-
-__device__ inline void la_inv_diag(Mat L, double *inv_diag, int n) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) inv_diag[i] = 1.0 / L(i, i);
   __syncthreads();
 }
 
-// in-place Cholesky of the lower triangle of A (upper part untouched / ignored); returns through *bad
-// (shared int, pre-set to 0) the 1-based index of the first non-positive pivot
-__device__ inline void la_chol(Mat A, int n, int *bad) {
-  for (int j = 0; j < n; ++j) {
-    const double djj = A(j, j);
-    if (threadIdx.x == 0 && !(djj > 0.0) && *bad == 0) *bad = j + 1;
-    const double d = sqrt(djj), inv = 1.0 / d;
-    __syncthreads();                       // everyone has read A(j,j)
-    for (int i = j + threadIdx.x; i < n; i += blockDim.x) A(i, j) = (i == j) ? d : A(i, j) * inv;
-    __syncthreads();
-    const int m = n - j - 1;               // trailing update of the lower triangle
-    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
-      const int i = j + 1 + e / m, k = j + 1 + e % m;
-      if (k <= i) A(i, k) = fma(-A(i, j), A(k, j), A(i, k));
-    }
-    __syncthreads();
-  }
-}
-
-// Cyclic Jacobi eigen-decomposition of a symmetric matrix (full storage) A = Q diag(lam) Q^T with the
-// round-robin parallel ordering (m/2 disjoint rotations per step).  A is destroyed (its diagonal ends as
-// lam), Q must hold the identity on entry.  m = n rounded up to even; A and Q need m rows/cols of storage
-// with the padding row/col zero.  rot: scratch of 4 * (m/2) doubles.
-__device__ inline void la_jacobi(Mat A, Mat Q, double *lam, int n, double *rot, double *red /*[33]*/) {
-  const int m = (n + 1) & ~1, half = m / 2;
-  for (int sweep = 0; sweep < 30; ++sweep) {
-    // convergence: sum of squared off-diagonal entries vs squared diagonal
-    double off = 0.0, dia = 0.0;
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-      const int i = e / n, j = e % n;
-      const double v = A(i, j);
-      if (i == j) dia = fma(v, v, dia); else off = fma(v, v, off);
-    }
-    off = warp_sum(off); dia = warp_sum(dia);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = off; red[32 + (threadIdx.x >> 5)] = dia; }
-    __syncthreads();
-    double toff = 0.0, tdia = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { toff += red[w]; tdia += red[32 + w]; }
-    __syncthreads();
-    if (toff <= 1e-30 * tdia) break;
-    for (int step = 0; step < m - 1; ++step) {
-      if (threadIdx.x < half) {
-        const int k = threadIdx.x;
-        int p, q;
-        if (k == 0) { p = m - 1; q = step % (m - 1); }
-        else { p = (step + k) % (m - 1); q = (step - k + (m - 1)) % (m - 1); }
-        if (p > q) { const int t = p; p = q; q = t; }
-        double c = 1.0, s = 0.0;
-        if (q < n) {
-          const double apq = A(p, q);
-          if (fabs(apq) > 1e-300) {
-            const double tau = (A(q, q) - A(p, p)) / (2.0 * apq);
-            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-            c = 1.0 / sqrt(1.0 + t * t);
-            s = t * c;
+// X <- L^-1 X, L lower triangular n x n, X n x ncols, dinv from la_diag_block_inverses(L).  Four lanes
+// share one column (split-k over the already solved rows), one barrier per block row.
+// x_lower: X(i, c) = 0 for i < c on entry (and on exit), those entries are skipped.
+__device__ inline void la_trsm_lower(Mat L, const double *dinv, Mat X, int n, int ncols, bool x_lower) {
+  constexpr int SUB = 4;
+  const int sub = threadIdx.x % SUB;
+  const unsigned gmask = ((1u << SUB) - 1u) << ((threadIdx.x & 31) & ~(SUB - 1));
+  const int ncols_pad = ((ncols + 7) / 8) * 8;          // keep whole warps in the loop (shuffles below)
+  for (int r0 = 0; r0 < n; r0 += LA_NB) {
+    const int bk = r0 / LA_NB;
+    for (int cc = threadIdx.x / SUB; cc < ncols_pad; cc += (int)blockDim.x / SUB) {
+      const bool live = cc < ncols && !(x_lower && cc >= r0 + LA_NB);    // else structurally zero / padding
+      const int c = cc < ncols ? cc : ncols - 1;
+      double acc[LA_NB];
+#pragma unroll
+      for (int i = 0; i < LA_NB; ++i) acc[i] = 0.0;
+      if (live) {
+        const int q_lo = x_lower ? (c / SUB) * SUB : 0;       // aligned so that the SUB lanes partition it
+        for (int q = q_lo + sub; q < r0; q += SUB) {
+          const double xq = X(q, c);
+#pragma unroll
+          for (int i = 0; i < LA_NB; ++i) acc[i] = fma(L(min(r0 + i, n - 1), q), xq, acc[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < LA_NB; ++i) {
+        acc[i] += __shfl_xor_sync(gmask, acc[i], 1);
+        acc[i] += __shfl_xor_sync(gmask, acc[i], 2);
+      }
+      if (live && sub == 0) {
+        double x[LA_NB];
+#pragma unroll
+        for (int i = 0; i < LA_NB; ++i) x[i] = (r0 + i < n) ? X(r0 + i, c) - acc[i] : 0.0;
+#pragma unroll
+        for (int i = 0; i < LA_NB; ++i) {
+          if (r0 + i < n) {
+            double y = 0.0;
+#pragma unroll
+            for (int q = 0; q <= i; ++q) y = fma(dinv[(bk * LA_NB + i) * LA_NB + q], x[q], y);
+            if (!(x_lower && r0 + i < c)) X(r0 + i, c) = y;
           }
         }
-        rot[4 * k] = c; rot[4 * k + 1] = s; rot[4 * k + 2] = (double)p; rot[4 * k + 3] = (double)q;
       }
-      __syncthreads();
-      // columns: A <- A J, Q <- Q J   (J(p,p)=c, J(p,q)=s, J(q,p)=-s, J(q,q)=c)
-      for (int e = threadIdx.x; e < 2 * half * n; e += blockDim.x) {
-        const int which = e / (half * n), r = (e % (half * n)) / half, k = e % half;
-        const double c = rot[4 * k], s = rot[4 * k + 1];
-        const int p = (int)rot[4 * k + 2], q = (int)rot[4 * k + 3];
-        if (s == 0.0 || q >= n) continue;
-        Mat M = which ? Q : A;
-        const double x = M(r, p), y = M(r, q);
-        M(r, p) = c * x - s * y;
-        M(r, q) = s * x + c * y;
-      }
-      __syncthreads();
-      // rows: A <- J^T A
-      for (int e = threadIdx.x; e < half * n; e += blockDim.x) {
-        const int col = e / half, k = e % half;
-        const double c = rot[4 * k], s = rot[4 * k + 1];
-        const int p = (int)rot[4 * k + 2], q = (int)rot[4 * k + 3];
-        if (s == 0.0 || q >= n) continue;
-        const double x = A(p, col), y = A(q, col);
-        A(p, col) = c * x - s * y;
-        A(q, col) = s * x + c * y;
-      }
-      __syncthreads();
     }
+    __syncthreads();
   }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) lam[i] = A(i, i);
-  __syncthreads();
 }
 
-// One-sided (Hestenes) Jacobi SVD of W (n x n, destroyed): W V = U diag(sigma), i.e. W^T W = V diag(sigma^2) V^T.
-// V must hold the identity on entry; on exit lam[i] = sigma_i^2.  Round-robin ordering, ONE WARP PER COLUMN
-// PAIR (needs blockDim.x >= 32 * ceil(n/2)), one barrier per step.  Works on W directly (no W^T W), which
-// keeps the small generalised eigenvalues accurate.  Latency matters (a single matrix sits on the critical
-// path of every policy epoch): squared column norms are cached in `nrm` (>= n doubles) and updated in closed
-// form, so a step needs ONE warp reduction; the rotation angle is evaluated in fp32 (it only steers
-// convergence) while (c, s) are normalised in fp64 so every rotation stays orthogonal to 1e-16.
-__device__ inline void la_jacobi_onesided(Mat W, Mat V, double *lam, double *nrm, int n) {
+// X <- L^-T X (back substitution with the transpose of the lower-triangular L)
+__device__ inline void la_trsm_lower_t(Mat L, const double *dinv, Mat X, int n, int ncols) {
+  constexpr int SUB = 4;
+  const int sub = threadIdx.x % SUB;
+  const unsigned gmask = ((1u << SUB) - 1u) << ((threadIdx.x & 31) & ~(SUB - 1));
+  const int nblk = (n + LA_NB - 1) / LA_NB;
+  const int ncols_pad = ((ncols + 7) / 8) * 8;
+  for (int bk = nblk - 1; bk >= 0; --bk) {
+    const int r0 = bk * LA_NB, r1 = min(r0 + LA_NB, n);
+    for (int cc = threadIdx.x / SUB; cc < ncols_pad; cc += (int)blockDim.x / SUB) {
+      const bool live = cc < ncols;
+      const int c = live ? cc : ncols - 1;
+      double acc[LA_NB];
+#pragma unroll
+      for (int i = 0; i < LA_NB; ++i) acc[i] = 0.0;
+      if (live) {
+        for (int q = r1 + sub; q < n; q += SUB) {
+          const double xq = X(q, c);
+#pragma unroll
+          for (int i = 0; i < LA_NB; ++i) acc[i] = fma(L(q, min(r0 + i, n - 1)), xq, acc[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < LA_NB; ++i) {
+        acc[i] += __shfl_xor_sync(gmask, acc[i], 1);
+        acc[i] += __shfl_xor_sync(gmask, acc[i], 2);
+      }
+      if (live && sub == 0) {
+        double x[LA_NB];
+#pragma unroll
+        for (int i = 0; i < LA_NB; ++i) x[i] = (r0 + i < n) ? X(r0 + i, c) - acc[i] : 0.0;
+#pragma unroll
+        for (int i = 0; i < LA_NB; ++i) {
+          if (r0 + i < n) {
+            double y = 0.0;                                   // (D^-1)^T : y_i = sum_{q >= i} dinv[q][i] x_q
+#pragma unroll
+            for (int q = i; q < LA_NB; ++q) y = fma(dinv[(bk * LA_NB + q) * LA_NB + i], x[q], y);
+            X(r0 + i, c) = y;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// in-place blocked Cholesky of the lower triangle of A (upper part ignored); *bad (shared int, pre-set to 0)
+// receives the 1-based index of the first non-positive pivot.  Per block column: diagonal block by one warp,
+// panel rows by one thread each, rank-LA_NB trailing update by everybody: 3 barriers per 8 columns.
+__device__ inline void la_chol(Mat A, int n, int *bad) {
+  const int lane = threadIdx.x & 31;
+  for (int r0 = 0; r0 < n; r0 += LA_NB) {
+    const int nb = min(LA_NB, n - r0);
+    if (threadIdx.x < 32) {                       // factor the diagonal block: lane i owns row r0 + i
+      for (int j = 0; j < nb; ++j) {
+        const double djj = A(r0 + j, r0 + j);
+        if (lane == 0 && !(djj > 0.0) && *bad == 0) *bad = r0 + j + 1;
+        const double d = sqrt(djj), inv = 1.0 / d;
+        __syncwarp();
+        if (lane == j) A(r0 + j, r0 + j) = d;
+        if (lane > j && lane < nb) A(r0 + lane, r0 + j) *= inv;
+        __syncwarp();
+        if (lane > j && lane < nb) {
+          const double lij = A(r0 + lane, r0 + j);
+          for (int q = j + 1; q <= lane; ++q) A(r0 + lane, r0 + q) = fma(-lij, A(r0 + q, r0 + j), A(r0 + lane, r0 + q));
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    for (int i = r0 + nb + threadIdx.x; i < n; i += blockDim.x) {      // panel: row i of L21 = A21 L11^-T
+      double x[LA_NB];
+#pragma unroll
+      for (int j = 0; j < LA_NB; ++j) {
+        if (j < nb) {
+          double v = A(i, r0 + j);
+#pragma unroll
+          for (int q = 0; q < j; ++q) v = fma(-x[q], A(r0 + j, r0 + q), v);
+          x[j] = v / A(r0 + j, r0 + j);
+          A(i, r0 + j) = x[j];
+        } else {
+          x[j] = 0.0;
+        }
+      }
+    }
+    __syncthreads();
+    const int t0 = r0 + nb, mrem = n - t0;                               // trailing update (lower part)
+    for (int e = threadIdx.x; e < mrem * mrem; e += blockDim.x) {
+      const int ii = e / mrem, qq = e - ii * mrem;
+      if (qq > ii) continue;
+      const int i = t0 + ii, q = t0 + qq;
+      double v = A(i, q);
+#pragma unroll
+      for (int j = 0; j < LA_NB; ++j) if (j < nb) v = fma(-A(i, r0 + j), A(q, r0 + j), v);
+      A(i, q) = v;
+    }
+    __syncthreads();
+  }
+}
+
+// One-sided (Hestenes) Jacobi on the columns of W (n x n, in place): on exit the columns are mutually
+// orthogonal, W_out = W_in V for an (implicit) orthogonal V, and lam[j] = |W_out(:, j)|^2 are the
+// eigenvalues of W_in^T W_in.  V is never formed: callers only need W_out (see proj_kl_cov_fwd_kernel).
+// Round-robin ordering, ONE WARP PER COLUMN PAIR (blockDim.x >= 32 * ceil(n/2)), one barrier per step.
+// The step cost is shared-memory traffic (every pair streams its two columns), so nothing but W moves;
+// squared column norms are cached in `nrm` (>= n doubles) and updated in closed form (one warp reduction
+// per step); the rotation angle is evaluated in fp32 (it only steers convergence) while (c, s) are
+// normalised in fp64 so that every rotation is orthogonal to ~1e-15.
+__device__ inline int la_jacobi_onesided(Mat W, double *lam, double *nrm, int n) {
+  // nrm: scratch of n + 3 * 32 doubles ([n] squared norms, [32] dot products, [64] (c, s) per pair)
   const int m = (n + 1) & ~1, half = m / 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = (int)(blockDim.x >> 5);
+  double *gbuf = nrm + n, *cs = gbuf + 32;
+  int sweeps = 0;
   for (int sweep = 0; sweep < 40; ++sweep) {
-    // (re)compute the squared column norms once per sweep (also bounds the drift of the closed-form update)
-    for (int j = warp; j < n; j += nwarp) {
+    for (int j = warp; j < n; j += nwarp) {      // exact norms once per sweep (bounds the closed-form drift)
       double a = 0.0;
       for (int r = lane; r < n; r += 32) a = fma(W(r, j), W(r, j), a);
       a = warp_sum(a);
       if (lane == 0) nrm[j] = a;
     }
     __syncthreads();
-    int rotated = 0;
+    int big = 0;      // some pair was still correlated above 1e-5 when it was visited in this sweep
     for (int step = 0; step < m - 1; ++step) {
-      if (warp < half) {
-        int p, q;
-        if (warp == 0) { p = m - 1; q = step % (m - 1); }
-        else { p = (step + warp) % (m - 1); q = (step - warp + (m - 1)) % (m - 1); }
+      // pair of warp w (round robin): every warp also needs the pair of "its lane" in phase B
+      auto pair_of = [&](int w, int &p, int &q) {
+        if (w == 0) { p = m - 1; q = step; }
+        else { p = step + w; if (p >= m - 1) p -= m - 1; q = step - w; if (q < 0) q += m - 1; }
         if (p > q) { const int t = p; p = q; q = t; }
+      };
+      int p = 0, q = n;
+      double x0 = 0.0, y0 = 0.0, x1 = 0.0, y1 = 0.0;
+      const int r0 = lane, r1 = lane + 32;
+      // phase A: dot products of the column pairs (one warp per pair)
+      if (warp < half) {
+        pair_of(warp, p, q);
         if (q < n) {
-          const int r0 = lane, r1 = lane + 32;
-          const double x0 = r0 < n ? W(r0, p) : 0.0, y0 = r0 < n ? W(r0, q) : 0.0;
-          const double x1 = r1 < n ? W(r1, p) : 0.0, y1 = r1 < n ? W(r1, q) : 0.0;
+          if (r0 < n) { x0 = W(r0, p); y0 = W(r0, q); }
+          if (r1 < n) { x1 = W(r1, p); y1 = W(r1, q); }
           double g = fma(x0, y0, x1 * y1);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-          const double a = nrm[p], b = nrm[q];
-          if (g * g > 1e-22 * a * b) {
-            rotated = 1;
-            const float zeta = (float)((b - a) / (2.0 * g));
-            const float tf = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
-            const double t = (double)tf;
-            const double c = rsqrt(fma(t, t, 1.0)), s = c * t;
-            if (r0 < n) {
-              W(r0, p) = c * x0 - s * y0; W(r0, q) = s * x0 + c * y0;
-              const double u = V(r0, p), v = V(r0, q);
-              V(r0, p) = c * u - s * v; V(r0, q) = s * u + c * v;
-            }
-            if (r1 < n) {
-              W(r1, p) = c * x1 - s * y1; W(r1, q) = s * x1 + c * y1;
-              const double u = V(r1, p), v = V(r1, q);
-              V(r1, p) = c * u - s * v; V(r1, q) = s * u + c * v;
-            }
-            if (lane == 0) {                       // |c x - s y|^2 and |s x + c y|^2
-              const double c2 = c * c, s2 = s * s, cs2 = 2.0 * c * s * g;
-              nrm[p] = c2 * a + s2 * b - cs2;
-              nrm[q] = s2 * a + c2 * b + cs2;
-            }
-          }
+          if (lane == 0) gbuf[warp] = g;
         }
       }
       __syncthreads();
+      // phase B: rotation parameters of all pairs by ONE warp (lane = pair): the scalar fp64 / conversion
+      // work is not replicated 32 times
+      if (warp == 0 && lane < half) {
+        int pp, qq;
+        pair_of(lane, pp, qq);
+        double c = 1.0, sn = 0.0;
+        if (qq < n) {
+          const double g = gbuf[lane], a = nrm[pp], b = nrm[qq];
+          const double g2 = g * g, ab = a * b;
+          if (g2 > 1e-10 * ab) big = 1;
+          if (g2 > 1e-24 * ab) {
+            const float zeta = (float)(b - a) / (2.0f * (float)g);
+            const float tf = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
+            const double t = (double)tf, h = fma(t, t, 1.0);
+            c = (double)rsqrtf((float)h);                          // fp32 seed + two Newton steps in fp64
+            c = c * fma(-0.5 * h, c * c, 1.5);
+            c = c * fma(-0.5 * h, c * c, 1.5);
+            sn = c * t;
+            const double c2 = c * c, s2 = sn * sn, cs2 = 2.0 * c * sn * g;   // |c x - s y|^2, |s x + c y|^2
+            nrm[pp] = c2 * a + s2 * b - cs2;
+            nrm[qq] = s2 * a + c2 * b + cs2;
+          }
+        }
+        cs[2 * lane] = c; cs[2 * lane + 1] = sn;
+      }
+      __syncthreads();
+      // phase C: apply the rotations (columns are disjoint between warps)
+      if (warp < half && q < n) {
+        const double c = cs[2 * warp], sn = cs[2 * warp + 1];
+        if (sn != 0.0) {
+          if (r0 < n) { W(r0, p) = c * x0 - sn * y0; W(r0, q) = sn * x0 + c * y0; }
+          if (r1 < n) { W(r1, p) = c * x1 - sn * y1; W(r1, q) = sn * x1 + c * y1; }
+        }
+      }
+      // (no barrier needed here: the next phase A of a warp touches two columns that were written by at most
+      //  two other warps in this phase C -> protect with the barrier below)
+      __syncthreads();
     }
-    if (!__syncthreads_or(rotated)) break;
+    ++sweeps;
+    // quadratic convergence: a sweep that only met cosines <= 1e-5 leaves them at ~1e-10 or below, i.e.
+    // eigenvalues exact to ~1e-20 and vectors to ~1e-10 -- no separate verification sweep is needed
+    if (!__syncthreads_or(big)) break;
   }
   for (int j = warp; j < n; j += nwarp) {
     double a = 0.0;
@@ -267,4 +327,5 @@ __device__ inline void la_jacobi_onesided(Mat W, Mat V, double *lam, double *nrm
     if (lane == 0) lam[j] = a;
   }
   __syncthreads();
+  return sweeps;
 }

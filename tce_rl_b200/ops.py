@@ -715,49 +715,68 @@ def _pe_backward(ctx, g, g_ent):
 proj_entropy.register_autograd(_pe_backward, setup_context=_pe_setup)
 
 
-@torch.library.custom_op("tce::proj_kl_cov", mutates_args=())
-def proj_kl_cov(L: Tensor, L_o: Tensor, eps_cov: float) -> Tuple[Tensor, Tensor, Tensor]:
-    """-> (proj_L [Bc,n,n], save (fp64: Q, lambda, eta/active/kl0), info [Bc])."""
+def kl_state_size(batch: int, n: int) -> int:
+    return _lib.load().tce_proj_kl_save_doubles(batch, n)
+
+
+def kl_state(batch: int, n: int, device) -> Tensor:
+    """Zero-initialised state buffer of the KL covariance projection ({M, lambda, eta/active/kl0/fingerprint})."""
+    return torch.zeros(_lib.load().tce_proj_kl_save_doubles(batch, n), device=device, dtype=torch.float64)
+
+
+@torch.library.custom_op("tce::proj_kl_cov_fwd", mutates_args=("state",))
+def proj_kl_cov_fwd(L: Tensor, L_o: Tensor, eps_cov: float, state: Tensor, warm: bool) -> Tuple[Tensor, Tensor]:
     L, L_o = _chk(L, name="L"), _chk(L_o, name="L_o")
     Bc, n = L.shape[0], L.shape[-1]
+    if state.dtype != torch.float64 or not state.is_cuda or state.numel() != _lib.load().tce_proj_kl_save_doubles(Bc, n):
+        raise TceError("state must come from ops.kl_state(batch, n, device)")
     out = torch.empty_like(L)
-    save = torch.empty(_lib.load().tce_proj_kl_save_doubles(Bc, n), device=L.device, dtype=torch.float64)
     info = torch.empty(Bc, device=L.device, dtype=torch.int32)
-    _lib.call("tce_proj_kl_cov_fwd", _p(L), _p(L_o), float(eps_cov), _p(out), _p(save), _p(info), Bc, n, _stream())
-    return out, save, info
+    _lib.call("tce_proj_kl_cov_fwd", _p(L), _p(L_o), float(eps_cov), _p(out), _p(state), _p(info), int(warm), Bc, n,
+              _stream())
+    return out, info
 
 
-@proj_kl_cov.register_fake
-def _(L, L_o, eps_cov):
-    Bc, n = L.shape[0], L.shape[-1]
-    return torch.empty_like(L), L.new_empty(Bc * (n * n + n + 4), dtype=torch.float64), L.new_empty(Bc, dtype=torch.int32)
+@proj_kl_cov_fwd.register_fake
+def _(L, L_o, eps_cov, state, warm):
+    return torch.empty_like(L), L.new_empty(L.shape[0], dtype=torch.int32)
 
 
 @torch.library.custom_op("tce::proj_kl_cov_bwd", mutates_args=())
-def proj_kl_cov_bwd(grad_out: Tensor, L: Tensor, L_o: Tensor, proj_L: Tensor, save: Tensor) -> Tensor:
-    g, L, L_o, proj_L = _chk(grad_out), _chk(L), _chk(L_o), _chk(proj_L)
+def proj_kl_cov_bwd(grad_out: Tensor, L: Tensor, proj_L: Tensor, state: Tensor) -> Tensor:
+    g, L, proj_L = _chk(grad_out), _chk(L), _chk(proj_L)
     out = torch.empty_like(L)
-    _lib.call("tce_proj_kl_cov_bwd", _p(L), _p(L_o), _p(proj_L), _p(g), _p(save), _p(out), L.shape[0], L.shape[-1],
-              _stream())
+    _lib.call("tce_proj_kl_cov_bwd", _p(L), _p(proj_L), _p(g), _p(state), _p(out), L.shape[0], L.shape[-1], _stream())
     return out
 
 
 @proj_kl_cov_bwd.register_fake
-def _(grad_out, L, L_o, proj_L, save):
+def _(grad_out, L, proj_L, state):
     return torch.empty_like(L)
 
 
-def _pk_setup(ctx, inputs, output):
-    L, L_o, eps_cov = inputs
-    ctx.save_for_backward(L, L_o, output[0], output[1])
+class _ProjKLCov(torch.autograd.Function):
+    """Autograd wrapper (a mutating custom op cannot carry an autograd formula itself)."""
+
+    @staticmethod
+    def forward(ctx, L, L_o, eps_cov, state, warm):
+        proj_L, info = proj_kl_cov_fwd(L, L_o, eps_cov, state, warm)
+        ctx.save_for_backward(L, proj_L)
+        ctx.state = state        # overwritten by the NEXT forward only (after this backward has run)
+        ctx.mark_non_differentiable(info)
+        return proj_L, info
+
+    @staticmethod
+    def backward(ctx, g, g_info):
+        L, proj_L = ctx.saved_tensors
+        return proj_kl_cov_bwd(g.contiguous(), L, proj_L, ctx.state), None, None, None, None
 
 
-def _pk_backward(ctx, g, g_save, g_info):
-    L, L_o, proj_L, save = ctx.saved_tensors
-    return proj_kl_cov_bwd(g, L, L_o, proj_L, save), None, None
-
-
-proj_kl_cov.register_autograd(_pk_backward, setup_context=_pk_setup)
+def proj_kl_cov(L: Tensor, L_o: Tensor, eps_cov: float, state: Tensor, warm: bool) -> Tuple[Tensor, Tensor]:
+    """-> (proj_L [Bc,n,n], info [Bc]); ``state`` (``kl_state``) is overwritten with {M = L_o Q, lambda, eta, ...}:
+    it feeds the backward and, with ``warm``, the next call with the same ``L_o`` starts its eigen-solve from it
+    (2-3 Jacobi sweeps instead of ~9; guarded by a fingerprint of ``L_o`` inside the kernel)."""
+    return _ProjKLCov.apply(L, L_o, eps_cov, state, warm)
 
 
 @torch.library.custom_op("tce::proj_frob_cov", mutates_args=())

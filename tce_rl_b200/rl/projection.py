@@ -165,13 +165,29 @@ class BaseProjectionLayer:
 
 
 class KLProjectionLayer(BaseProjectionLayer):
+    """KL projection.  ``warm_start`` (default on): the eigen-basis found by the previous call is handed to the
+    next one; the kernel uses it only when the old covariance is bit-identical (fingerprint), i.e. across the
+    epochs of one ``update_policy`` -- results are unchanged, the Jacobi solve needs 2-3 sweeps instead of ~9."""
+
+    def __init__(self, *args, warm_start=True, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.warm_start = bool(warm_start)
+        self._kl_state = None
+
     def _mean_part(self, policy, p, q):
         return 0.5 * ops.gauss_maha(p[0], q[0], q[1])
 
     def _cov_projection(self, policy, L, L_old):
         if policy.is_diag:
             raise NotImplementedError("diagonal KL projection is outside the TCE configs")
-        return ops.proj_kl_cov(L.contiguous(), L_old.contiguous(), self.cov_bound)[0]
+        Lc = L.contiguous()
+        state = self._kl_state
+        if (not self.warm_start or state is None or state.device != Lc.device
+                or state.numel() != ops.kl_state_size(Lc.shape[0], Lc.shape[-1])):
+            state = ops.kl_state(Lc.shape[0], Lc.shape[-1], Lc.device)
+            if self.warm_start:
+                self._kl_state = state
+        return ops.proj_kl_cov(Lc, L_old.contiguous(), self.cov_bound, state, self.warm_start)[0]
 
 
 class FrobeniusProjectionLayer(BaseProjectionLayer):

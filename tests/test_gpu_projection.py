@@ -205,3 +205,27 @@ def test_policy_epoch_matches_oracle(name, typ, contextual):
     o_seg = oa.get_segment_advantage(inp["rewards"].double(), inp["values"].double(), o_adv, pairs.cpu(), 1.0,
                                      "value_subtraction", True)
     assert (f64(seg_adv) - o_seg).abs().max() <= 1e-4
+
+
+def test_kl_projection_warm_start_is_exact():
+    """Warm-starting the eigen-solve from the previous call's basis must not change the projection;
+    a different old covariance must fall back to a cold start (fingerprint guard)."""
+    n, Bc = 63, 3
+    inp = case("box", Bc, True, seed=5)
+    c = lambda k: inp[k].to(DEV)
+    L, Lo = c("L"), c("L_old")
+    cold = ops.proj_kl_cov(L, Lo, 5e-4, ops.kl_state(Bc, n, DEV), False)[0]
+    state = ops.kl_state(Bc, n, DEV)
+    ops.proj_kl_cov(L * 1.001, Lo, 5e-4, state, True)                 # previous "epoch"
+    warm = ops.proj_kl_cov(L, Lo, 5e-4, state, True)[0]
+    assert (warm - cold).abs().max().item() <= 2e-6
+    other = ops.proj_kl_cov(L, Lo * 1.01, 5e-4, state, True)[0]       # state belongs to another L_old
+    ref = ops.proj_kl_cov(L, Lo * 1.01, 5e-4, ops.kl_state(Bc, n, DEV), False)[0]
+    assert (other - ref).abs().max().item() <= 2e-6
+    # gradients through a warm-started forward
+    Lg = L.clone().requires_grad_(True)
+    W = torch.tril(torch.randn_like(L))
+    (ops.proj_kl_cov(Lg, Lo, 5e-4, state, True)[0] * W).sum().backward()
+    Lg2 = L.clone().requires_grad_(True)
+    (ops.proj_kl_cov(Lg2, Lo, 5e-4, ops.kl_state(Bc, n, DEV), False)[0] * W).sum().backward()
+    assert (Lg.grad - Lg2.grad).abs().max().item() <= 1e-4 * Lg2.grad.abs().max().item()
