@@ -91,7 +91,7 @@ __device__ void load_lower(const float *__restrict__ L, float *Ls, int n, int NR
 // Stage 1: gram.  One CTA per episode.
 // =====================================================================================================
 template <int D, int K1>
-__global__ void __launch_bounds__(SL_THREADS)
+__global__ void __launch_bounds__(SL_THREADS, 4)
 seglik_gram_kernel(TabDev tb, const float *__restrict__ smp_traj, const float *__restrict__ mean,
                    const float *__restrict__ L, long long ldb_L, const float *__restrict__ times,
                    const float *__restrict__ init_time, const float *__restrict__ init_pos,
@@ -329,7 +329,7 @@ seglik_chol_kernel(const double *Cmat, const double *Rres, double *Gout, double 
 // Stage 3: backward accumulation.  One CTA per episode.
 // =====================================================================================================
 template <int D, int K1>
-__global__ void __launch_bounds__(SL_THREADS)
+__global__ void __launch_bounds__(SL_THREADS, 4)
 seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__restrict__ Alpha,
                   const float *__restrict__ L, long long ldb_L, const float *__restrict__ times,
                   const float *__restrict__ init_time, const int64_t *__restrict__ pairs,
@@ -339,9 +339,9 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
   constexpr int NR = (Dp + 1) & ~1;
   constexpr int LD = NR + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *Gs = reinterpret_cast<double *>(smem_raw);              // [NT][P] staged adjoints (later: out tile)
-  const int gs_doubles = NT * P > (Dp * Dp + 1) / 2 ? NT * P : (Dp * Dp + 1) / 2;   // same rule as bwd_smem()
-  double *hs = Gs + gs_doubles;                                   // [2P][K1]
+  float *Gs = reinterpret_cast<float *>(smem_raw);                // [NT][P] staged adjoints, fp32 (later: out tile)
+  const int gs_floats = (NT * P > Dp * Dp ? NT * P : Dp * Dp + 1) & ~1;              // same rule as bwd_smem()
+  double *hs = reinterpret_cast<double *>(Gs + gs_floats);       // [2P][K1]
   double *xi = hs + 2 * P * K1;                                   // [2P][2]
   double *init_row = xi + 4 * P;                                  // [5 + 2 K1]
   float *Ls = reinterpret_cast<float *>(init_row + 5 + 2 * K1 + 1);  // [NR][LD]
@@ -353,7 +353,7 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
   const float up = upstream ? *upstream : 1.0f;       // scalar gradient of the fused surrogate loss
 
   load_lower(L + b * ldb_L, Ls, Dp, NR, LD);
-  for (int e = threadIdx.x; e < NT * P; e += blockDim.x) Gs[e] = Gb[e];
+  for (int e = threadIdx.x; e < NT * P; e += blockDim.x) Gs[e] = (float)Gb[e];
   for (int e = threadIdx.x; e < NR * LD; e += blockDim.x) Ms[e] = 0.f;
   basis_points<K1>(tb, (double)init_time[b], times + b * T, pairs, P, hs, xi, init_row);
 
@@ -377,14 +377,14 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
 #pragma unroll
     for (int j = 0; j < K1; ++j) acc[j] = 0.0;
     const int r0 = 2 * d, q0 = 2 * dd;
-    const double *g00 = Gs + (size_t)tri_idx(r0, q0) * P;
-    const double *g10 = Gs + (size_t)tri_idx(r0 + 1, q0) * P;
-    const double *g11 = Gs + (size_t)tri_idx(r0 + 1, q0 + 1) * P;
-    const double *g01 = (d != dd) ? Gs + (size_t)tri_idx(r0, q0 + 1) * P : g10;   // symmetric inside a diagonal block
+    const float *g00 = Gs + (size_t)tri_idx(r0, q0) * P;
+    const float *g10 = Gs + (size_t)tri_idx(r0 + 1, q0) * P;
+    const float *g11 = Gs + (size_t)tri_idx(r0 + 1, q0 + 1) * P;
+    const float *g01 = (d != dd) ? Gs + (size_t)tri_idx(r0, q0 + 1) * P : g10;    // symmetric inside a diagonal block
     for (int p = 0; p < P; ++p) {
       const double a0 = hs[(2 * p) * K1 + i], a1 = hs[(2 * p + 1) * K1 + i];
-      const double w0 = a0 * g00[p] + a1 * g10[p];      // coefficient of h_p0[:]
-      const double w1 = a0 * g01[p] + a1 * g11[p];      // coefficient of h_p1[:]
+      const double w0 = a0 * (double)g00[p] + a1 * (double)g10[p];      // coefficient of h_p0[:]
+      const double w1 = a0 * (double)g01[p] + a1 * (double)g11[p];      // coefficient of h_p1[:]
 #pragma unroll
       for (int j = 0; j < K1; ++j)
         acc[j] = fma(w0, hs[(2 * p) * K1 + j], fma(w1, hs[(2 * p + 1) * K1 + j], acc[j]));
@@ -399,7 +399,7 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
   __syncthreads();
 
   // ---- grad_L = 2 * tril(M L)  (fp32 FFMA, 2x2 tiles over the lower triangle), staged in the Gs buffer
-  float *out = reinterpret_cast<float *>(Gs);     // [Dp][Dp] dense (the Gs region is sized for it)
+  float *out = Gs;                                // [Dp][Dp] dense (the Gs region is sized for it)
   for (int e = threadIdx.x; e < Dp * Dp; e += blockDim.x) out[e] = 0.f;
   __syncthreads();
   {
@@ -439,8 +439,8 @@ size_t gram_smem(int P) {
 template <int D, int K1>
 size_t bwd_smem(int P) {
   constexpr int Dp = D * K1, N = 2 * D, NT = tri(N), NR = (Dp + 1) & ~1, LD = NR + 1;
-  const size_t gs_doubles = (size_t)NT * P > (size_t)(Dp * Dp + 1) / 2 ? (size_t)NT * P : (size_t)(Dp * Dp + 1) / 2;
-  const size_t g = sizeof(double) * gs_doubles;
+  const size_t gs_floats = (size_t)((NT * P > Dp * Dp ? NT * P : Dp * Dp + 1) & ~1);
+  const size_t g = sizeof(float) * gs_floats;
   return g + sizeof(double) * (2 * P * K1 + 4 * P + 5 + 2 * K1 + 1) + sizeof(float) * 2 * NR * LD + 16;
 }
 
@@ -476,6 +476,8 @@ extern "C" int tce_seglik_gram(const tce_tables_t *t, const float *smp_traj, con
     if (smem > 200 * 1024) return TCE_ERR_UNSUPPORTED_SHAPE;                                                      \
     TCE_CUDA(cudaFuncSetAttribute(seglik_gram_kernel<Dv, Kv>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                   (int)smem), "gram smem attr");                                                  \
+    cudaFuncSetAttribute(seglik_gram_kernel<Dv, Kv>, cudaFuncAttributePreferredSharedMemoryCarveout,              \
+                         cudaSharedmemCarveoutMaxShared);                                                         \
     seglik_gram_kernel<Dv, Kv><<<(unsigned)B, SL_THREADS, smem, st>>>(tab_dev(t), smp_traj, mean, L, ldb_L, times, \
                                                                      init_time, init_pos, init_vel, pred_pairs,  \
                                                                      Cmat, R, diag_max, (int)T, (int)P);          \
@@ -531,6 +533,8 @@ extern "C" int tce_seglik_bwd(const tce_tables_t *t, const void *work, const flo
     if (smem > 200 * 1024) return TCE_ERR_UNSUPPORTED_SHAPE;                                                     \
     TCE_CUDA(cudaFuncSetAttribute(seglik_bwd_kernel<Dv, Kv>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                   (int)smem), "bwd smem attr");                                                  \
+    cudaFuncSetAttribute(seglik_bwd_kernel<Dv, Kv>, cudaFuncAttributePreferredSharedMemoryCarveout,              \
+                         cudaSharedmemCarveoutMaxShared);                                                        \
     seglik_bwd_kernel<Dv, Kv><<<(unsigned)B, SL_THREADS, smem, st>>>(tab_dev(t), G, A, L, ldb_L, times, init_time, \
                                                                     pred_pairs, upstream, grad_mean, grad_L, (int)T, (int)P); \
     TCE_CHECK_LAUNCH("seglik_bwd_kernel");                                                                       \

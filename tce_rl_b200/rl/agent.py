@@ -80,10 +80,12 @@ class TemporalCorrelatedAgent:
         self.evaluation_interval = kwargs.get("evaluation_interval", 1)
         self.use_cuda_graph = bool(kwargs.get("use_cuda_graph", False))
         self.fused_surrogate = bool(kwargs.get("fused_surrogate", True))
+        self.overlap_logging = bool(kwargs.get("overlap_logging", True))
+        self._log_stream = None
         self.process_group = kwargs.get("process_group", None)      # torch.distributed group (None = single GPU)
         self.policy_net_params = policy.parameters
         self.critic_net_params = critic.parameters if critic is not None else []
-        capt = dict(capturable=True) if self.device.type == "cuda" else {}
+        capt = dict(capturable=True, fused=True) if self.device.type == "cuda" else {}   # one multi-tensor kernel
         self.policy_optimizer = torch.optim.Adam(self.policy_net_params, lr=self.lr_policy,
                                                  weight_decay=self.wd_policy, **capt)
         self.critic_optimizer = (torch.optim.Adam(self.critic_net_params, lr=self.lr_critic,
@@ -184,16 +186,13 @@ class TemporalCorrelatedAgent:
         projection / trust-region loss of this epoch already evaluated (``projection.cache``) are reused."""
         cache = getattr(self.projection, "cache", {})
         kl_metric = isinstance(self.projection, KLProjectionLayer)
-        out = []
         with torch.no_grad():
             mp = cache.get("new_old_mean") if kl_metric else None
-            out += [x.mean() for x in gaussian_kl_details(self.policy, new, old, mean_part=mp)]
-            if "new_proj" in cache:
-                out += [x.mean() for x in cache["new_proj"]]
-            else:
-                out += [x.mean() for x in gaussian_kl_details(self.policy, new, proj)]
-            out += [x.mean() for x in gaussian_kl_details(self.policy, proj, old)]
-        return torch.stack(out)
+            parts = list(gaussian_kl_details(self.policy, new, old, mean_part=mp))
+            parts += list(cache["new_proj"]) if "new_proj" in cache else list(
+                gaussian_kl_details(self.policy, new, proj))
+            parts += list(gaussian_kl_details(self.policy, proj, old))
+            return torch.stack([x.expand(new[0].shape[0]) for x in parts]).mean(dim=1)    # one reduction
 
     # ---- critic ---------------------------------------------------------------------------------------------
     def update_critic(self, dataset):
@@ -220,7 +219,7 @@ class TemporalCorrelatedAgent:
 
     def _grad_norm_clip(self, params):
         """util_numerical.py:244-275 without the per-parameter .item(): norm on the device."""
-        norm = torch.sqrt(sum((p.grad.detach() ** 2).sum() for p in params))
+        norm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm([p.grad for p in params])))
         if self.clip_grad_norm > 0:
             torch.nn.utils.clip_grad_norm_(params, self.clip_grad_norm)
         return norm
@@ -252,13 +251,27 @@ class TemporalCorrelatedAgent:
             with torch.no_grad():
                 ent_loss, ent_stats = self.entropy_loss(proj[0], proj[1])
         tr_loss = self.projection.get_trust_region_loss(self.policy, new, proj, set_variance=self.set_variance)
-        kl = self.kl_old_new_proj(new, old, proj)
         policy_loss = surrogate + ent_loss + tr_loss
+        # logging-only KL decomposition: a parallel branch (side stream) next to backward + Adam
+        main, side = None, None
+        if self.overlap_logging and policy_loss.is_cuda:
+            main = torch.cuda.current_stream()
+            if self._log_stream is None:
+                self._log_stream = torch.cuda.Stream(device=policy_loss.device)
+            side = self._log_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                kl = self.kl_old_new_proj(new, old, proj)
+                kl.record_stream(main)
+        else:
+            kl = self.kl_old_new_proj(new, old, proj)
         self.policy_optimizer.zero_grad(set_to_none=False)
         policy_loss.backward()
         self._allreduce_grads(self.policy_net_params)
         grad_norm = self._grad_norm_clip(self.policy_net_params)
         self.policy_optimizer.step()
+        if side is not None:
+            main.wait_stream(side)
         head = torch.stack([surrogate.detach(), ent_loss.detach().to(surrogate.dtype), tr_loss.detach(),
                             policy_loss.detach(), ent_stats["entropy"].detach().to(surrogate.dtype),
                             sur_stats["imp_smp_ratio"].detach(), grad_norm.detach()])

@@ -84,6 +84,8 @@ class BaseProjectionLayer:
         # detached by-products of the last projection / trust-region-loss call, reused by the agent's logging
         # (temporal_correlated_agent.py:641-686 recomputes them): {"new_old_mean": [B], "new_proj": 4 x [B]}
         self.cache = {}
+        self.overlap = bool(kwargs.get("overlap", True))      # run independent chains on a side stream
+        self._side = None
 
     @property
     def initial_entropy(self):
@@ -128,12 +130,39 @@ class BaseProjectionLayer:
             proj_L = self._cov_projection(policy, L, old_L)
         return proj_mean, proj_L
 
+    def _side_stream(self, device):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=device)
+        return self._side
+
     def __call__(self, policy, p, q, step, *args, **kwargs):
         beta = self._entropy_bound(step, p[0].device)
+        if self.overlap and not policy.contextual_std and not self.entropy_first and p[1].is_cuda:
+            return self._call_overlapped(policy, p, q, beta)
         if self.entropy_first:
             p = self._entropy_projection(policy, p, beta)
         proj = self._trust_region_projection(policy, p, q)
         return proj if self.entropy_first else self._entropy_projection(policy, proj, beta)
+
+    def _call_overlapped(self, policy, p, q, beta):
+        """Non-contextual covariance: the covariance chain (ONE matrix: projection + entropy scaling, a
+        latency-bound single-CTA sequence) does not depend on the batch-sized mean chain, so it runs on a side
+        stream (a parallel branch when captured in a CUDA graph); autograd replays the same split backwards."""
+        mean, L = p
+        old_mean, old_L = q
+        main = torch.cuda.current_stream()
+        side = self._side_stream(mean.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            proj_L1 = self._cov_projection(policy, L[:1], old_L[:1])
+            if beta is not None:
+                proj_L1 = ops.proj_entropy(proj_L1.contiguous(), beta, self.entropy_eq)[0]
+            proj_L1.record_stream(main)
+        mean_part = self._mean_part(policy, p, q)
+        self.cache = {"new_old_mean": mean_part.detach()}
+        proj_mean = ops.proj_mean(mean, old_mean, mean_part, self.mean_bound)
+        main.wait_stream(side)
+        return proj_mean, _expand_first(proj_L1, mean.shape[0])
 
     def trust_region_value(self, policy, p, q):
         return gaussian_kl(policy, p, q)
