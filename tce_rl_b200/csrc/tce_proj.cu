@@ -322,7 +322,7 @@ __device__ inline double kl_solve_eta(const double *lam, int n, double eps, doub
   }
   if (warp == 0) {
     double eta = 0.5 * (lo + hi);
-    for (int it = 0; it < 8; ++it) {              // bracket is ~1e-3 wide: Newton converges in 3-4 steps
+    for (int it = 0; it < 5; ++it) {              // bracket is ~1e-3 wide: Newton converges in 3-4 steps
       double df;
       const double f = kl_of_eta(lam, n, eta, &df) - eps;
       if (f > 0.0) lo = eta; else hi = eta;

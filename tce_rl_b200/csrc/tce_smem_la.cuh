@@ -182,15 +182,16 @@ __device__ inline void la_trsm_lower_t(Mat L, const double *dinv, Mat X, int n, 
 // panel rows by one thread each, rank-LA_NB trailing update by everybody: 3 barriers per 8 columns.
 __device__ inline void la_chol(Mat A, int n, int *bad) {
   const int lane = threadIdx.x & 31;
+  __shared__ double s_invd[LA_NB];                 // 1 / L_jj of the current diagonal block
   for (int r0 = 0; r0 < n; r0 += LA_NB) {
     const int nb = min(LA_NB, n - r0);
     if (threadIdx.x < 32) {                       // factor the diagonal block: lane i owns row r0 + i
       for (int j = 0; j < nb; ++j) {
         const double djj = A(r0 + j, r0 + j);
         if (lane == 0 && !(djj > 0.0) && *bad == 0) *bad = r0 + j + 1;
-        const double d = sqrt(djj), inv = 1.0 / d;
+        const double inv = rsqrt(djj);           // one special-function op instead of sqrt + divide
         __syncwarp();
-        if (lane == j) A(r0 + j, r0 + j) = d;
+        if (lane == j) { A(r0 + j, r0 + j) = djj * inv; s_invd[j] = inv; }
         if (lane > j && lane < nb) A(r0 + lane, r0 + j) *= inv;
         __syncwarp();
         if (lane > j && lane < nb) {
@@ -209,7 +210,7 @@ __device__ inline void la_chol(Mat A, int n, int *bad) {
           double v = A(i, r0 + j);
 #pragma unroll
           for (int q = 0; q < j; ++q) v = fma(-x[q], A(r0 + j, r0 + q), v);
-          x[j] = v / A(r0 + j, r0 + j);
+          x[j] = v * s_invd[j];
           A(i, r0 + j) = x[j];
         } else {
           x[j] = 0.0;
