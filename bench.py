@@ -241,6 +241,11 @@ def roofline_numbers(agent, dataset, times, pairs, device, peaks):
     return roof
 
 
+def _mark(msg):
+    if os.environ.get("TCE_BENCH_DEBUG"):
+        print(f"[bench r{os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -262,7 +267,9 @@ def run_ours(args):
     except Exception:
         pass
 
+    _mark("init done")
     agent, dataset, times, pairs = build_gpu_workload(device, rank, world)
+    _mark("workload built")
     K, W = args.steps, max(args.warmup, 3)
     flush = torch.empty(192 * 1024 * 1024, device=device, dtype=torch.int32)
 
@@ -274,6 +281,7 @@ def run_ours(args):
             agent.policy_epoch(dataset, times, pairs)
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    _mark("eager warm-up epochs done")
     graph, metrics, launches_per_step = None, None, 0
     try:
         l0 = _lib.LAUNCHES
@@ -283,6 +291,7 @@ def run_ours(args):
         launches_per_step = _lib.LAUNCHES - l0
         step_fn = graph.replay
         mode = "cuda_graph"
+        _mark("graph captured")
     except Exception as exc:                                     # pragma: no cover
         if rank == 0:
             print(f"[bench] CUDA-graph capture failed ({exc!r}); timing eager steps", file=sys.stderr)
@@ -307,6 +316,7 @@ def run_ours(args):
         flush.zero_()
         step_fn()
     barrier()
+    _mark("warm-up replays done")
     events = []
     with ClockSampler(local) as clocks:
         t_wall0 = time.perf_counter()
@@ -326,6 +336,7 @@ def run_ours(args):
     total_ms = tt.item()
     ms_per_step = total_ms / K
     value = world * B_PER_GPU / (ms_per_step * 1e-3)
+    _mark("timed region done")
     final = metrics.cpu()
     if not torch.isfinite(final).all():
         raise SystemExit("non-finite loss in the timed region")
@@ -347,6 +358,7 @@ def run_ours(args):
     for _ in range(3):
         e2e_step()
     barrier()
+    _mark("e2e warm-up done")
     ev = []
     for _ in range(K):
         flush.zero_()
@@ -361,11 +373,14 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * B_PER_GPU / (e2e_ms.item() * 1e-3)
+    _mark("e2e done")
 
     roof = roofline_numbers(agent, dataset, times, pairs, device, peaks) if rank == 0 else None
     cpu = cpu_baseline(budget_s=12.0) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    _mark("roofline / cpu baseline done")
     if world > 1:
         dist.barrier()
+    _mark("final barrier passed")
     if rank == 0:
         P = int(pairs.shape[0])
         line = {
@@ -375,7 +390,10 @@ def run_ours(args):
             "config": {"workload": f"boxpush_tce_policy_epoch_B{B_PER_GPU}_P{P}", "episodes_per_gpu": B_PER_GPU,
                        "global_episodes": world * B_PER_GPU, "segments": P, "num_dof": D, "num_basis_g": K1,
                        "dim_params": DP, "num_times": T_STEPS, "projection": "KLProjectionLayer",
-                       "contextual_cov": False, "L_layout": "per-episode [B,63,63] into the likelihood",
+                       "contextual_cov": False,
+                       "L_layout": "head emits [B,63,63]; projected factor is one matrix broadcast with batch stride 0 "
+                                   "(as the reference KL layer returns for non-contextual policies)",
+                       "kl_warm_start": True,
                        "step": "policy MLP + head + KL/entropy projection + segment likelihood + losses + backward "
                                "+ grad all-reduce + Adam", "replay": mode, "l2": "flushed between timed steps",
                        "segment_logprobs_per_s_fwd_bwd": round(value * P, 1)},
@@ -392,7 +410,12 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL kernels captured in the CUDA graph keep the communicator busy at teardown (observed: hang in
+        # destroy_process_group); all results are out, so leave without the collective teardown.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 # =============================================================================================================
