@@ -142,17 +142,21 @@ chol_bwd_kernel(const float *__restrict__ S, const float *__restrict__ gS, float
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
-__global__ void head_fwd_kernel(const float *__restrict__ vec, long long ldb_vec, float min_std,
-                                float *__restrict__ L, long long total, int n) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= total) return;
-  const long long b = e / (n * n);
-  const int r = (int)(e % (n * n)) / n, c = (int)(e % n);
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const float *__restrict__ vec, long long ldb_vec, float min_std, float *__restrict__ L, int n) {
+  const long long b = blockIdx.x;
   const float *v = vec + b * ldb_vec;
-  float out = 0.f;
-  if (c == r) out = softplus_f(v[r]) + min_std;
-  else if (c < r) out = v[n + r * (r - 1) / 2 + c];
-  L[e] = out;
+  float *Lb = L + (size_t)b * n * n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = warp; r < n; r += nw) {
+    const float *off = v + n + r * (r - 1) / 2;
+    for (int c = lane; c < n; c += 32) {
+      float o = 0.f;
+      if (c < r) o = off[c];
+      else if (c == r) o = softplus_f(v[r]) + min_std;
+      Lb[r * n + c] = o;
+    }
+  }
 }
 
 // grid (ceil(nvec/128), batch chunks); grad_vec zero-initialised by the launcher when reducing
@@ -190,7 +194,7 @@ __global__ void head_bwd_kernel(const float *__restrict__ vec, long long ldb_vec
 
 extern "C" int tce_mvn_rsample(const float *mean, const float *L, int64_t ldb_L, const float *eps, uint64_t seed,
                                uint64_t offset, float *out, int64_t B, int n, void *stream) {
-  if (!mean || !L || !out || B < 0 || n < 1 || n > 1024) return TCE_ERR_INVALID_ARGUMENT;
+  if (!mean || !L || !out || B < 0 || n < 1 || n > 200) return TCE_ERR_INVALID_ARGUMENT;
   if (B == 0) return TCE_OK;
   rsample_kernel<<<(unsigned)B, 128, n * sizeof(float), (cudaStream_t)stream>>>(mean, L, ldb_L, eps, seed, offset, out, n);
   TCE_CHECK_LAUNCH("rsample_kernel");
@@ -222,8 +226,7 @@ extern "C" int tce_policy_head_fwd(const float *vec, int64_t ldb_vec, float min_
                                    void *stream) {
   if (!vec || !L || B < 0 || n < 1) return TCE_ERR_INVALID_ARGUMENT;
   if (B == 0) return TCE_OK;
-  const long long total = (long long)B * n * n;
-  head_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(vec, ldb_vec, min_std, L, total, n);
+  head_fwd_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(vec, ldb_vec, min_std, L, n);
   TCE_CHECK_LAUNCH("head_fwd_kernel");
   return TCE_OK;
 }

@@ -162,9 +162,10 @@ maha_kernel(const float *__restrict__ mean, const float *__restrict__ mean_o, co
   float *sL = reinterpret_cast<float *>(smd + 2 * n);
   const long long b = blockIdx.x;
   const float *Lo = L_o + b * ldb_Lo;
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-    const int i = e / n, j = e - i * n;
-    if (j <= i) sL[i * LD + j] = Lo[e];
+  {
+    const int warp = threadIdx.x >> 5, lane_ = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int i = warp; i < n; i += nw)                       // lower triangle only, no index divisions
+      for (int j = lane_; j <= i; j += 32) sL[i * LD + j] = Lo[(size_t)i * n + j];
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     bv[i] = (double)mean[b * n + i] - (double)mean_o[b * n + i];

@@ -5,6 +5,8 @@
 // HBM-bound (algorithmic bytes/episode = 4*[Dp + (1+2D) + T + 2D*T]).  The fp32 basis rows are staged
 // in shared memory once per (persistent) CTA; every thread owns one (episode, time) point, results go
 // through a shared tile so that the global stores are contiguous float4.
+#include <stdlib.h>
+
 #include "tce_common.cuh"
 
 namespace {
@@ -21,6 +23,17 @@ __device__ __forceinline__ const float *tab_row(const TabDev &tb, const float *s
   return i < staged_rows ? srow + (size_t)i * tb.row32_stride : tb.row32 + (size_t)i * tb.row32_stride;
 }
 
+// index of a time in the pre-computed grid without divisions (inv_tau = 1 / tau, fp64)
+__device__ __forceinline__ void time_to_index_fast(const TabDev &tb, double inv_tau, float t, int &i0, float &w) {
+  double s = ((double)t - tb.delay) * inv_tau;
+  s = s > 0.0 ? s : 0.0;
+  const double idx = s * tb.inv_scaled_dt;
+  int f = (int)idx;                          // idx >= 0: truncation == floor
+  f = f > tb.num_pc - 2 ? tb.num_pc - 2 : f;
+  i0 = f;
+  w = (float)(idx - (double)f);
+}
+
 template <int K1>
 __global__ void __launch_bounds__(TRAJ_THREADS)
 traj_fwd_kernel(TabDev tb, const float *__restrict__ params, const float *__restrict__ times,
@@ -28,10 +41,12 @@ traj_fwd_kernel(TabDev tb, const float *__restrict__ params, const float *__rest
                 const float *__restrict__ init_vel, float *__restrict__ traj, long long B, int T,
                 int staged_rows) {
   extern __shared__ __align__(16) float smem[];
-  const int D = tb.D, D2 = 2 * D, stride = tb.row32_stride;
-  float *tile = smem;                                            // [TRAJ_THREADS][2D] output tile (16B aligned)
+  const int D = tb.D, D2 = 2 * D, Dp = D * K1, stride = tb.row32_stride;
+  const int ep_floats = Dp + D2;                                  // theta | y0 | v0 * tau  per episode
+  float *tile = smem;                                             // [TRAJ_THREADS][2D] output tile (16B aligned)
   EpInit *eps = reinterpret_cast<EpInit *>(tile + TRAJ_THREADS * D2);
-  float *srow = reinterpret_cast<float *>(eps + MAX_EP_PER_CHUNK);   // staged table rows
+  float *epd = reinterpret_cast<float *>(eps + MAX_EP_PER_CHUNK);  // [MAX_EP_PER_CHUNK][ep_floats]
+  float *srow = epd + MAX_EP_PER_CHUNK * ep_floats;               // staged table rows
   __shared__ float s_scale[TCE_MAX_K1];
 
   for (int i = threadIdx.x; i < staged_rows * stride; i += blockDim.x) srow[i] = tb.row32[i];
@@ -39,17 +54,18 @@ traj_fwd_kernel(TabDev tb, const float *__restrict__ params, const float *__rest
   __syncthreads();
 
   const long long total = B * (long long)T;
-  const float tau = (float)tb.tau;
+  const float tau = (float)tb.tau, inv_tau_f = 1.0f / tau;
+  const double inv_tau = 1.0 / tb.tau;
+  const float goal_shift_scale = tb.relative_goal ? (tb.relative_goal_scaled ? 1.0f : 1.0f / s_scale[K1 - 1]) : 0.0f;
   for (long long g0 = (long long)blockIdx.x * TRAJ_THREADS; g0 < total; g0 += (long long)gridDim.x * TRAJ_THREADS) {
     const long long b_first = g0 / T;
     long long g_last = g0 + TRAJ_THREADS - 1;
     if (g_last >= total) g_last = total - 1;
     const int n_ep = (int)(g_last / T - b_first) + 1;
-    // per-episode initial-condition values
+    // per-episode data: initial-condition basis values, parameters, y0, v0 * tau
     for (int e = threadIdx.x; e < n_ep; e += blockDim.x) {
-      int i0; double w;
-      time_to_index(tb, (double)init_time[b_first + e], i0, w);
-      const float wf = (float)w;
+      int i0; float wf;
+      time_to_index_fast(tb, inv_tau, init_time[b_first + e], i0, wf);
       const float *r0 = tab_row(tb, srow, staged_rows, i0), *r1 = tab_row(tb, srow, staged_rows, i0 + 1);
       EpInit &E = eps[e];
       E.y1b = lerp_t(r0[0], r1[0], wf); E.y2b = lerp_t(r0[1], r1[1], wf);
@@ -61,14 +77,23 @@ traj_fwd_kernel(TabDev tb, const float *__restrict__ params, const float *__rest
         E.vb[j] = lerp_t(r0[4 + K1 + j], r1[4 + K1 + j], wf);
       }
     }
+    for (int i = threadIdx.x; i < n_ep * ep_floats; i += blockDim.x) {
+      const int e = i / ep_floats, k = i - e * ep_floats;
+      const long long bb = b_first + e;
+      float v;
+      if (k < Dp) v = params[bb * Dp + k];
+      else if (k < Dp + D) v = init_pos[bb * D + (k - Dp)];
+      else v = init_vel[bb * D + (k - Dp - D)] * tau;
+      epd[i] = v;
+    }
     __syncthreads();
     const long long g = g0 + threadIdx.x;
     if (g < total) {
-      const long long b = g / T;
-      const EpInit &E = eps[(int)(b - b_first)];
-      int i0; double w;
-      time_to_index(tb, (double)times[g], i0, w);
-      const float wf = (float)w;
+      const int e = (int)(g / T - b_first);
+      const EpInit &E = eps[e];
+      const float *ed = epd + e * ep_floats;
+      int i0; float wf;
+      time_to_index_fast(tb, inv_tau, times[g], i0, wf);
       const float *r0 = tab_row(tb, srow, staged_rows, i0), *r1 = tab_row(tb, srow, staged_rows, i0 + 1);
       const float y1 = lerp_t(r0[0], r1[0], wf), y2 = lerp_t(r0[1], r1[1], wf);
       const float dy1 = lerp_t(r0[2], r1[2], wf), dy2 = lerp_t(r0[3], r1[3], wf);
@@ -81,24 +106,21 @@ traj_fwd_kernel(TabDev tb, const float *__restrict__ params, const float *__rest
         hp[j] = (pj - xi1 * E.pb[j] - xi2 * E.vb[j]) * s_scale[j];
         hv[j] = (vj - xi3 * E.pb[j] - xi4 * E.vb[j]) * s_scale[j];
       }
-      const float *th = params + b * (long long)(D * K1);
       float *o = tile + threadIdx.x * D2;
       for (int d = 0; d < D; ++d) {
-        const float y0 = init_pos[b * D + d], v0 = init_vel[b * D + d] * tau;
+        const float y0 = ed[Dp + d], v0 = ed[Dp + D + d];
         float p = xi1 * y0 + xi2 * v0, v = xi3 * y0 + xi4 * v0;
+        const float *th = ed + d * K1;
 #pragma unroll
         for (int j = 0; j < K1; ++j) {
-          const float t = __ldg(th + d * K1 + j);
-          p = fmaf(hp[j], t, p);
-          v = fmaf(hv[j], t, v);
+          p = fmaf(hp[j], th[j], p);
+          v = fmaf(hv[j], th[j], v);
         }
-        if (tb.relative_goal) {
-          const float shift = tb.relative_goal_scaled ? y0 : y0 / s_scale[K1 - 1];
-          p = fmaf(hp[K1 - 1], shift, p);
-          v = fmaf(hv[K1 - 1], shift, v);
-        }
+        const float shift = goal_shift_scale * y0;         // relative goal (0 otherwise)
+        p = fmaf(hp[K1 - 1], shift, p);
+        v = fmaf(hv[K1 - 1], shift, v);
         o[d] = p;
-        o[D + d] = v / tau;
+        o[D + d] = v * inv_tau_f;
       }
     }
     __syncthreads();
@@ -191,27 +213,41 @@ int num_sms() {
   return g_num_sms;
 }
 
+int g_traj_stage = -1;      // TCE_TRAJ_STAGE: 0 = read the basis rows through L1, 1 = stage them in smem (default)
+
 template <int K1>
 int launch_traj_fwd(const tce_tables *t, const float *params, const float *times, const float *init_time,
                     const float *init_pos, const float *init_vel, float *traj, int64_t B, int64_t T,
                     cudaStream_t st) {
+  if (g_traj_stage < 0) {
+    const char *e = getenv("TCE_TRAJ_STAGE");
+    g_traj_stage = e ? atoi(e) : 1;
+  }
   const int stride = t->row32_stride;
   const size_t row_bytes = (size_t)stride * sizeof(float);
   const long long chunks = (B * T + TRAJ_THREADS - 1) / TRAJ_THREADS;
-  long long grid = 2LL * num_sms();
-  if (grid > chunks) grid = chunks;
   // Staging the rows pays only when a persistent CTA reuses them over several chunks; short-lived
   // CTAs read the (few, hot) rows through L1 instead.
-  int staged = (int)((96 * 1024) / row_bytes);
+  int staged = (int)((64 * 1024) / row_bytes);
   if (staged > t->num_pc) staged = t->num_pc;
-  if (chunks < 4 * grid) staged = 0;
-  const size_t smem = (size_t)staged * row_bytes + (size_t)TRAJ_THREADS * 2 * t->D * sizeof(float) +
-                      MAX_EP_PER_CHUNK * sizeof(EpInit) + 16;
+  const size_t base_smem = (size_t)TRAJ_THREADS * 2 * t->D * sizeof(float) + MAX_EP_PER_CHUNK * sizeof(EpInit) +
+                           (size_t)MAX_EP_PER_CHUNK * (t->D * K1 + 2 * t->D) * sizeof(float) + 16;
+  int ctas_per_sm = (int)((220 * 1024) / (base_smem + (size_t)staged * row_bytes));
+  if (ctas_per_sm > 8) ctas_per_sm = 8;
+  long long grid = (long long)ctas_per_sm * num_sms();
+  if (!g_traj_stage || chunks < 4 * grid) {
+    staged = 0;
+    grid = 8LL * num_sms();
+  }
+  if (grid > chunks) grid = chunks;
+  const size_t smem = base_smem + (size_t)staged * row_bytes;
   if ((TRAJ_THREADS + T - 1) / T + 2 > MAX_EP_PER_CHUNK) return TCE_ERR_INVALID_ARGUMENT;  // T < 9
   static bool attr_set = false;
   if (!attr_set) {
     TCE_CUDA(cudaFuncSetAttribute(traj_fwd_kernel<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024),
              "traj smem attr");
+    cudaFuncSetAttribute(traj_fwd_kernel<K1>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
   traj_fwd_kernel<K1><<<(unsigned)grid, TRAJ_THREADS, smem, st>>>(tab_dev(t), params, times, init_time, init_pos,
