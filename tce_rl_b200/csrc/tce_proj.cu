@@ -419,7 +419,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
 // rho_i = 1/(lam_i + eta), Sbar = d/dSigma_proj (from the Cholesky adjoint):
 //   Ft = M^T Sbar M ;  Nt_ij = -(1+eta) rho_i rho_j Ft_ij - delta_ij etabar (df/dlam_i) / (df/deta) ,
 //   etabar = sum_i Ft_ii (rho_i - (1+eta) rho_i^2) ;  grad_Lt = -2 tril(Lt^-T U~ Nt U~^T).
-__global__ void __launch_bounds__(PJ_THREADS)
+__global__ void __launch_bounds__(KL_THREADS)
 proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ proj_L, const float *__restrict__ gout,
                        const double *__restrict__ save_M, const double *__restrict__ save_lam,
                        const double *__restrict__ save_sc, float *__restrict__ grad_L, int n) {
@@ -836,7 +836,7 @@ extern "C" int tce_proj_kl_cov_bwd(const float *L, const float *proj_L, const fl
   int rc = set_smem(proj_kl_cov_bwd_kernel, smem);
   if (rc) return rc;
   const double *M = save, *lam = M + (size_t)B * n * n, *sc = lam + (size_t)B * n;
-  proj_kl_cov_bwd_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(L, proj_L, grad_out, M, lam, sc, grad_L, n);
+  proj_kl_cov_bwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, proj_L, grad_out, M, lam, sc, grad_L, n);
   TCE_CHECK_LAUNCH("proj_kl_cov_bwd_kernel");
   return TCE_OK;
 }

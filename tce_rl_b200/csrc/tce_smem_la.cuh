@@ -240,23 +240,26 @@ __device__ inline void la_chol(Mat A, int n, int *bad) {
 // squared column norms are cached in `nrm` (>= n doubles) and updated in closed form (one warp reduction
 // per step); the rotation angle is evaluated in fp32 (it only steers convergence) while (c, s) are
 // normalised in fp64 so that every rotation is orthogonal to ~1e-15.
-__device__ inline int la_jacobi_onesided(Mat W, double *lam, double *nrm, int n) {
-  // nrm: scratch of n + 3 * 32 doubles ([n] squared norms, [32] dot products, [64] (c, s) per pair)
+__device__ inline int la_jacobi_onesided(Mat W, double *lam, double *scratch, int n) {
+  // scratch: >= n/2 + 3 * 32 doubles: [n] squared norms as FLOATS, [32] dot products, [64] (c, s) per pair.
+  // The dependent fp64 chain of a step is what costs time on one SM (~40 cycles per op), so everything that
+  // only steers convergence (norms, thresholds, the rotation angle) is kept in fp32; fp64 is used for the
+  // dot product, for normalising (c, s) and for applying the rotation.
   const int m = (n + 1) & ~1, half = m / 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = (int)(blockDim.x >> 5);
-  double *gbuf = nrm + n, *cs = gbuf + 32;
+  float *nrm = reinterpret_cast<float *>(scratch);
+  double *gbuf = scratch + (n + 1) / 2 + 1, *cs = gbuf + 32;
   int sweeps = 0;
   for (int sweep = 0; sweep < 40; ++sweep) {
-    for (int j = warp; j < n; j += nwarp) {      // exact norms once per sweep (bounds the closed-form drift)
+    for (int j = warp; j < n; j += nwarp) {      // norms once per sweep (bounds the closed-form drift)
       double a = 0.0;
       for (int r = lane; r < n; r += 32) a = fma(W(r, j), W(r, j), a);
       a = warp_sum(a);
-      if (lane == 0) nrm[j] = a;
+      if (lane == 0) nrm[j] = (float)a;
     }
     __syncthreads();
-    int big = 0;      // some pair was still correlated above 1e-5 when it was visited in this sweep
+    int big = 0;      // some pair was still correlated above 1e-4 when it was visited in this sweep
     for (int step = 0; step < m - 1; ++step) {
-      // pair of warp w (round robin): every warp also needs the pair of "its lane" in phase B
       auto pair_of = [&](int w, int &p, int &q) {
         if (w == 0) { p = m - 1; q = step; }
         else { p = step + w; if (p >= m - 1) p -= m - 1; q = step - w; if (q < 0) q += m - 1; }
@@ -278,27 +281,26 @@ __device__ inline int la_jacobi_onesided(Mat W, double *lam, double *nrm, int n)
         }
       }
       __syncthreads();
-      // phase B: rotation parameters of all pairs by ONE warp (lane = pair): the scalar fp64 / conversion
-      // work is not replicated 32 times
+      // phase B: rotation parameters of all pairs by ONE warp (lane = pair)
       if (warp == 0 && lane < half) {
         int pp, qq;
         pair_of(lane, pp, qq);
         double c = 1.0, sn = 0.0;
         if (qq < n) {
-          const double g = gbuf[lane], a = nrm[pp], b = nrm[qq];
-          const double g2 = g * g, ab = a * b;
-          if (g2 > 1e-10 * ab) big = 1;
-          if (g2 > 1e-24 * ab) {
-            const float zeta = (float)(b - a) / (2.0f * (float)g);
+          const float g = (float)gbuf[lane], a = nrm[pp], b = nrm[qq];
+          const float g2 = g * g, ab = a * b;
+          if (g2 > 1e-8f * ab) big = 1;
+          if (g2 > 1e-24f * ab) {
+            const float zeta = (b - a) / (2.0f * g);
             const float tf = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
+            const float hf = fmaf(tf, tf, 1.0f), c0 = rsqrtf(hf);
             const double t = (double)tf, h = fma(t, t, 1.0);
-            c = (double)rsqrtf((float)h);                          // fp32 seed + two Newton steps in fp64
-            c = c * fma(-0.5 * h, c * c, 1.5);
-            c = c * fma(-0.5 * h, c * c, 1.5);
+            c = (double)c0;
+            c = c * fma(-0.5 * h, c * c, 1.5);       // one Newton step: c^2 h = 1 to ~1e-14
             sn = c * t;
-            const double c2 = c * c, s2 = sn * sn, cs2 = 2.0 * c * sn * g;   // |c x - s y|^2, |s x + c y|^2
-            nrm[pp] = c2 * a + s2 * b - cs2;
-            nrm[qq] = s2 * a + c2 * b + cs2;
+            const float cf = c0, sf = c0 * tf, cs2 = 2.0f * cf * sf * g;   // |c x - s y|^2, |s x + c y|^2 (fp32)
+            nrm[pp] = cf * cf * a + sf * sf * b - cs2;
+            nrm[qq] = sf * sf * a + cf * cf * b + cs2;
           }
         }
         cs[2 * lane] = c; cs[2 * lane + 1] = sn;
@@ -312,13 +314,11 @@ __device__ inline int la_jacobi_onesided(Mat W, double *lam, double *nrm, int n)
           if (r1 < n) { W(r1, p) = c * x1 - sn * y1; W(r1, q) = sn * x1 + c * y1; }
         }
       }
-      // (no barrier needed here: the next phase A of a warp touches two columns that were written by at most
-      //  two other warps in this phase C -> protect with the barrier below)
       __syncthreads();
     }
     ++sweeps;
-    // quadratic convergence: a sweep that only met cosines <= 1e-5 leaves them at ~1e-10 or below, i.e.
-    // eigenvalues exact to ~1e-20 and vectors to ~1e-10 -- no separate verification sweep is needed
+    // quadratic convergence: a sweep that only met cosines <= 1e-4 leaves them at ~1e-8 or below, i.e.
+    // eigenvalues exact to ~1e-16 and vectors to ~1e-8 -- no separate verification sweep is needed
     if (!__syncthreads_or(big)) break;
   }
   for (int j = warp; j < n; j += nwarp) {

@@ -112,6 +112,8 @@ class BaseProjectionLayer:
         out, _ = ops.proj_entropy(L_in.contiguous(), beta, self.entropy_eq)
         return mean, (_expand_first(out, mean.shape[0]) if shared else out)
 
+    projects = False        # the base layer only applies the entropy control (its trust-region step is the identity)
+
     def _mean_part(self, policy, p, q):
         raise NotImplementedError
 
@@ -119,6 +121,8 @@ class BaseProjectionLayer:
         return L
 
     def _trust_region_projection(self, policy, p, q):
+        if not self.projects:
+            return p
         mean, L = p
         old_mean, old_L = q
         mean_part = self._mean_part(policy, p, q)
@@ -137,7 +141,7 @@ class BaseProjectionLayer:
 
     def __call__(self, policy, p, q, step, *args, **kwargs):
         beta = self._entropy_bound(step, p[0].device)
-        if self.overlap and not policy.contextual_std and not self.entropy_first and p[1].is_cuda:
+        if self.projects and self.overlap and not policy.contextual_std and not self.entropy_first and p[1].is_cuda:
             return self._call_overlapped(policy, p, q, beta)
         if self.entropy_first:
             p = self._entropy_projection(policy, p, beta)
@@ -194,7 +198,8 @@ class BaseProjectionLayer:
 
 
 class KLProjectionLayer(BaseProjectionLayer):
-    """KL projection.  ``warm_start`` (default on): the eigen-basis found by the previous call is handed to the
+    projects = True
+    __doc__ = """KL projection.  ``warm_start`` (default on): the eigen-basis found by the previous call is handed to the
     next one; the kernel uses it only when the old covariance is bit-identical (fingerprint), i.e. across the
     epochs of one ``update_policy`` -- results are unchanged, the Jacobi solve needs 2-3 sweeps instead of ~9."""
 
@@ -220,6 +225,8 @@ class KLProjectionLayer(BaseProjectionLayer):
 
 
 class FrobeniusProjectionLayer(BaseProjectionLayer):
+    projects = True
+
     def _mean_dist(self, p, q):
         if self.scale_prec:
             return ops.gauss_maha(p[0], q[0], q[1])
@@ -231,14 +238,23 @@ class FrobeniusProjectionLayer(BaseProjectionLayer):
     def _cov_projection(self, policy, L, L_old):
         return ops.proj_frob_cov(L.contiguous(), L_old, self.cov_bound)[0]
 
+    def _cov_dist(self, policy, kind, L, L_o, scale_prec):
+        """Covariance distance [B]; a shared (non-contextual) covariance is evaluated once and broadcast."""
+        B = L.shape[0]
+        if _shared(policy, L):
+            L, L_o = L[:1], L_o[:1]
+        val = ops.cov_distance(kind, L.contiguous(), L_o, scale_prec)
+        return val.expand(B) if val.shape[0] != B else val
+
     def trust_region_value(self, policy, p, q):
-        return self._mean_dist(p, q), ops.cov_distance(0, p[1].contiguous(), q[1], False)
+        return self._mean_dist(p, q), self._cov_dist(policy, 0, p[1], q[1], False)
 
     def get_trust_region_loss(self, policy, p, proj_p, set_variance=None):
         target = (proj_p[0].detach(), proj_p[1].detach())
         diff = self._mean_dist(p, target)
         if self._with_cov(policy, set_variance):               # squared L difference instead of the Frobenius metric
-            diff = diff + (p[1] - target[1]).pow(2).sum([-1, -2]).to(torch.float64)
+            Lp, Lt = (p[1][:1], target[1][:1]) if _shared(policy, p[1]) else (p[1], target[1])
+            diff = diff + (Lp - Lt).pow(2).sum([-1, -2]).to(torch.float64)
         return (diff.mean() * self.trust_region_coeff).to(p[0].dtype)
 
 
@@ -247,7 +263,7 @@ class WassersteinProjectionLayer(FrobeniusProjectionLayer):
         return ops.proj_w2_cov(L.contiguous(), L_old, self.cov_bound, self.scale_prec)[0]
 
     def trust_region_value(self, policy, p, q):
-        return self._mean_dist(p, q), ops.cov_distance(1, p[1].contiguous(), q[1], self.scale_prec)
+        return self._mean_dist(p, q), self._cov_dist(policy, 1, p[1], q[1], self.scale_prec)
 
     def get_trust_region_loss(self, policy, p, proj_p, set_variance=None):
         return BaseProjectionLayer.get_trust_region_loss(self, policy, p, proj_p, set_variance)
