@@ -224,6 +224,8 @@ int tce_normalize_by_stats(float *x, const double *stats, int64_t N, void *strea
  * FLOPs executed.  bench.py times it to obtain the FMA-pipe roofline denominators.                      */
 /* debugging aid: SM-clock stamps taken between the phases of the last tce_proj_kl_cov_fwd launch */
 int tce_debug_kl_phase_cycles(long long *out16);
+/* same for block 0 of the last tce_seglik_gram ([0..6]) / tce_seglik_bwd ([16..21]) launches */
+int tce_debug_seglik_phase_cycles(long long *out32);
 int tce_bench_fma(int fp64, int iters, void *scratch, double *flops, void *stream);
 
 #ifdef __cplusplus

@@ -31,3 +31,12 @@ for _ in range(3):
     _lib.call("tce_seglik_bwd", tabs.handle, p(adj), p(g["L"]), Dp * Dp, p(times_g), p(g["init_time"]), p(pairs_g), None, p(gm), p(gL), B, T, P, st)
 torch.cuda.synchronize()
 print("ok", float(logp.sum()))
+
+import ctypes
+buf = (ctypes.c_longlong * 32)()
+_lib.call("tce_debug_seglik_phase_cycles", buf)
+s = list(buf)
+for nm, i in (("gram load L", 0), ("gram basis", 1), ("gram Sigma", 2), ("gram C blocks", 3), ("gram residual", 4), ("gram max", 5)):
+    print(f"{nm:16s} {s[i + 1] - s[i]:8d} cycles")
+for nm, i in (("bwd load+basis", 16), ("bwd grad_mean", 17), ("bwd M (fp64)", 18), ("bwd M.L", 19), ("bwd store", 20)):
+    print(f"{nm:16s} {s[i + 1] - s[i]:8d} cycles")

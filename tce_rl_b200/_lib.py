@@ -68,6 +68,7 @@ SIGNATURES = {
     "tce_sum_stats": (C.c_int, [_P, _P, _I64, _P]),
     "tce_normalize_by_stats": (C.c_int, [_P, _P, _I64, _P]),
     "tce_debug_kl_phase_cycles": (C.c_int, [_P]),
+    "tce_debug_seglik_phase_cycles": (C.c_int, [_P]),
     "tce_bench_fma": (C.c_int, [_I32, _I32, _P, C.POINTER(C.c_double), _P]),
 }
 
@@ -99,7 +100,7 @@ def check(status: int, what: str = "") -> None:
 
 
 LAUNCHES = 0          # kernel launches issued through the C ABI (bench.py reports them as gpu_launches)
-_NO_KERNEL = {"tce_prodmp_tables_export", "tce_prodmp_tables_create", "tce_debug_kl_phase_cycles"}
+_NO_KERNEL = {"tce_prodmp_tables_export", "tce_prodmp_tables_create", "tce_debug_kl_phase_cycles", "tce_debug_seglik_phase_cycles"}
 
 
 def call(name: str, *args) -> None:

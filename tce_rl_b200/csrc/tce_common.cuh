@@ -31,7 +31,7 @@ struct TabDev {
   const double *y1, *y2, *dy1, *dy2, *pos, *vel, *scale;
   const float *row32;
   int num_pc, K1, D, row32_stride;
-  double inv_scaled_dt, tau, delay;
+  double inv_scaled_dt, tau, inv_tau, delay;
   int relative_goal, relative_goal_scaled;
 };
 
@@ -39,7 +39,7 @@ static inline TabDev tab_dev(const tce_tables *t) {
   TabDev d;
   d.y1 = t->y1; d.y2 = t->y2; d.dy1 = t->dy1; d.dy2 = t->dy2; d.pos = t->pos; d.vel = t->vel;
   d.scale = t->scale; d.row32 = t->row32; d.num_pc = t->num_pc; d.K1 = t->K1; d.D = t->D;
-  d.row32_stride = t->row32_stride; d.inv_scaled_dt = t->inv_scaled_dt; d.tau = t->cfg.tau;
+  d.row32_stride = t->row32_stride; d.inv_scaled_dt = t->inv_scaled_dt; d.tau = t->cfg.tau; d.inv_tau = 1.0 / t->cfg.tau;
   d.delay = t->cfg.delay; d.relative_goal = t->cfg.relative_goal;
   d.relative_goal_scaled = t->cfg.relative_goal_scaled;
   return d;
@@ -92,11 +92,11 @@ __device__ __forceinline__ T lerp_t(T a, T b, T w) {
 // float index of a time point in the pre-computed grid + clamped integer base
 // (ProDMPBasisGenerator.times_to_indices + indexing_interpolate, util_matrix.py:195-227)
 __device__ __forceinline__ void time_to_index(const TabDev &tb, double t, int &i0, double &w) {
-  double s = (t - tb.delay) / tb.tau;
+  double s = (t - tb.delay) * tb.inv_tau;        // multiply by 1/tau: no fp64 division on the device
   s = s > 0.0 ? s : 0.0;
   double idx = s * tb.inv_scaled_dt;
-  int f = (int)floor(idx);
-  f = f < 0 ? 0 : (f > tb.num_pc - 2 ? tb.num_pc - 2 : f);
+  int f = (int)idx;                              // idx >= 0: truncation == floor
+  f = f > tb.num_pc - 2 ? tb.num_pc - 2 : f;
   i0 = f;
   w = idx - (double)f;
 }

@@ -21,6 +21,9 @@
 
 #include "tce_common.cuh"
 
+__device__ long long g_sl_prof[32];   // SM-clock stamps of block 0 of the last gram [0..15] / bwd [16..31] kernel
+#define SL_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_sl_prof[i] = clock64(); } while (0)
+
 namespace {
 
 constexpr int SL_THREADS = 256;
@@ -52,10 +55,9 @@ __device__ void basis_points(const TabDev &tb, double t_init, const float *__res
   __syncthreads();
   const double y1b = init_row[0], y2b = init_row[1], dy1b = init_row[2], dy2b = init_row[3], idet = init_row[4];
   for (int it = threadIdx.x; it < 2 * P * (K1 + 1); it += blockDim.x) {
-    const int q = it / (K1 + 1), j = it % (K1 + 1);
-    const int64_t ti = pairs[q];                       // pairs is [P][2] row-major -> q = 2p + k
+    const int q = it / (K1 + 1), j = it - q * (K1 + 1);
     int i0; double w;
-    time_to_index(tb, (double)times_b[ti], i0, w);
+    time_to_index(tb, (double)times_b[pairs[q]], i0, w);           // pairs is [P][2] row-major -> q = 2p + k
     const double y1 = lerp_t(tb.y1[i0], tb.y1[i0 + 1], w), y2 = lerp_t(tb.y2[i0], tb.y2[i0 + 1], w);
     const double xi1 = (dy2b * y1 - dy1b * y2) * idet, xi2 = (y1b * y2 - y2b * y1) * idet;
     if (j < K1) {
@@ -98,46 +100,63 @@ seglik_gram_kernel(TabDev tb, const float *__restrict__ smp_traj, const float *_
                    const float *__restrict__ init_vel, const int64_t *__restrict__ pairs, double *__restrict__ Cmat,
                    double *__restrict__ Rres, double *__restrict__ diag_max, int T, int P) {
   constexpr int Dp = D * K1, N = 2 * D, NT = tri(N);
-  constexpr int NR = (Dp + 1) & ~1;          // rows padded to even for the 2x2 tiles
-  constexpr int LD = NR + 1;                 // padded row stride of Ls (floats)
+  constexpr int NR = (Dp + 1) & ~1;          // Sg rows / cols (even)
+  constexpr int NR4 = (Dp + 3) & ~3;         // Ls rows padded to a multiple of 4 for the 4x4 tiles
+  constexpr int LD = NR4 + 1;                // padded row stride of Ls (floats)
   constexpr int SD = NR + 1;                 // row stride of Sg (doubles), odd, >= NR (tile padding)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *Sg = reinterpret_cast<double *>(smem_raw);              // [NR][SD]
   double *hs = Sg + NR * SD;                                      // [2P][K1]
   double *xi = hs + 2 * P * K1;                                   // [2P][2]
   double *init_row = xi + 4 * P;                                  // [5 + 2 K1]
-  float *Ls = reinterpret_cast<float *>(init_row + 5 + 2 * K1 + 1);  // [NR][LD]
+  float *Ls = reinterpret_cast<float *>(init_row + 5 + 2 * K1 + 1);  // [NR4][LD]
   __shared__ double s_max[SL_THREADS / 32];
 
   const long long b = blockIdx.x;
   const float *times_b = times + b * T;
 
-  load_lower(L + b * ldb_L, Ls, Dp, NR, LD);
+  SL_STAMP(0);
+  load_lower(L + b * ldb_L, Ls, Dp, NR4, LD);
+  __syncthreads();
+  SL_STAMP(1);
   basis_points<K1>(tb, (double)init_time[b], times_b, pairs, P, hs, xi, init_row);   // ends with a barrier
+  SL_STAMP(2);
 
-  // ---- Sigma = L L^T (fp32 FFMA, 2x2 register tiles over the lower triangle) -> Sg (fp64, mirrored)
+  // ---- Sigma = L L^T (fp32 FFMA, 4x4 register tiles over the lower triangle: 8 LDS per 16 FFMA) -> Sg (fp64,
+  //      mirrored).  Rows/cols are padded to NR4 (multiple of 4) with zeros.
   {
-    constexpr int NTILE = NR / 2;
-    for (int t = threadIdx.x; t < tri(NTILE); t += blockDim.x) {
+    constexpr int NT4 = NR4 / 4;
+    for (int t = threadIdx.x; t < tri(NT4); t += blockDim.x) {
       int I, J;
       tri_decode(t, I, J);
-      const float *a0 = Ls + (2 * I) * LD, *a1 = a0 + LD, *b0 = Ls + (2 * J) * LD, *b1 = b0 + LD;
-      float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
-      const int kmax = 2 * J + 1;                                 // L[j][k] = 0 for k > j
+      const float *a = Ls + (4 * I) * LD, *bq = Ls + (4 * J) * LD;
+      float c[4][4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) c[x][y] = 0.f;
+      const int kmax = 4 * J + 3;                                 // L[j][k] = 0 for k > j
       for (int k = 0; k <= kmax; ++k) {
-        const float x0 = a0[k], x1 = a1[k], y0 = b0[k], y1 = b1[k];
-        c00 = fmaf(x0, y0, c00); c01 = fmaf(x0, y1, c01);
-        c10 = fmaf(x1, y0, c10); c11 = fmaf(x1, y1, c11);
+        float av[4], bv[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) { av[x] = a[x * LD + k]; bv[x] = bq[x * LD + k]; }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) c[x][y] = fmaf(av[x], bv[y], c[x][y]);
       }
-      const int i0 = 2 * I, j0 = 2 * J;
-      Sg[i0 * SD + j0] = c00; Sg[j0 * SD + i0] = c00;
-      Sg[(i0 + 1) * SD + j0] = c10; Sg[j0 * SD + i0 + 1] = c10;
-      Sg[i0 * SD + j0 + 1] = c01; Sg[(j0 + 1) * SD + i0] = c01;
-      Sg[(i0 + 1) * SD + j0 + 1] = c11; Sg[(j0 + 1) * SD + i0 + 1] = c11;
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          const int i = 4 * I + x, j = 4 * J + y;
+          if (i < NR && j < NR) { Sg[i * SD + j] = c[x][y]; Sg[j * SD + i] = c[x][y]; }
+        }
     }
   }
   __syncthreads();
 
+  SL_STAMP(3);
   // ---- C blocks (fp64): task (blk = (d, d' <= d), p); p fastest so that a warp broadcasts Sigma reads
   double my_max = 0.0;
   double *Cb = Cmat + (size_t)b * NT * P;
@@ -173,6 +192,7 @@ seglik_gram_kernel(TabDev tb, const float *__restrict__ smp_traj, const float *_
     }
   }
 
+  SL_STAMP(4);
   // ---- residual r = x - mu (fp64): task (p, k, d)
   double *Rb = Rres + (size_t)b * N * P;
   const double tau = tb.tau;
@@ -192,6 +212,7 @@ seglik_gram_kernel(TabDev tb, const float *__restrict__ smp_traj, const float *_
     Rb[(size_t)(2 * d + k) * P + p] = x - mu;
   }
 
+  SL_STAMP(5);
   // ---- batch-global max of the un-regularised diagonal
   my_max = warp_max(my_max);
   if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = my_max;
@@ -201,6 +222,7 @@ seglik_gram_kernel(TabDev tb, const float *__restrict__ smp_traj, const float *_
     for (int w = 0; w < SL_THREADS / 32; ++w) m = fmax(m, s_max[w]);
     atomic_max_pos_double(diag_max, m);
   }
+  SL_STAMP(6);
 }
 
 // =====================================================================================================
@@ -336,7 +358,7 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
                   const float *__restrict__ upstream, float *__restrict__ grad_mean, float *__restrict__ grad_L,
                   int T, int P) {
   constexpr int Dp = D * K1, N = 2 * D, NT = tri(N);
-  constexpr int NR = (Dp + 1) & ~1;
+  constexpr int NR = (Dp + 3) & ~3;          // rows padded to a multiple of 4 for the 4x4 tiles
   constexpr int LD = NR + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *Gs = reinterpret_cast<float *>(smem_raw);                // [NT][P] staged adjoints, fp32 (later: out tile)
@@ -352,11 +374,13 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
   const double *Ab = Alpha + (size_t)b * N * P;
   const float up = upstream ? *upstream : 1.0f;       // scalar gradient of the fused surrogate loss
 
+  SL_STAMP(16);
   load_lower(L + b * ldb_L, Ls, Dp, NR, LD);
   for (int e = threadIdx.x; e < NT * P; e += blockDim.x) Gs[e] = (float)Gb[e];
   for (int e = threadIdx.x; e < NR * LD; e += blockDim.x) Ms[e] = 0.f;
   basis_points<K1>(tb, (double)init_time[b], times + b * T, pairs, P, hs, xi, init_row);
 
+  SL_STAMP(17);
   // ---- grad_mean[d*K1 + j] = sum_{p,k} h_pk[j] * (g alpha)[(d,k)]
   if (grad_mean) {
     for (int o = threadIdx.x; o < Dp; o += blockDim.x) {
@@ -368,6 +392,7 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
   }
   if (!grad_L) return;
 
+  SL_STAMP(18);
   // ---- M_{dd'}[i][:] = sum_p sum_{k,k'} G[(d,k),(d',k')] h_pk[i] h_pk'[:]   (fp64), task (blk, i)
   for (int task = threadIdx.x; task < tri(D) * K1; task += blockDim.x) {
     const int blk = task / K1, i = task % K1;
@@ -398,47 +423,56 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
   }
   __syncthreads();
 
-  // ---- grad_L = 2 * tril(M L)  (fp32 FFMA, 2x2 tiles over the lower triangle), staged in the Gs buffer
+  SL_STAMP(19);
+  // ---- grad_L = 2 * tril(M L)  (fp32 FFMA, 4x4 tiles over the lower triangle), staged in the Gs buffer
   float *out = Gs;                                // [Dp][Dp] dense (the Gs region is sized for it)
   for (int e = threadIdx.x; e < Dp * Dp; e += blockDim.x) out[e] = 0.f;
   __syncthreads();
   {
-    constexpr int NTILE = NR / 2;
-    for (int t = threadIdx.x; t < tri(NTILE); t += blockDim.x) {
+    constexpr int NT4 = NR / 4;
+    for (int t = threadIdx.x; t < tri(NT4); t += blockDim.x) {
       int I, J;
       tri_decode(t, I, J);
-      const float *m0 = Ms + (2 * I) * LD, *m1 = m0 + LD;
-      float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
-      for (int k = 2 * J; k < NR; ++k) {              // L[k][c] = 0 for k < c
-        const float x0 = m0[k], x1 = m1[k], y0 = Ls[k * LD + 2 * J], y1 = Ls[k * LD + 2 * J + 1];
-        c00 = fmaf(x0, y0, c00); c01 = fmaf(x0, y1, c01);
-        c10 = fmaf(x1, y0, c10); c11 = fmaf(x1, y1, c11);
+      const float *mrow = Ms + (4 * I) * LD;
+      float c[4][4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) c[x][y] = 0.f;
+      for (int k = NR - 1; k >= 4 * J; --k) {            // L[k][c] = 0 for k < c; descending: lanes share k
+        float mv[4], lv[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) { mv[x] = mrow[x * LD + k]; lv[x] = Ls[k * LD + 4 * J + x]; }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) c[x][y] = fmaf(mv[x], lv[y], c[x][y]);
       }
-      const int i0 = 2 * I, j0 = 2 * J;
-      if (i0 < Dp) {
-        out[i0 * Dp + j0] = 2.f * up * c00;
-        if (j0 + 1 <= i0) out[i0 * Dp + j0 + 1] = 2.f * up * c01;
-      }
-      if (i0 + 1 < Dp) {
-        out[(i0 + 1) * Dp + j0] = 2.f * up * c10;
-        if (j0 + 1 < Dp) out[(i0 + 1) * Dp + j0 + 1] = 2.f * up * c11;
-      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          const int i = 4 * I + x, j = 4 * J + y;
+          if (i < Dp && j <= i) out[i * Dp + j] = 2.f * up * c[x][y];
+        }
     }
   }
   __syncthreads();
+  SL_STAMP(20);
   float *gL = grad_L + (size_t)b * Dp * Dp;
   for (int e = threadIdx.x; e < Dp * Dp; e += blockDim.x) gL[e] = out[e];
+  SL_STAMP(21);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
 template <int D, int K1>
 size_t gram_smem(int P) {
-  constexpr int Dp = D * K1, NR = (Dp + 1) & ~1, LD = NR + 1, SD = NR + 1;
-  return sizeof(double) * ((size_t)NR * SD + 2 * P * K1 + 4 * P + 5 + 2 * K1 + 1) + sizeof(float) * NR * LD + 16;
+  constexpr int Dp = D * K1, NR = (Dp + 1) & ~1, NR4 = (Dp + 3) & ~3, LD = NR4 + 1, SD = NR + 1;
+  return sizeof(double) * ((size_t)NR * SD + 2 * P * K1 + 4 * P + 5 + 2 * K1 + 1) + sizeof(float) * NR4 * LD + 16;
 }
 template <int D, int K1>
 size_t bwd_smem(int P) {
-  constexpr int Dp = D * K1, N = 2 * D, NT = tri(N), NR = (Dp + 1) & ~1, LD = NR + 1;
+  constexpr int Dp = D * K1, N = 2 * D, NT = tri(N), NR = (Dp + 3) & ~3, LD = NR + 1;
   const size_t gs_floats = (size_t)((NT * P > Dp * Dp ? NT * P : Dp * Dp + 1) & ~1);
   const size_t g = sizeof(float) * gs_floats;
   return g + sizeof(double) * (2 * P * K1 + 4 * P + 5 + 2 * K1 + 1) + sizeof(float) * 2 * NR * LD + 16;
@@ -448,6 +482,14 @@ size_t bwd_smem(int P) {
 
 // (D, K1) combinations with instantiated kernels
 #define TCE_FOR_SHAPES(X) X(7, 9) X(4, 9) X(7, 4) X(3, 4) X(2, 3)
+
+// debugging aid: SM-clock stamps of block 0 of the last gram ([0..6]) and bwd ([16..21]) launches (synchronises)
+extern "C" int tce_debug_seglik_phase_cycles(long long *out32) {
+  if (!out32) return TCE_ERR_INVALID_ARGUMENT;
+  TCE_CUDA(cudaDeviceSynchronize(), "seglik prof sync");
+  TCE_CUDA(cudaMemcpyFromSymbol(out32, g_sl_prof, 32 * sizeof(long long)), "seglik prof copy");
+  return TCE_OK;
+}
 
 extern "C" size_t tce_seglik_work_bytes(const tce_tables_t *t, int64_t B, int64_t P) {
   if (!t || B < 0 || P < 0) return 0;
