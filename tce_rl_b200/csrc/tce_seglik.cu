@@ -157,9 +157,49 @@ seglik_gram_kernel(TabDev tb, const float *__restrict__ smp_traj, const float *_
   __syncthreads();
 
   SL_STAMP(3);
-  // ---- C blocks (fp64): task (blk = (d, d' <= d), p); p fastest so that a warp broadcasts Sigma reads
+  // ---- C blocks (fp64).  When the pairs form a chain (second time of pair p == first time of pair p+1: the
+  //      fixed-interval selection of every TCE config) the P+1 distinct time points are processed once:
+  //      task (blk, u): v = Sigma_dd' h_u, then K[u,u], K[u+1,u], K[u-1,u] -> 108 instead of 198 DFMA per pair.
   double my_max = 0.0;
   double *Cb = Cmat + (size_t)b * NT * P;
+  int chain_ok = 1;
+  for (int pp = threadIdx.x; pp + 1 < P; pp += blockDim.x) chain_ok &= (pairs[2 * pp + 1] == pairs[2 * pp + 2]);
+  const bool chained = __syncthreads_and(chain_ok) != 0;
+  if (chained) {
+    const int U = P + 1;
+    for (int task = threadIdx.x; task < tri(D) * U; task += blockDim.x) {
+      const int blk = task / U, u = task - blk * U;
+      int d, dd;
+      tri_decode(blk, d, dd);
+      const double *hu = hs + (u < P ? 2 * u : 2 * P - 1) * K1;
+      const double *hn = hs + (u + 1 < P ? 2 * (u + 1) : 2 * P - 1) * K1;      // time u + 1 (valid when u < P)
+      const double *hm = hs + (u >= 1 ? 2 * (u - 1) : 0) * K1;                  // time u - 1 (valid when u >= 1)
+      double h[K1];
+#pragma unroll
+      for (int j = 0; j < K1; ++j) h[j] = hu[j];
+      double kuu = 0.0, kup = 0.0, kum = 0.0;
+      const double *S = Sg + (d * K1) * SD + dd * K1;
+#pragma unroll
+      for (int i = 0; i < K1; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < K1; ++j) v = fma(S[i * SD + j], h[j], v);
+        kuu = fma(hu[i], v, kuu);
+        kup = fma(hn[i], v, kup);
+        kum = fma(hm[i], v, kum);
+      }
+      const int r0 = 2 * d, q0 = 2 * dd;
+      if (u < P) {                      // pair p = u: time u is its first point
+        Cb[(size_t)tri_idx(r0, q0) * P + u] = kuu;
+        Cb[(size_t)tri_idx(r0 + 1, q0) * P + u] = kup;          // (d, t_{u+1}) x (d', t_u)
+      }
+      if (u >= 1) {                     // pair p = u - 1: time u is its second point
+        Cb[(size_t)tri_idx(r0 + 1, q0 + 1) * P + (u - 1)] = kuu;
+        if (d != dd) Cb[(size_t)tri_idx(r0, q0 + 1) * P + (u - 1)] = kum;   // (d, t_{u-1}) x (d', t_u)
+      }
+      if (d == dd) my_max = fmax(my_max, kuu);
+    }
+  } else
   for (int task = threadIdx.x; task < tri(D) * P; task += blockDim.x) {
     const int blk = task / P, p = task % P;
     int d, dd;
