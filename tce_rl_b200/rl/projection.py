@@ -16,6 +16,11 @@ import torch
 from .. import ops, util
 
 
+# the covariance chain deliberately runs (forward and backward) on a side stream, see _call_overlapped
+if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+
+
 def _expand_first(t, batch):
     return t.expand(batch, -1, -1)
 
