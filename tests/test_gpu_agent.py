@@ -1,0 +1,98 @@
+"""The drop-in agent API on the GPU: process_dataset -> update_critic -> update_policy (eager and CUDA graph)."""
+import copy
+
+import pytest
+import torch
+
+from oracle.gen_golden import MP_CONFIGS, NUM_TIMES, synthetic_inputs
+
+pytestmark = pytest.mark.gpu
+if torch.cuda.is_available():
+    from tce_rl_b200.rl import (TemporalCorrelatedAgent, critic_factory, policy_factory, projection_factory)
+    from tce_rl_b200.rl.agent import SegmentTimeSampler
+
+DEV = "cuda:0"
+
+
+def build(name="box", B=64, use_graph=False, epochs=4, seed=0):
+    cfg, T = MP_CONFIGS[name], NUM_TIMES[name]
+    D, K1 = cfg["num_dof"], cfg["num_basis"] + 1
+    Dp, obs_dim = D * K1, 12
+    torch.manual_seed(seed)
+    policy = policy_factory("TemporalCorrelatedPolicy", dim_in=obs_dim, dim_out=Dp,
+                            mean_net_args=dict(avg_neuron=32, num_hidden=2, shape=0.0),
+                            variance_net_args=dict(std_only=False, contextual=False), init_method="orthogonal",
+                            out_layer_gain=0.01, act_func_hidden="leaky_relu", act_func_last=None, dtype="float32",
+                            device=DEV, min_std=1e-4, mp=dict(type="prodmp", args=dict(cfg)))
+    critic = critic_factory("ValueFunction", dim_in=obs_dim, dim_out=1, hidden=dict(avg_neuron=32, num_hidden=2, shape=0.0),
+                            init_method="orthogonal", out_layer_gain=1, act_func_hidden="leaky_relu",
+                            act_func_last=None, dtype="float32", device=DEV)
+    proj = projection_factory("KLProjectionLayer", proj_type="kl", mean_bound=0.05, cov_bound=5e-4,
+                              trust_region_coeff=1.0, scale_prec=True, entropy_schedule="linear", action_dim=Dp,
+                              total_train_steps=100, target_entropy=0.0, temperature=0.7, entropy_eq=False,
+                              entropy_first=False, do_regression=False, dtype="float32", device=DEV)
+    sampler = SegmentTimeSampler(cfg["dt"], T, dict(num_select=25, fixed_interval=True), device=DEV)
+    torch.manual_seed(1)
+    pairs = sampler.get_time_pairs()
+    agent = TemporalCorrelatedAgent(policy, critic, sampler, proj, dtype="float32", device=DEV, lr_policy=3e-4,
+                                    lr_critic=1e-3, wd_policy=5e-5, wd_critic=5e-5, discount_factor=1.0,
+                                    epochs_policy=epochs, epochs_critic=2, num_minibatchs=2, norm_advantages=True,
+                                    segment_advantage="value_subtraction", set_variance=False, gae_scaling=0.95,
+                                    use_cuda_graph=use_graph, schedule_lr_policy=True, schedule_lr_critic=True)
+    inp = synthetic_inputs(name, B, seed=3, dtype=torch.float32)
+    c = lambda t: t.to(DEV)
+    g = torch.Generator().manual_seed(5)
+    obs = torch.randn(B, obs_dim + 2 * D, generator=g)
+    step_states = torch.randn(B, T, obs_dim + 2 * D, generator=g)
+    with torch.no_grad():
+        times = sampler.get_times(c(inp["init_time"]), T)
+        mean_old, L_old = policy.policy(c(obs)[..., :-2 * D])
+        smp = policy.sample(False, mean_old, L_old, times, c(inp["init_time"]), c(inp["init_pos"]), c(inp["init_vel"]),
+                            eps=c(inp["eps"]))
+        lp_old = policy.log_prob(smp, mean_old, L_old, times, c(inp["init_time"]), c(inp["init_pos"]),
+                                 c(inp["init_vel"]), pred_pairs=pairs)
+    dataset = dict(segment_state=c(obs), step_actions=smp, segment_log_prob_estimate=lp_old,
+                   segment_params_mean=mean_old.clone(), segment_params_L=L_old.clone(),
+                   segment_init_time=c(inp["init_time"]), segment_init_pos=c(inp["init_pos"]),
+                   segment_init_vel=c(inp["init_vel"]), step_states=c(step_states), step_rewards=c(inp["rewards"]),
+                   step_values=c(inp["values"]), step_dones=c(inp["dones"]),
+                   step_time_limit_dones=c(inp["time_limit_dones"]))
+    return agent, dataset
+
+
+def test_full_update_eager_and_graph_agree():
+    outs, params = [], []
+    for use_graph in (False, True):
+        agent, dataset = build(use_graph=use_graph)
+        agent.num_iterations = 1
+        dataset = agent.process_dataset(dataset)
+        assert dataset["segment_advantage"].shape == (64, 24)
+        assert abs(dataset["segment_advantage"].mean().item()) < 1e-4            # normalised
+        p0 = [p.detach().clone() for p in agent.policy.parameters]
+        out = agent.update_policy(dataset)
+        assert all(torch.isfinite(torch.tensor(float(v))) for v in out.values())
+        assert any((p - q).abs().max() > 0 for p, q in zip(agent.policy.parameters, p0))      # Adam moved them
+        for key in ("surrogate_loss_mean", "trust_region_loss_mean", "policy_loss_mean", "entropy_mean",
+                    "policy_grad_norm_mean", "projection_proj_old_cov_diff_mean", "projection_new_old_mean_diff_max"):
+            assert key in out
+        outs.append(out)
+        params.append([p.detach().clone() for p in agent.policy.parameters])
+    for k in outs[0]:
+        assert abs(outs[0][k] - outs[1][k]) <= 1e-4 * max(1.0, abs(outs[0][k])), k
+    for p, q in zip(*params):
+        assert (p - q).abs().max().item() <= 1e-5
+
+
+def test_update_critic_and_projection_bounds_hold():
+    agent, dataset = build(epochs=6)
+    agent.num_iterations = 1
+    dataset = agent.process_dataset(dataset)
+    c0 = [p.detach().clone() for p in agent.critic.parameters]
+    out = agent.update_critic(dataset)
+    assert out["critic_loss_mean"] > 0 and any((p - q).abs().max() > 0 for p, q in zip(agent.critic.parameters, c0))
+    out = agent.update_policy(dataset)
+    # the projected policy respects the trust region at every epoch (KL metric, logged means)
+    assert out["projection_proj_old_mean_diff_max"] <= 0.05 * (1 + 1e-3)
+    assert out["projection_proj_old_cov_diff_max"] <= 5e-4 * (1 + 1e-2)
+    with pytest.raises(NotImplementedError):
+        agent.step()                     # environment rollout is outside the B200 path
