@@ -277,7 +277,7 @@ __device__ inline int la_jacobi_onesided(Mat W, double *lam, double *scratch, in
           double g = fma(x0, y0, x1 * y1);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-          if (lane == 0) gbuf[warp] = g;
+          if (lane == 0) reinterpret_cast<float *>(gbuf)[warp] = (float)g;
         }
       }
       __syncthreads();
@@ -287,12 +287,12 @@ __device__ inline int la_jacobi_onesided(Mat W, double *lam, double *scratch, in
         pair_of(lane, pp, qq);
         double c = 1.0, sn = 0.0;
         if (qq < n) {
-          const float g = (float)gbuf[lane], a = nrm[pp], b = nrm[qq];
+          const float g = reinterpret_cast<const float *>(gbuf)[lane], a = nrm[pp], b = nrm[qq];
           const float g2 = g * g, ab = a * b;
           if (g2 > 1e-8f * ab) big = 1;
           if (g2 > 1e-24f * ab) {
-            const float zeta = (b - a) / (2.0f * g);
-            const float tf = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
+            const float zeta = __fdividef(b - a, 2.0f * g);
+            const float tf = copysignf(__frcp_rn(fabsf(zeta) + __fsqrt_rn(fmaf(zeta, zeta, 1.0f))), zeta);
             const float hf = fmaf(tf, tf, 1.0f), c0 = rsqrtf(hf);
             const double t = (double)tf, h = fma(t, t, 1.0);
             c = (double)c0;
