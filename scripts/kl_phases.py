@@ -25,3 +25,8 @@ for _ in range(10):
     ops.proj_kl_cov(L, Lo, 5e-4, state, warm)
 b.record(); torch.cuda.synchronize()
 print("us per call (incl. python)", a.elapsed_time(b) * 100)
+if any(buf[10:15]):
+    nm = ["dot+STS", "barrier", "combine+F2F", "rotation", "apply+shfl(loop)"]
+    tot = sum(buf[10:15])
+    for i, k in enumerate(nm):
+        print(f"  jacobi/{k:18s} {buf[10+i]:9d} cycles (last sweep)  {buf[10+i]/max(tot,1):.2f}")

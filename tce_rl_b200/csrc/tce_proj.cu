@@ -354,7 +354,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
   Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1};
-  double *dinv = sd + 3 * MS, *lam = dinv + LA_DINV_DOUBLES, *nrm = lam + m, *red = nrm + m + 96;   // red: >= 48
+  double *dinv = sd + 3 * MS, *lam = dinv + LA_DINV_DOUBLES, *nrm = lam + m, *red = nrm + LA_JACOBI_SCRATCH;   // red: >= 48
   __shared__ int s_bad;
   const long long b = blockIdx.x;
   const size_t off = (size_t)b * n * n;
@@ -807,6 +807,11 @@ extern "C" int tce_debug_kl_phase_cycles(long long *out16) {
   if (!out16) return TCE_ERR_INVALID_ARGUMENT;
   TCE_CUDA(cudaDeviceSynchronize(), "kl prof sync");
   TCE_CUDA(cudaMemcpyFromSymbol(out16, g_kl_prof, 16 * sizeof(long long)), "kl prof copy");
+#ifdef JAC_PROF
+  unsigned int jp[8];
+  TCE_CUDA(cudaMemcpyFromSymbol(jp, g_jac_prof, sizeof jp), "jac prof copy");
+  for (int i = 0; i < 5; ++i) out16[10 + i] = jp[i];
+#endif
   return TCE_OK;
 }
 
@@ -817,7 +822,7 @@ extern "C" int tce_proj_kl_cov_fwd(const float *L, const float *L_o, double eps_
   if (!L || !L_o || !proj_L || !save || B < 0 || !(eps_cov > 0)) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
   if (B == 0) return TCE_OK;
-  const size_t smem = pj_smem(n, 3);
+  const size_t smem = pj_smem(n, 3) + sizeof(double) * LA_JACOBI_SCRATCH;
   int rc = set_smem(proj_kl_cov_fwd_kernel, smem);
   if (rc) return rc;
   double *M = save, *lam = M + (size_t)B * n * n, *sc = lam + (size_t)B * n;

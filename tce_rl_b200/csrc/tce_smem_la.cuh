@@ -232,100 +232,173 @@ __device__ inline void la_chol(Mat A, int n, int *bad) {
   }
 }
 
-// One-sided (Hestenes) Jacobi on the columns of W (n x n, in place): on exit the columns are mutually
-// orthogonal, W_out = W_in V for an (implicit) orthogonal V, and lam[j] = |W_out(:, j)|^2 are the
-// eigenvalues of W_in^T W_in.  V is never formed: callers only need W_out (see proj_kl_cov_fwd_kernel).
-// Round-robin ordering, ONE WARP PER COLUMN PAIR (blockDim.x >= 32 * ceil(n/2)), one barrier per step.
-// The step cost is shared-memory traffic (every pair streams its two columns), so nothing but W moves;
-// squared column norms are cached in `nrm` (>= n doubles) and updated in closed form (one warp reduction
-// per step); the rotation angle is evaluated in fp32 (it only steers convergence) while (c, s) are
-// normalised in fp64 so that every rotation is orthogonal to ~1e-15.
+// One-sided (Hestenes) Jacobi: rotate the columns of W (n x n, n <= 64) until they are orthogonal; on exit
+// lam_j = |W_j|^2.  A single CTA is bound by instruction issue and by the SM's one-shuffle-per-clock unit, not
+// by fp64 latency (DFMA: 8.5 cycles dependent, scripts/ubench/lat.cu), so the matrix lives in REGISTERS for
+// the whole iteration: warp w holds rows 8w..8w+7, lane t holds the two columns (P_t, Q_t) of pair slot t, and
+// a step is
+//   8 DFMA (partial dot) -> one 8-way combine through shared memory (ONE named barrier over the active warps)
+//   -> the rotation (computed redundantly and bit-identically by every warp) -> 32 fp64 ops to apply it
+//   -> ONE shuffle per register of Q.
+// Pair ordering (recursive halving): with the P columns X and the Q columns Y of a segment of `w` lanes,
+// w steps that ring-shift Q inside the segment (__shfl_sync with width = w, no selects) meet all X x Y pairs;
+// then the halves trade a column set (lower lanes keep P and receive the upper lanes' P as Q, upper lanes
+// keep Q and receive the lower lanes' Q as P) and the same is done at width w/2 inside X and inside Y.
+// 32 + 16 + ... + 1 = 63 steps meet all 2016 pairs while only Q moves.  Column ids travel with the data;
+// any arrangement is a valid start for the next sweep.  Everything that only steers convergence (norms,
+// thresholds, the rotation angle) is fp32; the dot product, the normalisation of (c, s) and the rotation
+// itself are fp64.  scratch: LA_JACOBI_SCRATCH doubles.  All threads of the CTA must call this.
+constexpr int LA_JACOBI_SCRATCH = 2 * 8 * 32;
+#ifdef JAC_PROF
+__device__ unsigned int g_jac_prof[8];
+#define JP(i) do { const unsigned int _t = clock(); if (threadIdx.x == 0) jp[i] += _t - jt; jt = _t; } while (0)
+#else
+#define JP(i)
+#endif
+
+__device__ __forceinline__ float la_rsqrt_approx(float x) {   // bare MUFU: no denormal fix-up code around it
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float la_rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void la_named_barrier(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ double la_combine8(const double *col) {   // fixed-order sum of the 8 warps' partials
+  return ((col[0] + col[32]) + (col[64] + col[96])) + ((col[128] + col[160]) + (col[192] + col[224]));
+}
+
 __device__ inline int la_jacobi_onesided(Mat W, double *lam, double *scratch, int n) {
-  // scratch: >= n/2 + 3 * 32 doubles: [n] squared norms as FLOATS, [32] dot products, [64] (c, s) per pair.
-  // The dependent fp64 chain of a step is what costs time on one SM (~40 cycles per op), so everything that
-  // only steers convergence (norms, thresholds, the rotation angle) is kept in fp32; fp64 is used for the
-  // dot product, for normalising (c, s) and for applying the rotation.
-  const int m = (n + 1) & ~1, half = m / 2;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = (int)(blockDim.x >> 5);
-  float *nrm = reinterpret_cast<float *>(scratch);
-  double *gbuf = scratch + (n + 1) / 2 + 1, *cs = gbuf + 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nw = (n + 7) >> 3, nbar = nw * 32;         // warps that hold rows
+  int w0 = 1;                                          // pair slots: power of two >= ceil(n / 2), <= 32
+  while (2 * w0 < n) w0 <<= 1;
   int sweeps = 0;
-  for (int sweep = 0; sweep < 40; ++sweep) {
-    for (int j = warp; j < n; j += nwarp) {      // norms once per sweep (bounds the closed-form drift)
-      double a = 0.0;
-      for (int r = lane; r < n; r += 32) a = fma(W(r, j), W(r, j), a);
-      a = warp_sum(a);
-      if (lane == 0) nrm[j] = (float)a;
-    }
-    __syncthreads();
-    int big = 0;      // some pair was still correlated above 1e-4 when it was visited in this sweep
-    for (int step = 0; step < m - 1; ++step) {
-      auto pair_of = [&](int w, int &p, int &q) {
-        if (w == 0) { p = m - 1; q = step; }
-        else { p = step + w; if (p >= m - 1) p -= m - 1; q = step - w; if (q < 0) q += m - 1; }
-        if (p > q) { const int t = p; p = q; q = t; }
-      };
-      int p = 0, q = n;
-      double x0 = 0.0, y0 = 0.0, x1 = 0.0, y1 = 0.0;
-      const int r0 = lane, r1 = lane + 32;
-      // phase A: dot products of the column pairs (one warp per pair)
-      if (warp < half) {
-        pair_of(warp, p, q);
-        if (q < n) {
-          if (r0 < n) { x0 = W(r0, p); y0 = W(r0, q); }
-          if (r1 < n) { x1 = W(r1, p); y1 = W(r1, q); }
-          double g = fma(x0, y0, x1 * y1);
+  for (int i = threadIdx.x; i < LA_JACOBI_SCRATCH; i += blockDim.x) scratch[i] = 0.0;   // warps >= nw add 0
+  __syncthreads();
+  if (warp < nw) {
+    double *mine = scratch + warp * 32 + lane;         // this thread's partial; its lane's column of partials
+    const double *col = scratch + lane;
+    int idp = lane, idq = w0 + lane;                   // column ids (>= n or lane >= w0: zero padding)
+    if (lane >= w0) idp = idq = n;
+    double xp[8], xq[8];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-          if (lane == 0) reinterpret_cast<float *>(gbuf)[warp] = (float)g;
-        }
-      }
-      __syncthreads();
-      // phase B: rotation parameters of all pairs by ONE warp (lane = pair)
-      if (warp == 0 && lane < half) {
-        int pp, qq;
-        pair_of(lane, pp, qq);
-        double c = 1.0, sn = 0.0;
-        if (qq < n) {
-          const float g = reinterpret_cast<const float *>(gbuf)[lane], a = nrm[pp], b = nrm[qq];
+    for (int i = 0; i < 8; ++i) {
+      const int r = warp * 8 + i;
+      xp[i] = (idp < n && r < n) ? W(r, idp) : 0.0;
+      xq[i] = (idq < n && r < n) ? W(r, idq) : 0.0;
+    }
+    double ap, aq;
+    bool done = false;
+    for (;;) {
+      // exact squared norms (once per sweep: bounds the drift of the closed-form fp32 updates)
+      double sp = 0.0, sq = 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sp = fma(xp[i], xp[i], sp); sq = fma(xq[i], xq[i], sq); }
+      mine[0] = sp;
+      mine[256] = sq;
+      la_named_barrier(nbar);
+      ap = la_combine8(col);
+      aq = la_combine8(col + 256);
+      la_named_barrier(nbar);                          // the step buffers alias these partial sums
+      if (done || sweeps == 40) break;
+      float a = (float)ap, b = (float)aq;
+      int big = 0;      // some pair was still correlated above 1e-4 when it was visited in this sweep
+      int buf = 0;                                     // double buffered partials: one barrier per step
+#ifdef JAC_PROF
+      unsigned int jp[5] = {0, 0, 0, 0, 0}, jt = clock();
+#endif
+#pragma unroll 1
+      for (int w = w0; w >= 1; w >>= 1) {
+#pragma unroll 1
+        for (int k = 0; k < w; ++k, buf ^= 256) {
+          JP(4);
+          double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) { g0 = fma(xp[i], xq[i], g0); g1 = fma(xp[i + 1], xq[i + 1], g1); }
+          mine[buf] = g0 + g1;
+          JP(0);
+          la_named_barrier(nbar);
+          JP(1);
+          const float g = (float)la_combine8(col + buf);
+#ifdef JAC_PROF
+          if (g == 123.456f) jp[0]++;
+#endif
+          JP(2);
+          double c = 1.0, sn = 0.0;
+          float na = a, nb = b;
           const float g2 = g * g, ab = a * b;
           if (g2 > 1e-8f * ab) big = 1;
           if (g2 > 1e-24f * ab) {
-            const float zeta = __fdividef(b - a, 2.0f * g);
-            const float tf = copysignf(__frcp_rn(fabsf(zeta) + __fsqrt_rn(fmaf(zeta, zeta, 1.0f))), zeta);
-            const float hf = fmaf(tf, tf, 1.0f), c0 = rsqrtf(hf);
-            const double t = (double)tf, h = fma(t, t, 1.0);
+            // tan(theta) = 2g / (d + sgn(d) sqrt(d^2 + 4 g^2)), d = b - a: three MUFU ops, no IEEE fix-ups
+            const float d = b - a, s4 = fmaf(d, d, 4.0f * g2);
+            const float r = s4 * la_rsqrt_approx(s4);
+            const float tf = 2.0f * g * la_rcp_approx(d + copysignf(r, d));
+            const float c0 = la_rsqrt_approx(fmaf(tf, tf, 1.0f));
+            const double t = (double)tf, hh = fma(t, t, 1.0);
             c = (double)c0;
-            c = c * fma(-0.5 * h, c * c, 1.5);       // one Newton step: c^2 h = 1 to ~1e-14
+            c = c * fma(-0.5 * hh, c * c, 1.5);        // one Newton step: c^2 (1 + t^2) = 1 to ~1e-14
             sn = c * t;
-            const float cf = c0, sf = c0 * tf, cs2 = 2.0f * cf * sf * g;   // |c x - s y|^2, |s x + c y|^2 (fp32)
-            nrm[pp] = cf * cf * a + sf * sf * b - cs2;
-            nrm[qq] = sf * sf * a + cf * cf * b + cs2;
+            const float sf = c0 * tf, cs2 = 2.0f * c0 * sf * g;   // |c x - s y|^2, |s x + c y|^2 (fp32)
+            na = c0 * c0 * a + sf * sf * b - cs2;
+            nb = sf * sf * a + c0 * c0 * b + cs2;
           }
+          a = na;
+#ifdef JAC_PROF
+          if (sn == 123.456) jp[0]++;
+#endif
+          JP(3);
+          // rotate, then ring-shift Q inside the segment (not after the last step of a level: Q then stays
+          // shifted by w - 1, which is as good a start for the next level; a shift by 0 keeps the code branch-free)
+          const int src = lane + (k + 1 < w ? 1 : 0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const double np = fma(c, xp[i], -sn * xq[i]), nq = fma(sn, xp[i], c * xq[i]);
+            xp[i] = np;
+            xq[i] = __shfl_sync(0xffffffffu, nq, src, w);
+          }
+          b = __shfl_sync(0xffffffffu, nb, src, w);
         }
-        cs[2 * lane] = c; cs[2 * lane + 1] = sn;
-      }
-      __syncthreads();
-      // phase C: apply the rotations (columns are disjoint between warps)
-      if (warp < half && q < n) {
-        const double c = cs[2 * warp], sn = cs[2 * warp + 1];
-        if (sn != 0.0) {
-          if (r0 < n) { W(r0, p) = c * x0 - sn * y0; W(r0, q) = sn * x0 + c * y0; }
-          if (r1 < n) { W(r1, p) = c * x1 - sn * y1; W(r1, q) = sn * x1 + c * y1; }
+        idq = __shfl_sync(0xffffffffu, idq, lane + w - 1, w);
+        if (w > 1) {                                   // trade column sets between the halves of the segment
+          const int hw = w >> 1;
+          const bool upper = (lane & hw) != 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const double got = __shfl_xor_sync(0xffffffffu, upper ? xp[i] : xq[i], hw);
+            if (upper) xp[i] = got; else xq[i] = got;
+          }
+          const float fgot = __shfl_xor_sync(0xffffffffu, upper ? a : b, hw);
+          const int igot = __shfl_xor_sync(0xffffffffu, upper ? idp : idq, hw);
+          if (upper) { a = fgot; idp = igot; } else { b = fgot; idq = igot; }
         }
       }
-      __syncthreads();
+#ifdef JAC_PROF
+      if (threadIdx.x == 0 && blockIdx.x == 0) for (int i = 0; i < 5; ++i) g_jac_prof[i] = jp[i];
+#endif
+      ++sweeps;
+      la_named_barrier(nbar);                          // the last step's buffer is the next norm buffer
+      // quadratic convergence: a sweep that only met cosines <= 1e-4 leaves them at ~1e-8 or below, i.e.
+      // eigenvalues exact to ~1e-16 and vectors to ~1e-8 -- no separate verification sweep is needed
+      done = !__any_sync(0xffffffffu, big);            // identical in every warp (same data, same code)
     }
-    ++sweeps;
-    // quadratic convergence: a sweep that only met cosines <= 1e-4 leaves them at ~1e-8 or below, i.e.
-    // eigenvalues exact to ~1e-16 and vectors to ~1e-8 -- no separate verification sweep is needed
-    if (!__syncthreads_or(big)) break;
-  }
-  for (int j = warp; j < n; j += nwarp) {
-    double a = 0.0;
-    for (int r = lane; r < n; r += 32) a = fma(W(r, j), W(r, j), a);
-    a = warp_sum(a);
-    if (lane == 0) lam[j] = a;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = warp * 8 + i;
+      if (idp < n && r < n) W(r, idp) = xp[i];
+      if (idq < n && r < n) W(r, idq) = xq[i];
+    }
+    if (warp == 0) {
+      if (idp < n) lam[idp] = ap;
+      if (idq < n) lam[idq] = aq;
+    }
   }
   __syncthreads();
   return sweeps;
