@@ -32,6 +32,15 @@ def measure(tag, mutate):
         a.record(); g.replay(); b.record(); torch.cuda.synchronize()
         tot += a.elapsed_time(b)
     print(f"{tag:40s} {tot / 20 * 1000:8.1f} us/step", flush=True)
+    if tag == "baseline":                      # phase clocks of the last KL forward of the replayed epoch
+        import ctypes
+        from tce_rl_b200 import _lib
+        buf = (ctypes.c_longlong * 16)()
+        _lib.call("tce_debug_kl_phase_cycles", buf)
+        st = list(buf)
+        names = ["load", "trsm W", "jacobi", "eta solve", "gemm M + save", "scale", "gemm Sigma", "chol", "store"]
+        print("    KL fwd in the replayed epoch: sweeps", st[15], " ".join(f"{n}={st[i+1]-st[i]}" for i, n in enumerate(names)),
+              "total", st[9] - st[0], "cycles", flush=True)
 
 
 def swap_proj(typ, **kw):

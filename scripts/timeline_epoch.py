@@ -1,0 +1,43 @@
+"""Kernel timeline (stream, start, duration) of ONE graph-replayed policy epoch, from the torch profiler (CUPTI)."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from torch.profiler import profile, ProfilerActivity
+
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(0)
+agent, dataset, times, pairs = bench.build_gpu_workload(dev, 0, 1)
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    for _ in range(2):
+        agent.policy_epoch(dataset, times, pairs)
+torch.cuda.current_stream().wait_stream(side)
+torch.cuda.synchronize()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    agent.policy_epoch(dataset, times, pairs)
+for _ in range(5):
+    g.replay()
+torch.cuda.synchronize()
+out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/timeline.txt"
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    g.replay()
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
+tmp = "/tmp/trace.json"
+prof.export_chrome_trace(tmp)
+ev = [e for e in json.load(open(tmp))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+ev.sort(key=lambda e: e["ts"])
+# keep the last replay: split at the largest gap
+gaps = [(ev[i + 1]["ts"] - ev[i]["ts"] - ev[i]["dur"], i) for i in range(len(ev) - 1)]
+cut = max(gaps)[1] + 1
+ev = ev[cut:]
+t0 = ev[0]["ts"]
+with open(out, "w") as f:
+    f.write(f"# {len(ev)} GPU activities, span {ev[-1]['ts'] + ev[-1]['dur'] - t0:.1f} us\n# start_us dur_us stream name\n")
+    for e in ev:
+        f.write(f"{e['ts'] - t0:9.1f} {e['dur']:8.1f} s{e['args'].get('stream', '?'):<4} {e['name'][:90]}\n")
+print(open(out).read()[:300])

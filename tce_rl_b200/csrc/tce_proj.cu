@@ -297,9 +297,31 @@ __device__ inline double kl_of_eta(const double *lam, int n, double eta, double 
 }
 
 // Root of KL_cov(eta) = eps (monotone decreasing in eta).  All warps of the CTA evaluate candidates in
-// parallel (two grid-refinement rounds), warp 0 polishes with safeguarded Newton steps.  cand: >= 34 doubles.
-__device__ inline double kl_solve_eta(const double *lam, int n, double eps, double *cand) {
+// parallel (two grid-refinement rounds), warp 0 polishes with safeguarded Newton steps.  cand: >= 36 doubles.
+// eta0 > 0: the root found for the previous L~ of the same update (warm start) -- Newton from there first and
+// fall back to the bracketing search only if it leaves the positive axis or does not settle in 6 steps.
+__device__ inline double kl_solve_eta(const double *lam, int n, double eps, double *cand, double eta0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = (int)(blockDim.x >> 5);
+  if (eta0 > 0.0) {                                   // uniform over the CTA
+    if (warp == 0) {
+      double eta = eta0;
+      bool ok = false;
+      for (int it = 0; it < 6 && !ok; ++it) {       // quadratic: 3-4 steps; the last ones only move by rounding noise
+        double df;
+        const double f = kl_of_eta(lam, n, eta, &df) - eps;
+        const double nxt = eta - f / df;
+        if (!(df < 0.0) || !(nxt > 0.0) || !(nxt < 1e300)) break;
+        ok = fabs(nxt - eta) <= 1e-13 * fmax(1.0, fabs(eta));
+        eta = nxt;
+      }
+      if (lane == 0) { cand[34] = ok ? 1.0 : 0.0; cand[35] = eta; }
+    }
+    __syncthreads();
+    const bool ok = cand[34] != 0.0;
+    const double eta = cand[35];
+    __syncthreads();
+    if (ok) return eta;
+  }
   // round 1: geometric grid eta_w = 2^(w - 10), w = 0..nwarp-1  (1e-3 .. 2e6 for 32 warps)
   double lo = 0.0, hi = ldexp(1.0, nwarp - 10);
   for (int round = 0; round < 3; ++round) {
@@ -384,7 +406,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
     return v;
   }();
   const bool active = kl0 > eps_cov;
-  const double eta = active ? kl_solve_eta(lam, n, eps_cov, red) : 0.0;
+  const double eta = active ? kl_solve_eta(lam, n, eps_cov, red, warm && save_sc[b * 4 + 1] != 0.0 ? save_sc[b * 4 + 0] : 0.0) : 0.0;
   KL_STAMP(4);
   la_gemm(b2, b0, b1, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // M = Lt U~
   if (threadIdx.x == 0) {

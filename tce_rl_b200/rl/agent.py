@@ -82,6 +82,7 @@ class TemporalCorrelatedAgent:
         self.fused_surrogate = bool(kwargs.get("fused_surrogate", True))
         self.overlap_logging = bool(kwargs.get("overlap_logging", True))
         self._log_stream = None
+        self._tr_stream = None
         self.process_group = kwargs.get("process_group", None)      # torch.distributed group (None = single GPU)
         self.policy_net_params = policy.parameters
         self.critic_net_params = critic.parameters if critic is not None else []
@@ -181,6 +182,12 @@ class TemporalCorrelatedAgent:
         entropy = self.policy.entropy([params_mean, params_L]).mean()
         return -self.entropy_penalty_coef * entropy, {"entropy": entropy}
 
+    def _entropy_term(self, proj):
+        if self.entropy_penalty_coef != 0.0:
+            return self.entropy_loss(proj[0], proj[1])
+        with torch.no_grad():                             # coefficient 0 in every config: logging value only
+            return self.entropy_loss(proj[0], proj[1])
+
     def kl_old_new_proj(self, new, old, proj):
         """The 12 logging means of temporal_correlated_agent.py:641-686 as one device vector.  Parts that the
         projection / trust-region loss of this epoch already evaluated (``projection.cache``) are reused."""
@@ -230,8 +237,30 @@ class TemporalCorrelatedAgent:
         vector [7 + 12] (``_LOSS_KEYS`` then ``_KL_KEYS``) living on the device."""
         D2 = self.policy.num_dof * 2
         old = (dataset["segment_params_mean"], dataset["segment_params_L"])
-        new = self.policy.policy(dataset["segment_state"][..., :-D2])
-        proj = self.projection(self.policy, new, old, self.num_iterations)
+        obs = dataset["segment_state"][..., :-D2]
+        pre = None
+        if not self.policy.contextual_cov and hasattr(self.policy, "shared_params_L"):
+            # shared covariance: start its projection (side stream) before the mean net -- same values as
+            # policy.policy(obs) followed by the projection, see BaseProjectionLayer.start_cov_projection
+            params_L = self.policy.shared_params_L(obs.shape[0])
+            pre = self.projection.start_cov_projection(self.policy, params_L, old[1], self.num_iterations)
+            new = (self.policy.mean_net(obs), params_L)
+        else:
+            new = self.policy.policy(obs)
+        proj = self.projection(self.policy, new, old, self.num_iterations, cov_projected=pre)
+        # trust-region loss: small (partly single-CTA) kernels that only need `new` and `proj` -- a parallel
+        # branch next to the segment likelihood, forward and (autograd replays the streams) backward
+        tr_stream = None
+        if self.overlap_logging and proj[0].is_cuda:
+            if self._tr_stream is None:
+                self._tr_stream = torch.cuda.Stream(device=proj[0].device)
+            tr_stream, cur = self._tr_stream, torch.cuda.current_stream()
+            tr_stream.wait_stream(cur)
+            with torch.cuda.stream(tr_stream):
+                tr_loss = self.projection.get_trust_region_loss(self.policy, new, proj, set_variance=self.set_variance)
+                ent_loss, ent_stats = self._entropy_term(proj)
+                for t in (tr_loss, ent_loss, ent_stats["entropy"]):
+                    t.record_stream(cur)
         if self.fused_surrogate and hasattr(self.policy, "segment_surrogate"):
             surrogate, ratio, _ = self.policy.segment_surrogate(
                 dataset["step_actions"], proj[0], proj[1], times, dataset["segment_init_time"],
@@ -245,12 +274,11 @@ class TemporalCorrelatedAgent:
                                                 init_vel=dataset["segment_init_vel"], pred_pairs=pred_pairs)
             surrogate, sur_stats = self.surrogate_loss(dataset["segment_advantage"], log_prob_new,
                                                        dataset["segment_log_prob_estimate"])
-        if self.entropy_penalty_coef != 0.0:
-            ent_loss, ent_stats = self.entropy_loss(proj[0], proj[1])
-        else:                                             # coefficient 0 in every config: logging value only
-            with torch.no_grad():
-                ent_loss, ent_stats = self.entropy_loss(proj[0], proj[1])
-        tr_loss = self.projection.get_trust_region_loss(self.policy, new, proj, set_variance=self.set_variance)
+        if tr_stream is None:
+            ent_loss, ent_stats = self._entropy_term(proj)
+            tr_loss = self.projection.get_trust_region_loss(self.policy, new, proj, set_variance=self.set_variance)
+        else:
+            torch.cuda.current_stream().wait_stream(tr_stream)
         policy_loss = surrogate + ent_loss + tr_loss
         # logging-only KL decomposition: a parallel branch (side stream) next to backward + Adam
         main, side = None, None

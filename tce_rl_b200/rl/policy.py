@@ -89,12 +89,18 @@ class AbstractGaussianPolicy:
 class BlackBoxPolicy(AbstractGaussianPolicy):
     def policy(self, obs):
         """-> (params_mean [B, Dp], params_L [B, Dp, Dp])   (black_box_policy.py:30-56)."""
-        params_mean = self.mean_net(obs)
         if self.contextual_cov:
-            params_L = self._vector_to_cholesky(self.variance_net(obs))
-        else:
-            params_L = self._vector_to_cholesky(self.variance_net.variable, obs.shape[0])
-        return params_mean, params_L
+            return self.mean_net(obs), self._vector_to_cholesky(self.variance_net(obs))
+        return self.mean_net(obs), self.shared_params_L(obs.shape[0])
+
+    def shared_params_L(self, batch: int):
+        """The ONE factor of a non-contextual policy, broadcast over the batch with stride 0.  The reference
+        expands the parameter vector and materialises B equal factors (black_box_policy.py:50-53); every
+        consumer here reads the first one (``rl/projection.py:_first``) or a stride-0 view."""
+        first = self._vector_to_cholesky(self.variance_net.variable, 1)
+        params_L = first.expand(batch, -1, -1)
+        params_L._tce_first = first
+        return params_L
 
     def sample(self, require_grad, params_mean, params_L, use_mean=False, eps=None):
         if use_mean:

@@ -22,7 +22,17 @@ if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
 
 
 def _expand_first(t, batch):
-    return t.expand(batch, -1, -1)
+    """Broadcast ONE factor [1, n, n] over the batch (stride 0) and remember the original: ``_first`` then hands it
+    back without a slice node (the backward of ``expanded[:1]`` materialises and reduces a [B, n, n] gradient,
+    and -- worse -- queues on the main stream behind the covariance chain)."""
+    e = t.expand(batch, -1, -1)
+    e._tce_first = t
+    return e
+
+
+def _first(L):
+    base = getattr(L, "_tce_first", None)
+    return base if base is not None else L[:1]
 
 
 def _shared(policy, L):
@@ -35,7 +45,7 @@ def _cov_stats(policy, L, L_o):
     """gauss_stats on the covariance factors only (zero mean difference), broadcast when shared."""
     B = L.shape[0]
     if _shared(policy, L):
-        L, L_o = L[:1], L_o[:1]
+        L, L_o = _first(L), _first(L_o)
     zeros = torch.zeros(L.shape[0], L.shape[-1], device=L.device)
     st = ops.gauss_stats(zeros, L.contiguous(), zeros, L_o)
     return st.expand(B, -1) if st.shape[0] != B else st
@@ -91,6 +101,7 @@ class BaseProjectionLayer:
         self.cache = {}
         self.overlap = bool(kwargs.get("overlap", True))      # run independent chains on a side stream
         self._side = None
+        self._beta_cache = None
 
     @property
     def initial_entropy(self):
@@ -105,15 +116,18 @@ class BaseProjectionLayer:
     def _entropy_bound(self, step, device):
         if self.entropy_schedule is None:
             return None                                        # bound -inf: the projection is the identity
-        beta = self.entropy_schedule(self.initial_entropy, self.target_entropy, self.temperature, step)
-        return torch.as_tensor(beta, device=device).to(torch.float64).reshape(1)
+        key = (step, str(device), id(self._initial_entropy))
+        if self._beta_cache is None or self._beta_cache[0] != key:     # constant over the epochs of one update:
+            beta = self.entropy_schedule(self.initial_entropy, self.target_entropy, self.temperature, step)
+            self._beta_cache = (key, torch.as_tensor(beta, device=device).to(torch.float64).reshape(1))
+        return self._beta_cache[1]                                     # five tiny kernels once, not per epoch
 
     def _entropy_projection(self, policy, p, beta):
         if beta is None:
             return p
         mean, L = p
         shared = L.dim() == 3 and L.stride(0) == 0
-        L_in = L[:1] if shared else L
+        L_in = _first(L) if shared else L
         out, _ = ops.proj_entropy(L_in.contiguous(), beta, self.entropy_eq)
         return mean, (_expand_first(out, mean.shape[0]) if shared else out)
 
@@ -134,7 +148,7 @@ class BaseProjectionLayer:
         self.cache = {"new_old_mean": mean_part.detach()}
         proj_mean = ops.proj_mean(mean, old_mean, mean_part, self.mean_bound)
         if not policy.contextual_std:                          # one shared covariance: project the first only
-            proj_L = _expand_first(self._cov_projection(policy, L[:1], old_L[:1]), mean.shape[0])
+            proj_L = _expand_first(self._cov_projection(policy, _first(L), _first(old_L)), mean.shape[0])
         else:
             proj_L = self._cov_projection(policy, L, old_L)
         return proj_mean, proj_L
@@ -144,33 +158,48 @@ class BaseProjectionLayer:
             self._side = torch.cuda.Stream(device=device)
         return self._side
 
-    def __call__(self, policy, p, q, step, *args, **kwargs):
+    def _overlappable(self, policy, L):
+        return (self.projects and self.overlap and not policy.contextual_std and not self.entropy_first
+                and L.is_cuda)
+
+    def __call__(self, policy, p, q, step, *args, cov_projected=None, **kwargs):
+        if self._overlappable(policy, p[1]):
+            return self._call_overlapped(policy, p, q, step, cov_projected)
         beta = self._entropy_bound(step, p[0].device)
-        if self.projects and self.overlap and not policy.contextual_std and not self.entropy_first and p[1].is_cuda:
-            return self._call_overlapped(policy, p, q, beta)
         if self.entropy_first:
             p = self._entropy_projection(policy, p, beta)
         proj = self._trust_region_projection(policy, p, q)
         return proj if self.entropy_first else self._entropy_projection(policy, proj, beta)
 
-    def _call_overlapped(self, policy, p, q, beta):
+    def start_cov_projection(self, policy, L, old_L, step):
         """Non-contextual covariance: the covariance chain (ONE matrix: projection + entropy scaling, a
-        latency-bound single-CTA sequence) does not depend on the batch-sized mean chain, so it runs on a side
-        stream (a parallel branch when captured in a CUDA graph); autograd replays the same split backwards."""
-        mean, L = p
-        old_mean, old_L = q
+        latency-bound single-CTA sequence) depends neither on the observations nor on the mean net, so it can
+        be started on a side stream (a parallel branch when captured in a CUDA graph) BEFORE the mean net is
+        evaluated; pass the returned handle to ``__call__(..., cov_projected=handle)``.  Calling it first also
+        fixes the order of the backward: autograd runs nodes in reverse creation order, so the mean-net
+        backward is queued on the main stream before the (long) covariance backward is joined into it.
+        Returns None when the layer would not overlap (contextual covariance, CPU tensors, ...)."""
+        if not self._overlappable(policy, L):
+            return None
         main = torch.cuda.current_stream()
-        side = self._side_stream(mean.device)
+        side = self._side_stream(L.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            proj_L1 = self._cov_projection(policy, L[:1], old_L[:1])
+            proj_L1 = self._cov_projection(policy, _first(L), _first(old_L))
+            beta = self._entropy_bound(step, L.device)
             if beta is not None:
                 proj_L1 = ops.proj_entropy(proj_L1.contiguous(), beta, self.entropy_eq)[0]
             proj_L1.record_stream(main)
+        return proj_L1
+
+    def _call_overlapped(self, policy, p, q, step, cov_projected=None):
+        mean, L = p
+        old_mean, old_L = q
+        proj_L1 = cov_projected if cov_projected is not None else self.start_cov_projection(policy, L, old_L, step)
         mean_part = self._mean_part(policy, p, q)
         self.cache = {"new_old_mean": mean_part.detach()}
         proj_mean = ops.proj_mean(mean, old_mean, mean_part, self.mean_bound)
-        main.wait_stream(side)
+        torch.cuda.current_stream().wait_stream(self._side_stream(mean.device))
         return proj_mean, _expand_first(proj_L1, mean.shape[0])
 
     def trust_region_value(self, policy, p, q):
@@ -247,7 +276,7 @@ class FrobeniusProjectionLayer(BaseProjectionLayer):
         """Covariance distance [B]; a shared (non-contextual) covariance is evaluated once and broadcast."""
         B = L.shape[0]
         if _shared(policy, L):
-            L, L_o = L[:1], L_o[:1]
+            L, L_o = _first(L), _first(L_o)
         val = ops.cov_distance(kind, L.contiguous(), L_o, scale_prec)
         return val.expand(B) if val.shape[0] != B else val
 
@@ -258,7 +287,7 @@ class FrobeniusProjectionLayer(BaseProjectionLayer):
         target = (proj_p[0].detach(), proj_p[1].detach())
         diff = self._mean_dist(p, target)
         if self._with_cov(policy, set_variance):               # squared L difference instead of the Frobenius metric
-            Lp, Lt = (p[1][:1], target[1][:1]) if _shared(policy, p[1]) else (p[1], target[1])
+            Lp, Lt = (_first(p[1]), _first(target[1])) if _shared(policy, p[1]) else (p[1], target[1])
             diff = diff + (Lp - Lt).pow(2).sum([-1, -2]).to(torch.float64)
         return (diff.mean() * self.trust_region_coeff).to(p[0].dtype)
 
