@@ -119,6 +119,14 @@ int tce_gauss_stats_bwd(const float *mean, const float *L, int64_t ldb_L, const 
  * otherwise grad_mean [B,n] = grad_out[b] * 2 Sigma_o^-1 (mean - mean_o) (maha may also be written).      */
 int tce_gauss_maha(const float *mean, const float *mean_o, const float *L_o, int64_t ldb_Lo,
                    const double *grad_out, double *maha, float *grad_mean, int64_t B, int n, void *stream);
+/* Non-contextual policy: ONE L_o for all episodes (the reference repeats it B times,
+ * black_box_policy.py:50-53).  tce_tri_inverse writes Linv [B,n,n] = L^-1 (fp64, B is normally 1);
+ * tce_gauss_maha_shared is tce_gauss_maha with the two triangular solves per episode replaced by products
+ * with that shared inverse; with grad_out == NULL and grad_mean != NULL it also writes d maha / d mean
+ * (so that a backward pass is one elementwise product).                                                 */
+int tce_tri_inverse(const float *L, int64_t ldb, double *Linv, int64_t B, int n, void *stream);
+int tce_gauss_maha_shared(const float *mean, const float *mean_o, const double *Linv, const double *grad_out,
+                          double *maha, float *grad_mean, int64_t B, int n, void *stream);
 
 /* ---- (4a) differentiable trust-region projections ------------------------------------------------------
  * Replace the trust_region_projections layers (BruceGeLi/trust-region-layers@TCE_ICLR24) created by
@@ -141,8 +149,8 @@ int tce_proj_entropy_bwd(const float *L, const double *beta, int64_t ldb_beta, i
                          const float *grad_out, float *grad_L, int64_t B, int n, void *stream);
 /* KL covariance projection: min KL(N(.,S)||N(.,S~)) s.t. KL_cov(S||S_old) <= eps_cov, solved exactly on
  * the generalised eigenvalues (CTA-per-matrix one-sided Jacobi + Newton for eta); proj_L = chol(S_proj).
- * `save` (tce_proj_kl_save_doubles(B, n) doubles) carries M = L_old Q, lambda, eta to the backward
- * (implicit differentiation of eta*).  warm_start != 0: `save` still holds the state of a previous call;
+ * `save` (tce_proj_kl_save_doubles(B, n) doubles) carries M = L_old Q, U = L~^-1 M, lambda, eta to the
+ * backward (implicit differentiation of eta*).  warm_start != 0: `save` still holds the state of a previous call;
  * it is used to start the eigen-solve when it was produced with the same L_o (checked by a fingerprint),
  * e.g. across the epochs of one update_policy.  info [B]: non positive pivot of the final Cholesky.     */
 size_t tce_proj_kl_save_doubles(int64_t B, int n);

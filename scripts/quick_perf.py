@@ -51,6 +51,13 @@ for B in [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["10
     res["chol_grad_us"] = timeit(lambda: _lib.call("tce_seglik_chol", tabs.handle, p(work), p(adj), p(dmax), 1e-4, p(glp), None, None, 0.0, None, p(logp), p(info), B, P, st))
     res["bwd_us"] = timeit(lambda: _lib.call("tce_seglik_bwd", tabs.handle, p(adj), p(g["L"]), Dp*Dp, p(times_g), p(g["init_time"]), p(pairs_g), None, p(gm), p(gL), B, T, P, st))
     res["gauss_stats_us"] = timeit(lambda: ops.gauss_stats(g["mean"], g["L"], g["mean_old"], g["L_old"]))
+    Linv = ops.tri_inverse(g["L_old"][:1].contiguous())[0]
+    gm64 = torch.ones(B, device=dev, dtype=torch.float64)
+    res["tri_inverse_us"] = timeit(lambda: ops.tri_inverse(g["L_old"][:1].contiguous()))
+    res["maha_us"] = timeit(lambda: ops.gauss_maha(g["mean"], g["mean_old"], g["L_old"]))
+    res["maha_bwd_us"] = timeit(lambda: ops.gauss_maha_bwd(gm64, g["mean"], g["mean_old"], g["L_old"]))
+    res["maha_shared_us"] = timeit(lambda: ops.gauss_maha_shared(g["mean"], g["mean_old"], Linv))
+    res["maha_shared_bwd_us"] = timeit(lambda: ops.gauss_maha_shared_bwd(gm64, g["mean"], g["mean_old"], Linv))
     res["gae_us"] = timeit(lambda: ops.gae(g["rewards"], g["values"], g["dones"], g["time_limit_dones"], 1.0, 0.95, True))
     res["segadv_us"] = timeit(lambda: ops.segment_advantage(1, g["rewards"], g["values"], g["rewards"], pairs_g, 1.0, True))
     res["launch_floor_us"] = timeit(lambda: _lib.call("tce_normalize_by_stats", p(logp), p(dmax.new_ones(3)), 1, st))

@@ -31,9 +31,8 @@ tmp = "/tmp/trace.json"
 prof.export_chrome_trace(tmp)
 ev = [e for e in json.load(open(tmp))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
 ev.sort(key=lambda e: e["ts"])
-# keep the last replay: split at the largest gap
-gaps = [(ev[i + 1]["ts"] - ev[i]["ts"] - ev[i]["dur"], i) for i in range(len(ev) - 1)]
-cut = max(gaps)[1] + 1
+# keep the last replay: it starts with the last launch of the policy head
+cut = max(i for i, e in enumerate(ev) if "head_fwd_kernel" in e["name"])
 ev = ev[cut:]
 t0 = ev[0]["ts"]
 with open(out, "w") as f:

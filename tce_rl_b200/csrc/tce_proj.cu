@@ -19,19 +19,40 @@ constexpr double LOG_2PI = 1.8378770664093453;
 
 __device__ inline int pad_even(int n) { return (n + 1) & ~1; }
 
+// Stream `count` contiguous global elements through `sink(e, value)` with FOUR loads in flight per thread: a
+// plain `for (e...) smem[f(e)] = src[e]` loop is not unrolled (runtime trip count, index arithmetic in the
+// body) and pays one full memory latency per iteration -- 4 to 16 dependent round trips per matrix.
+template <typename T, typename Sink>
+__device__ __forceinline__ void batched_load(const T *__restrict__ src, int count, Sink sink) {
+  const int step = (int)blockDim.x;
+  for (int e0 = threadIdx.x; e0 < count; e0 += 4 * step) {
+    T v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (e0 + u * step < count) ? src[e0 + u * step] : T(0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (e0 + u * step < count) sink(e0 + u * step, v[u]);
+  }
+}
+
+__device__ inline void zero_padding(Mat M, int n, int m) {           // row / column n of an odd-sized problem
+  if (m > n) for (int t = threadIdx.x; t < m; t += blockDim.x) { M(n, t) = 0.0; M(t, n) = 0.0; }
+}
+
 // load the lower triangle of a dense fp32 [n,n] matrix into an fp64 shared buffer (m x LD, zero elsewhere)
 __device__ inline void load_lower_d(Mat M, const float *__restrict__ src, int n, int m) {
-  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
-    const int i = e / m, j = e % m;
-    M(i, j) = (i < n && j <= i) ? (double)src[(size_t)i * n + j] : 0.0;
-  }
+  batched_load(src, n * n, [&](int e, float v) {
+    const int i = e / n, j = e - i * n;
+    M(i, j) = j <= i ? (double)v : 0.0;
+  });
+  zero_padding(M, n, m);
   __syncthreads();
 }
 __device__ inline void load_full_d(Mat M, const double *__restrict__ src, int n, int m) {
-  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
-    const int i = e / m, j = e % m;
-    M(i, j) = (i < n && j < n) ? src[(size_t)i * n + j] : 0.0;
-  }
+  batched_load(src, n * n, [&](int e, double v) {
+    const int i = e / n, j = e - i * n;
+    M(i, j) = v;
+  });
+  zero_padding(M, n, m);
   __syncthreads();
 }
 __device__ inline void store_lower_f(float *__restrict__ dst, Mat M, int n, double scale) {
@@ -195,6 +216,98 @@ maha_kernel(const float *__restrict__ mean, const float *__restrict__ mean_o, co
   }
   for (int i = lane; i < n; i += 32) grad_mean[b * n + i] = (float)(g2 * bv[i]);
 }
+
+// Shared-covariance variants (non-contextual policy: every episode has the same L_o).  L_o^-1 is formed once
+// (tri_inverse_kernel, fp64) and the two triangular solves per episode become dense matrix-vector products
+// without a dependent chain: one warp per episode, Linv staged once per CTA (row stride n | 1).
+__global__ void __launch_bounds__(256)
+tri_inverse_kernel(const float *__restrict__ L, long long ldb, double *__restrict__ Linv, int n) {
+  extern __shared__ double sd[];
+  const int m = pad_even(n), LD = m + 1, MS = m * LD;
+  Mat A{sd, LD, 1}, X{sd + MS, LD, 1};
+  double *dinv = sd + 2 * MS;
+  const long long b = blockIdx.x;
+  load_lower_d(A, L + b * ldb, n, m);
+  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+    const int i = e / m, j = e - i * m;
+    X(i, j) = (i == j && i < n) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  la_diag_block_inverses(A, dinv, n);
+  la_trsm_lower(A, dinv, X, n, n, true);
+  double *out = Linv + (size_t)b * n * n;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    out[e] = j <= i ? X(i, j) : 0.0;
+  }
+}
+
+#ifdef MAHA_DBG
+__device__ unsigned long long g_maha_dbg[8][160][4];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid() { unsigned t; asm volatile("mov.u32 %0, %%smid;" : "=r"(t)); return t; }
+#endif
+__global__ void __launch_bounds__(256)
+maha_shared_kernel(const float *__restrict__ mean, const float *__restrict__ mean_o, const double *__restrict__ Linv,
+                   const double *__restrict__ gout, double *__restrict__ out, float *__restrict__ grad_mean,
+                   long long B, int n, int dbg_slot) {
+  extern __shared__ double smd[];
+#ifdef MAHA_DBG
+  unsigned long long t_start = gtimer();
+#endif
+  const int LD = n | 1, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  double *sA = smd, *dv = smd + (size_t)n * LD + (size_t)warp * 2 * n, *zv = dv + n;
+  batched_load(Linv, n * n, [&](int e, double v) {
+    const int i = e / n, j = e - i * n;
+    sA[i * LD + j] = v;
+  });
+  __syncthreads();
+  for (long long b = (long long)blockIdx.x * nw + warp; b < B; b += (long long)gridDim.x * nw) {
+#pragma unroll 1
+    for (int i = lane; i < n; i += 32) dv[i] = (double)mean[b * n + i] - (double)mean_o[b * n + i];
+    __syncwarp();
+    // NOTE on `#pragma unroll 1`: this kernel runs each instruction once or twice per launch, so it is bound by
+    // instruction fetch (cold I-cache every launch), not by the pipes -- compact loops beat unrolled ones here.
+    double maha = 0.0;
+#pragma unroll 1
+    for (int i = lane; i < n; i += 32) {                 // z = Linv d (rows of different lanes: stride LD is odd)
+      double z0 = 0.0, z1 = 0.0;
+      const double *row = sA + i * LD;
+      int j = 0;
+#pragma unroll 1
+      for (; j + 1 <= i; j += 2) { z0 = fma(row[j], dv[j], z0); z1 = fma(row[j + 1], dv[j + 1], z1); }
+      if (j <= i) z0 = fma(row[j], dv[j], z0);
+      const double z = z0 + z1;
+      zv[i] = z;
+      maha = fma(z, z, maha);
+    }
+    maha = warp_sum(maha);
+    if (out && lane == 0) out[b] = maha;
+    if (grad_mean) {                                     // grad = 2 g Linv^T z (columns: consecutive lanes)
+      __syncwarp();
+      const double g2 = gout ? 2.0 * gout[b] : 2.0;      // gout == NULL: d maha / d mean, saved for the backward
+#pragma unroll 1
+      for (int j = lane; j < n; j += 32) {
+        double u0 = 0.0, u1 = 0.0;
+        const double *colp = sA + j;
+        int i = j;
+#pragma unroll 1
+        for (; i + 1 < n; i += 2) { u0 = fma(colp[i * LD], zv[i], u0); u1 = fma(colp[(i + 1) * LD], zv[i + 1], u1); }
+        if (i < n) u0 = fma(colp[i * LD], zv[i], u0);
+        grad_mean[b * n + j] = (float)(g2 * (u0 + u1));
+      }
+    }
+    __syncwarp();
+  }
+#ifdef MAHA_DBG
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x < 160) {
+    unsigned long long *d = g_maha_dbg[dbg_slot & 7][blockIdx.x];
+    d[0] = t_start; d[1] = gtimer(); d[2] = smid(); d[3] = gout != nullptr;
+  }
+#endif
+}
+
 
 // =====================================================================================================
 // mean projection (closed form) -- elementwise, one warp per episode
@@ -366,13 +479,14 @@ __device__ inline double kl_solve_eta(const double *lam, int n, double eps, doub
 // Forward.  With W = Lt^-1 Lo, one-sided Jacobi rotates the columns of W into U~ = W Q (orthogonal columns,
 // |U~_j|^2 = lam_j = eigenvalues of W^T W); then M := Lo Q = Lt U~ and
 //   Sigma_proj = Lo Q diag((1+eta)/(lam+eta)) Q^T Lo^T = M D M^T ,   proj_L = chol(Sigma_proj).
-// `save` = { M [n,n], lam [n], {eta, active, kl0, fingerprint(Lo)} } per matrix: state for the backward AND a
+// `save` = { M [n,n], U~ [n,n], lam [n], {eta, active, kl0, fingerprint(Lo)} } per matrix: state for the backward AND a
 // warm start for the next call with the same Lo (the 50 epochs of one update_policy): starting Jacobi from
 // Lt^-1 M_prev = W Q_prev is an orthogonal change of basis of the same problem, so 2-3 sweeps suffice.
 __global__ void __launch_bounds__(KL_THREADS)
 proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_o, double eps_cov,
-                       float *__restrict__ proj_L, double *__restrict__ save_M, double *__restrict__ save_lam,
-                       double *__restrict__ save_sc, int32_t *__restrict__ info, int n, int warm_start) {
+                       float *__restrict__ proj_L, double *__restrict__ save_M, double *__restrict__ save_U,
+                       double *__restrict__ save_lam, double *__restrict__ save_sc, int32_t *__restrict__ info, int n,
+                       int warm_start) {
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
   Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1};
@@ -386,7 +500,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   load_lower_d(b0, Lt, n, m);
   // fingerprint of Lo (position weighted sum, deterministic order): guards the warm start
   double fp = 0.0;
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) fp = fma((double)(e % 251 + 1), (double)Lo[e], fp);
+  batched_load(Lo, n * n, [&](int e, float v) { fp = fma((double)(e % 251 + 1), (double)v, fp); });
   fp = block_sum(fp, red);
   const bool warm = warm_start && save_sc[b * 4 + 3] == fp;
   if (warm) load_full_d(b1, save_M + off, n, m); else load_lower_d(b1, Lo, n, m);
@@ -414,7 +528,11 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
     if (blockIdx.x == 0) g_kl_prof[15] = sweeps;
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) save_lam[b * n + i] = lam[i];
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) save_M[off + e] = b2(e / n, e % n);
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    save_M[off + e] = b2(i, j);
+    save_U[off + e] = b1(i, j);                                                     // U~ = Lt^-1 M for the backward
+  }
   KL_STAMP(5);
   float *out = proj_L + off;
   if (!active) {                                                                    // identity
@@ -437,14 +555,18 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   KL_STAMP(9);
 }
 
-// Backward (implicit differentiation of eta*, no eigen-derivative singularities).  With U~ = Lt^-1 M,
-// rho_i = 1/(lam_i + eta), Sbar = d/dSigma_proj (from the Cholesky adjoint):
-//   Ft = M^T Sbar M ;  Nt_ij = -(1+eta) rho_i rho_j Ft_ij - delta_ij etabar (df/dlam_i) / (df/deta) ,
-//   etabar = sum_i Ft_ii (rho_i - (1+eta) rho_i^2) ;  grad_Lt = -2 tril(Lt^-T U~ Nt U~^T).
+// Backward (implicit differentiation of eta*, no eigen-derivative singularities).  With P = proj_L, G the
+// upstream gradient, Phi = Phi(P^T G) (lower triangle, halved diagonal) the Cholesky adjoint is
+// Sbar = sym(P^-T Phi P^-1); only M^T Sbar M is needed, so with Y = P^-1 M (ONE triangular solve)
+//   Ft = sym(Y^T Phi Y) ;  rho_i = 1/(lam_i + eta) ;
+//   Nt_ij = -(1+eta) rho_i rho_j Ft_ij - delta_ij etabar (df/dlam_i) / (df/deta) ,
+//   etabar = sum_i Ft_ii (rho_i - (1+eta) rho_i^2) ;  grad_Lt = -2 tril(Lt^-T U~ Nt U~^T)
+// with U~ = Lt^-1 M saved by the forward (second and last triangular solve: Lt^-T).
 __global__ void __launch_bounds__(KL_THREADS)
 proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ proj_L, const float *__restrict__ gout,
-                       const double *__restrict__ save_M, const double *__restrict__ save_lam,
-                       const double *__restrict__ save_sc, float *__restrict__ grad_L, int n) {
+                       const double *__restrict__ save_M, const double *__restrict__ save_U,
+                       const double *__restrict__ save_lam, const double *__restrict__ save_sc,
+                       float *__restrict__ grad_L, int n) {
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
   Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
@@ -458,32 +580,38 @@ proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ pr
     return;
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) { lam[i] = save_lam[b * n + i]; rho[i] = 1.0 / (lam[i] + eta); }
-  load_lower_d(b0, proj_L + off, n, m);
-  load_lower_d(b1, gout + off, n, m);
-  chol_backward(b0, b1, b2, dinv, n);                                              // b2 = Sbar (sym)
-  load_full_d(b0, save_M + off, n, m);                                             // M
-  la_gemm(b1, b2, b0, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);            // Sbar M
-  la_gemm(b2, b0.T(), b1, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // Ft = M^T Sbar M
+  load_lower_d(b0, proj_L + off, n, m);                                            // P
+  load_lower_d(b1, gout + off, n, m);                                              // G
+  la_gemm(b2, b0.T(), b1, n, n, n, TRI_UPPER, TRI_LOWER, TRI_FULL, 1.0, 0.0);      // P^T G
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    if (j > i) b2(i, j) = 0.0; else if (i == j) b2(i, j) *= 0.5;                   // Phi
+  }
+  load_full_d(b1, save_M + off, n, m);                                             // M (G is consumed)
+  la_diag_block_inverses(b0, dinv, n);
+  la_trsm_lower(b0, dinv, b1, n, n, false);                                        // Y = P^-1 M
+  la_gemm(b3, b2, b1, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // Phi Y
+  la_gemm(b0, b1.T(), b3, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // F' = Y^T Phi Y ; Ft = sym(F')
   double eb = 0.0, dfe = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    eb += b2(i, i) * (rho[i] - (1.0 + eta) * rho[i] * rho[i]);
+    eb += b0(i, i) * (rho[i] - (1.0 + eta) * rho[i] * rho[i]);
     dfe += 2.0 * rho[i] - (1.0 + eta) * rho[i] * rho[i] - 1.0 / (1.0 + eta);
   }
   eb = block_sum(eb, red);
   dfe = 0.5 * block_sum(dfe, red);
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-    const int i = e / n, j = e % n;
-    double v = -(1.0 + eta) * rho[i] * rho[j] * b2(i, j);
+    const int i = e / n, j = e - i * n;
+    double v = -(1.0 + eta) * rho[i] * rho[j] * (0.5 * (b0(i, j) + b0(j, i)));
     if (i == j) v -= eb * (0.5 * (rho[i] - (1.0 + eta) * rho[i] * rho[i])) / dfe;
-    b2(i, j) = v;                                                                  // Nt
+    b2(i, j) = v;                                                                  // Nt (Phi is consumed)
   }
+  load_full_d(b1, save_U + off, n, m);                                             // U~ (Y is consumed)
   __syncthreads();
-  load_lower_d(b1, L + off, n, m);                                                 // Lt
-  la_diag_block_inverses(b1, dinv, n);
-  la_trsm_lower(b1, dinv, b0, n, n, false);                                        // U~ = Lt^-1 M   (in b0)
-  la_gemm(b3, b0, b2, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);            // U~ Nt
-  la_gemm(b2, b3, b0.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // U~ Nt U~^T
-  la_trsm_lower_t(b1, dinv, b2, n, n);                                             // Lt^-T (.)
+  la_gemm(b3, b1, b2, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);            // U~ Nt
+  la_gemm(b2, b3, b1.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // U~ Nt U~^T
+  load_lower_d(b0, L + off, n, m);                                                 // Lt (F' is consumed)
+  la_diag_block_inverses(b0, dinv, n);
+  la_trsm_lower_t(b0, dinv, b2, n, n);                                             // Lt^-T (.)
   store_lower_f(gl, b2, n, -2.0);
 }
 
@@ -731,6 +859,12 @@ size_t pj_smem(int n, int nbuf) {
   return sizeof(double) * ((size_t)nbuf * m * (m + 1) + LA_DINV_DOUBLES + 8 * m + 256);
 }
 
+// CTA-per-matrix kernels launched for a FEW matrices (shared covariance: B = 1) are latency chains on the
+// critical path of the epoch, and batch-sized kernels of parallel graph branches would be co-scheduled onto
+// their SMs (issue slots shared with 8-32 busy warps: the unlucky CTA of the batch kernel then finishes 3-5x
+// late and so does the chain).  Asking for (almost) all shared memory of the SM keeps the SM exclusive.
+size_t pj_smem_exclusive(size_t smem, int64_t B) { return B <= 16 && smem < 200 * 1024 ? 200 * 1024 : smem; }
+
 template <typename K>
 int set_smem(K kernel, size_t smem) {
   if (smem > 220 * 1024) return TCE_ERR_UNSUPPORTED_SHAPE;
@@ -747,7 +881,7 @@ extern "C" int tce_gauss_stats(const float *mean, const float *L, int64_t ldb_L,
   if (!mean || !mean_o || !L_o || !out || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
   if (B == 0) return TCE_OK;
-  const size_t smem = pj_smem(n, 2);
+  const size_t smem = pj_smem_exclusive(pj_smem(n, 2), B);
   int rc = set_smem(gauss_kl_kernel, smem);
   if (rc) return rc;
   gauss_kl_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(mean, L, ldb_L, mean_o, L_o, ldb_Lo, out,
@@ -762,7 +896,7 @@ extern "C" int tce_gauss_stats_bwd(const float *mean, const float *L, int64_t ld
   if (!mean || !mean_o || !L_o || !grad_out || B < 0 || (grad_L && !L)) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
   if (B == 0) return TCE_OK;
-  const size_t smem = pj_smem(n, 2);
+  const size_t smem = pj_smem_exclusive(pj_smem(n, 2), B);
   int rc = set_smem(gauss_kl_kernel, smem);
   if (rc) return rc;
   gauss_kl_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(mean, L, ldb_L, mean_o, L_o, ldb_Lo, nullptr,
@@ -781,6 +915,45 @@ extern "C" int tce_gauss_maha(const float *mean, const float *mean_o, const floa
     TCE_CUDA(cudaFuncSetAttribute(maha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "maha attr");
   maha_kernel<<<(unsigned)B, 128, smem, (cudaStream_t)stream>>>(mean, mean_o, L_o, ldb_Lo, grad_out, maha, grad_mean, n);
   TCE_CHECK_LAUNCH("maha_kernel");
+  return TCE_OK;
+}
+
+#ifdef MAHA_DBG
+extern "C" int tce_debug_maha(unsigned long long *out) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, g_maha_dbg, sizeof(unsigned long long) * 8 * 160 * 4) == cudaSuccess ? 0 : 1;
+}
+#endif
+extern "C" int tce_tri_inverse(const float *L, int64_t ldb, double *Linv, int64_t B, int n, void *stream) {
+  if (!L || !Linv || B < 0) return TCE_ERR_INVALID_ARGUMENT;
+  PJ_CHECK_N(n);
+  if (B == 0) return TCE_OK;
+  const size_t smem = pj_smem(n, 2);
+  int rc = set_smem(tri_inverse_kernel, smem);
+  if (rc) return rc;
+  tri_inverse_kernel<<<(unsigned)B, 256, smem, (cudaStream_t)stream>>>(L, ldb, Linv, n);
+  TCE_CHECK_LAUNCH("tri_inverse_kernel");
+  return TCE_OK;
+}
+
+extern "C" int tce_gauss_maha_shared(const float *mean, const float *mean_o, const double *Linv, const double *grad_out,
+                                     double *maha, float *grad_mean, int64_t B, int n, void *stream) {
+  if (!mean || !mean_o || !Linv || B < 0 || n < 1 || n > 128 || (grad_out && !grad_mean) || (!grad_mean && !maha))
+    return TCE_ERR_INVALID_ARGUMENT;
+  if (B == 0) return TCE_OK;
+  const int nw = 8;
+  static int dbg_slot = 0;
+  const size_t smem = sizeof(double) * ((size_t)n * (n | 1) + (size_t)nw * 2 * n);
+  int rc = set_smem(maha_shared_kernel, smem);
+  if (rc) return rc;
+  // same L1 / shared-memory split as the single-CTA kernels of the parallel graph branches: an SM only switches
+  // its carve-out when idle, so a CTA placed next to one of those would otherwise wait for it to finish
+  TCE_CUDA(cudaFuncSetAttribute(maha_shared_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                (int)cudaSharedmemCarveoutMaxShared), "maha carve-out");
+  const long long blocks = (B + nw - 1) / nw;
+  maha_shared_kernel<<<(unsigned)(blocks < 148 * 2 ? blocks : 148 * 2), nw * 32, smem, (cudaStream_t)stream>>>(
+      mean, mean_o, Linv, grad_out, maha, grad_mean, B, n, dbg_slot++);
+  TCE_CHECK_LAUNCH("maha_shared_kernel");
   return TCE_OK;
 }
 
@@ -837,19 +1010,19 @@ extern "C" int tce_debug_kl_phase_cycles(long long *out16) {
   return TCE_OK;
 }
 
-extern "C" size_t tce_proj_kl_save_doubles(int64_t B, int n) { return (size_t)B * ((size_t)n * n + n + 4); }
+extern "C" size_t tce_proj_kl_save_doubles(int64_t B, int n) { return (size_t)B * (2 * (size_t)n * n + n + 4); }
 
 extern "C" int tce_proj_kl_cov_fwd(const float *L, const float *L_o, double eps_cov, float *proj_L, double *save,
                                    int32_t *info, int warm_start, int64_t B, int n, void *stream) {
   if (!L || !L_o || !proj_L || !save || B < 0 || !(eps_cov > 0)) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
   if (B == 0) return TCE_OK;
-  const size_t smem = pj_smem(n, 3) + sizeof(double) * LA_JACOBI_SCRATCH;
+  const size_t smem = pj_smem_exclusive(pj_smem(n, 3) + sizeof(double) * LA_JACOBI_SCRATCH, B);
   int rc = set_smem(proj_kl_cov_fwd_kernel, smem);
   if (rc) return rc;
-  double *M = save, *lam = M + (size_t)B * n * n, *sc = lam + (size_t)B * n;
-  proj_kl_cov_fwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, eps_cov, proj_L, M, lam, sc, info, n,
-                                                                                 warm_start);
+  double *M = save, *U = M + (size_t)B * n * n, *lam = U + (size_t)B * n * n, *sc = lam + (size_t)B * n;
+  proj_kl_cov_fwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, eps_cov, proj_L, M, U, lam, sc, info,
+                                                                                 n, warm_start);
   TCE_CHECK_LAUNCH("proj_kl_cov_fwd_kernel");
   return TCE_OK;
 }
@@ -859,11 +1032,11 @@ extern "C" int tce_proj_kl_cov_bwd(const float *L, const float *proj_L, const fl
   if (!L || !proj_L || !grad_out || !save || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
   if (B == 0) return TCE_OK;
-  const size_t smem = pj_smem(n, 4);
+  const size_t smem = pj_smem_exclusive(pj_smem(n, 4), B);
   int rc = set_smem(proj_kl_cov_bwd_kernel, smem);
   if (rc) return rc;
-  const double *M = save, *lam = M + (size_t)B * n * n, *sc = lam + (size_t)B * n;
-  proj_kl_cov_bwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, proj_L, grad_out, M, lam, sc, grad_L, n);
+  const double *M = save, *U = M + (size_t)B * n * n, *lam = U + (size_t)B * n * n, *sc = lam + (size_t)B * n;
+  proj_kl_cov_bwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, proj_L, grad_out, M, U, lam, sc, grad_L, n);
   TCE_CHECK_LAUNCH("proj_kl_cov_bwd_kernel");
   return TCE_OK;
 }
@@ -873,7 +1046,7 @@ extern "C" int tce_proj_frob_cov_fwd(const float *L, const float *L_o, int64_t l
   if (!L || !L_o || !proj_L || !save_sc || B < 0 || !(eps_cov > 0)) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
   if (B == 0) return TCE_OK;
-  const size_t smem = pj_smem(n, 3);
+  const size_t smem = pj_smem_exclusive(pj_smem(n, 3), B);
   int rc = set_smem(proj_frob_cov_fwd_kernel, smem);
   if (rc) return rc;
   proj_frob_cov_fwd_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, ldb_Lo, eps_cov, proj_L, save_sc, info, n);
@@ -887,7 +1060,7 @@ extern "C" int tce_proj_frob_cov_bwd(const float *L, const float *L_o, int64_t l
   if (!L || !L_o || !proj_L || !grad_out || !save_sc || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
   if (B == 0) return TCE_OK;
-  const size_t smem = pj_smem(n, 4);
+  const size_t smem = pj_smem_exclusive(pj_smem(n, 4), B);
   int rc = set_smem(proj_frob_cov_bwd_kernel, smem);
   if (rc) return rc;
   proj_frob_cov_bwd_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, ldb_Lo, eps_cov, proj_L, grad_out, save_sc, grad_L, n);
@@ -900,7 +1073,7 @@ extern "C" int tce_proj_w2_cov_fwd(const float *L, const float *L_o, int64_t ldb
   if (!L || !L_o || !proj_L || !save_sc || B < 0 || !(eps_cov > 0)) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
   if (B == 0) return TCE_OK;
-  const size_t smem = pj_smem(n, 5);
+  const size_t smem = pj_smem_exclusive(pj_smem(n, 5), B);
   int rc = set_smem(proj_w2_cov_kernel, smem);
   if (rc) return rc;
   proj_w2_cov_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, ldb_Lo, eps_cov, scale_prec, nullptr, proj_L, save_sc, n);
@@ -913,7 +1086,7 @@ extern "C" int tce_proj_w2_cov_bwd(const float *L, const float *L_o, int64_t ldb
   if (!L || !L_o || !grad_out || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
   if (B == 0) return TCE_OK;
-  const size_t smem = pj_smem(n, 5);
+  const size_t smem = pj_smem_exclusive(pj_smem(n, 5), B);
   int rc = set_smem(proj_w2_cov_kernel, smem);
   if (rc) return rc;
   proj_w2_cov_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, ldb_Lo, eps_cov, scale_prec, grad_out, grad_L, nullptr, n);
@@ -927,7 +1100,7 @@ extern "C" int tce_cov_distance(int kind, const float *L, const float *L_o, int6
     return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
   if (B == 0) return TCE_OK;
-  const size_t smem = pj_smem(n, 5);
+  const size_t smem = pj_smem_exclusive(pj_smem(n, 5), B);
   int rc = set_smem(cov_distance_kernel, smem);
   if (rc) return rc;
   cov_distance_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(kind, L, L_o, ldb_Lo, scale_prec, grad_val, val, grad_L, n);

@@ -584,6 +584,77 @@ def _gm_backward(ctx, g):
 gauss_maha.register_autograd(_gm_backward, setup_context=_gm_setup)
 
 
+@torch.library.custom_op("tce::tri_inverse", mutates_args=())
+def tri_inverse(L: Tensor) -> Tensor:
+    """L^-1 [Bc, n, n] fp64 of lower-triangular factors (not differentiable: used for detached / old factors)."""
+    L = _chk(L, name="L")
+    Bc, n = L.shape[0], L.shape[-1]
+    out = torch.empty(Bc, n, n, device=L.device, dtype=torch.float64)
+    _lib.call("tce_tri_inverse", _p(L), n * n, _p(out), Bc, n, _stream())
+    return out
+
+
+@tri_inverse.register_fake
+def _(L):
+    return L.new_empty(L.shape, dtype=torch.float64)
+
+
+@torch.library.custom_op("tce::gauss_maha_shared_fwd", mutates_args=())
+def gauss_maha_shared_fwd(mean: Tensor, mean_o: Tensor, Linv: Tensor, with_grad: bool) -> Tuple[Tensor, Tensor]:
+    """-> (maha [B] fp64, d maha / d mean [B, n] fp32 or an empty tensor): the gradient is formed in the forward
+    (two more matrix-vector products per episode) so that the backward is a single elementwise product."""
+    mean, mean_o, Linv = _chk(mean), _chk(mean_o), _chk(Linv, torch.float64, "Linv")
+    B, n = mean.shape
+    out = torch.empty(B, device=mean.device, dtype=torch.float64)
+    dmean = torch.empty_like(mean) if with_grad else mean.new_empty(0)
+    _lib.call("tce_gauss_maha_shared", _p(mean), _p(mean_o), _p(Linv), None, _p(out),
+              _p(dmean) if with_grad else None, B, n, _stream())
+    return out, dmean
+
+
+@gauss_maha_shared_fwd.register_fake
+def _(mean, mean_o, Linv, with_grad):
+    return mean.new_empty(mean.shape[0], dtype=torch.float64), (torch.empty_like(mean) if with_grad else mean.new_empty(0))
+
+
+def _gms_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+    ctx.set_materialize_grads(False)
+
+
+def _gms_backward(ctx, g, g_dmean):
+    (dmean,) = ctx.saved_tensors
+    if g is None or dmean.numel() == 0:
+        return None, None, None, None
+    return g.to(dmean.dtype).unsqueeze(-1) * dmean, None, None, None
+
+
+gauss_maha_shared_fwd.register_autograd(_gms_backward, setup_context=_gms_setup)
+
+
+def gauss_maha_shared(mean: Tensor, mean_o: Tensor, Linv: Tensor) -> Tensor:
+    """``gauss_maha`` for ONE covariance shared by all episodes, given ``Linv = tri_inverse(L_o)[0]`` [n, n];
+    differentiable w.r.t. ``mean``."""
+    need = torch.is_grad_enabled() and mean.requires_grad
+    return gauss_maha_shared_fwd(mean, mean_o, Linv, need)[0]
+
+
+@torch.library.custom_op("tce::gauss_maha_shared_bwd", mutates_args=())
+def gauss_maha_shared_bwd(grad: Tensor, mean: Tensor, mean_o: Tensor, Linv: Tensor) -> Tensor:
+    """Stand-alone gradient kernel (tests, C-ABI coverage): grad[b] * d maha / d mean."""
+    mean, mean_o, Linv = _chk(mean), _chk(mean_o), _chk(Linv, torch.float64, "Linv")
+    B, n = mean.shape
+    g = _chk(grad, torch.float64, "grad")
+    g_mean = torch.empty_like(mean)
+    _lib.call("tce_gauss_maha_shared", _p(mean), _p(mean_o), _p(Linv), _p(g), None, _p(g_mean), B, n, _stream())
+    return g_mean
+
+
+@gauss_maha_shared_bwd.register_fake
+def _(grad, mean, mean_o, Linv):
+    return torch.empty_like(mean)
+
+
 # --------------------------------------------------------------------------------------------------
 # (4a) trust-region projection building blocks (each: hand-written forward + backward kernels)
 # --------------------------------------------------------------------------------------------------

@@ -195,10 +195,10 @@ class TemporalCorrelatedAgent:
         kl_metric = isinstance(self.projection, KLProjectionLayer)
         with torch.no_grad():
             mp = cache.get("new_old_mean") if kl_metric else None
-            parts = list(gaussian_kl_details(self.policy, new, old, mean_part=mp))
+            parts = list(gaussian_kl_details(self.policy, new, old, mean_part=mp, q_is_data=True))
             parts += list(cache["new_proj"]) if "new_proj" in cache else list(
                 gaussian_kl_details(self.policy, new, proj))
-            parts += list(gaussian_kl_details(self.policy, proj, old))
+            parts += list(gaussian_kl_details(self.policy, proj, old, q_is_data=True))
             return torch.stack([x.expand(new[0].shape[0]) for x in parts]).mean(dim=1)    # one reduction
 
     # ---- critic ---------------------------------------------------------------------------------------------
@@ -251,6 +251,9 @@ class TemporalCorrelatedAgent:
         # trust-region loss: small (partly single-CTA) kernels that only need `new` and `proj` -- a parallel
         # branch next to the segment likelihood, forward and (autograd replays the streams) backward
         tr_stream = None
+        # entropy coefficient 0 (every config): the entropy term is a logging value, policy_loss + (-0.0) is
+        # policy_loss -- evaluate it with the other logging values next to the backward
+        defer_entropy = self.entropy_penalty_coef == 0.0 and self.overlap_logging and proj[0].is_cuda
         if self.overlap_logging and proj[0].is_cuda:
             if self._tr_stream is None:
                 self._tr_stream = torch.cuda.Stream(device=proj[0].device)
@@ -258,9 +261,11 @@ class TemporalCorrelatedAgent:
             tr_stream.wait_stream(cur)
             with torch.cuda.stream(tr_stream):
                 tr_loss = self.projection.get_trust_region_loss(self.policy, new, proj, set_variance=self.set_variance)
-                ent_loss, ent_stats = self._entropy_term(proj)
-                for t in (tr_loss, ent_loss, ent_stats["entropy"]):
-                    t.record_stream(cur)
+                tr_loss.record_stream(cur)
+                if not defer_entropy:
+                    ent_loss, ent_stats = self._entropy_term(proj)
+                    ent_loss.record_stream(cur)
+                    ent_stats["entropy"].record_stream(cur)
         if self.fused_surrogate and hasattr(self.policy, "segment_surrogate"):
             surrogate, ratio, _ = self.policy.segment_surrogate(
                 dataset["step_actions"], proj[0], proj[1], times, dataset["segment_init_time"],
@@ -279,7 +284,7 @@ class TemporalCorrelatedAgent:
             tr_loss = self.projection.get_trust_region_loss(self.policy, new, proj, set_variance=self.set_variance)
         else:
             torch.cuda.current_stream().wait_stream(tr_stream)
-        policy_loss = surrogate + ent_loss + tr_loss
+        policy_loss = surrogate + tr_loss if defer_entropy else surrogate + ent_loss + tr_loss
         # logging-only KL decomposition: a parallel branch (side stream) next to backward + Adam
         main, side = None, None
         if self.overlap_logging and policy_loss.is_cuda:
@@ -291,6 +296,10 @@ class TemporalCorrelatedAgent:
             with torch.cuda.stream(side):
                 kl = self.kl_old_new_proj(new, old, proj)
                 kl.record_stream(main)
+                if defer_entropy:
+                    ent_loss, ent_stats = self._entropy_term(proj)
+                    ent_loss.record_stream(main)
+                    ent_stats["entropy"].record_stream(main)
         else:
             kl = self.kl_old_new_proj(new, old, proj)
         self.policy_optimizer.zero_grad(set_to_none=False)

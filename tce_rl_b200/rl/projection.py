@@ -41,6 +41,38 @@ def _shared(policy, L):
     return not policy.contextual_std and L.dim() == 3 and L.shape[0] > 1
 
 
+_HELPER_STREAMS = {}
+
+
+def _helper_stream(device):
+    key = str(device)
+    if key not in _HELPER_STREAMS:
+        _HELPER_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _HELPER_STREAMS[key]
+
+
+_LINV_CACHE = []          # [(L tensor, version, Linv)]: inverse factors of long-lived (old-policy) covariances
+
+
+def _maha(policy, mean, mean_o, L_o, cache=False):
+    """|L_o^-1 (mean - mean_o)|^2 [B] fp64.  One shared covariance (non-contextual policy): invert the factor once
+    (``cache=True``: keep the inverse while the SAME tensor object is passed again, i.e. for the old policy's
+    factor over the epochs of one update) and use matrix-vector products per episode."""
+    if not (_shared(policy, L_o) and L_o.is_cuda):
+        return ops.gauss_maha(mean, mean_o, L_o)
+    Linv = None
+    if cache:
+        for ref, version, inv in _LINV_CACHE:
+            if ref is L_o and version == L_o._version:
+                Linv = inv
+    if Linv is None:
+        Linv = ops.tri_inverse(_first(L_o).detach().contiguous())[0]
+        if cache and not torch.cuda.is_current_stream_capturing():
+            del _LINV_CACHE[:-1]                       # keep at most two entries
+            _LINV_CACHE.append((L_o, L_o._version, Linv))
+    return ops.gauss_maha_shared(mean, mean_o, Linv)
+
+
 def _cov_stats(policy, L, L_o):
     """gauss_stats on the covariance factors only (zero mean difference), broadcast when shared."""
     B = L.shape[0]
@@ -51,15 +83,27 @@ def _cov_stats(policy, L, L_o):
     return st.expand(B, -1) if st.shape[0] != B else st
 
 
-def gaussian_kl_details(policy, p, q, mean_part=None):
+def gaussian_kl_details(policy, p, q, mean_part=None, q_is_data=False):
     """(mean, cov, shape, volume) parts of KL(p || q), each [B] fp64, cov = shape + volume
     (gaussian_kl_details of the fork, used for logging at temporal_correlated_agent.py:641-686).
-    ``mean_part`` may carry an already computed 1/2 maha (avoids a second batch-sized launch)."""
+    ``mean_part`` may carry an already computed 1/2 maha (avoids a second batch-sized launch); ``q_is_data``:
+    q is the old policy stored with the dataset (its inverse factor is kept over the epochs, see ``_maha``)."""
+    helper = None
+    if mean_part is None and p[0].is_cuda and _shared(policy, q[1]):
+        # shared covariance: the mean part (factor inverse + batch kernel) and the covariance part (one
+        # latency-bound CTA) are independent chains -- fork the first onto a helper stream
+        cur, helper = torch.cuda.current_stream(), _helper_stream(p[0].device)
+        helper.wait_stream(cur)
+        with torch.cuda.stream(helper):
+            mean_part = 0.5 * _maha(policy, p[0], q[0], q[1], cache=q_is_data)
+            mean_part.record_stream(cur)
     st = _cov_stats(policy, p[1], q[1])
     k = p[0].shape[-1]
     shape, volume = 0.5 * (st[:, 1] - k), 0.5 * (st[:, 3] - st[:, 2])
+    if helper is not None:
+        torch.cuda.current_stream().wait_stream(helper)
     if mean_part is None:
-        mean_part = 0.5 * ops.gauss_maha(p[0], q[0], q[1])
+        mean_part = 0.5 * _maha(policy, p[0], q[0], q[1], cache=q_is_data)
     return mean_part, shape + volume, shape, volume
 
 
@@ -190,17 +234,19 @@ class BaseProjectionLayer:
             if beta is not None:
                 proj_L1 = ops.proj_entropy(proj_L1.contiguous(), beta, self.entropy_eq)[0]
             proj_L1.record_stream(main)
-        return proj_L1
+            # broadcast here: the backward of the expand (a [B, n, n] -> [n, n] reduction) then runs on the side
+            # stream in front of the covariance backward instead of delaying the mean chain on the main stream
+            return _expand_first(proj_L1, L.shape[0])
 
     def _call_overlapped(self, policy, p, q, step, cov_projected=None):
         mean, L = p
         old_mean, old_L = q
-        proj_L1 = cov_projected if cov_projected is not None else self.start_cov_projection(policy, L, old_L, step)
+        proj_L = cov_projected if cov_projected is not None else self.start_cov_projection(policy, L, old_L, step)
         mean_part = self._mean_part(policy, p, q)
         self.cache = {"new_old_mean": mean_part.detach()}
         proj_mean = ops.proj_mean(mean, old_mean, mean_part, self.mean_bound)
         torch.cuda.current_stream().wait_stream(self._side_stream(mean.device))
-        return proj_mean, _expand_first(proj_L1, mean.shape[0])
+        return proj_mean, proj_L
 
     def trust_region_value(self, policy, p, q):
         return gaussian_kl(policy, p, q)
@@ -243,7 +289,7 @@ class KLProjectionLayer(BaseProjectionLayer):
         self._kl_state = None
 
     def _mean_part(self, policy, p, q):
-        return 0.5 * ops.gauss_maha(p[0], q[0], q[1])
+        return 0.5 * _maha(policy, p[0], q[0], q[1], cache=True)          # q: the old policy (data of the update)
 
     def _cov_projection(self, policy, L, L_old):
         if policy.is_diag:

@@ -229,3 +229,29 @@ def test_kl_projection_warm_start_is_exact():
     Lg2 = L.clone().requires_grad_(True)
     (ops.proj_kl_cov(Lg2, Lo, 5e-4, ops.kl_state(Bc, n, DEV), False)[0] * W).sum().backward()
     assert (Lg.grad - Lg2.grad).abs().max().item() <= 1e-4 * Lg2.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("name", ["box", "table_tennis"])
+def test_shared_covariance_maha_matches_per_episode_kernel(name):
+    """tce_tri_inverse + tce_gauss_maha_shared (one L_o for all episodes) == tce_gauss_maha on B copies == fp64
+    torch, values and gradient w.r.t. the mean (tolerance 1e-9 relative: everything is fp64 on fp32 inputs)."""
+    inp = synthetic_inputs(name, 37, dtype=torch.float32)
+    mean, mean_o = inp["mean"].to(DEV).requires_grad_(True), inp["mean_old"].to(DEV)
+    L1 = inp["L_old"][:1].to(DEV)
+    n = L1.shape[-1]
+    Linv = ops.tri_inverse(L1)[0]
+    ref_inv = torch.linalg.inv(L1[0].double())
+    assert (Linv - ref_inv).abs().max() <= 1e-10 * ref_inv.abs().max()
+    assert torch.equal(Linv, torch.tril(Linv))
+    w = torch.linspace(0.5, 1.5, mean.shape[0], device=DEV, dtype=torch.float64)
+    got = ops.gauss_maha_shared(mean, mean_o, Linv)
+    (g_got,) = torch.autograd.grad((got * w).sum(), mean)
+    ref = ops.gauss_maha(mean, mean_o, L1.expand(mean.shape[0], n, n).contiguous())
+    (g_ref,) = torch.autograd.grad((ref * w).sum(), mean)
+    z = torch.linalg.solve_triangular(L1[0].double(), (mean.detach().double() - mean_o.double()).T, upper=False)
+    exact = (z * z).sum(0)
+    assert (got - exact).abs().max() <= 1e-9 * exact.abs().max()
+    assert (ref - exact).abs().max() <= 1e-9 * exact.abs().max()
+    assert (g_got - g_ref).abs().max() <= 2e-6 * g_ref.abs().max()     # fp32 outputs
+    g_kernel = ops.gauss_maha_shared_bwd(w, mean.detach(), mean_o, Linv)  # stand-alone gradient entry point
+    assert (g_kernel - g_ref).abs().max() <= 2e-6 * g_ref.abs().max()
