@@ -134,6 +134,34 @@ class TemporalCorrelatedAgent:
         return m
 
     # ---- dataset processing -----------------------------------------------------------------------------
+    def dataset_to_device(self, host_dataset, out=None, non_blocking=True):
+        """Move a (pinned) host dataset in the reference's layout (sampler output / ``process_dataset``) to the
+        device.  ``out``: a dict returned by an earlier call -- its buffers are overwritten in place (static
+        addresses: a captured epoch graph can be replayed on the new data).
+
+        A non-contextual policy stores ONE old covariance factor B times in ``segment_params_L`` [B, n, n]
+        (black_box_policy.py:50-53 repeats the parameter): only the first is transferred and the device tensor
+        is a stride-0 broadcast of it -- 16 KB instead of 16 MB per 1024 box-pushing episodes."""
+        dev = self.device
+        shared_L = not self.policy.contextual_cov
+        res = out if out is not None else {}
+        for k, v in host_dataset.items():
+            if not torch.is_tensor(v):
+                res[k] = v
+                continue
+            if k == "segment_params_L" and shared_L and v.dim() == 3:
+                first = getattr(res.get(k), "_tce_first", None)
+                if first is None:
+                    first = torch.empty((1,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
+                    res[k] = first.expand(v.shape[0], -1, -1)
+                    res[k]._tce_first = first
+                first.copy_(v[:1], non_blocking=non_blocking)
+            elif k in res and torch.is_tensor(res[k]) and res[k].shape == v.shape:
+                res[k].copy_(v, non_blocking=non_blocking)
+            else:
+                res[k] = v.to(dev, non_blocking=non_blocking)
+        return res
+
     def process_dataset(self, dataset):
         adv, ret = self.get_advantage_return(dataset["step_rewards"], dataset["step_values"], dataset["step_dones"],
                                              dataset["step_time_limit_dones"])
@@ -195,10 +223,11 @@ class TemporalCorrelatedAgent:
         kl_metric = isinstance(self.projection, KLProjectionLayer)
         with torch.no_grad():
             mp = cache.get("new_old_mean") if kl_metric else None
-            parts = list(gaussian_kl_details(self.policy, new, old, mean_part=mp, q_is_data=True))
+            linv = getattr(self.projection, "_old_linv", None) if kl_metric else None
+            parts = list(gaussian_kl_details(self.policy, new, old, mean_part=mp, q_linv=linv))
             parts += list(cache["new_proj"]) if "new_proj" in cache else list(
                 gaussian_kl_details(self.policy, new, proj))
-            parts += list(gaussian_kl_details(self.policy, proj, old, q_is_data=True))
+            parts += list(gaussian_kl_details(self.policy, proj, old, q_linv=linv))
             return torch.stack([x.expand(new[0].shape[0]) for x in parts]).mean(dim=1)    # one reduction
 
     # ---- critic ---------------------------------------------------------------------------------------------

@@ -51,26 +51,18 @@ def _helper_stream(device):
     return _HELPER_STREAMS[key]
 
 
-_LINV_CACHE = []          # [(L tensor, version, Linv)]: inverse factors of long-lived (old-policy) covariances
-
-
-def _maha(policy, mean, mean_o, L_o, cache=False):
+def _maha(policy, mean, mean_o, L_o, linv=None):
     """|L_o^-1 (mean - mean_o)|^2 [B] fp64.  One shared covariance (non-contextual policy): invert the factor once
-    (``cache=True``: keep the inverse while the SAME tensor object is passed again, i.e. for the old policy's
-    factor over the epochs of one update) and use matrix-vector products per episode."""
+    (``linv``: an inverse already formed in this epoch, see ``shared_inverse``) and use matrix-vector products
+    per episode instead of two triangular solves."""
     if not (_shared(policy, L_o) and L_o.is_cuda):
         return ops.gauss_maha(mean, mean_o, L_o)
-    Linv = None
-    if cache:
-        for ref, version, inv in _LINV_CACHE:
-            if ref is L_o and version == L_o._version:
-                Linv = inv
-    if Linv is None:
-        Linv = ops.tri_inverse(_first(L_o).detach().contiguous())[0]
-        if cache and not torch.cuda.is_current_stream_capturing():
-            del _LINV_CACHE[:-1]                       # keep at most two entries
-            _LINV_CACHE.append((L_o, L_o._version, Linv))
-    return ops.gauss_maha_shared(mean, mean_o, Linv)
+    return ops.gauss_maha_shared(mean, mean_o, linv if linv is not None else shared_inverse(L_o))
+
+
+def shared_inverse(L_o):
+    """fp64 inverse [n, n] of the ONE factor behind a broadcast covariance (not differentiable)."""
+    return ops.tri_inverse(_first(L_o).detach().contiguous())[0]
 
 
 def _cov_stats(policy, L, L_o):
@@ -83,11 +75,11 @@ def _cov_stats(policy, L, L_o):
     return st.expand(B, -1) if st.shape[0] != B else st
 
 
-def gaussian_kl_details(policy, p, q, mean_part=None, q_is_data=False):
+def gaussian_kl_details(policy, p, q, mean_part=None, q_linv=None):
     """(mean, cov, shape, volume) parts of KL(p || q), each [B] fp64, cov = shape + volume
     (gaussian_kl_details of the fork, used for logging at temporal_correlated_agent.py:641-686).
-    ``mean_part`` may carry an already computed 1/2 maha (avoids a second batch-sized launch); ``q_is_data``:
-    q is the old policy stored with the dataset (its inverse factor is kept over the epochs, see ``_maha``)."""
+    ``mean_part`` may carry an already computed 1/2 maha (avoids a second batch-sized launch), ``q_linv`` the
+    inverse factor of a shared q covariance formed earlier in the epoch (``shared_inverse``)."""
     helper = None
     if mean_part is None and p[0].is_cuda and _shared(policy, q[1]):
         # shared covariance: the mean part (factor inverse + batch kernel) and the covariance part (one
@@ -95,7 +87,7 @@ def gaussian_kl_details(policy, p, q, mean_part=None, q_is_data=False):
         cur, helper = torch.cuda.current_stream(), _helper_stream(p[0].device)
         helper.wait_stream(cur)
         with torch.cuda.stream(helper):
-            mean_part = 0.5 * _maha(policy, p[0], q[0], q[1], cache=q_is_data)
+            mean_part = 0.5 * _maha(policy, p[0], q[0], q[1], linv=q_linv)
             mean_part.record_stream(cur)
     st = _cov_stats(policy, p[1], q[1])
     k = p[0].shape[-1]
@@ -103,7 +95,7 @@ def gaussian_kl_details(policy, p, q, mean_part=None, q_is_data=False):
     if helper is not None:
         torch.cuda.current_stream().wait_stream(helper)
     if mean_part is None:
-        mean_part = 0.5 * _maha(policy, p[0], q[0], q[1], cache=q_is_data)
+        mean_part = 0.5 * _maha(policy, p[0], q[0], q[1], linv=q_linv)
     return mean_part, shape + volume, shape, volume
 
 
@@ -289,7 +281,9 @@ class KLProjectionLayer(BaseProjectionLayer):
         self._kl_state = None
 
     def _mean_part(self, policy, p, q):
-        return 0.5 * _maha(policy, p[0], q[0], q[1], cache=True)          # q: the old policy (data of the update)
+        linv = shared_inverse(q[1]) if (_shared(policy, q[1]) and q[1].is_cuda) else None
+        self._old_linv = linv                                   # reused by the logging branch of the same epoch
+        return 0.5 * _maha(policy, p[0], q[0], q[1], linv=linv)
 
     def _cov_projection(self, policy, L, L_old):
         if policy.is_diag:
