@@ -155,8 +155,7 @@ def build_gpu_workload(device, rank, world):
     agent.host_dataset = host_dataset
     projection.initial_entropy = agent._global_mean(policy.entropy([mean_old, L_old]))
     agent.num_iterations = 100
-    for p in policy.parameters:
-        p.grad = torch.zeros_like(p)
+    agent.ensure_flat_grads(agent.policy_net_params)
     return agent, dataset, times, pairs
 
 

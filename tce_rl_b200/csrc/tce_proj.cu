@@ -14,7 +14,7 @@ __device__ long long g_kl_prof[16];   // SM-clock stamps of the last KL forward 
 namespace {
 
 constexpr int PJ_THREADS = 512;
-constexpr int KL_THREADS = 1024;  // one warp per Jacobi column pair (n <= 64 -> 32 pairs)
+constexpr int KL_THREADS = 512;   // 128 registers per thread: 4x4 fp64 GEMM tiles and the register-resident Jacobi
 constexpr double LOG_2PI = 1.8378770664093453;
 
 __device__ inline int pad_even(int n) { return (n + 1) & ~1; }
@@ -435,8 +435,8 @@ __device__ inline double kl_solve_eta(const double *lam, int n, double eps, doub
     __syncthreads();
     if (ok) return eta;
   }
-  // round 1: geometric grid eta_w = 2^(w - 10), w = 0..nwarp-1  (1e-3 .. 2e6 for 32 warps)
-  double lo = 0.0, hi = ldexp(1.0, nwarp - 10);
+  // round 1: geometric grid eta_w = 2^(w - 10), w = 0..31  (1e-3 .. 2e6)
+  double lo = 0.0, hi = ldexp(1.0, 32 - 10);
   for (int round = 0; round < 3; ++round) {
     for (int w = warp; w < 32; w += nwarp) {
       const double e = round == 0 ? ldexp(1.0, w - 10) : lo + (hi - lo) * (double)(w + 1) / 33.0;

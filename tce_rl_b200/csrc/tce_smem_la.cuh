@@ -13,39 +13,53 @@ struct Mat {            // strided view; a transpose is a stride swap
 
 enum { TRI_FULL = 0, TRI_LOWER = 1, TRI_UPPER = 2 };
 
-// C = beta * C + alpha * A B (m x n x k) with 2x2 register tiles (halves the shared-memory traffic per DFMA).
-// a_tri / b_tri describe the structure of A and B and only clip the k range of a tile: the unused triangle
-// of a triangular operand MUST hold zeros.  c_tri = TRI_LOWER / TRI_UPPER: tiles entirely on the other side
-// of the diagonal are skipped; inside diagonal tiles both triangles are written (callers read one only).
+// C = beta * C + alpha * A B (m x n x k, all <= 64) with 4x4 register tiles: thread (I, J) of the first
+// 16 * ceil(m/4) threads owns rows 4I..4I+3 and the INTERLEAVED columns J, J+16, J+32, J+48, so that per k step
+// a warp (two I, sixteen J) reads A as four broadcasts and B as four conflict-free rows: 8 shared-memory
+// wavefronts per 16 DFMA per lane (the 2x2 version needed 6 per 4 and was shared-memory bound at ~13k cycles
+// for 64^3; this one is bound by the fp64 pipe at ~4-5k).  Needs >= 48 registers of tile state: callers run
+// with <= 512 threads per CTA.
+// a_tri / b_tri describe the structure of A and B and only clip the k range: the unused triangle of a
+// triangular operand MUST hold zeros.  c_tri is a hint that only that triangle of C is read afterwards (the
+// whole of C may be written).
 __device__ inline void la_gemm(Mat C, Mat A, Mat B, int m, int n, int k, int a_tri, int b_tri, int c_tri,
                                double alpha, double beta) {
-  const int tm = (m + 1) >> 1, tn = (n + 1) >> 1;
-  for (int t = threadIdx.x; t < tm * tn; t += blockDim.x) {
-    const int I = t / tn, J = t - I * tn;
-    const int i0 = 2 * I, j0 = 2 * J;
-    const int i1 = i0 + 1 < m ? i0 + 1 : i0, j1 = j0 + 1 < n ? j0 + 1 : j0;     // clamped (odd sizes)
-    if ((c_tri == TRI_LOWER && j0 > i1) || (c_tri == TRI_UPPER && j1 < i0)) continue;
+  (void)c_tri;
+  const int TI = (m + 3) >> 2;
+  for (int t = threadIdx.x; t < TI * 16; t += blockDim.x) {
+    const int I = t >> 4, J = t & 15, i0 = 4 * I;
     int lo = 0, hi = k;
-    if (a_tri == TRI_LOWER) hi = min(hi, i1 + 1);
+    if (a_tri == TRI_LOWER) hi = min(hi, i0 + 4);
     if (a_tri == TRI_UPPER) lo = max(lo, i0);
-    if (b_tri == TRI_LOWER) lo = max(lo, j0);
-    if (b_tri == TRI_UPPER) hi = min(hi, j1 + 1);
-    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+    if (b_tri == TRI_LOWER) lo = max(lo, J);
+    const double *ap[4], *bp[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) ap[r] = &A(min(i0 + r, m - 1), 0);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bp[c] = &B(0, min(J + 16 * c, n - 1));
+    double acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+#pragma unroll 2
     for (int q = lo; q < hi; ++q) {
-      const double a0 = A(i0, q), a1 = A(i1, q), b0 = B(q, j0), b1 = B(q, j1);
-      c00 = fma(a0, b0, c00); c01 = fma(a0, b1, c01);
-      c10 = fma(a1, b0, c10); c11 = fma(a1, b1, c11);
+      double a[4], b[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = ap[r][q * A.cs];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) b[c] = bp[c][q * B.rs];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
     }
-    if (beta == 0.0) {
-      C(i0, j0) = alpha * c00;
-      if (j1 != j0) C(i0, j1) = alpha * c01;
-      if (i1 != i0) { C(i1, j0) = alpha * c10; if (j1 != j0) C(i1, j1) = alpha * c11; }
-    } else {
-      C(i0, j0) = fma(beta, C(i0, j0), alpha * c00);
-      if (j1 != j0) C(i0, j1) = fma(beta, C(i0, j1), alpha * c01);
-      if (i1 != i0) {
-        C(i1, j0) = fma(beta, C(i1, j0), alpha * c10);
-        if (j1 != j0) C(i1, j1) = fma(beta, C(i1, j1), alpha * c11);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = i0 + r, jj = J + 16 * c;
+        if (i < m && jj < n) C(i, jj) = beta == 0.0 ? alpha * acc[r][c] : fma(beta, C(i, jj), alpha * acc[r][c]);
       }
     }
   }

@@ -83,6 +83,7 @@ class TemporalCorrelatedAgent:
         self.overlap_logging = bool(kwargs.get("overlap_logging", True))
         self._log_stream = None
         self._tr_stream = None
+        self._flat_grad = None
         self.process_group = kwargs.get("process_group", None)      # torch.distributed group (None = single GPU)
         self.policy_net_params = policy.parameters
         self.critic_net_params = critic.parameters if critic is not None else []
@@ -116,6 +117,14 @@ class TemporalCorrelatedAgent:
         """One flat all-reduce(SUM) of the gradients; losses are local means, so divide by the world size."""
         if not self._distributed:
             return
+        flat = self._flat_grad
+        if flat is not None and self._flat_grad_ok(params):        # gradients already live in one buffer
+            if dist.get_backend(self._group()) == "nccl":
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self._group())
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self._group())
+                flat.div_(self.world_size)
+            return
         grads = [p.grad for p in params if p.grad is not None]
         flat = torch.cat([g.reshape(-1) for g in grads])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self._group())
@@ -124,6 +133,30 @@ class TemporalCorrelatedAgent:
         for g in grads:
             g.copy_(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
+
+    def _flat_grad_ok(self, params):
+        off, base = 0, self._flat_grad.data_ptr()
+        for p in params:
+            if p.grad is None or p.grad.data_ptr() != base + off * self._flat_grad.element_size():
+                return False
+            off += p.numel()
+        return off == self._flat_grad.numel()
+
+    def ensure_flat_grads(self, params):
+        """Give every parameter a ``.grad`` that is a view into ONE flat buffer (autograd accumulates in place):
+        the data-parallel all-reduce then needs no gather / scatter kernels around it."""
+        params = list(params)
+        if self._flat_grad is not None and self._flat_grad_ok(params):
+            return
+        flat = torch.zeros(sum(p.numel() for p in params), dtype=params[0].dtype, device=params[0].device)
+        off = 0
+        for p in params:
+            view = flat[off:off + p.numel()].view_as(p)
+            if p.grad is not None:
+                view.copy_(p.grad)
+            p.grad = view
+            off += p.numel()
+        self._flat_grad = flat
 
     def _global_mean(self, x):
         """Mean over the global batch (equal shard sizes)."""
@@ -255,6 +288,11 @@ class TemporalCorrelatedAgent:
 
     def _grad_norm_clip(self, params):
         """util_numerical.py:244-275 without the per-parameter .item(): norm on the device."""
+        if self._flat_grad is not None and self._flat_grad_ok(params):     # one reduction over the flat buffer
+            norm = torch.linalg.vector_norm(self._flat_grad)
+            if self.clip_grad_norm > 0:                                     # clip_grad_norm_: coef = max / (norm + 1e-6)
+                self._flat_grad.mul_(torch.clamp(self.clip_grad_norm / (norm + 1e-6), max=1.0))
+            return norm
         norm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm([p.grad for p in params])))
         if self.clip_grad_norm > 0:
             torch.nn.utils.clip_grad_norm_(params, self.clip_grad_norm)
@@ -350,9 +388,7 @@ class TemporalCorrelatedAgent:
         old = (dataset["segment_params_mean"], dataset["segment_params_L"])
         if self.projection.initial_entropy is None:
             self.projection.initial_entropy = self._global_mean(self.policy.entropy(list(old)))
-        for p in self.policy_net_params:
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
+        self.ensure_flat_grads(self.policy_net_params)
         rows = []
         if self.use_cuda_graph and not self._distributed:
             metrics = self._graphed_epochs(dataset, times, pred_pairs, rows)
