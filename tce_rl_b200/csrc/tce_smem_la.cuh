@@ -13,6 +13,18 @@ struct Mat {            // strided view; a transpose is a stride swap
 
 enum { TRI_FULL = 0, TRI_LOWER = 1, TRI_UPPER = 2 };
 
+__device__ __forceinline__ float la_rsqrt_approx(float x) {   // bare MUFU: no denormal fix-up code around it
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float la_rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+
 // C = beta * C + alpha * A B (m x n x k, all <= 64) with 4x4 register tiles: thread (I, J) of the first
 // 16 * ceil(m/4) threads owns rows 4I..4I+3 and the INTERLEAVED columns J, J+16, J+32, J+48, so that per k step
 // a warp (two I, sixteen J) reads A as four broadcasts and B as four conflict-free rows: 8 shared-memory
@@ -191,58 +203,60 @@ __device__ inline void la_trsm_lower_t(Mat L, const double *dinv, Mat X, int n, 
   }
 }
 
-// in-place blocked Cholesky of the lower triangle of A (upper part ignored); *bad (shared int, pre-set to 0)
-// receives the 1-based index of the first non-positive pivot.  Per block column: diagonal block by one warp,
-// panel rows by one thread each, rank-LA_NB trailing update by everybody: 3 barriers per 8 columns.
+// in-place blocked Cholesky of the lower triangle of A (n <= 64; the upper triangle is scratch on exit); *bad
+// (shared int, pre-set to 0) receives the 1-based index of the first non-positive pivot.  Per block of 8
+// columns: warp 0 factors the whole panel (rows r0..n-1) in REGISTERS -- lane l holds rows l and l + 32, pivots
+// and multipliers travel by shuffle, one rsqrt per column -- then everybody applies the rank-8 update to the
+// trailing matrix with the 4x4-tile GEMM.  Two barriers per 8 columns, ~2.3k cycles per block.
 __device__ inline void la_chol(Mat A, int n, int *bad) {
-  const int lane = threadIdx.x & 31;
-  __shared__ double s_invd[LA_NB];                 // 1 / L_jj of the current diagonal block
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int r0 = 0; r0 < n; r0 += LA_NB) {
     const int nb = min(LA_NB, n - r0);
-    if (threadIdx.x < 32) {                       // factor the diagonal block: lane i owns row r0 + i
-      for (int j = 0; j < nb; ++j) {
-        const double djj = A(r0 + j, r0 + j);
-        if (lane == 0 && !(djj > 0.0) && *bad == 0) *bad = r0 + j + 1;
-        const double inv = rsqrt(djj);           // one special-function op instead of sqrt + divide
-        __syncwarp();
-        if (lane == j) { A(r0 + j, r0 + j) = djj * inv; s_invd[j] = inv; }
-        if (lane > j && lane < nb) A(r0 + lane, r0 + j) *= inv;
-        __syncwarp();
-        if (lane > j && lane < nb) {
-          const double lij = A(r0 + lane, r0 + j);
-          for (int q = j + 1; q <= lane; ++q) A(r0 + lane, r0 + q) = fma(-lij, A(r0 + q, r0 + j), A(r0 + lane, r0 + q));
+    if (warp == 0) {
+      double p[2][LA_NB];
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int c = 0; c < LA_NB; ++c) {
+          const int row = lane + 32 * s;
+          p[s][c] = (row >= r0 && row < n && c < nb) ? A(row, r0 + c) : 0.0;
         }
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    for (int i = r0 + nb + threadIdx.x; i < n; i += blockDim.x) {      // panel: row i of L21 = A21 L11^-T
-      double x[LA_NB];
 #pragma unroll
       for (int j = 0; j < LA_NB; ++j) {
-        if (j < nb) {
-          double v = A(i, r0 + j);
+        if (j < nb) {                                               // uniform
+          const int col = r0 + j;
+          const double djj = __shfl_sync(0xffffffffu, col >= 32 ? p[1][j] : p[0][j], col & 31);
+          if (lane == 0 && !(djj > 0.0) && *bad == 0) *bad = col + 1;
+          // 1/sqrt: fp32 MUFU seed + two fp64 Newton steps (1e-7 -> 1e-14 -> rounding); the library rsqrt(double)
+          // is a ~40-instruction subroutine on the critical path of every column
+          double inv = (double)la_rsqrt_approx((float)djj);
+          inv = inv * fma(-0.5 * djj, inv * inv, 1.5);
+          inv = inv * fma(-0.5 * djj, inv * inv, 1.5);
 #pragma unroll
-          for (int q = 0; q < j; ++q) v = fma(-x[q], A(r0 + j, r0 + q), v);
-          x[j] = v * s_invd[j];
-          A(i, r0 + j) = x[j];
-        } else {
-          x[j] = 0.0;
+          for (int s = 0; s < 2; ++s) p[s][j] = (lane + 32 * s == col) ? djj * inv : p[s][j] * inv;
+#pragma unroll
+          for (int c = j + 1; c < LA_NB; ++c) {
+            const int rc = r0 + c;                                  // L(rc, col) sits in lane rc % 32
+            const double lcj = __shfl_sync(0xffffffffu, rc >= 32 ? p[1][j] : p[0][j], rc & 31);
+            p[0][c] = fma(-p[0][j], lcj, p[0][c]);
+            p[1][c] = fma(-p[1][j], lcj, p[1][c]);
+          }
         }
       }
-    }
-    __syncthreads();
-    const int t0 = r0 + nb, mrem = n - t0;                               // trailing update (lower part)
-    for (int e = threadIdx.x; e < mrem * mrem; e += blockDim.x) {
-      const int ii = e / mrem, qq = e - ii * mrem;
-      if (qq > ii) continue;
-      const int i = t0 + ii, q = t0 + qq;
-      double v = A(i, q);
 #pragma unroll
-      for (int j = 0; j < LA_NB; ++j) if (j < nb) v = fma(-A(i, r0 + j), A(q, r0 + j), v);
-      A(i, q) = v;
+      for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int c = 0; c < LA_NB; ++c) {
+          const int row = lane + 32 * s;
+          if (row >= r0 && row < n && c < nb) A(row, r0 + c) = p[s][c];
+        }
     }
     __syncthreads();
+    const int t0 = r0 + nb, mrem = n - t0;
+    if (mrem > 0) {                                                 // A22 -= L21 L21^T (barrier inside)
+      const Mat L21{&A(t0, r0), A.rs, A.cs};
+      la_gemm(Mat{&A(t0, t0), A.rs, A.cs}, L21, L21.T(), mrem, mrem, nb, TRI_FULL, TRI_FULL, TRI_LOWER, -1.0, 1.0);
+    }
   }
 }
 
@@ -269,17 +283,6 @@ __device__ unsigned int g_jac_prof[8];
 #else
 #define JP(i)
 #endif
-
-__device__ __forceinline__ float la_rsqrt_approx(float x) {   // bare MUFU: no denormal fix-up code around it
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float la_rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 __device__ __forceinline__ void la_named_barrier(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
