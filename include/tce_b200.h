@@ -149,8 +149,8 @@ int tce_proj_entropy_bwd(const float *L, const double *beta, int64_t ldb_beta, i
                          const float *grad_out, float *grad_L, int64_t B, int n, void *stream);
 /* KL covariance projection: min KL(N(.,S)||N(.,S~)) s.t. KL_cov(S||S_old) <= eps_cov, solved exactly on
  * the generalised eigenvalues (CTA-per-matrix one-sided Jacobi + Newton for eta); proj_L = chol(S_proj).
- * `save` (tce_proj_kl_save_doubles(B, n) doubles) carries M = L_old Q, U = L~^-1 M, lambda, eta to the
- * backward (implicit differentiation of eta*).  warm_start != 0: `save` still holds the state of a previous call;
+ * `save` (tce_proj_kl_save_doubles(B, n) doubles) carries M = L_old Q, U = L~^-1 M, L~^-1, lambda, eta to
+ * the backward (implicit differentiation of eta*).  warm_start != 0: `save` still holds the state of a previous call;
  * it is used to start the eigen-solve when it was produced with the same L_o (checked by a fingerprint),
  * e.g. across the epochs of one update_policy.  info [B]: non positive pivot of the final Cholesky.     */
 size_t tce_proj_kl_save_doubles(int64_t B, int n);

@@ -53,7 +53,8 @@ def swap_proj(typ, **kw):
 
 
 measure("baseline", lambda a: None)
-measure("no side streams", lambda a: (setattr(a.projection, "overlap", False), setattr(a, "overlap_logging", False)))
+measure("no side streams", lambda a: (setattr(a.projection, "overlap", False), setattr(a, "overlap_logging", False),
+                                      setattr(a.policy.mean_net, "side_wgrad", False)))
 measure("no KL warm start", lambda a: setattr(a.projection, "warm_start", False))
 measure("unfused surrogate", lambda a: setattr(a, "fused_surrogate", False))
 measure("BaseProjectionLayer (no cov projection)", swap_proj("BaseProjectionLayer"))

@@ -228,13 +228,7 @@ tri_inverse_kernel(const float *__restrict__ L, long long ldb, double *__restric
   double *dinv = sd + 2 * MS;
   const long long b = blockIdx.x;
   load_lower_d(A, L + b * ldb, n, m);
-  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
-    const int i = e / m, j = e - i * m;
-    X(i, j) = (i == j && i < n) ? 1.0 : 0.0;
-  }
-  __syncthreads();
-  la_diag_block_inverses(A, dinv, n);
-  la_trsm_lower(A, dinv, X, n, n, true);
+  la_tri_inverse(A, X, dinv, n);
   double *out = Linv + (size_t)b * n * n;
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     const int i = e / n, j = e - i * n;
@@ -479,18 +473,18 @@ __device__ inline double kl_solve_eta(const double *lam, int n, double eps, doub
 // Forward.  With W = Lt^-1 Lo, one-sided Jacobi rotates the columns of W into U~ = W Q (orthogonal columns,
 // |U~_j|^2 = lam_j = eigenvalues of W^T W); then M := Lo Q = Lt U~ and
 //   Sigma_proj = Lo Q diag((1+eta)/(lam+eta)) Q^T Lo^T = M D M^T ,   proj_L = chol(Sigma_proj).
-// `save` = { M [n,n], U~ [n,n], lam [n], {eta, active, kl0, fingerprint(Lo)} } per matrix: state for the backward AND a
+// `save` = { M, U~, Lt^-1 [n,n each], lam [n], {eta, active, kl0, fingerprint(Lo)} } per matrix: state for the backward AND a
 // warm start for the next call with the same Lo (the 50 epochs of one update_policy): starting Jacobi from
 // Lt^-1 M_prev = W Q_prev is an orthogonal change of basis of the same problem, so 2-3 sweeps suffice.
 __global__ void __launch_bounds__(KL_THREADS)
 proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_o, double eps_cov,
                        float *__restrict__ proj_L, double *__restrict__ save_M, double *__restrict__ save_U,
-                       double *__restrict__ save_lam, double *__restrict__ save_sc, int32_t *__restrict__ info, int n,
-                       int warm_start) {
+                       double *__restrict__ save_Li, double *__restrict__ save_lam, double *__restrict__ save_sc,
+                       int32_t *__restrict__ info, int n, int warm_start) {
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
-  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1};
-  double *dinv = sd + 3 * MS, *lam = dinv + LA_DINV_DOUBLES, *nrm = lam + m, *red = nrm + LA_JACOBI_SCRATCH;   // red: >= 48
+  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
+  double *dinv = sd + 4 * MS, *lam = dinv + LA_DINV_DOUBLES, *nrm = lam + m, *red = nrm + LA_JACOBI_SCRATCH;   // red: >= 48
   __shared__ int s_bad;
   const long long b = blockIdx.x;
   const size_t off = (size_t)b * n * n;
@@ -504,11 +498,16 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   fp = block_sum(fp, red);
   const bool warm = warm_start && save_sc[b * 4 + 3] == fp;
   if (warm) load_full_d(b1, save_M + off, n, m); else load_lower_d(b1, Lo, n, m);
-  la_diag_block_inverses(b0, dinv, n);
   KL_STAMP(1);
-  la_trsm_lower(b0, dinv, b1, n, n, !warm);                                        // W (or W Q_prev)
+  la_tri_inverse(b0, b2, dinv, n);                                                 // Lt^-1 (kept for the backward)
+  zero_padding(b3, n, m);
+  la_gemm(b3, b2, b1, n, n, n, TRI_LOWER, warm ? TRI_FULL : TRI_LOWER, TRI_FULL, 1.0, 0.0);   // W (or W Q_prev)
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    save_Li[off + e] = b2(i, j);
+  }
   KL_STAMP(2);
-  const int sweeps = la_jacobi_onesided(b1, lam, nrm, n);                          // b1 = U~
+  const int sweeps = la_jacobi_onesided(b3, lam, nrm, n);                          // b3 = U~
   KL_STAMP(3);
   const double kl0 = [&] {
     double v = 0.0;
@@ -522,7 +521,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   const bool active = kl0 > eps_cov;
   const double eta = active ? kl_solve_eta(lam, n, eps_cov, red, warm && save_sc[b * 4 + 1] != 0.0 ? save_sc[b * 4 + 0] : 0.0) : 0.0;
   KL_STAMP(4);
-  la_gemm(b2, b0, b1, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // M = Lt U~
+  la_gemm(b2, b0, b3, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // M = Lt U~
   if (threadIdx.x == 0) {
     save_sc[b * 4 + 0] = eta; save_sc[b * 4 + 1] = active ? 1.0 : 0.0; save_sc[b * 4 + 2] = kl0; save_sc[b * 4 + 3] = fp;
     if (blockIdx.x == 0) g_kl_prof[15] = sweeps;
@@ -531,7 +530,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     const int i = e / n, j = e - i * n;
     save_M[off + e] = b2(i, j);
-    save_U[off + e] = b1(i, j);                                                     // U~ = Lt^-1 M for the backward
+    save_U[off + e] = b3(i, j);                                                     // U~ = Lt^-1 M for the backward
   }
   KL_STAMP(5);
   float *out = proj_L + off;
@@ -557,16 +556,17 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
 
 // Backward (implicit differentiation of eta*, no eigen-derivative singularities).  With P = proj_L, G the
 // upstream gradient, Phi = Phi(P^T G) (lower triangle, halved diagonal) the Cholesky adjoint is
-// Sbar = sym(P^-T Phi P^-1); only M^T Sbar M is needed, so with Y = P^-1 M (ONE triangular solve)
+// Sbar = sym(P^-T Phi P^-1); only M^T Sbar M is needed, so with Y = P^-1 M
 //   Ft = sym(Y^T Phi Y) ;  rho_i = 1/(lam_i + eta) ;
 //   Nt_ij = -(1+eta) rho_i rho_j Ft_ij - delta_ij etabar (df/dlam_i) / (df/deta) ,
 //   etabar = sum_i Ft_ii (rho_i - (1+eta) rho_i^2) ;  grad_Lt = -2 tril(Lt^-T U~ Nt U~^T)
-// with U~ = Lt^-1 M saved by the forward (second and last triangular solve: Lt^-T).
+// with U~ = Lt^-1 M and Lt^-1 saved by the forward.  No triangular solves: P^-1 by recursive doubling
+// (la_tri_inverse), everything else is 4x4-tile GEMMs on four shared buffers.
 __global__ void __launch_bounds__(KL_THREADS)
 proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ proj_L, const float *__restrict__ gout,
                        const double *__restrict__ save_M, const double *__restrict__ save_U,
-                       const double *__restrict__ save_lam, const double *__restrict__ save_sc,
-                       float *__restrict__ grad_L, int n) {
+                       const double *__restrict__ save_Li, const double *__restrict__ save_lam,
+                       const double *__restrict__ save_sc, float *__restrict__ grad_L, int n) {
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
   Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
@@ -574,6 +574,7 @@ proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ pr
   const long long b = blockIdx.x;
   const size_t off = (size_t)b * n * n;
   float *gl = grad_L + off;
+  (void)L;
   const double eta = save_sc[b * 4 + 0];
   if (save_sc[b * 4 + 1] == 0.0) {                                                 // inactive: identity
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) gl[e] = (e % n <= e / n) ? gout[off + e] : 0.f;
@@ -588,31 +589,29 @@ proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ pr
     if (j > i) b2(i, j) = 0.0; else if (i == j) b2(i, j) *= 0.5;                   // Phi
   }
   load_full_d(b1, save_M + off, n, m);                                             // M (G is consumed)
-  la_diag_block_inverses(b0, dinv, n);
-  la_trsm_lower(b0, dinv, b1, n, n, false);                                        // Y = P^-1 M
-  la_gemm(b3, b2, b1, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // Phi Y
-  la_gemm(b0, b1.T(), b3, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // F' = Y^T Phi Y ; Ft = sym(F')
+  la_tri_inverse(b0, b3, dinv, n);                                                 // P^-1
+  la_gemm(b0, b3, b1, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // Y = P^-1 M (P is consumed)
+  la_gemm(b3, b2, b0, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // Phi Y
+  la_gemm(b1, b0.T(), b3, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // F' = Y^T Phi Y ; Ft = sym(F')
   double eb = 0.0, dfe = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    eb += b0(i, i) * (rho[i] - (1.0 + eta) * rho[i] * rho[i]);
+    eb += b1(i, i) * (rho[i] - (1.0 + eta) * rho[i] * rho[i]);
     dfe += 2.0 * rho[i] - (1.0 + eta) * rho[i] * rho[i] - 1.0 / (1.0 + eta);
   }
   eb = block_sum(eb, red);
   dfe = 0.5 * block_sum(dfe, red);
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     const int i = e / n, j = e - i * n;
-    double v = -(1.0 + eta) * rho[i] * rho[j] * (0.5 * (b0(i, j) + b0(j, i)));
+    double v = -(1.0 + eta) * rho[i] * rho[j] * (0.5 * (b1(i, j) + b1(j, i)));
     if (i == j) v -= eb * (0.5 * (rho[i] - (1.0 + eta) * rho[i] * rho[i])) / dfe;
     b2(i, j) = v;                                                                  // Nt (Phi is consumed)
   }
-  load_full_d(b1, save_U + off, n, m);                                             // U~ (Y is consumed)
-  __syncthreads();
-  la_gemm(b3, b1, b2, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);            // U~ Nt
-  la_gemm(b2, b3, b1.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // U~ Nt U~^T
-  load_lower_d(b0, L + off, n, m);                                                 // Lt (F' is consumed)
-  la_diag_block_inverses(b0, dinv, n);
-  la_trsm_lower_t(b0, dinv, b2, n, n);                                             // Lt^-T (.)
-  store_lower_f(gl, b2, n, -2.0);
+  load_full_d(b0, save_U + off, n, m);                                             // U~ (Y is consumed)
+  la_gemm(b3, b0, b2, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);            // U~ Nt
+  la_gemm(b1, b3, b0.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // U~ Nt U~^T (F' is consumed)
+  load_full_d(b2, save_Li + off, n, m);                                            // Lt^-1 (Nt is consumed)
+  la_gemm(b3, b2.T(), b1, n, n, n, TRI_UPPER, TRI_FULL, TRI_LOWER, 1.0, 0.0);      // Lt^-T (.)
+  store_lower_f(gl, b3, n, -2.0);
 }
 
 // =====================================================================================================
@@ -1010,19 +1009,20 @@ extern "C" int tce_debug_kl_phase_cycles(long long *out16) {
   return TCE_OK;
 }
 
-extern "C" size_t tce_proj_kl_save_doubles(int64_t B, int n) { return (size_t)B * (2 * (size_t)n * n + n + 4); }
+extern "C" size_t tce_proj_kl_save_doubles(int64_t B, int n) { return (size_t)B * (3 * (size_t)n * n + n + 4); }
 
 extern "C" int tce_proj_kl_cov_fwd(const float *L, const float *L_o, double eps_cov, float *proj_L, double *save,
                                    int32_t *info, int warm_start, int64_t B, int n, void *stream) {
   if (!L || !L_o || !proj_L || !save || B < 0 || !(eps_cov > 0)) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
   if (B == 0) return TCE_OK;
-  const size_t smem = pj_smem_exclusive(pj_smem(n, 3) + sizeof(double) * LA_JACOBI_SCRATCH, B);
+  const size_t smem = pj_smem_exclusive(pj_smem(n, 4) + sizeof(double) * LA_JACOBI_SCRATCH, B);
   int rc = set_smem(proj_kl_cov_fwd_kernel, smem);
   if (rc) return rc;
-  double *M = save, *U = M + (size_t)B * n * n, *lam = U + (size_t)B * n * n, *sc = lam + (size_t)B * n;
-  proj_kl_cov_fwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, eps_cov, proj_L, M, U, lam, sc, info,
-                                                                                 n, warm_start);
+  const size_t nn = (size_t)B * n * n;
+  double *M = save, *U = M + nn, *Li = U + nn, *lam = Li + nn, *sc = lam + (size_t)B * n;
+  proj_kl_cov_fwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, eps_cov, proj_L, M, U, Li, lam, sc,
+                                                                                 info, n, warm_start);
   TCE_CHECK_LAUNCH("proj_kl_cov_fwd_kernel");
   return TCE_OK;
 }
@@ -1035,8 +1035,10 @@ extern "C" int tce_proj_kl_cov_bwd(const float *L, const float *proj_L, const fl
   const size_t smem = pj_smem_exclusive(pj_smem(n, 4), B);
   int rc = set_smem(proj_kl_cov_bwd_kernel, smem);
   if (rc) return rc;
-  const double *M = save, *U = M + (size_t)B * n * n, *lam = U + (size_t)B * n * n, *sc = lam + (size_t)B * n;
-  proj_kl_cov_bwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, proj_L, grad_out, M, U, lam, sc, grad_L, n);
+  const size_t nn = (size_t)B * n * n;
+  const double *M = save, *U = M + nn, *Li = U + nn, *lam = Li + nn, *sc = lam + (size_t)B * n;
+  proj_kl_cov_bwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, proj_L, grad_out, M, U, Li, lam, sc, grad_L,
+                                                                                 n);
   TCE_CHECK_LAUNCH("proj_kl_cov_bwd_kernel");
   return TCE_OK;
 }

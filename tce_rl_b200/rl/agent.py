@@ -81,6 +81,8 @@ class TemporalCorrelatedAgent:
         self.use_cuda_graph = bool(kwargs.get("use_cuda_graph", False))
         self.fused_surrogate = bool(kwargs.get("fused_surrogate", True))
         self.overlap_logging = bool(kwargs.get("overlap_logging", True))
+        if self.overlap_logging and hasattr(policy, "mean_net") and hasattr(policy.mean_net, "side_wgrad"):
+            policy.mean_net.side_wgrad = True              # joined after every backward of policy_epoch
         self._log_stream = None
         self._tr_stream = None
         self._flat_grad = None
@@ -371,6 +373,7 @@ class TemporalCorrelatedAgent:
             kl = self.kl_old_new_proj(new, old, proj)
         self.policy_optimizer.zero_grad(set_to_none=False)
         policy_loss.backward()
+        util.join_side_grads()                             # weight gradients of the mean net (side streams)
         self._allreduce_grads(self.policy_net_params)
         grad_norm = self._grad_norm_clip(self.policy_net_params)
         self.policy_optimizer.step()

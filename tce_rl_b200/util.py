@@ -138,6 +138,51 @@ _ACT = {"tanh": torch.tanh, "relu": nn.functional.relu, "leaky_relu": nn.functio
         "softplus": nn.functional.softplus, None: None}
 
 
+_SIDE_GRAD_STREAMS = set()          # streams with parameter-gradient work still to be joined
+
+
+def join_side_grads():
+    """Make the current stream wait for every weight/bias gradient that ``MLP(side_wgrad=True)`` queued on side
+    streams during the last backward pass.  Call it after ``loss.backward()`` and before the gradients are read."""
+    cur = torch.cuda.current_stream() if _SIDE_GRAD_STREAMS else None
+    for st in _SIDE_GRAD_STREAMS:
+        cur.wait_stream(st)
+    _SIDE_GRAD_STREAMS.clear()
+
+
+class _SideGradLinear(torch.autograd.Function):
+    """y = x W^T + b.  Backward: only d/dx stays on the critical chain of the backward pass; the weight and bias
+    gradients (two library GEMM calls per layer, leaves of the graph) are ACCUMULATED into the pre-allocated
+    ``.grad`` buffers on a per-layer side stream and autograd is handed no gradient for them.  The caller joins
+    the streams (``join_side_grads``) before it reads the gradients."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, owner):
+        ctx.save_for_backward(x, weight)
+        ctx.owner = owner
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        owner = ctx.owner
+        g = g.contiguous()
+        main = torch.cuda.current_stream()
+        if owner._side_stream is None:
+            owner._side_stream = torch.cuda.Stream(device=g.device)
+        side = owner._side_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            g2, x2 = g.reshape(-1, g.shape[-1]), x.reshape(-1, x.shape[-1])
+            owner.weight.grad.addmm_(g2.t(), x2)
+            owner.bias.grad.addmv_(g2.t(), g2.new_ones(g2.shape[0]))
+            g.record_stream(side)
+            x.record_stream(side)
+        _SIDE_GRAD_STREAMS.add(side)
+        gx = g @ weight if ctx.needs_input_grad[0] else None
+        return gx, None, None, None
+
+
 class MLP(nn.Module):
     """Dense net of util_nn.py:75-246 (orthogonal init with gain sqrt(2), output layer gain configurable).
 
@@ -161,10 +206,20 @@ class MLP(nn.Module):
                 raise ValueError(f"unsupported init_method {init_method}")
             nn.init.zeros_(lin.bias)
 
+    side_wgrad = False      # opt-in (the agent's update loops): see _SideGradLinear / join_side_grads
+
+    def _linear(self, lin, x):
+        if (self.side_wgrad and x.is_cuda and torch.is_grad_enabled() and lin.weight.grad is not None
+                and lin.bias.grad is not None):
+            if not hasattr(lin, "_side_stream"):
+                lin._side_stream = None
+            return _SideGradLinear.apply(x, lin.weight, lin.bias, lin)
+        return lin(x)
+
     def forward(self, x):
         for lin in self.layers[:-1]:
-            x = self.act_hidden(lin(x))
-        x = self.layers[-1](x)
+            x = self.act_hidden(self._linear(lin, x))
+        x = self._linear(self.layers[-1], x)
         return x if self.act_last is None else self.act_last(x)
 
 
