@@ -391,12 +391,14 @@ proj_entropy_kernel(const float *__restrict__ L, const double *__restrict__ beta
 // Warp-cooperative evaluation of KL_cov(eta) = 1/2 sum_i g((lam_i + eta) / (1 + eta)), g(r) = 1/r - 1 + ln r,
 // and of d/d eta (every lane of the calling warp participates).
 __device__ inline double kl_of_eta(const double *lam, int n, double eta, double *dfd_eta) {
+  // with s = lam + eta, r = s / (1 + eta):  g(r) = (1+eta)/s - 1 + ln s - ln(1+eta),
+  // d g / d eta = -(lam - 1)^2 / ((1+eta) s^2)  -- one division and one logarithm per eigenvalue
   double f = 0.0, df = 0.0;
-  const double ope = 1.0 + eta;
+  const double ope = 1.0 + eta, iope = 1.0 / ope, lope = log(ope);
   for (int i = threadIdx.x & 31; i < n; i += 32) {
-    const double r = (lam[i] + eta) / ope;
-    f += 1.0 / r - 1.0 + log(r);
-    df += ((r - 1.0) / (r * r)) * ((1.0 - lam[i]) / (ope * ope));
+    const double s = lam[i] + eta, is = 1.0 / s, d = lam[i] - 1.0;
+    f += fma(ope, is, -1.0) + (log(s) - lope);
+    df -= d * d * is * is * iope;
   }
   f = warp_sum(f); df = warp_sum(df);
   if (dfd_eta) *dfd_eta = 0.5 * df;
@@ -413,12 +415,12 @@ __device__ inline double kl_solve_eta(const double *lam, int n, double eps, doub
     if (warp == 0) {
       double eta = eta0;
       bool ok = false;
-      for (int it = 0; it < 6 && !ok; ++it) {       // quadratic: 3-4 steps; the last ones only move by rounding noise
+      for (int it = 0; it < 6 && !ok; ++it) {       // quadratic: 2-3 steps from the previous epoch's root
         double df;
         const double f = kl_of_eta(lam, n, eta, &df) - eps;
         const double nxt = eta - f / df;
         if (!(df < 0.0) || !(nxt > 0.0) || !(nxt < 1e300)) break;
-        ok = fabs(nxt - eta) <= 1e-13 * fmax(1.0, fabs(eta));
+        ok = fabs(nxt - eta) <= 1e-9 * fmax(1.0, fabs(eta));      // error after this step ~ (1e-9)^2: rounding level
         eta = nxt;
       }
       if (lane == 0) { cand[34] = ok ? 1.0 : 0.0; cand[35] = eta; }

@@ -339,10 +339,10 @@ __device__ inline void la_chol(Mat A, int n, int *bad) {
 // One-sided (Hestenes) Jacobi: rotate the columns of W (n x n, n <= 64) until they are orthogonal; on exit
 // lam_j = |W_j|^2.  A single CTA is bound by instruction issue and by the SM's one-shuffle-per-clock unit, not
 // by fp64 latency (DFMA: 8.5 cycles dependent, scripts/ubench/lat.cu), so the matrix lives in REGISTERS for
-// the whole iteration: warp w holds rows 8w..8w+7, lane t holds the two columns (P_t, Q_t) of pair slot t, and
+// the whole iteration: warp w holds rows 16w..16w+15, lane t holds the two columns (P_t, Q_t) of pair slot t, and
 // a step is
-//   8 DFMA (partial dot) -> one 8-way combine through shared memory (ONE named barrier over the active warps)
-//   -> the rotation (computed redundantly and bit-identically by every warp) -> 32 fp64 ops to apply it
+//   16 DFMA (partial dot) -> one 4-way combine through shared memory (ONE named barrier over the active warps)
+//   -> the rotation (computed redundantly and bit-identically by every warp) -> 64 fp64 ops to apply it
 //   -> ONE shuffle per register of Q.
 // Pair ordering (recursive halving): with the P columns X and the Q columns Y of a segment of `w` lanes,
 // w steps that ring-shift Q inside the segment (__shfl_sync with width = w, no selects) meet all X x Y pairs;
@@ -352,6 +352,8 @@ __device__ inline void la_chol(Mat A, int n, int *bad) {
 // any arrangement is a valid start for the next sweep.  Everything that only steers convergence (norms,
 // thresholds, the rotation angle) is fp32; the dot product, the normalisation of (c, s) and the rotation
 // itself are fp64.  scratch: LA_JACOBI_SCRATCH doubles.  All threads of the CTA must call this.
+constexpr int LA_JACOBI_ROWS = 16;                    // rows per thread: 4 warps hold a 64 x 64 matrix
+constexpr int LA_JACOBI_WARPS = 64 / LA_JACOBI_ROWS;
 constexpr int LA_JACOBI_SCRATCH = 2 * 8 * 32;
 #ifdef JAC_PROF
 __device__ unsigned int g_jac_prof[8];
@@ -364,13 +366,16 @@ __device__ __forceinline__ void la_named_barrier(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
-__device__ __forceinline__ double la_combine8(const double *col) {   // fixed-order sum of the 8 warps' partials
-  return ((col[0] + col[32]) + (col[64] + col[96])) + ((col[128] + col[160]) + (col[192] + col[224]));
+__device__ __forceinline__ double la_combine(const double *col) {   // fixed-order sum of the warps' partials
+  double v = 0.0;
+  if (LA_JACOBI_WARPS == 4) v = (col[0] + col[32]) + (col[64] + col[96]);
+  else v = ((col[0] + col[32]) + (col[64] + col[96])) + ((col[128] + col[160]) + (col[192] + col[224]));
+  return v;
 }
 
 __device__ inline int la_jacobi_onesided(Mat W, double *lam, double *scratch, int n) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nw = (n + 7) >> 3, nbar = nw * 32;         // warps that hold rows
+  const int nw = (n + LA_JACOBI_ROWS - 1) / LA_JACOBI_ROWS, nbar = nw * 32;   // warps that hold rows
   int w0 = 1;                                          // pair slots: power of two >= ceil(n / 2), <= 32
   while (2 * w0 < n) w0 <<= 1;
   int sweeps = 0;
@@ -381,10 +386,10 @@ __device__ inline int la_jacobi_onesided(Mat W, double *lam, double *scratch, in
     const double *col = scratch + lane;
     int idp = lane, idq = w0 + lane;                   // column ids (>= n or lane >= w0: zero padding)
     if (lane >= w0) idp = idq = n;
-    double xp[8], xq[8];
+    double xp[LA_JACOBI_ROWS], xq[LA_JACOBI_ROWS];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = warp * 8 + i;
+    for (int i = 0; i < LA_JACOBI_ROWS; ++i) {
+      const int r = warp * LA_JACOBI_ROWS + i;
       xp[i] = (idp < n && r < n) ? W(r, idp) : 0.0;
       xq[i] = (idq < n && r < n) ? W(r, idq) : 0.0;
     }
@@ -394,12 +399,12 @@ __device__ inline int la_jacobi_onesided(Mat W, double *lam, double *scratch, in
       // exact squared norms (once per sweep: bounds the drift of the closed-form fp32 updates)
       double sp = 0.0, sq = 0.0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { sp = fma(xp[i], xp[i], sp); sq = fma(xq[i], xq[i], sq); }
+      for (int i = 0; i < LA_JACOBI_ROWS; ++i) { sp = fma(xp[i], xp[i], sp); sq = fma(xq[i], xq[i], sq); }
       mine[0] = sp;
       mine[256] = sq;
       la_named_barrier(nbar);
-      ap = la_combine8(col);
-      aq = la_combine8(col + 256);
+      ap = la_combine(col);
+      aq = la_combine(col + 256);
       la_named_barrier(nbar);                          // the step buffers alias these partial sums
       if (done || sweeps == 40) break;
       float a = (float)ap, b = (float)aq;
@@ -415,12 +420,12 @@ __device__ inline int la_jacobi_onesided(Mat W, double *lam, double *scratch, in
           JP(4);
           double g0 = 0.0, g1 = 0.0;
 #pragma unroll
-          for (int i = 0; i < 8; i += 2) { g0 = fma(xp[i], xq[i], g0); g1 = fma(xp[i + 1], xq[i + 1], g1); }
+          for (int i = 0; i < LA_JACOBI_ROWS; i += 2) { g0 = fma(xp[i], xq[i], g0); g1 = fma(xp[i + 1], xq[i + 1], g1); }
           mine[buf] = g0 + g1;
           JP(0);
           la_named_barrier(nbar);
           JP(1);
-          const float g = (float)la_combine8(col + buf);
+          const float g = (float)la_combine(col + buf);
 #ifdef JAC_PROF
           if (g == 123.456f) jp[0]++;
 #endif
@@ -452,7 +457,7 @@ __device__ inline int la_jacobi_onesided(Mat W, double *lam, double *scratch, in
           // shifted by w - 1, which is as good a start for the next level; a shift by 0 keeps the code branch-free)
           const int src = lane + (k + 1 < w ? 1 : 0);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < LA_JACOBI_ROWS; ++i) {
             const double np = fma(c, xp[i], -sn * xq[i]), nq = fma(sn, xp[i], c * xq[i]);
             xp[i] = np;
             xq[i] = __shfl_sync(0xffffffffu, nq, src, w);
@@ -464,7 +469,7 @@ __device__ inline int la_jacobi_onesided(Mat W, double *lam, double *scratch, in
           const int hw = w >> 1;
           const bool upper = (lane & hw) != 0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < LA_JACOBI_ROWS; ++i) {
             const double got = __shfl_xor_sync(0xffffffffu, upper ? xp[i] : xq[i], hw);
             if (upper) xp[i] = got; else xq[i] = got;
           }
@@ -483,8 +488,8 @@ __device__ inline int la_jacobi_onesided(Mat W, double *lam, double *scratch, in
       done = !__any_sync(0xffffffffu, big);            // identical in every warp (same data, same code)
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = warp * 8 + i;
+    for (int i = 0; i < LA_JACOBI_ROWS; ++i) {
+      const int r = warp * LA_JACOBI_ROWS + i;
       if (idp < n && r < n) W(r, idp) = xp[i];
       if (idq < n && r < n) W(r, idq) = xq[i];
     }
