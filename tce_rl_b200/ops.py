@@ -459,7 +459,32 @@ def seg_surrogate(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_
     """-> (surrogate loss = -mean(exp(lp - lp_old) * adv) [fp32 scalar, differentiable], mean ratio, logp)."""
     stats, logp, _adj, _info = seglik_surrogate_fwd(smp_traj, mean, L, times, init_time, init_pos, init_vel,
                                                     pred_pairs, logp_old, advantage, tables.handle, reg_rel)
-    return stats[0].to(torch.float32), stats[1].detach().to(torch.float32), logp.detach()
+    loss, ratio = _StatsToFloat.apply(stats)
+    return loss, ratio.detach(), logp.detach()
+
+
+_E0 = {}
+
+
+class _StatsToFloat(torch.autograd.Function):
+    """fp64 {loss, ratio} [2] -> two fp32 scalars with ONE kernel each way (select + cast + zero-fill + scatter
+    of the plain formulation are four launches on the critical path between the likelihood's stage 2 and 3)."""
+
+    @staticmethod
+    def forward(ctx, stats):
+        key = str(stats.device)
+        if key not in _E0:
+            _E0[key] = torch.tensor([1.0, 0.0], dtype=torch.float64, device=stats.device)
+        ctx.e0 = _E0[key]
+        ctx.set_materialize_grads(False)
+        s32 = stats.to(torch.float32)
+        return s32[0], s32[1]
+
+    @staticmethod
+    def backward(ctx, g_loss, g_ratio):
+        if g_loss is None:
+            return None
+        return ctx.e0 * g_loss                            # fp64 [2] = {d/d loss, 0}
 
 
 # --------------------------------------------------------------------------------------------------

@@ -307,14 +307,21 @@ class TemporalCorrelatedAgent:
         D2 = self.policy.num_dof * 2
         old = (dataset["segment_params_mean"], dataset["segment_params_L"])
         obs = dataset["segment_state"][..., :-D2]
+        # gradients are cleared early (after the covariance chain is launched, while this stream has slack), not in
+        # front of backward()
+        zeroed_early = self._flat_grad is not None and self._flat_grad_ok(self.policy_net_params)
         pre = None
         if not self.policy.contextual_cov and hasattr(self.policy, "shared_params_L"):
             # shared covariance: start its projection (side stream) before the mean net -- same values as
             # policy.policy(obs) followed by the projection, see BaseProjectionLayer.start_cov_projection
             params_L = self.policy.shared_params_L(obs.shape[0])
             pre = self.projection.start_cov_projection(self.policy, params_L, old[1], self.num_iterations)
+            if zeroed_early:
+                self._flat_grad.zero_()
             new = (self.policy.mean_net(obs), params_L)
         else:
+            if zeroed_early:
+                self._flat_grad.zero_()
             new = self.policy.policy(obs)
         proj = self.projection(self.policy, new, old, self.num_iterations, cov_projected=pre)
         # trust-region loss: small (partly single-CTA) kernels that only need `new` and `proj` -- a parallel
@@ -371,7 +378,8 @@ class TemporalCorrelatedAgent:
                     ent_stats["entropy"].record_stream(main)
         else:
             kl = self.kl_old_new_proj(new, old, proj)
-        self.policy_optimizer.zero_grad(set_to_none=False)
+        if not zeroed_early:
+            self.policy_optimizer.zero_grad(set_to_none=False)
         policy_loss.backward()
         util.join_side_grads()                             # weight gradients of the mean net (side streams)
         self._allreduce_grads(self.policy_net_params)
