@@ -96,3 +96,49 @@ def test_update_critic_and_projection_bounds_hold():
     assert out["projection_proj_old_cov_diff_max"] <= 5e-4 * (1 + 1e-2)
     with pytest.raises(NotImplementedError):
         agent.step()                     # environment rollout is outside the B200 path
+
+
+def test_overlapped_epoch_equals_serial_epoch():
+    """Side streams (covariance chain first, trust-region loss / logging branches, weight gradients on per-layer
+    streams, early gradient clearing) only reorder independent work: metrics and updated parameters of two epochs
+    must equal those of the fully serial schedule (tolerance 1e-6: the flat-buffer gradient norm sums in another
+    order)."""
+    res = []
+    for overlap in (True, False):
+        agent, dataset = build(epochs=2)
+        agent.num_iterations = 1
+        dataset = agent.process_dataset(dataset)
+        agent.ensure_flat_grads(agent.policy_net_params)
+        old = [dataset["segment_params_mean"], dataset["segment_params_L"]]
+        agent.projection.initial_entropy = agent.policy.entropy(old).mean()       # as update_policy does
+        if not overlap:
+            agent.overlap_logging = False
+            agent.projection.overlap = False
+            agent.policy.mean_net.side_wgrad = False
+        times = agent.sampler.get_times(dataset["segment_init_time"], agent.sampler.num_times)
+        rows = [agent.policy_epoch(dataset, times, agent.sampler.pred_pairs) for _ in range(2)]
+        torch.cuda.synchronize()
+        res.append((torch.stack(rows).cpu(), [p.detach().clone().cpu() for p in agent.policy.parameters]))
+    (m1, p1), (m2, p2) = res
+    assert torch.isfinite(m1).all()
+    assert (m1 - m2).abs().max().item() <= 1e-6 * max(1.0, m2.abs().max().item())
+    for a, b in zip(p1, p2):
+        assert (a - b).abs().max().item() <= 1e-6
+
+
+def test_dataset_to_device_broadcasts_the_shared_old_factor():
+    agent, dataset = build()
+    host = {k: v.cpu().pin_memory() for k, v in dataset.items()}
+    dev = agent.dataset_to_device(host)
+    L = dev["segment_params_L"]
+    assert L.shape == dataset["segment_params_L"].shape and L.stride(0) == 0 and L._tce_first.shape[0] == 1
+    assert torch.equal(L[5], dataset["segment_params_L"][5])
+    for k, v in dataset.items():
+        if k != "segment_params_L":
+            assert torch.equal(dev[k], v), k
+    ptrs = {k: v.data_ptr() for k, v in dev.items()}
+    host["segment_params_mean"] = (host["segment_params_mean"] + 1.0).pin_memory()
+    dev2 = agent.dataset_to_device(host, out=dev)
+    torch.cuda.synchronize()
+    assert dev2 is dev and all(dev[k].data_ptr() == ptrs[k] for k in dev)          # static addresses
+    assert torch.equal(dev["segment_params_mean"].cpu(), host["segment_params_mean"])
