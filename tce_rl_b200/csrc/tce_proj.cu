@@ -73,7 +73,8 @@ __device__ inline double block_sum(double v, double *red) {   // red: >= 32 doub
 }
 
 // grad_A (sym) of a Cholesky factor P with upstream G (lower): Sbar = sym(P^-T Phi(P^T G) P^-1)
-// P in bP, G in bG; result in bM (full symmetric); bG is destroyed.
+// P in bP, G in bG; result in bM (full symmetric); bP and bG are destroyed.  P^-1 by recursive doubling and
+// two GEMMs instead of two triangular solves with n right-hand sides.
 __device__ inline void chol_backward(Mat bP, Mat bG, Mat bM, double *inv_diag, int n) {
   // M = Phi(P^T G)  (lower, halved diagonal, zero above)
   la_gemm(bM, bP.T(), bG, n, n, n, TRI_UPPER, TRI_LOWER, TRI_FULL, 1.0, 0.0);
@@ -82,9 +83,9 @@ __device__ inline void chol_backward(Mat bP, Mat bG, Mat bM, double *inv_diag, i
     if (j > i) bM(i, j) = 0.0; else if (i == j) bM(i, j) *= 0.5;
   }
   __syncthreads();
-  la_diag_block_inverses(bP, inv_diag, n);
-  la_trsm_lower_t(bP, inv_diag, bM, n, n);            // Y = P^-T M
-  la_trsm_lower_t(bP, inv_diag, bM.T(), n, n);        // X^T = P^-T Y^T  -> bM = X
+  la_tri_inverse(bP, bG, inv_diag, n);                                              // bG = P^-1 (G is consumed)
+  la_gemm(bP, bM, bG, n, n, n, TRI_LOWER, TRI_LOWER, TRI_FULL, 1.0, 0.0);           // Phi P^-1 (P is consumed)
+  la_gemm(bM, bG.T(), bP, n, n, n, TRI_UPPER, TRI_FULL, TRI_FULL, 1.0, 0.0);        // X = P^-T Phi P^-1
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     const int i = e / n, j = e % n;
     if (j < i) { const double s = 0.5 * (bM(i, j) + bM(j, i)); bG(i, j) = s; }
@@ -717,10 +718,8 @@ proj_w2_cov_kernel(const float *__restrict__ L, const float *__restrict__ L_o, l
   load_lower_d(S, L_o + b * ldb_Lo, n, m);
   double cp;
   if (scale_prec) {
-    for (int e = threadIdx.x; e < m * m; e += blockDim.x) A(e / m, e % m) = (e / m == e % m && e / m < n) ? 1.0 : 0.0;
-    __syncthreads();
-    la_diag_block_inverses(S, inv_diag, n);
-    la_trsm_lower(S, inv_diag, A, n, n, true);                                     // A = S^-1 (lower)
+    zero_padding(A, n, m);
+    la_tri_inverse(S, A, inv_diag, n);                                             // A = S^-1 (lower)
     la_gemm(T, A, R, n, n, n, TRI_LOWER, TRI_LOWER, TRI_FULL, 1.0, 0.0);           // T = A R (lower)
     la_gemm(U, A.T(), R, n, n, n, TRI_UPPER, TRI_LOWER, TRI_FULL, 1.0, 0.0);       // U = A^T R
     double v = 0.0;
@@ -815,10 +814,8 @@ cov_distance_kernel(int kind /*0 frob, 1 w2*/, const float *__restrict__ L, cons
       store_lower_f(grad_L + off, T, n, 1.0);
     }
   } else if (scale_prec) {
-    for (int e = threadIdx.x; e < m * m; e += blockDim.x) A(e / m, e % m) = (e / m == e % m && e / m < n) ? 1.0 : 0.0;
-    __syncthreads();
-    la_diag_block_inverses(S, inv_diag, n);
-    la_trsm_lower(S, inv_diag, A, n, n, true);
+    zero_padding(A, n, m);
+    la_tri_inverse(S, A, inv_diag, n);
     la_gemm(T, A, R, n, n, n, TRI_LOWER, TRI_LOWER, TRI_FULL, 1.0, 0.0);
     la_gemm(U, A.T(), R, n, n, n, TRI_UPPER, TRI_LOWER, TRI_FULL, 1.0, 0.0);
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
