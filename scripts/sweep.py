@@ -113,8 +113,7 @@ def epoch_point(name, B, typ, mean_bound, cov_bound):
               segment_init_pos=c(inp["init_pos"]), segment_init_vel=c(inp["init_vel"]))
     proj.initial_entropy = policy.entropy([mean_old, L_old]).mean()
     agent.num_iterations = 100
-    for q in policy.parameters:
-        q.grad = torch.zeros_like(q)
+    agent.ensure_flat_grads(agent.policy_net_params)
     side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         for _ in range(2):
