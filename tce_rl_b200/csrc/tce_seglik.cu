@@ -278,7 +278,11 @@ seglik_chol_kernel(const double *Cmat, const double *Rres, double *Gout, double 
                    const float *__restrict__ advantage, double grad_scale, double *__restrict__ loss_acc,
                    float *__restrict__ logp, int32_t *__restrict__ info, long long BP, int P, int want_grad) {
   constexpr int NT = tri(N);
+#ifndef SEGLIK_CHOL_SMEM
+  double c[NT];                      // fully unrolled below: every index is a compile-time constant -> registers
+#else
   __shared__ double sm[NT * CH_THREADS];
+#endif
   const long long gid = (long long)blockIdx.x * CH_THREADS + threadIdx.x;
   const bool active = gid < BP;
   double loss_part = 0.0, ratio_part = 0.0;
@@ -289,11 +293,17 @@ seglik_chol_kernel(const double *Cmat, const double *Rres, double *Gout, double 
     const double *Rb = Rres + (size_t)b * N * P + p;
     double *Gb = Gout + (size_t)b * NT * P + p;
     double *Ab = Aout + (size_t)b * N * P + p;
+#ifndef SEGLIK_CHOL_SMEM
+#define CE(r, q) c[tri_idx(r, q)]
+#define CLIN(e) c[e]
+#else
     double *c = sm + threadIdx.x;
 #define CE(r, q) c[(tri_idx(r, q)) * CH_THREADS]
+#define CLIN(e) c[(e) * CH_THREADS]
+#endif
     const double reg = reg_rel * (*diag_max);
 #pragma unroll
-    for (int e = 0; e < NT; ++e) c[e * CH_THREADS] = Cb[(size_t)e * P];
+    for (int e = 0; e < NT; ++e) CLIN(e) = Cb[(size_t)e * P];
     double z[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) z[i] = Rb[(size_t)i * P];
@@ -306,9 +316,14 @@ seglik_chol_kernel(const double *Cmat, const double *Rres, double *Gout, double 
 #pragma unroll
       for (int k = 0; k < j; ++k) dj = fma(-CE(j, k), CE(j, k), dj);
       if (!(dj > 0.0) && bad == 0) bad = j + 1;
-      const double sj = sqrt(dj), inv = 1.0 / sj;
-      CE(j, j) = sj;
-      half_logdet += log(sj);
+      // 1/sqrt(dj): fp32 MUFU seed + two fp64 Newton steps (1e-7 -> 1e-14 -> rounding).  The DIAGONAL STORES THE
+      // RECIPROCAL 1/S_jj: every later division (substitutions, inverse) becomes a multiplication -- fp64 divide
+      // and sqrt are ~40-instruction subroutines and there were ~130 of them per segment.
+      double inv = (double)rsqrtf((float)dj);
+      inv = inv * fma(-0.5 * dj, inv * inv, 1.5);
+      inv = inv * fma(-0.5 * dj, inv * inv, 1.5);
+      CE(j, j) = inv;
+      half_logdet += 0.5 * log(dj);
 #pragma unroll
       for (int i = j + 1; i < N; ++i) {
         double v = CE(i, j);
@@ -342,22 +357,20 @@ seglik_chol_kernel(const double *Cmat, const double *Rres, double *Gout, double 
         double v = z[i];
 #pragma unroll
         for (int k = i + 1; k < N; ++k) v = fma(-CE(k, i), z[k], v);
-        z[i] = v / CE(i, i);
+        z[i] = v * CE(i, i);
       }
-      // S <- S^-1 (lower, in place)
+      // S <- S^-1 (lower, in place; the diagonal already holds 1/S_jj = X_jj)
 #pragma unroll
       for (int j = 0; j < N; ++j) {
-        const double inv = 1.0 / CE(j, j);
-        CE(j, j) = inv;
 #pragma unroll
         for (int i = j + 1; i < N; ++i) {
           double v = 0.0;
 #pragma unroll
           for (int k = j; k < i; ++k) v = fma(CE(i, k), CE(k, j), v);
-          CE(i, j) = -v / CE(i, i);
+          CE(i, j) = -v * CE(i, i);
         }
       }
-      // (column j: S[i][k], k >= j, and S[i][i] are still the Cholesky entries; X[k][j], k < i, are done)
+      // (column j: S[i][k], j <= k < i, are still the Cholesky entries; X[k][j], k < i, are done)
       // C^-1 = X^T X (lower, in place, row by row: entry (i,j) only reads rows k >= i, and within row i
       // the diagonal X[i][i] is consumed last), then G = g/2 (alpha alpha^T - C^-1)
 #pragma unroll
@@ -371,11 +384,12 @@ seglik_chol_kernel(const double *Cmat, const double *Rres, double *Gout, double 
         }
       }
 #pragma unroll
-      for (int e = 0; e < NT; ++e) Gb[(size_t)e * P] = c[e * CH_THREADS];
+      for (int e = 0; e < NT; ++e) Gb[(size_t)e * P] = CLIN(e);
 #pragma unroll
       for (int i = 0; i < N; ++i) Ab[(size_t)i * P] = g * z[i];
     }
 #undef CE
+#undef CLIN
   }
   if (loss_acc) {
     loss_part = warp_sum(loss_part);
