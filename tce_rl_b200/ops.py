@@ -36,13 +36,16 @@ def _chk(t: Tensor, dtype=torch.float32, name="tensor") -> Tensor:
     return t.contiguous()
 
 
-def _batched_matrix(L: Tensor, name="L") -> Tuple[Tensor, int]:
-    """Return (storage tensor, batch stride in elements); keeps a stride-0 batch expand un-materialised."""
+def _batched_matrix(L: Tensor, name="L", batch: Optional[int] = None) -> Tuple[Tensor, int]:
+    """Return (storage tensor, batch stride in elements); keeps a stride-0 batch expand un-materialised.
+    ``batch``: a single matrix [1, n, n] is broadcast over that many episodes (batch stride 0)."""
     if not L.is_cuda or L.dtype != torch.float32:
         raise TceError(f"{name} must be a CUDA float32 tensor")
     n = L.shape[-1]
     if L.dim() == 3 and L.stride(0) == 0 and L.stride(1) == n and L.stride(2) == 1:
         return L, 0
+    if L.dim() == 3 and L.shape[0] == 1 and batch is not None and batch > 1:
+        return L.contiguous(), 0
     L = L.contiguous()
     return L, n * n
 
@@ -386,8 +389,8 @@ def seglik_surrogate_fwd(smp_traj: Tensor, mean: Tensor, L: Tensor, times: Tenso
     init_time, init_pos, init_vel = _chk(init_time), _chk(init_pos), _chk(init_vel)
     logp_old, advantage = _chk(logp_old, name="logp_old"), _chk(advantage, name="advantage")
     pairs = _chk(pred_pairs, torch.int64, "pred_pairs")
-    L, ldb = _batched_matrix(L)
     B, T = times.shape
+    L, ldb = _batched_matrix(L, batch=B)
     P = pairs.shape[0]
     dev = mean.device
     work = _work(tables, B, P, dev)
@@ -418,20 +421,34 @@ def seglik_surrogate_bwd(upstream: Tensor, adj: Tensor, L: Tensor, times: Tensor
     times, init_time = _chk(times), _chk(init_time)
     pairs = _chk(pred_pairs, torch.int64)
     up = _chk(upstream, torch.float32, "upstream")
-    L, ldb = _batched_matrix(L)
     B, T = times.shape
+    single = L.dim() == 3 and L.shape[0] == 1 and B > 1     # ONE factor [1, n, n] shared by the batch
+    L, ldb = _batched_matrix(L, batch=B)
     P = pairs.shape[0]
     g_mean = torch.empty(B, dim_params, device=times.device, dtype=torch.float32)
     g_L = torch.empty(B, dim_params, dim_params, device=times.device, dtype=torch.float32)
     _lib.call("tce_seglik_bwd", tables, _p(adj), _p(L), ldb, _p(times), _p(init_time), _p(pairs), _p(up), _p(g_mean),
               _p(g_L), B, T, P, _stream())
+    if single:                                              # batch sum as one library GEMV (ones^T G)
+        g_L = torch.mv(g_L.view(B, -1).t(), _ones(B, times.device)).view(1, dim_params, dim_params)
     return g_mean, g_L
+
+
+_ONES = {}
+
+
+def _ones(n: int, device) -> Tensor:
+    key = (n, str(device))
+    if key not in _ONES:
+        _ONES[key] = torch.ones(n, device=device, dtype=torch.float32)
+    return _ONES[key]
 
 
 @seglik_surrogate_bwd.register_fake
 def _(upstream, adj, L, times, init_time, pred_pairs, tables, dim_params):
     B = times.shape[0]
-    return times.new_empty(B, dim_params), times.new_empty(B, dim_params, dim_params)
+    Bl = 1 if (L.dim() == 3 and L.shape[0] == 1) else B
+    return times.new_empty(B, dim_params), times.new_empty(Bl, dim_params, dim_params)
 
 
 def _sur_setup(ctx, inputs, output):
@@ -457,6 +474,9 @@ seglik_surrogate_fwd.register_autograd(_sur_backward, setup_context=_sur_setup)
 def seg_surrogate(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, logp_old, advantage,
                   tables: Tables, reg_rel: float = 1e-4):
     """-> (surrogate loss = -mean(exp(lp - lp_old) * adv) [fp32 scalar, differentiable], mean ratio, logp)."""
+    first = getattr(L, "_tce_first", None)       # a broadcast factor: differentiate w.r.t. the ONE matrix behind it
+    if first is not None and first.shape[0] == 1:
+        L = first
     stats, logp, _adj, _info = seglik_surrogate_fwd(smp_traj, mean, L, times, init_time, init_pos, init_vel,
                                                     pred_pairs, logp_old, advantage, tables.handle, reg_rel)
     loss, ratio = _StatsToFloat.apply(stats)
