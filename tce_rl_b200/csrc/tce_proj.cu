@@ -237,19 +237,11 @@ tri_inverse_kernel(const float *__restrict__ L, long long ldb, double *__restric
   }
 }
 
-#ifdef MAHA_DBG
-__device__ unsigned long long g_maha_dbg[8][160][4];
-__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-__device__ __forceinline__ unsigned smid() { unsigned t; asm volatile("mov.u32 %0, %%smid;" : "=r"(t)); return t; }
-#endif
 __global__ void __launch_bounds__(256)
 maha_shared_kernel(const float *__restrict__ mean, const float *__restrict__ mean_o, const double *__restrict__ Linv,
                    const double *__restrict__ gout, double *__restrict__ out, float *__restrict__ grad_mean,
-                   long long B, int n, int dbg_slot) {
+                   long long B, int n) {
   extern __shared__ double smd[];
-#ifdef MAHA_DBG
-  unsigned long long t_start = gtimer();
-#endif
   const int LD = n | 1, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   double *sA = smd, *dv = smd + (size_t)n * LD + (size_t)warp * 2 * n, *zv = dv + n;
   batched_load(Linv, n * n, [&](int e, double v) {
@@ -261,8 +253,8 @@ maha_shared_kernel(const float *__restrict__ mean, const float *__restrict__ mea
 #pragma unroll 1
     for (int i = lane; i < n; i += 32) dv[i] = (double)mean[b * n + i] - (double)mean_o[b * n + i];
     __syncwarp();
-    // NOTE on `#pragma unroll 1`: this kernel runs each instruction once or twice per launch, so it is bound by
-    // instruction fetch (cold I-cache every launch), not by the pipes -- compact loops beat unrolled ones here.
+    // compact loops (`#pragma unroll 1`): the kernel is a chain of memory latencies (Linv staging, the episode's
+    // means, the result), not pipe bound; unrolling only grew the code
     double maha = 0.0;
 #pragma unroll 1
     for (int i = lane; i < n; i += 32) {                 // z = Linv d (rows of different lanes: stride LD is odd)
@@ -294,13 +286,6 @@ maha_shared_kernel(const float *__restrict__ mean, const float *__restrict__ mea
     }
     __syncwarp();
   }
-#ifdef MAHA_DBG
-  __syncthreads();
-  if (threadIdx.x == 0 && blockIdx.x < 160) {
-    unsigned long long *d = g_maha_dbg[dbg_slot & 7][blockIdx.x];
-    d[0] = t_start; d[1] = gtimer(); d[2] = smid(); d[3] = gout != nullptr;
-  }
-#endif
 }
 
 
@@ -916,12 +901,6 @@ extern "C" int tce_gauss_maha(const float *mean, const float *mean_o, const floa
   return TCE_OK;
 }
 
-#ifdef MAHA_DBG
-extern "C" int tce_debug_maha(unsigned long long *out) {
-  cudaDeviceSynchronize();
-  return cudaMemcpyFromSymbol(out, g_maha_dbg, sizeof(unsigned long long) * 8 * 160 * 4) == cudaSuccess ? 0 : 1;
-}
-#endif
 extern "C" int tce_tri_inverse(const float *L, int64_t ldb, double *Linv, int64_t B, int n, void *stream) {
   if (!L || !Linv || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
@@ -940,17 +919,12 @@ extern "C" int tce_gauss_maha_shared(const float *mean, const float *mean_o, con
     return TCE_ERR_INVALID_ARGUMENT;
   if (B == 0) return TCE_OK;
   const int nw = 8;
-  static int dbg_slot = 0;
   const size_t smem = sizeof(double) * ((size_t)n * (n | 1) + (size_t)nw * 2 * n);
   int rc = set_smem(maha_shared_kernel, smem);
   if (rc) return rc;
-  // same L1 / shared-memory split as the single-CTA kernels of the parallel graph branches: an SM only switches
-  // its carve-out when idle, so a CTA placed next to one of those would otherwise wait for it to finish
-  TCE_CUDA(cudaFuncSetAttribute(maha_shared_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                (int)cudaSharedmemCarveoutMaxShared), "maha carve-out");
   const long long blocks = (B + nw - 1) / nw;
   maha_shared_kernel<<<(unsigned)(blocks < 148 * 2 ? blocks : 148 * 2), nw * 32, smem, (cudaStream_t)stream>>>(
-      mean, mean_o, Linv, grad_out, maha, grad_mean, B, n, dbg_slot++);
+      mean, mean_o, Linv, grad_out, maha, grad_mean, B, n);
   TCE_CHECK_LAUNCH("maha_shared_kernel");
   return TCE_OK;
 }
