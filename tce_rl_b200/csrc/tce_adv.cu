@@ -127,8 +127,8 @@ normalize_kernel(float *__restrict__ x, const double *__restrict__ stats, long l
 extern "C" int tce_gae(const float *rewards, const float *values, const uint8_t *dones, const uint8_t *tl_dones,
                        float gamma, float lam, int use_gae, float *adv, float *ret, int64_t B, int64_t T,
                        void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!rewards || !values || !dones || !adv || !ret || B < 0 || T < 1) return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   const unsigned grid = (unsigned)((B * 32 + 255) / 256);
   gae_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rewards, values, dones, tl_dones, gamma, lam, use_gae, adv, ret, B, (int)T);
   TCE_CHECK_LAUNCH("gae_kernel");
@@ -138,9 +138,9 @@ extern "C" int tce_gae(const float *rewards, const float *values, const uint8_t 
 extern "C" int tce_segment_advantage_raw(int mode, const float *rewards, const float *values, const float *advantages,
                                          const int64_t *pred_pairs, float gamma, float *seg, double *stats, int64_t B,
                                          int64_t T, int64_t P, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (mode < 0 || mode > 2 || !pred_pairs || !seg || B < 0 || T < 1 || P < 1) return TCE_ERR_INVALID_ARGUMENT;
   if (mode == 0 ? !advantages : (!rewards || !values)) return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   const unsigned grid = (unsigned)((B * P + 255) / 256);
   segadv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mode, rewards, values, advantages, pred_pairs, gamma, seg, stats, B, (int)T, (int)P);
   TCE_CHECK_LAUNCH("segadv_kernel");

@@ -194,16 +194,16 @@ __global__ void head_bwd_kernel(const float *__restrict__ vec, long long ldb_vec
 
 extern "C" int tce_mvn_rsample(const float *mean, const float *L, int64_t ldb_L, const float *eps, uint64_t seed,
                                uint64_t offset, float *out, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!mean || !L || !out || B < 0 || n < 1 || n > 200) return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   rsample_kernel<<<(unsigned)B, 128, n * sizeof(float), (cudaStream_t)stream>>>(mean, L, ldb_L, eps, seed, offset, out, n);
   TCE_CHECK_LAUNCH("rsample_kernel");
   return TCE_OK;
 }
 
 extern "C" int tce_chol_fwd(const float *A, float *L, int32_t *info, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!A || !L || B < 0 || n < 1 || n > 128) return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   const size_t smem = (size_t)n * (n + 1) * sizeof(float);
   if (smem > 48 * 1024)
     TCE_CUDA(cudaFuncSetAttribute(chol_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "chol attr");
@@ -213,8 +213,8 @@ extern "C" int tce_chol_fwd(const float *A, float *L, int32_t *info, int64_t B, 
 }
 
 extern "C" int tce_chol_bwd(const float *L, const float *grad_L, float *grad_A, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!L || !grad_L || !grad_A || B < 0 || n < 1 || n > 96) return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   const size_t smem = 3 * (size_t)n * (n + 1) * sizeof(double);
   TCE_CUDA(cudaFuncSetAttribute(chol_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cholb attr");
   chol_bwd_kernel<<<(unsigned)B, 128, smem, (cudaStream_t)stream>>>(L, grad_L, grad_A, n);
@@ -224,8 +224,8 @@ extern "C" int tce_chol_bwd(const float *L, const float *grad_L, float *grad_A, 
 
 extern "C" int tce_policy_head_fwd(const float *vec, int64_t ldb_vec, float min_std, float *L, int64_t B, int n,
                                    void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!vec || !L || B < 0 || n < 1) return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   head_fwd_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(vec, ldb_vec, min_std, L, n);
   TCE_CHECK_LAUNCH("head_fwd_kernel");
   return TCE_OK;
@@ -233,11 +233,11 @@ extern "C" int tce_policy_head_fwd(const float *vec, int64_t ldb_vec, float min_
 
 extern "C" int tce_policy_head_bwd(const float *vec, int64_t ldb_vec, const float *grad_L, float *grad_vec,
                                    int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!vec || !grad_L || !grad_vec || B < 0 || n < 1) return TCE_ERR_INVALID_ARGUMENT;
   const int nvec = n + n * (n - 1) / 2;
   cudaStream_t st = (cudaStream_t)stream;
   if (ldb_vec == 0) TCE_CUDA(cudaMemsetAsync(grad_vec, 0, nvec * sizeof(float), st), "head bwd memset");
-  if (B == 0) return TCE_OK;
   const int chunk = 32;
   dim3 grid((nvec + 127) / 128, (unsigned)((B + chunk - 1) / chunk));
   head_bwd_kernel<<<grid, 128, 0, st>>>(vec, ldb_vec, grad_L, grad_vec, B, n, chunk);

@@ -861,9 +861,9 @@ int set_smem(K kernel, size_t smem) {
 
 extern "C" int tce_gauss_stats(const float *mean, const float *L, int64_t ldb_L, const float *mean_o,
                                const float *L_o, int64_t ldb_Lo, double *out, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!mean || !mean_o || !L_o || !out || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
-  if (B == 0) return TCE_OK;
   const size_t smem = pj_smem_exclusive(pj_smem(n, 2), B);
   int rc = set_smem(gauss_kl_kernel, smem);
   if (rc) return rc;
@@ -876,9 +876,9 @@ extern "C" int tce_gauss_stats(const float *mean, const float *L, int64_t ldb_L,
 extern "C" int tce_gauss_stats_bwd(const float *mean, const float *L, int64_t ldb_L, const float *mean_o,
                                    const float *L_o, int64_t ldb_Lo, const double *grad_out, float *grad_mean,
                                    float *grad_L, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!mean || !mean_o || !L_o || !grad_out || B < 0 || (grad_L && !L)) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
-  if (B == 0) return TCE_OK;
   const size_t smem = pj_smem_exclusive(pj_smem(n, 2), B);
   int rc = set_smem(gauss_kl_kernel, smem);
   if (rc) return rc;
@@ -890,9 +890,9 @@ extern "C" int tce_gauss_stats_bwd(const float *mean, const float *L, int64_t ld
 
 extern "C" int tce_gauss_maha(const float *mean, const float *mean_o, const float *L_o, int64_t ldb_Lo,
                               const double *grad_out, double *maha, float *grad_mean, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!mean || !mean_o || !L_o || B < 0 || n < 1 || n > 128 || (grad_out && !grad_mean) || (!grad_out && !maha))
     return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   const size_t smem = 2 * (size_t)n * sizeof(double) + (size_t)n * (n | 1) * sizeof(float);
   if (smem > 48 * 1024)
     TCE_CUDA(cudaFuncSetAttribute(maha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "maha attr");
@@ -902,9 +902,9 @@ extern "C" int tce_gauss_maha(const float *mean, const float *mean_o, const floa
 }
 
 extern "C" int tce_tri_inverse(const float *L, int64_t ldb, double *Linv, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!L || !Linv || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
-  if (B == 0) return TCE_OK;
   const size_t smem = pj_smem(n, 2);
   int rc = set_smem(tri_inverse_kernel, smem);
   if (rc) return rc;
@@ -915,9 +915,9 @@ extern "C" int tce_tri_inverse(const float *L, int64_t ldb, double *Linv, int64_
 
 extern "C" int tce_gauss_maha_shared(const float *mean, const float *mean_o, const double *Linv, const double *grad_out,
                                      double *maha, float *grad_mean, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!mean || !mean_o || !Linv || B < 0 || n < 1 || n > 128 || (grad_out && !grad_mean) || (!grad_mean && !maha))
     return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   const int nw = 8;
   const size_t smem = sizeof(double) * ((size_t)n * (n | 1) + (size_t)nw * 2 * n);
   int rc = set_smem(maha_shared_kernel, smem);
@@ -931,8 +931,8 @@ extern "C" int tce_gauss_maha_shared(const float *mean, const float *mean_o, con
 
 extern "C" int tce_proj_mean_fwd(const float *mean, const float *mean_o, const double *mean_part, double eps,
                                  float *proj_mean, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!mean || !mean_o || !mean_part || !proj_mean || B < 0 || n < 1 || !(eps > 0)) return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   proj_mean_fwd_kernel<<<(unsigned)((B * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mean, mean_o, mean_part, eps,
                                                                                           proj_mean, B, n);
   TCE_CHECK_LAUNCH("proj_mean_fwd_kernel");
@@ -942,9 +942,9 @@ extern "C" int tce_proj_mean_fwd(const float *mean, const float *mean_o, const d
 extern "C" int tce_proj_mean_bwd(const float *mean, const float *mean_o, const double *mean_part, double eps,
                                  const float *grad_out, float *grad_mean, double *grad_mean_part, int64_t B, int n,
                                  void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!mean || !mean_o || !mean_part || !grad_out || !grad_mean || !grad_mean_part || B < 0 || n < 1)
     return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   proj_mean_bwd_kernel<<<(unsigned)((B * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       mean, mean_o, mean_part, eps, grad_out, grad_mean, grad_mean_part, B, n);
   TCE_CHECK_LAUNCH("proj_mean_bwd_kernel");
@@ -953,8 +953,8 @@ extern "C" int tce_proj_mean_bwd(const float *mean, const float *mean_o, const d
 
 extern "C" int tce_proj_entropy_fwd(const float *L, const double *beta, int64_t ldb_beta, int equality, float *out,
                                     double *entropy, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!L || !beta || !out || B < 0 || n < 1) return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   proj_entropy_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(L, beta, ldb_beta, equality, nullptr, out, entropy, n);
   TCE_CHECK_LAUNCH("proj_entropy_kernel");
   return TCE_OK;
@@ -962,8 +962,8 @@ extern "C" int tce_proj_entropy_fwd(const float *L, const double *beta, int64_t 
 
 extern "C" int tce_proj_entropy_bwd(const float *L, const double *beta, int64_t ldb_beta, int equality,
                                     const float *grad_out, float *grad_L, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!L || !beta || !grad_out || !grad_L || B < 0 || n < 1) return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   proj_entropy_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(L, beta, ldb_beta, equality, grad_out, grad_L, nullptr, n);
   TCE_CHECK_LAUNCH("proj_entropy_kernel(bwd)");
   return TCE_OK;
@@ -986,9 +986,9 @@ extern "C" size_t tce_proj_kl_save_doubles(int64_t B, int n) { return (size_t)B 
 
 extern "C" int tce_proj_kl_cov_fwd(const float *L, const float *L_o, double eps_cov, float *proj_L, double *save,
                                    int32_t *info, int warm_start, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!L || !L_o || !proj_L || !save || B < 0 || !(eps_cov > 0)) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
-  if (B == 0) return TCE_OK;
   const size_t smem = pj_smem_exclusive(pj_smem(n, 4) + sizeof(double) * LA_JACOBI_SCRATCH, B);
   int rc = set_smem(proj_kl_cov_fwd_kernel, smem);
   if (rc) return rc;
@@ -1002,9 +1002,9 @@ extern "C" int tce_proj_kl_cov_fwd(const float *L, const float *L_o, double eps_
 
 extern "C" int tce_proj_kl_cov_bwd(const float *L, const float *proj_L, const float *grad_out, const double *save,
                                    float *grad_L, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!L || !proj_L || !grad_out || !save || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
-  if (B == 0) return TCE_OK;
   const size_t smem = pj_smem_exclusive(pj_smem(n, 4), B);
   int rc = set_smem(proj_kl_cov_bwd_kernel, smem);
   if (rc) return rc;
@@ -1018,9 +1018,9 @@ extern "C" int tce_proj_kl_cov_bwd(const float *L, const float *proj_L, const fl
 
 extern "C" int tce_proj_frob_cov_fwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov, float *proj_L,
                                      double *save_sc, int32_t *info, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!L || !L_o || !proj_L || !save_sc || B < 0 || !(eps_cov > 0)) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
-  if (B == 0) return TCE_OK;
   const size_t smem = pj_smem_exclusive(pj_smem(n, 3), B);
   int rc = set_smem(proj_frob_cov_fwd_kernel, smem);
   if (rc) return rc;
@@ -1032,9 +1032,9 @@ extern "C" int tce_proj_frob_cov_fwd(const float *L, const float *L_o, int64_t l
 extern "C" int tce_proj_frob_cov_bwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov,
                                      const float *proj_L, const float *grad_out, const double *save_sc, float *grad_L,
                                      int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!L || !L_o || !proj_L || !grad_out || !save_sc || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
-  if (B == 0) return TCE_OK;
   const size_t smem = pj_smem_exclusive(pj_smem(n, 4), B);
   int rc = set_smem(proj_frob_cov_bwd_kernel, smem);
   if (rc) return rc;
@@ -1045,9 +1045,9 @@ extern "C" int tce_proj_frob_cov_bwd(const float *L, const float *L_o, int64_t l
 
 extern "C" int tce_proj_w2_cov_fwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov, int scale_prec,
                                    float *proj_L, double *save_sc, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!L || !L_o || !proj_L || !save_sc || B < 0 || !(eps_cov > 0)) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
-  if (B == 0) return TCE_OK;
   const size_t smem = pj_smem_exclusive(pj_smem(n, 5), B);
   int rc = set_smem(proj_w2_cov_kernel, smem);
   if (rc) return rc;
@@ -1058,9 +1058,9 @@ extern "C" int tce_proj_w2_cov_fwd(const float *L, const float *L_o, int64_t ldb
 
 extern "C" int tce_proj_w2_cov_bwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov, int scale_prec,
                                    const float *grad_out, float *grad_L, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!L || !L_o || !grad_out || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
-  if (B == 0) return TCE_OK;
   const size_t smem = pj_smem_exclusive(pj_smem(n, 5), B);
   int rc = set_smem(proj_w2_cov_kernel, smem);
   if (rc) return rc;
@@ -1071,10 +1071,10 @@ extern "C" int tce_proj_w2_cov_bwd(const float *L, const float *L_o, int64_t ldb
 
 extern "C" int tce_cov_distance(int kind, const float *L, const float *L_o, int64_t ldb_Lo, int scale_prec,
                                 const double *grad_val, double *val, float *grad_L, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (kind < 0 || kind > 1 || !L || !L_o || B < 0 || (grad_val && !grad_L) || (!grad_val && !val))
     return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
-  if (B == 0) return TCE_OK;
   const size_t smem = pj_smem_exclusive(pj_smem(n, 5), B);
   int rc = set_smem(cov_distance_kernel, smem);
   if (rc) return rc;

@@ -560,10 +560,10 @@ extern "C" int tce_seglik_gram(const tce_tables_t *t, const float *smp_traj, con
                                int64_t ldb_L, const float *times, const float *init_time, const float *init_pos,
                                const float *init_vel, const int64_t *pred_pairs, void *work, double *diag_max,
                                int64_t B, int64_t T, int64_t P, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!t || !smp_traj || !mean || !L || !times || !init_time || !init_pos || !init_vel || !pred_pairs || !work ||
       !diag_max || B < 0 || T < 1 || P < 1 || P > 4096)
     return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   cudaStream_t st = (cudaStream_t)stream;
   double *Cmat = (double *)work, *R = work_R(t, work, B, P);
 #define X(Dv, Kv)                                                                                                 \
@@ -589,9 +589,9 @@ extern "C" int tce_seglik_chol(const tce_tables_t *t, const void *work, void *ad
                                const float *grad_logp, const float *logp_old, const float *advantage,
                                double grad_scale, double *loss_acc, float *logp, int32_t *info, int64_t B,
                                int64_t P, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!t || !work || !diag_max || B < 0 || P < 1) return TCE_ERR_INVALID_ARGUMENT;
   if (logp_old && !advantage) return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const double *Cmat = (const double *)work, *R = work_R(t, const_cast<void *>(work), B, P);
   double *G = (double *)adj, *A = adj ? work_R(t, adj, B, P) : nullptr;
@@ -618,9 +618,9 @@ extern "C" int tce_seglik_bwd(const tce_tables_t *t, const void *work, const flo
                               const float *times, const float *init_time, const int64_t *pred_pairs,
                               const float *upstream, float *grad_mean, float *grad_L, int64_t B, int64_t T,
                               int64_t P, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!t || !work || !L || !times || !init_time || !pred_pairs || B < 0 || T < 1 || P < 1)
     return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const double *G = (const double *)work, *A = work_R(t, const_cast<void *>(work), B, P);
 #define X(Dv, Kv)                                                                                                \

@@ -271,9 +271,9 @@ int launch_traj_fwd(const tce_tables *t, const float *params, const float *times
 extern "C" int tce_prodmp_traj_fwd(const tce_tables_t *t, const float *params, const float *times,
                                    const float *init_time, const float *init_pos, const float *init_vel,
                                    float *traj, int64_t B, int64_t T, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!t || !params || !times || !init_time || !init_pos || !init_vel || !traj || B < 0 || T < 1)
     return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   TCE_DISPATCH_K1(t->K1, return launch_traj_fwd<K1>(t, params, times, init_time, init_pos, init_vel, traj, B, T,
                                                     (cudaStream_t)stream));
   return TCE_OK;
@@ -282,8 +282,8 @@ extern "C" int tce_prodmp_traj_fwd(const tce_tables_t *t, const float *params, c
 extern "C" int tce_prodmp_traj_bwd(const tce_tables_t *t, const float *grad_traj, const float *times,
                                    const float *init_time, float *grad_params, float *grad_init_pos,
                                    float *grad_init_vel, int64_t B, int64_t T, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!t || !grad_traj || !times || !init_time || B < 0 || T < 1) return TCE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return TCE_OK;
   const int threads = ((t->D * t->K1 + 2 * t->D + 31) / 32) * 32;
   TCE_DISPATCH_K1(t->K1, (traj_bwd_kernel<K1><<<(unsigned)B, threads, 0, (cudaStream_t)stream>>>(
                              tab_dev(t), grad_traj, times, init_time, grad_params, grad_init_pos, grad_init_vel,

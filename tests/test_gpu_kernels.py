@@ -240,3 +240,54 @@ def test_policy_head_and_gauss_stats():
     assert (st[:, 2] - pol.log_determinant(d("L"))).abs().max() < 1e-10
     assert (st[:, 3] - pol.log_determinant(d("L_old"))).abs().max() < 1e-10
     assert (st[:, 4] - pol.entropy([d("mean"), d("L")])).abs().max() < 1e-10
+
+
+def test_empty_batch_is_a_no_op():
+    """B = 0 (an empty shard of a data-parallel split): every entry point returns an empty result, no launch error."""
+    name = "box"
+    cfg, T, inp, times, pairs = setup_case(name, 4)
+    tabs = ops.Tables(**cfg)
+    c = lambda t: t.to(DEV)[:0].contiguous()
+    D, P = cfg["num_dof"], pairs.shape[0]
+    traj = ops.prodmp_traj(c(inp["mean"]), c(times), c(inp["init_time"]), c(inp["init_pos"]), c(inp["init_vel"]),
+                           tabs.handle, D)
+    assert traj.shape == (0, T, 2 * D)
+    lp = ops.seg_logprob(traj, c(inp["mean"]), c(inp["L"]), c(times), c(inp["init_time"]), c(inp["init_pos"]),
+                         c(inp["init_vel"]), pairs.to(DEV), tabs)
+    assert lp.shape == (0, P)
+    adv, ret = ops.gae(c(inp["rewards"]), c(inp["values"]), c(inp["dones"]), c(inp["time_limit_dones"]), 1.0, 0.95, True)
+    assert adv.shape[0] == 0 and ret.shape[0] == 0
+    z = ops.mvn_rsample(c(inp["mean"]), c(inp["L"]), c(inp["eps"]), 0, 0)
+    assert z.shape[0] == 0
+    torch.cuda.synchronize()
+
+
+def test_surrogate_single_factor_path_equals_broadcast_path():
+    """seg_surrogate on a stride-0 broadcast factor that carries its [1, n, n] origin (gradient = one GEMV batch
+    sum) == the same call on a materialised [B, n, n] factor followed by the batch sum."""
+    name, B = "box", 40
+    cfg, T, inp, times, pairs = setup_case(name, B)
+    tabs = ops.Tables(**cfg)
+    c = lambda t: t.to(DEV)
+    smp = ops.prodmp_traj(c(inp["mean"]) + 0.01, c(times), c(inp["init_time"]), c(inp["init_pos"]), c(inp["init_vel"]),
+                          tabs.handle, cfg["num_dof"])
+    P = pairs.shape[0]
+    lp_old = torch.zeros(B, P, device=DEV) - 30.0
+    adv = torch.linspace(-1, 1, B * P, device=DEV).reshape(B, P)
+    res = []
+    for mode in ("first", "dense"):
+        L1 = c(inp["L"][:1]).requires_grad_(True)
+        mean = c(inp["mean"]).requires_grad_(True)
+        if mode == "first":
+            L = L1.expand(B, -1, -1)
+            L._tce_first = L1
+        else:
+            L = L1.expand(B, -1, -1).contiguous()
+        loss, ratio, lp = ops.seg_surrogate(smp, mean, L, c(times), c(inp["init_time"]), c(inp["init_pos"]),
+                                            c(inp["init_vel"]), c(pairs), lp_old, adv, tabs)
+        loss.backward()
+        res.append((loss.detach(), lp, mean.grad, L1.grad))
+    (l0, lp0, gm0, gL0), (l1, lp1, gm1, gL1) = res
+    assert torch.equal(lp0, lp1) and torch.equal(l0, l1) and torch.equal(gm0, gm1)
+    assert gL0.shape == gL1.shape == (1,) + tuple(inp["L"].shape[1:])
+    assert (gL0 - gL1).abs().max() <= 2e-6 * gL1.abs().max()       # two fp32 summation orders
