@@ -158,6 +158,15 @@ int tce_proj_kl_cov_fwd(const float *L, const float *L_o, double eps_cov, float 
                         int32_t *info, int warm_start, int64_t B, int n, void *stream);
 int tce_proj_kl_cov_bwd(const float *L, const float *proj_L, const float *grad_out, const double *save,
                         float *grad_L, int64_t B, int n, void *stream);
+/* The same projection followed by the entropy control of tce_proj_entropy_fwd in ONE launch (the two are
+ * consecutive single-CTA kernels on the critical path of an epoch with a non-contextual covariance):
+ * proj_L = KL projection (kept for the backward), out_L = alpha(proj_L) * proj_L.  The backward takes the
+ * gradient w.r.t. out_L.                                                                                  */
+int tce_proj_kl_entropy_fwd(const float *L, const float *L_o, double eps_cov, const double *beta,
+                            int64_t ldb_beta, int equality, float *proj_L, float *out_L, double *save,
+                            int32_t *info, int warm_start, int64_t B, int n, void *stream);
+int tce_proj_kl_entropy_bwd(const float *L, const float *proj_L, const float *grad_out, const double *save,
+                            float *grad_L, int64_t B, int n, void *stream);
 /* Frobenius: S_new = (S + eta S_old) / (1 + eta), eta = sqrt(|S_old - S|_F^2 / eps_cov) - 1; save_sc [B,4] */
 int tce_proj_frob_cov_fwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov, float *proj_L,
                           double *save_sc, int32_t *info, int64_t B, int n, void *stream);

@@ -15,7 +15,7 @@ buf = (ctypes.c_longlong * 16)()
 _lib.call("tce_debug_kl_phase_cycles", buf)
 st = list(buf)[:10]
 names = ["load", "trsm W", "jacobi", "eta solve", "save", "load+gemm M", "gemm Sigma", "chol", "store"]
-print("state tail", state[-4:].tolist(), "sweeps", buf[15])
+print("state tail {eta, active, kl0, fingerprint, alpha, ent_active}", state[-8:-2].tolist(), "sweeps", buf[15])
 for i, n in enumerate(names):
     print(f"{n:14s} {st[i+1]-st[i]:9d} cycles")
 print("total", st[9]-st[0])

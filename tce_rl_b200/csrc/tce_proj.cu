@@ -16,6 +16,7 @@ namespace {
 constexpr int PJ_THREADS = 512;
 constexpr int KL_THREADS = 512;   // 128 registers per thread: 4x4 fp64 GEMM tiles and the register-resident Jacobi
 constexpr double LOG_2PI = 1.8378770664093453;
+constexpr int KL_SC = 8;      // scalars saved per matrix by the KL projection: eta, active, kl0, fingerprint, alpha, ent_active
 
 __device__ inline int pad_even(int n) { return (n + 1) & ~1; }
 
@@ -468,7 +469,8 @@ __global__ void __launch_bounds__(KL_THREADS)
 proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_o, double eps_cov,
                        float *__restrict__ proj_L, double *__restrict__ save_M, double *__restrict__ save_U,
                        double *__restrict__ save_Li, double *__restrict__ save_lam, double *__restrict__ save_sc,
-                       int32_t *__restrict__ info, int n, int warm_start) {
+                       int32_t *__restrict__ info, int n, int warm_start, const double *__restrict__ beta,
+                       long long ldb_beta, int entropy_eq, float *__restrict__ out_L) {
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
   Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
@@ -484,7 +486,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   double fp = 0.0;
   batched_load(Lo, n * n, [&](int e, float v) { fp = fma((double)(e % 251 + 1), (double)v, fp); });
   fp = block_sum(fp, red);
-  const bool warm = warm_start && save_sc[b * 4 + 3] == fp;
+  const bool warm = warm_start && save_sc[b * KL_SC + 3] == fp;
   if (warm) load_full_d(b1, save_M + off, n, m); else load_lower_d(b1, Lo, n, m);
   KL_STAMP(1);
   la_tri_inverse(b0, b2, dinv, n);                                                 // Lt^-1 (kept for the backward)
@@ -507,11 +509,11 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
     return v;
   }();
   const bool active = kl0 > eps_cov;
-  const double eta = active ? kl_solve_eta(lam, n, eps_cov, red, warm && save_sc[b * 4 + 1] != 0.0 ? save_sc[b * 4 + 0] : 0.0) : 0.0;
+  const double eta = active ? kl_solve_eta(lam, n, eps_cov, red, warm && save_sc[b * KL_SC + 1] != 0.0 ? save_sc[b * KL_SC + 0] : 0.0) : 0.0;
   KL_STAMP(4);
   la_gemm(b2, b0, b3, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // M = Lt U~
   if (threadIdx.x == 0) {
-    save_sc[b * 4 + 0] = eta; save_sc[b * 4 + 1] = active ? 1.0 : 0.0; save_sc[b * 4 + 2] = kl0; save_sc[b * 4 + 3] = fp;
+    save_sc[b * KL_SC + 0] = eta; save_sc[b * KL_SC + 1] = active ? 1.0 : 0.0; save_sc[b * KL_SC + 2] = kl0; save_sc[b * KL_SC + 3] = fp;
     if (blockIdx.x == 0) g_kl_prof[15] = sweeps;
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) save_lam[b * n + i] = lam[i];
@@ -522,8 +524,26 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   }
   KL_STAMP(5);
   float *out = proj_L + off;
+  // Fused entropy control (optional, `beta` != NULL): out_L = alpha * proj_L with
+  // alpha = exp((beta - H(proj_L)) / n) where H < beta (or always: equality variant), as proj_entropy_kernel.
+  auto entropy_scale = [&](Mat P) -> double {
+    if (!beta) return 1.0;
+    double sl = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sl += log(P(i, i));
+    sl = block_sum(sl, red);
+    const double H = 0.5 * n * (1.0 + LOG_2PI) + sl, bt = beta[b * ldb_beta];
+    const bool ent_active = entropy_eq || (H < bt);
+    const double alpha = ent_active ? exp((bt - H) / n) : 1.0;
+    if (threadIdx.x == 0) { save_sc[b * KL_SC + 4] = alpha; save_sc[b * KL_SC + 5] = ent_active ? 1.0 : 0.0; }
+    return alpha;
+  };
   if (!active) {                                                                    // identity
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) out[e] = (e % n <= e / n) ? Lt[e] : 0.f;
+    const double alpha = entropy_scale(b0);
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const float v = (e % n <= e / n) ? Lt[e] : 0.f;
+      out[e] = v;
+      if (out_L) out_L[off + e] = (float)(alpha * (double)v);
+    }
     if (info && threadIdx.x == 0) info[b] = 0;
     return;
   }
@@ -537,7 +557,9 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   KL_STAMP(7);
   la_chol(b1, n, &s_bad);
   KL_STAMP(8);
+  const double alpha = entropy_scale(b1);
   store_lower_f(out, b1, n, 1.0);
+  if (out_L) store_lower_f(out_L + off, b1, n, alpha);
   if (info && threadIdx.x == 0) info[b] = s_bad;
   KL_STAMP(9);
 }
@@ -554,7 +576,7 @@ __global__ void __launch_bounds__(KL_THREADS)
 proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ proj_L, const float *__restrict__ gout,
                        const double *__restrict__ save_M, const double *__restrict__ save_U,
                        const double *__restrict__ save_Li, const double *__restrict__ save_lam,
-                       const double *__restrict__ save_sc, float *__restrict__ grad_L, int n) {
+                       const double *__restrict__ save_sc, float *__restrict__ grad_L, int n, int fused_entropy) {
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
   Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
@@ -563,14 +585,37 @@ proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ pr
   const size_t off = (size_t)b * n * n;
   float *gl = grad_L + off;
   (void)L;
-  const double eta = save_sc[b * 4 + 0];
-  if (save_sc[b * 4 + 1] == 0.0) {                                                 // inactive: identity
+  const double eta = save_sc[b * KL_SC + 0];
+  const bool kl_active = save_sc[b * KL_SC + 1] != 0.0;
+  if (!kl_active && !fused_entropy) {                                              // identity
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) gl[e] = (e % n <= e / n) ? gout[off + e] : 0.f;
     return;
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) { lam[i] = save_lam[b * n + i]; rho[i] = 1.0 / (lam[i] + eta); }
   load_lower_d(b0, proj_L + off, n, m);                                            // P
   load_lower_d(b1, gout + off, n, m);                                              // G
+  if (fused_entropy) {               // G <- adjoint of out_L = alpha(P) P  (proj_entropy_kernel, backward branch)
+    const double alpha = save_sc[b * KL_SC + 4];
+    const bool ent_active = save_sc[b * KL_SC + 5] != 0.0;
+    double dot = 0.0;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e - i * n;
+      if (j <= i) dot = fma(b1(i, j), b0(i, j), dot);
+    }
+    dot = block_sum(dot, red);
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e - i * n;
+      if (j > i) continue;
+      double v = alpha * b1(i, j);
+      if (i == j && ent_active) v -= dot * alpha / (n * b0(i, i));
+      b1(i, j) = v;
+    }
+    __syncthreads();
+    if (!kl_active) {                                                              // identity KL step
+      store_lower_f(gl, b1, n, 1.0);
+      return;
+    }
+  }
   la_gemm(b2, b0.T(), b1, n, n, n, TRI_UPPER, TRI_LOWER, TRI_FULL, 1.0, 0.0);      // P^T G
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     const int i = e / n, j = e - i * n;
@@ -982,10 +1027,11 @@ extern "C" int tce_debug_kl_phase_cycles(long long *out16) {
   return TCE_OK;
 }
 
-extern "C" size_t tce_proj_kl_save_doubles(int64_t B, int n) { return (size_t)B * (3 * (size_t)n * n + n + 4); }
+extern "C" size_t tce_proj_kl_save_doubles(int64_t B, int n) { return (size_t)B * (3 * (size_t)n * n + n + KL_SC); }
 
-extern "C" int tce_proj_kl_cov_fwd(const float *L, const float *L_o, double eps_cov, float *proj_L, double *save,
-                                   int32_t *info, int warm_start, int64_t B, int n, void *stream) {
+static int kl_fwd_launch(const float *L, const float *L_o, double eps_cov, const double *beta, int64_t ldb_beta,
+                         int equality, float *proj_L, float *out_L, double *save, int32_t *info, int warm_start,
+                         int64_t B, int n, void *stream) {
   if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!L || !L_o || !proj_L || !save || B < 0 || !(eps_cov > 0)) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
@@ -994,14 +1040,14 @@ extern "C" int tce_proj_kl_cov_fwd(const float *L, const float *L_o, double eps_
   if (rc) return rc;
   const size_t nn = (size_t)B * n * n;
   double *M = save, *U = M + nn, *Li = U + nn, *lam = Li + nn, *sc = lam + (size_t)B * n;
-  proj_kl_cov_fwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, L_o, eps_cov, proj_L, M, U, Li, lam, sc,
-                                                                                 info, n, warm_start);
+  proj_kl_cov_fwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(
+      L, L_o, eps_cov, proj_L, M, U, Li, lam, sc, info, n, warm_start, beta, (long long)ldb_beta, equality, out_L);
   TCE_CHECK_LAUNCH("proj_kl_cov_fwd_kernel");
   return TCE_OK;
 }
 
-extern "C" int tce_proj_kl_cov_bwd(const float *L, const float *proj_L, const float *grad_out, const double *save,
-                                   float *grad_L, int64_t B, int n, void *stream) {
+static int kl_bwd_launch(const float *L, const float *proj_L, const float *grad_out, const double *save, float *grad_L,
+                         int64_t B, int n, int fused_entropy, void *stream) {
   if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!L || !proj_L || !grad_out || !save || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
@@ -1011,9 +1057,31 @@ extern "C" int tce_proj_kl_cov_bwd(const float *L, const float *proj_L, const fl
   const size_t nn = (size_t)B * n * n;
   const double *M = save, *U = M + nn, *Li = U + nn, *lam = Li + nn, *sc = lam + (size_t)B * n;
   proj_kl_cov_bwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, proj_L, grad_out, M, U, Li, lam, sc, grad_L,
-                                                                                 n);
+                                                                                 n, fused_entropy);
   TCE_CHECK_LAUNCH("proj_kl_cov_bwd_kernel");
   return TCE_OK;
+}
+
+extern "C" int tce_proj_kl_cov_fwd(const float *L, const float *L_o, double eps_cov, float *proj_L, double *save,
+                                   int32_t *info, int warm_start, int64_t B, int n, void *stream) {
+  return kl_fwd_launch(L, L_o, eps_cov, nullptr, 0, 0, proj_L, nullptr, save, info, warm_start, B, n, stream);
+}
+
+extern "C" int tce_proj_kl_cov_bwd(const float *L, const float *proj_L, const float *grad_out, const double *save,
+                                   float *grad_L, int64_t B, int n, void *stream) {
+  return kl_bwd_launch(L, proj_L, grad_out, save, grad_L, B, n, 0, stream);
+}
+
+extern "C" int tce_proj_kl_entropy_fwd(const float *L, const float *L_o, double eps_cov, const double *beta,
+                                       int64_t ldb_beta, int equality, float *proj_L, float *out_L, double *save,
+                                       int32_t *info, int warm_start, int64_t B, int n, void *stream) {
+  if (B != 0 && (!beta || !out_L)) return TCE_ERR_INVALID_ARGUMENT;
+  return kl_fwd_launch(L, L_o, eps_cov, beta, ldb_beta, equality, proj_L, out_L, save, info, warm_start, B, n, stream);
+}
+
+extern "C" int tce_proj_kl_entropy_bwd(const float *L, const float *proj_L, const float *grad_out, const double *save,
+                                       float *grad_L, int64_t B, int n, void *stream) {
+  return kl_bwd_launch(L, proj_L, grad_out, save, grad_L, B, n, 1, stream);
 }
 
 extern "C" int tce_proj_frob_cov_fwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov, float *proj_L,

@@ -888,6 +888,63 @@ class _ProjKLCov(torch.autograd.Function):
         return proj_kl_cov_bwd(g.contiguous(), L, proj_L, ctx.state), None, None, None, None
 
 
+@torch.library.custom_op("tce::proj_kl_entropy_fwd", mutates_args=("state",))
+def proj_kl_entropy_fwd(L: Tensor, L_o: Tensor, eps_cov: float, state: Tensor, warm: bool, beta: Tensor,
+                        equality: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """KL covariance projection + entropy control in one launch -> (out_L, proj_L (pre-entropy), info)."""
+    L, L_o = _chk(L, name="L"), _chk(L_o, name="L_o")
+    beta = _chk(beta, torch.float64, "beta")
+    Bc, n = L.shape[0], L.shape[-1]
+    if state.dtype != torch.float64 or not state.is_cuda or state.numel() != _lib.load().tce_proj_kl_save_doubles(Bc, n):
+        raise TceError("state must come from ops.kl_state(batch, n, device)")
+    out, proj = torch.empty_like(L), torch.empty_like(L)
+    info = torch.empty(Bc, device=L.device, dtype=torch.int32)
+    _lib.call("tce_proj_kl_entropy_fwd", _p(L), _p(L_o), float(eps_cov), _p(beta), 0 if beta.numel() == 1 else 1,
+              int(equality), _p(proj), _p(out), _p(state), _p(info), int(warm), Bc, n, _stream())
+    return out, proj, info
+
+
+@proj_kl_entropy_fwd.register_fake
+def _(L, L_o, eps_cov, state, warm, beta, equality):
+    return torch.empty_like(L), torch.empty_like(L), L.new_empty(L.shape[0], dtype=torch.int32)
+
+
+@torch.library.custom_op("tce::proj_kl_entropy_bwd", mutates_args=())
+def proj_kl_entropy_bwd(grad_out: Tensor, L: Tensor, proj_L: Tensor, state: Tensor) -> Tensor:
+    g, L, proj_L = _chk(grad_out), _chk(L), _chk(proj_L)
+    out = torch.empty_like(L)
+    _lib.call("tce_proj_kl_entropy_bwd", _p(L), _p(proj_L), _p(g), _p(state), _p(out), L.shape[0], L.shape[-1],
+              _stream())
+    return out
+
+
+@proj_kl_entropy_bwd.register_fake
+def _(grad_out, L, proj_L, state):
+    return torch.empty_like(L)
+
+
+class _ProjKLEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, L, L_o, eps_cov, state, warm, beta, equality):
+        out, proj_L, info = proj_kl_entropy_fwd(L, L_o, eps_cov, state, warm, beta, equality)
+        ctx.save_for_backward(L, proj_L)
+        ctx.state = state
+        ctx.mark_non_differentiable(proj_L, info)
+        return out, proj_L, info
+
+    @staticmethod
+    def backward(ctx, g, g_proj, g_info):
+        L, proj_L = ctx.saved_tensors
+        return proj_kl_entropy_bwd(g.contiguous(), L, proj_L, ctx.state), None, None, None, None, None, None
+
+
+def proj_kl_entropy(L: Tensor, L_o: Tensor, eps_cov: float, state: Tensor, warm: bool, beta: Tensor,
+                    equality: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """``proj_entropy(proj_kl_cov(L, L_o, ...)[0], beta, equality)[0]`` as ONE forward and ONE backward kernel
+    -> (out_L, proj_L before the entropy control [not differentiable], info)."""
+    return _ProjKLEntropy.apply(L, L_o, eps_cov, state, warm, beta, equality)
+
+
 def proj_kl_cov(L: Tensor, L_o: Tensor, eps_cov: float, state: Tensor, warm: bool) -> Tuple[Tensor, Tensor]:
     """-> (proj_L [Bc,n,n], info [Bc]); ``state`` (``kl_state``) is overwritten with {M = L_o Q, lambda, eta, ...}:
     it feeds the backward and, with ``warm``, the next call with the same ``L_o`` starts its eigen-solve from it

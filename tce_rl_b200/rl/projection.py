@@ -175,6 +175,10 @@ class BaseProjectionLayer:
     def _cov_projection(self, policy, L, L_old):
         return L
 
+    def _cov_projection_with_entropy(self, policy, L, L_old, beta):
+        """Covariance projection and entropy control as one op, or None if the layer has no fused kernel."""
+        return None
+
     def _trust_region_projection(self, policy, p, q):
         if not self.projects:
             return p
@@ -221,10 +225,14 @@ class BaseProjectionLayer:
         side = self._side_stream(L.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            proj_L1 = self._cov_projection(policy, _first(L), _first(old_L))
             beta = self._entropy_bound(step, L.device)
-            if beta is not None:
-                proj_L1 = ops.proj_entropy(proj_L1.contiguous(), beta, self.entropy_eq)[0]
+            fused = self._cov_projection_with_entropy(policy, _first(L), _first(old_L), beta) if beta is not None else None
+            if fused is not None:                               # one kernel each way (KL layer)
+                proj_L1 = fused
+            else:
+                proj_L1 = self._cov_projection(policy, _first(L), _first(old_L))
+                if beta is not None:
+                    proj_L1 = ops.proj_entropy(proj_L1.contiguous(), beta, self.entropy_eq)[0]
             proj_L1.record_stream(main)
             # broadcast here: the backward of the expand (a [B, n, n] -> [n, n] reduction) then runs on the side
             # stream in front of the covariance backward instead of delaying the mean chain on the main stream
@@ -280,6 +288,17 @@ class KLProjectionLayer(BaseProjectionLayer):
         self.warm_start = bool(warm_start)
         self._kl_state = None
 
+    fuse_entropy = True      # KL projection + entropy control in one launch (start_cov_projection)
+
+    def _state_for(self, Lc):
+        state = self._kl_state
+        if (not self.warm_start or state is None or state.device != Lc.device
+                or state.numel() != ops.kl_state_size(Lc.shape[0], Lc.shape[-1])):
+            state = ops.kl_state(Lc.shape[0], Lc.shape[-1], Lc.device)
+            if self.warm_start:
+                self._kl_state = state
+        return state
+
     def _mean_part(self, policy, p, q):
         linv = shared_inverse(q[1]) if (_shared(policy, q[1]) and q[1].is_cuda) else None
         self._old_linv = linv                                   # reused by the logging branch of the same epoch
@@ -289,13 +308,16 @@ class KLProjectionLayer(BaseProjectionLayer):
         if policy.is_diag:
             raise NotImplementedError("diagonal KL projection is outside the TCE configs")
         Lc = L.contiguous()
-        state = self._kl_state
-        if (not self.warm_start or state is None or state.device != Lc.device
-                or state.numel() != ops.kl_state_size(Lc.shape[0], Lc.shape[-1])):
-            state = ops.kl_state(Lc.shape[0], Lc.shape[-1], Lc.device)
-            if self.warm_start:
-                self._kl_state = state
+        state = self._state_for(Lc)
         return ops.proj_kl_cov(Lc, L_old.contiguous(), self.cov_bound, state, self.warm_start)[0]
+
+    def _cov_projection_with_entropy(self, policy, L, L_old, beta):
+        if policy.is_diag or not self.fuse_entropy:
+            return None
+        Lc = L.contiguous()
+        state = self._state_for(Lc)
+        return ops.proj_kl_entropy(Lc, L_old.contiguous(), self.cov_bound, state, self.warm_start, beta,
+                                   self.entropy_eq)[0]
 
 
 class FrobeniusProjectionLayer(BaseProjectionLayer):

@@ -255,3 +255,31 @@ def test_shared_covariance_maha_matches_per_episode_kernel(name):
     assert (g_got - g_ref).abs().max() <= 2e-6 * g_ref.abs().max()     # fp32 outputs
     g_kernel = ops.gauss_maha_shared_bwd(w, mean.detach(), mean_o, Linv)  # stand-alone gradient entry point
     assert (g_kernel - g_ref).abs().max() <= 2e-6 * g_ref.abs().max()
+
+
+@pytest.mark.parametrize("beta_shift,equality", [(+0.5, False), (-0.5, False), (-0.5, True)])
+def test_fused_kl_entropy_equals_the_two_separate_ops(beta_shift, equality):
+    """tce_proj_kl_entropy_fwd/bwd == tce_proj_kl_cov_* followed by tce_proj_entropy_* (values bit-equal up to the
+    fp32 store, gradients to 1e-6): entropy bound above (active), below (inactive) and the equality variant."""
+    inp = synthetic_inputs("box", 3, dtype=torch.float32)
+    L0, Lo = inp["L"].to(DEV), inp["L_old"].to(DEV)
+    n = L0.shape[-1]
+    H = 0.5 * n * (1.0 + 1.8378770664093453) + torch.diagonal(Lo, dim1=-2, dim2=-1).double().log().sum(-1)
+    beta = (H.mean() + beta_shift).reshape(1).to(torch.float64)
+    w = torch.linspace(0.5, 1.5, L0.numel(), device=DEV).reshape(L0.shape)
+    res = []
+    for fused in (True, False):
+        L = L0.clone().requires_grad_(True)
+        state = ops.kl_state(L.shape[0], n, DEV)
+        if fused:
+            out, proj, info = ops.proj_kl_entropy(L, Lo, 5e-4, state, False, beta, equality)
+        else:
+            proj, info = ops.proj_kl_cov(L, Lo, 5e-4, state, False)
+            out = ops.proj_entropy(proj, beta, equality)[0]
+        assert int(info.abs().max()) == 0
+        (out * w).sum().backward()
+        res.append((out.detach(), proj.detach(), L.grad))
+    (o1, p1, g1), (o2, p2, g2) = res
+    assert torch.equal(p1, p2)
+    assert (o1 - o2).abs().max() <= 2e-7 * o2.abs().max()
+    assert (g1 - g2).abs().max() <= 2e-6 * g2.abs().max()
