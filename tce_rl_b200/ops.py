@@ -463,7 +463,10 @@ def _sur_backward(ctx, g_stats, g_logp, g_adj, g_info):
     none = (None,) * 12
     if g_stats is None:
         return none
-    up = g_stats[0].to(torch.float32).reshape(1)           # d total / d surrogate loss (device scalar, no sync)
+    if g_stats is _E0.get(str(g_stats.device)):            # unit seed (see unit_seed): d total / d surrogate = 1
+        up = unit_seed(g_stats.device, torch.float32).reshape(1)
+    else:
+        up = g_stats[0].to(torch.float32).reshape(1)       # d total / d surrogate loss (device scalar, no sync)
     g_mean, g_L = seglik_surrogate_bwd(up, adj, L, times, init_time, pred_pairs, ctx.tables, ctx.dim_params)
     return None, g_mean, g_L, None, None, None, None, None, None, None, None, None
 
@@ -504,7 +507,21 @@ class _StatsToFloat(torch.autograd.Function):
     def backward(ctx, g_loss, g_ratio):
         if g_loss is None:
             return None
+        if g_loss is unit_seed(g_loss.device, g_loss.dtype):   # seeded with the cached 1: no kernel at all
+            return ctx.e0
         return ctx.e0 * g_loss                            # fp64 [2] = {d/d loss, 0}
+
+
+_UNIT = {}
+
+
+def unit_seed(device, dtype) -> Tensor:
+    """A cached 0-dim 1.0: pass it as the gradient of a loss term to ``torch.autograd.backward`` -- the likelihood
+    ops recognise it (by identity) and skip the scalar bookkeeping kernels in front of their backward stage."""
+    key = (str(device), dtype)
+    if key not in _UNIT:
+        _UNIT[key] = torch.ones((), device=device, dtype=dtype)
+    return _UNIT[key]
 
 
 # --------------------------------------------------------------------------------------------------

@@ -330,18 +330,13 @@ class TemporalCorrelatedAgent:
         # entropy coefficient 0 (every config): the entropy term is a logging value, policy_loss + (-0.0) is
         # policy_loss -- evaluate it with the other logging values next to the backward
         defer_entropy = self.entropy_penalty_coef == 0.0 and self.overlap_logging and proj[0].is_cuda
+        proj_ready = None
         if self.overlap_logging and proj[0].is_cuda:
             if self._tr_stream is None:
                 self._tr_stream = torch.cuda.Stream(device=proj[0].device)
-            tr_stream, cur = self._tr_stream, torch.cuda.current_stream()
-            tr_stream.wait_stream(cur)
-            with torch.cuda.stream(tr_stream):
-                tr_loss = self.projection.get_trust_region_loss(self.policy, new, proj, set_variance=self.set_variance)
-                tr_loss.record_stream(cur)
-                if not defer_entropy:
-                    ent_loss, ent_stats = self._entropy_term(proj)
-                    ent_loss.record_stream(cur)
-                    ent_stats["entropy"].record_stream(cur)
+            tr_stream = self._tr_stream
+            proj_ready = torch.cuda.Event()                # everything the trust-region branch reads exists here
+            proj_ready.record()
         if self.fused_surrogate and hasattr(self.policy, "segment_surrogate"):
             surrogate, ratio, _ = self.policy.segment_surrogate(
                 dataset["step_actions"], proj[0], proj[1], times, dataset["segment_init_time"],
@@ -359,16 +354,37 @@ class TemporalCorrelatedAgent:
             ent_loss, ent_stats = self._entropy_term(proj)
             tr_loss = self.projection.get_trust_region_loss(self.policy, new, proj, set_variance=self.set_variance)
         else:
-            torch.cuda.current_stream().wait_stream(tr_stream)
-        policy_loss = surrogate + tr_loss if defer_entropy else surrogate + ent_loss + tr_loss
+            # Built AFTER the likelihood in program order (autograd runs nodes in reverse creation order: this
+            # branch's backward -- a long single-CTA kernel -- is then queued before, not behind, the likelihood's
+            # backward stage) but ordered on the device only after `proj_ready`, i.e. next to the likelihood.
+            cur = torch.cuda.current_stream()
+            tr_stream.wait_event(proj_ready)
+            with torch.cuda.stream(tr_stream):
+                tr_loss = self.projection.get_trust_region_loss(self.policy, new, proj, set_variance=self.set_variance)
+                tr_loss.record_stream(cur)
+                if not defer_entropy:
+                    ent_loss, ent_stats = self._entropy_term(proj)
+                    ent_loss.record_stream(cur)
+                    ent_stats["entropy"].record_stream(cur)
+        # With the entropy term deferred the total loss is surrogate + tr_loss: the two terms are handed to autograd
+        # as separate roots seeded with a cached 1 (no add / fill / cast kernels in front of the likelihood's
+        # backward stage, and the main stream need not wait for the trust-region branch in the forward); the SUM
+        # is only a logging value and is formed on the logging branch.
+        split_roots = defer_entropy and tr_stream is not None
+        if not split_roots:
+            if tr_stream is not None:
+                torch.cuda.current_stream().wait_stream(tr_stream)
+            policy_loss = surrogate + tr_loss if defer_entropy else surrogate + ent_loss + tr_loss
         # logging-only KL decomposition: a parallel branch (side stream) next to backward + Adam
         main, side = None, None
-        if self.overlap_logging and policy_loss.is_cuda:
+        if self.overlap_logging and surrogate.is_cuda:
             main = torch.cuda.current_stream()
             if self._log_stream is None:
-                self._log_stream = torch.cuda.Stream(device=policy_loss.device)
+                self._log_stream = torch.cuda.Stream(device=surrogate.device)
             side = self._log_stream
             side.wait_stream(main)
+            if split_roots:
+                side.wait_stream(tr_stream)
             with torch.cuda.stream(side):
                 kl = self.kl_old_new_proj(new, old, proj)
                 kl.record_stream(main)
@@ -376,11 +392,18 @@ class TemporalCorrelatedAgent:
                     ent_loss, ent_stats = self._entropy_term(proj)
                     ent_loss.record_stream(main)
                     ent_stats["entropy"].record_stream(main)
+                if split_roots:
+                    policy_loss = surrogate.detach() + tr_loss.detach()
+                    policy_loss.record_stream(main)
         else:
             kl = self.kl_old_new_proj(new, old, proj)
         if not zeroed_early:
             self.policy_optimizer.zero_grad(set_to_none=False)
-        policy_loss.backward()
+        if split_roots:
+            torch.autograd.backward([surrogate, tr_loss], [ops.unit_seed(surrogate.device, surrogate.dtype),
+                                                           ops.unit_seed(tr_loss.device, tr_loss.dtype)])
+        else:
+            policy_loss.backward()
         util.join_side_grads()                             # weight gradients of the mean net (side streams)
         self._allreduce_grads(self.policy_net_params)
         grad_norm = self._grad_norm_clip(self.policy_net_params)
