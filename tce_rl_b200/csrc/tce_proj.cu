@@ -909,8 +909,8 @@ extern "C" int tce_gauss_stats(const float *mean, const float *L, int64_t ldb_L,
   if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!mean || !mean_o || !L_o || !out || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
-  const size_t smem = pj_smem_exclusive(pj_smem(n, 2), B);
-  int rc = set_smem(gauss_kl_kernel, smem);
+  const size_t smem = pj_smem(n, 2);      // NOT exclusive: these run beside the likelihood kernels (trust-region loss,
+  int rc = set_smem(gauss_kl_kernel, smem);   // logging) and must fit into the first CTA slot that frees up
   if (rc) return rc;
   gauss_kl_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(mean, L, ldb_L, mean_o, L_o, ldb_Lo, out,
                                                                           nullptr, nullptr, nullptr, n, L ? 0 : 1);
@@ -924,8 +924,8 @@ extern "C" int tce_gauss_stats_bwd(const float *mean, const float *L, int64_t ld
   if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!mean || !mean_o || !L_o || !grad_out || B < 0 || (grad_L && !L)) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
-  const size_t smem = pj_smem_exclusive(pj_smem(n, 2), B);
-  int rc = set_smem(gauss_kl_kernel, smem);
+  const size_t smem = pj_smem(n, 2);      // NOT exclusive: these run beside the likelihood kernels (trust-region loss,
+  int rc = set_smem(gauss_kl_kernel, smem);   // logging) and must fit into the first CTA slot that frees up
   if (rc) return rc;
   gauss_kl_kernel<<<(unsigned)B, PJ_THREADS, smem, (cudaStream_t)stream>>>(mean, L, ldb_L, mean_o, L_o, ldb_Lo, nullptr,
                                                                           grad_out, grad_mean, grad_L, n, grad_L ? 0 : 1);

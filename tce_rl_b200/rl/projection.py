@@ -45,7 +45,9 @@ _HELPER_STREAMS = {}
 
 
 def _helper_stream(device):
-    key = str(device)
+    """One helper stream PER PARENT stream: the trust-region branch and the logging branch both fork their mean part
+    off; on a shared helper the (critical) mean gradient of the first would queue behind logging kernels."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
     if key not in _HELPER_STREAMS:
         _HELPER_STREAMS[key] = torch.cuda.Stream(device=device)
     return _HELPER_STREAMS[key]
@@ -103,6 +105,38 @@ def gaussian_kl(policy, p, q):
     """(mean part, covariance part) of KL(p || q), each [B] fp64 (projection_utils.gaussian_kl)."""
     mean_part, cov_part, _, _ = gaussian_kl_details(policy, p, q)
     return mean_part, cov_part
+
+
+_KL_LOSS_CONST = {}
+
+
+class _SharedKLLoss(torch.autograd.Function):
+    """loss = coeff * (mean_b 1/2 maha_b + [with_cov] (shape + volume)),  shape = 1/2 (tr - k),
+    volume = 1/2 (logdet_q - logdet_p), from maha [B] and the five scalars st [1, 5] of ``gauss_stats``.
+    Also returns the detached per-term values for the logging branch."""
+
+    @staticmethod
+    def forward(ctx, maha, st, coeff, with_cov, k, out_dtype):
+        B, dev = maha.shape[0], maha.device
+        key = (B, coeff, with_cov, str(dev))
+        if key not in _KL_LOSS_CONST:
+            w = torch.tensor([[0.0, 0.5, -0.5, 0.5, 0.0]], dtype=torch.float64, device=dev)
+            _KL_LOSS_CONST[key] = (w, torch.full((B,), 0.5 * coeff / B, dtype=torch.float64, device=dev),
+                                   w * (coeff if with_cov else 0.0))
+        w, ctx.g_maha, ctx.g_st = _KL_LOSS_CONST[key]
+        mean_diff = 0.5 * maha
+        shape, volume = 0.5 * (st[:, 1] - k), 0.5 * (st[:, 3] - st[:, 2])
+        cov_diff = shape + volume
+        loss = mean_diff.mean() + cov_diff[0] if with_cov else mean_diff.mean()
+        ctx.mark_non_differentiable(mean_diff, cov_diff, shape, volume)
+        return (loss * coeff).to(out_dtype), mean_diff, cov_diff, shape, volume
+
+    @staticmethod
+    def backward(ctx, g, *_unused):
+        if g is ops.unit_seed(g.device, g.dtype):                          # the usual case: no kernel at all
+            return ctx.g_maha, ctx.g_st, None, None, None, None
+        g = g.to(torch.float64)
+        return ctx.g_maha * g, ctx.g_st * g, None, None, None, None
 
 
 def _entropy_schedule(kind, total_train_steps, dim):
@@ -257,13 +291,36 @@ class BaseProjectionLayer:
     def get_trust_region_loss(self, policy, p, proj_p, set_variance=None):
         """coeff * mean(mean_diff [+ cov_diff]) between p and the DETACHED projection."""
         target = (proj_p[0].detach(), proj_p[1].detach())
-        if type(self).trust_region_value is BaseProjectionLayer.trust_region_value:      # KL metric
+        kl_metric = type(self).trust_region_value is BaseProjectionLayer.trust_region_value
+        if kl_metric and p[0].is_cuda and _shared(policy, p[1]):
+            return self._shared_kl_trust_region_loss(policy, p, target, set_variance)
+        if kl_metric:      # KL metric
             mean_diff, cov_diff, shape, volume = gaussian_kl_details(policy, p, target)
             self.cache["new_proj"] = tuple(x.detach() for x in (mean_diff, cov_diff, shape, volume))
         else:
             mean_diff, cov_diff = self.trust_region_value(policy, p, target)
         loss = (mean_diff + cov_diff if self._with_cov(policy, set_variance) else mean_diff).mean()
         return (loss * self.trust_region_coeff).to(p[0].dtype)
+
+    def _shared_kl_trust_region_loss(self, policy, p, target, set_variance):
+        """KL metric, ONE covariance for the batch: same value as the generic path, but the loss arithmetic is one
+        autograd node (``_SharedKLLoss``) whose backward hands out cached constant gradients -- the generic
+        formulation costs ~12 small launches each way, and in the backward they sit between the loss seed and
+        the single-CTA covariance kernel / the mean gradient the mean net is waiting for."""
+        cur, helper = torch.cuda.current_stream(), _helper_stream(p[0].device)
+        helper.wait_stream(cur)
+        with torch.cuda.stream(helper):                                    # mean part beside the covariance part
+            maha = _maha(policy, p[0], target[0], target[1])
+            maha.record_stream(cur)
+        L1, Lt1 = _first(p[1]), _first(target[1])
+        zeros = torch.zeros(1, L1.shape[-1], device=L1.device)
+        st = ops.gauss_stats(zeros, L1.contiguous(), zeros, Lt1)          # [1, 5]
+        cur.wait_stream(helper)
+        with_cov = self._with_cov(policy, set_variance)
+        loss, mean_diff, cov_diff, shape, volume = _SharedKLLoss.apply(
+            maha, st, float(self.trust_region_coeff), bool(with_cov), int(p[0].shape[-1]), p[0].dtype)
+        self.cache["new_proj"] = (mean_diff, cov_diff, shape, volume)
+        return loss
 
     def compute_metrics(self, policy, p, q, step=None):
         with torch.no_grad():
