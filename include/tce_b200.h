@@ -236,6 +236,18 @@ int tce_sum_stats(const float *x, double *stats, int64_t N, void *stream);
 /* (x - mean) / (std_unbiased + 1e-8) with mean/std from stats[3] (temporal_correlated_agent.py:281-284) */
 int tce_normalize_by_stats(float *x, const double *stats, int64_t N, void *stream);
 
+/* ---- optimiser step of the policy epoch (temporal_correlated_agent.py:561-589: clip_grad_norm_, Adam.step) ----
+ * All gradients live in ONE flat fp32 buffer (16-byte aligned) in the order of `params`.
+ * tce_grad_sumsq: state[0] += 1 (step counter), state[1] += sum g^2 (caller zeroes state[1] beforehand).
+ * tce_adam_step : torch.optim.Adam (L2 weight decay, bias correction with t = state[0], no amsgrad) on the
+ *                 gradient scaled by min(1, max_norm / (sqrt(state[1]) + 1e-6)) (max_norm <= 0: no clipping).
+ * `params` / `sizes` are HOST arrays (count <= 32) of device pointers and element counts; m, v are flat fp32
+ * moment buffers of sum(sizes) elements.                                                                   */
+int tce_grad_sumsq(const float *grad_flat, int64_t n, double *state, void *stream);
+int tce_adam_step(int count, float *const *params, const int64_t *sizes, const float *grad_flat, float *m,
+                  float *v, const double *state, double max_norm, double lr, double beta1, double beta2,
+                  double eps, double weight_decay, void *stream);
+
 /* ---- measurement helper ---------------------------------------------------------------------------------
  * One register-resident FMA-chain kernel (fp32 or fp64) over the whole chip; *flops (host) receives the
  * FLOPs executed.  bench.py times it to obtain the FMA-pipe roofline denominators.                      */

@@ -81,11 +81,14 @@ class TemporalCorrelatedAgent:
         self.use_cuda_graph = bool(kwargs.get("use_cuda_graph", False))
         self.fused_surrogate = bool(kwargs.get("fused_surrogate", True))
         self.overlap_logging = bool(kwargs.get("overlap_logging", True))
+        self.use_flat_adam = bool(kwargs.get("flat_adam", True))
         if self.overlap_logging and hasattr(policy, "mean_net") and hasattr(policy.mean_net, "side_wgrad"):
             policy.mean_net.side_wgrad = True              # joined after every backward of policy_epoch
         self._log_stream = None
+        self._log_stream2 = None
         self._tr_stream = None
         self._flat_grad = None
+        self._flat_adam_tried = False
         self.process_group = kwargs.get("process_group", None)      # torch.distributed group (None = single GPU)
         self.policy_net_params = policy.parameters
         self.critic_net_params = critic.parameters if critic is not None else []
@@ -159,6 +162,8 @@ class TemporalCorrelatedAgent:
             p.grad = view
             off += p.numel()
         self._flat_grad = flat
+        if params and params[0] is self.policy_net_params[0] and self.use_flat_adam:
+            self._use_flat_adam()
 
     def _global_mean(self, x):
         """Mean over the global batch (equal shard sizes)."""
@@ -259,10 +264,25 @@ class TemporalCorrelatedAgent:
         with torch.no_grad():
             mp = cache.get("new_old_mean") if kl_metric else None
             linv = getattr(self.projection, "_old_linv", None) if kl_metric else None
+            second = None
+            if new[0].is_cuda and self.overlap_logging:     # the two decompositions are independent chains (each
+                cur = torch.cuda.current_stream()            # has a single-CTA kernel): run them side by side
+                if self._log_stream2 is None:
+                    self._log_stream2 = torch.cuda.Stream(device=new[0].device)
+                second = self._log_stream2
+                second.wait_stream(cur)
+                with torch.cuda.stream(second):
+                    last = list(gaussian_kl_details(self.policy, proj, old, q_linv=linv))
+                    for x in last:
+                        x.record_stream(cur)
             parts = list(gaussian_kl_details(self.policy, new, old, mean_part=mp, q_linv=linv))
             parts += list(cache["new_proj"]) if "new_proj" in cache else list(
                 gaussian_kl_details(self.policy, new, proj))
-            parts += list(gaussian_kl_details(self.policy, proj, old, q_linv=linv))
+            if second is not None:
+                cur.wait_stream(second)
+            else:
+                last = list(gaussian_kl_details(self.policy, proj, old, q_linv=linv))
+            parts += last
             return torch.stack([x.expand(new[0].shape[0]) for x in parts]).mean(dim=1)    # one reduction
 
     # ---- critic ---------------------------------------------------------------------------------------------
@@ -287,6 +307,36 @@ class TemporalCorrelatedAgent:
         losses = torch.stack(losses).cpu().numpy()
         norms = torch.stack(norms).cpu().numpy()
         return {**_stats(losses, "critic_loss"), **_stats(norms, "critic_grad_norm")}
+
+    def _zero_policy_grads(self):
+        from .optim import FlatAdam
+        if isinstance(self.policy_optimizer, FlatAdam):
+            self.policy_optimizer.begin()               # gradients + norm accumulator
+        else:
+            self._flat_grad.zero_()
+
+    def _use_flat_adam(self):
+        """Swap the policy optimiser for ``FlatAdam`` once the flat gradient buffer exists (CUDA only; same maths,
+        the learning-rate scheduler is re-attached to it with its progress preserved)."""
+        from .optim import FlatAdam
+        if (self._flat_adam_tried or self.device.type != "cuda" or self._flat_grad is None
+                or not self._flat_grad_ok(self.policy_net_params)):
+            return
+        self._flat_adam_tried = True
+        old = self.policy_optimizer
+        if old.state:                                   # already stepped with torch's Adam: keep it
+            return
+        g = old.param_groups[0]
+        opt = FlatAdam(self.policy_net_params, self._flat_grad, lr=g["lr"], betas=g["betas"], eps=g["eps"],
+                       weight_decay=g["weight_decay"])
+        if "initial_lr" in g:
+            opt.param_groups[0]["initial_lr"] = g["initial_lr"]
+        if self.policy_lr_scheduler is not None:
+            sched = LinearLR(opt, start_factor=1, end_factor=0.01, total_iters=self.total_iterations)
+            sched.load_state_dict(self.policy_lr_scheduler.state_dict())
+            opt.param_groups[0]["lr"] = g["lr"]
+            self.policy_lr_scheduler = sched
+        self.policy_optimizer = opt
 
     def _grad_norm_clip(self, params):
         """util_numerical.py:244-275 without the per-parameter .item(): norm on the device."""
@@ -317,11 +367,11 @@ class TemporalCorrelatedAgent:
             params_L = self.policy.shared_params_L(obs.shape[0])
             pre = self.projection.start_cov_projection(self.policy, params_L, old[1], self.num_iterations)
             if zeroed_early:
-                self._flat_grad.zero_()
+                self._zero_policy_grads()
             new = (self.policy.mean_net(obs), params_L)
         else:
             if zeroed_early:
-                self._flat_grad.zero_()
+                self._zero_policy_grads()
             new = self.policy.policy(obs)
         proj = self.projection(self.policy, new, old, self.num_iterations, cov_projected=pre)
         # trust-region loss: small (partly single-CTA) kernels that only need `new` and `proj` -- a parallel
@@ -395,6 +445,13 @@ class TemporalCorrelatedAgent:
                 if split_roots:
                     policy_loss = surrogate.detach() + tr_loss.detach()
                     policy_loss.record_stream(main)
+                # everything of the metrics vector but the gradient norm is known here: assemble it on this branch
+                early = torch.stack([surrogate.detach(), ent_loss.detach().to(surrogate.dtype), tr_loss.detach(),
+                                     policy_loss.detach(), ent_stats["entropy"].detach().to(surrogate.dtype),
+                                     sur_stats["imp_smp_ratio"].detach()]).double()
+                kl = kl.double()
+                early.record_stream(main)
+                kl.record_stream(main)
         else:
             kl = self.kl_old_new_proj(new, old, proj)
         if not zeroed_early:
@@ -406,10 +463,18 @@ class TemporalCorrelatedAgent:
             policy_loss.backward()
         util.join_side_grads()                             # weight gradients of the mean net (side streams)
         self._allreduce_grads(self.policy_net_params)
-        grad_norm = self._grad_norm_clip(self.policy_net_params)
-        self.policy_optimizer.step()
+        if hasattr(self.policy_optimizer, "grad_norm"):     # FlatAdam: norm, clipping and update in two launches
+            self.policy_optimizer.step(max_norm=float(self.clip_grad_norm))
+            grad_norm = None
+        else:
+            grad_norm = self._grad_norm_clip(self.policy_net_params)
+            self.policy_optimizer.step()
         if side is not None:
             main.wait_stream(side)
+        if grad_norm is None:
+            grad_norm = self.policy_optimizer.grad_norm()
+        if side is not None:                                  # two launches after the optimiser step: sqrt/cast + cat
+            return torch.cat([early, grad_norm.detach().double().reshape(1), kl])
         head = torch.stack([surrogate.detach(), ent_loss.detach().to(surrogate.dtype), tr_loss.detach(),
                             policy_loss.detach(), ent_stats["entropy"].detach().to(surrogate.dtype),
                             sur_stats["imp_smp_ratio"].detach(), grad_norm.detach()])

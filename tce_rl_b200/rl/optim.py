@@ -1,0 +1,66 @@
+"""Flat-buffer Adam for the policy network: gradient norm, clipping and the update in two launches.
+
+``torch.optim.Adam`` semantics (L2 weight decay, bias correction, no amsgrad; ``clip_grad_norm_`` in front) as used at
+temporal_correlated_agent.py:561-589, on parameters whose ``.grad`` tensors are views of ONE flat buffer
+(``TemporalCorrelatedAgent.ensure_flat_grads``).  It is a ``torch.optim.Optimizer`` (param_groups / lr schedulers work);
+the moments live in two flat fp32 buffers, the step counter and the squared gradient norm in ``stats`` on the device,
+so a step is CUDA-graph capturable and needs no host synchronisation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _lib
+from .._lib import TceError
+
+
+class FlatAdam(torch.optim.Optimizer):
+    def __init__(self, params, flat_grad: torch.Tensor, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        params = list(params)
+        if not params or len(params) > 32:
+            raise TceError("FlatAdam takes 1..32 parameter tensors")
+        if not flat_grad.is_cuda or flat_grad.dtype != torch.float32:
+            raise TceError("FlatAdam needs a CUDA float32 flat gradient buffer (there is no CPU path)")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.flat_grad = flat_grad
+        n = flat_grad.numel()
+        if n != sum(p.numel() for p in params):
+            raise TceError("flat gradient buffer does not match the parameters")
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=flat_grad.device)
+        self.exp_avg_sq = torch.zeros_like(self.exp_avg)
+        self.stats = torch.zeros(2, dtype=torch.float64, device=flat_grad.device)     # {step, sum g^2}
+        self._params = params
+        self._sizes = (C.c_int64 * len(params))(*[p.numel() for p in params])
+
+    def _check_views(self):
+        off, base, es = 0, self.flat_grad.data_ptr(), self.flat_grad.element_size()
+        for p in self._params:
+            if p.grad is None or p.grad.data_ptr() != base + off * es or not p.is_contiguous():
+                raise TceError("FlatAdam: parameter gradients must be views of the flat buffer (ensure_flat_grads)")
+            off += p.numel()
+
+    def begin(self):
+        """Clear the gradients and the norm accumulator (call before backward; cheap, can be issued early)."""
+        self.flat_grad.zero_()
+        self.stats[1:].zero_()
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.begin()
+
+    def grad_norm(self) -> torch.Tensor:
+        """2-norm of the (unclipped) flat gradient of the last ``step`` (device scalar, fp64)."""
+        return self.stats[1].sqrt()
+
+    @torch.no_grad()
+    def step(self, max_norm: float = 0.0):
+        self._check_views()
+        g = self.param_groups[0]
+        st = torch.cuda.current_stream().cuda_stream
+        ptrs = (C.c_void_p * len(self._params))(*[p.data_ptr() for p in self._params])
+        _lib.call("tce_grad_sumsq", self.flat_grad.data_ptr(), self.flat_grad.numel(), self.stats.data_ptr(), st)
+        _lib.call("tce_adam_step", len(self._params), C.cast(ptrs, C.c_void_p), C.cast(self._sizes, C.c_void_p),
+                  self.flat_grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                  self.stats.data_ptr(), float(max_norm), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
+                  float(g["eps"]), float(g["weight_decay"]), st)

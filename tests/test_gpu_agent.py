@@ -142,3 +142,36 @@ def test_dataset_to_device_broadcasts_the_shared_old_factor():
     torch.cuda.synchronize()
     assert dev2 is dev and all(dev[k].data_ptr() == ptrs[k] for k in dev)          # static addresses
     assert torch.equal(dev["segment_params_mean"].cpu(), host["segment_params_mean"])
+
+
+@pytest.mark.parametrize("max_norm,wd", [(0.0, 0.0), (0.5, 5e-5)])
+def test_flat_adam_matches_torch_adam(max_norm, wd):
+    """tce_grad_sumsq + tce_adam_step == clip_grad_norm_ + torch.optim.Adam.step over several steps (fp32 updates:
+    1e-6 relative), including the reported gradient norm."""
+    from tce_rl_b200.rl.optim import FlatAdam
+    torch.manual_seed(0)
+    shapes = [(33, 7), (33,), (5, 33), (5,), (2016,)]
+    ref = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes]
+    mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    flat = torch.zeros(sum(p.numel() for p in mine), device=DEV)
+    off = 0
+    for p in mine:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    opt_ref = torch.optim.Adam(ref, lr=3e-3, weight_decay=wd)
+    opt = FlatAdam(mine, flat, lr=3e-3, weight_decay=wd)
+    for it in range(6):
+        opt.begin()
+        gs = [torch.randn_like(p) * (10.0 if it == 2 else 0.1) for p in ref]
+        for p, q, g in zip(ref, mine, gs):
+            p.grad = g.clone()
+            q.grad.add_(g)
+        norm_ref = torch.linalg.vector_norm(torch.cat([g.reshape(-1) for g in gs]))
+        if max_norm > 0:
+            torch.nn.utils.clip_grad_norm_(ref, max_norm)
+        opt_ref.step()
+        opt.step(max_norm=max_norm)
+        assert abs(opt.grad_norm().item() - norm_ref.item()) <= 1e-5 * norm_ref.item()
+        for p, q in zip(ref, mine):
+            assert (p - q).abs().max().item() <= 2e-6 * max(1.0, p.abs().max().item()), it
+    assert opt.stats[0].item() == 6.0
