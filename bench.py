@@ -231,12 +231,12 @@ def roofline_numbers(agent, dataset, times, pairs, device, peaks):
            "seglik_bwd": (bwd_bytes, 2 * fwd_flops)}[dom]
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
     # exact configuration (profiles/r01_seglik_full_summary.txt); refreshed whenever the kernels change
-    NCU_TRAFFIC = {"seglik_gram": 18268928 + 1280, "seglik_chol": 23622656 + 145920, "seglik_bwd": 38078976 + 234752}
+    NCU_TRAFFIC = {"seglik_gram": 18276608 + 4352, "seglik_chol": 23564288 + 39680, "seglik_bwd": 38071552 + 48896}
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg[0] * B / t[dom] / 1e9
     roof = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
             "frac": round(achieved / hbm_peak, 5), "traffic": NCU_TRAFFIC.get(dom),
-            "traffic_source": "profiles/r01_seglik_full_summary.txt (ncu --set full, same shapes)",
+            "traffic_source": "profiles/r01_seglik_full_final_summary.txt (ncu --set full, same shapes)",
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst, kernel timed alone)" if "hbm_gbs" in peaks
             else "fallback 6650 GB/s (B200_PROFILING.md)",
             "algorithmic_bytes_per_launch": alg[0] * B, "kernel_us": {k: round(v * 1e6, 2) for k, v in t.items()},
