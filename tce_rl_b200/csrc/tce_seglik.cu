@@ -404,7 +404,10 @@ seglik_chol_kernel(const double *Cmat, const double *Rres, double *Gout, double 
 // =====================================================================================================
 // Stage 3: backward accumulation.  One CTA per episode.
 // =====================================================================================================
-template <int D, int K1>
+// DSIGMA: write up * d logp / d Sigma (symmetric [Dp, Dp]) instead of grad_L = 2 up tril(dSigma L).  With ONE
+// covariance for the batch the product with L is linear in dSigma, so it is applied once to the batch sum
+// (dsigma_to_dl_kernel) instead of once per episode, and L is not loaded at all.
+template <int D, int K1, bool DSIGMA>
 __global__ void __launch_bounds__(SL_THREADS, 4)
 seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__restrict__ Alpha,
                   const float *__restrict__ L, long long ldb_L, const float *__restrict__ times,
@@ -429,7 +432,7 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
   const float up = upstream ? *upstream : 1.0f;       // scalar gradient of the fused surrogate loss
 
   SL_STAMP(16);
-  load_lower(L + b * ldb_L, Ls, Dp, NR, LD);
+  if (!DSIGMA) load_lower(L + b * ldb_L, Ls, Dp, NR, LD);
   for (int e = threadIdx.x; e < NT * P; e += blockDim.x) Gs[e] = (float)Gb[e];
   for (int e = threadIdx.x; e < NR * LD; e += blockDim.x) Ms[e] = 0.f;
   basis_points<K1>(tb, (double)init_time[b], times + b * T, pairs, P, hs, xi, init_row);
@@ -478,6 +481,11 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
   __syncthreads();
 
   SL_STAMP(19);
+  if (DSIGMA) {                                   // up * dSigma, symmetric, dense [Dp][Dp]
+    float *gS = grad_L + (size_t)b * Dp * Dp;
+    for (int e = threadIdx.x; e < Dp * Dp; e += blockDim.x) gS[e] = up * Ms[(e / Dp) * LD + (e % Dp)];
+    return;
+  }
   // ---- grad_L = 2 * tril(M L)  (fp32 FFMA, 4x4 tiles over the lower triangle), staged in the Gs buffer
   float *out = Gs;                                // [Dp][Dp] dense (the Gs region is sized for it)
   for (int e = threadIdx.x; e < Dp * Dp; e += blockDim.x) out[e] = 0.f;
@@ -516,6 +524,29 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
   float *gL = grad_L + (size_t)b * Dp * Dp;
   for (int e = threadIdx.x; e < Dp * Dp; e += blockDim.x) gL[e] = out[e];
   SL_STAMP(21);
+}
+
+// grad_L = 2 tril(dSigma L) for ONE [n, n] pair (fp32, as the per-episode product it replaces): CTA per row i,
+// thread per column j; L is read coalesced straight from L2, eight loads in flight per thread.
+__global__ void __launch_bounds__(128)
+dsigma_to_dl_kernel(const float *__restrict__ dS, const float *__restrict__ L, float *__restrict__ out, int n) {
+  extern __shared__ float srow[];
+  const int i = blockIdx.x;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) srow[k] = dS[(size_t)i * n + k];
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (j <= i) {
+      int k = j;                                                   // L[k][j] = 0 for k < j
+#pragma unroll 2
+      for (; k + 3 < n; k += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fmaf(srow[k + u], L[(size_t)(k + u) * n + j], acc[u]);
+      }
+      for (; k < n; ++k) acc[0] = fmaf(srow[k], L[(size_t)k * n + j], acc[0]);
+    }
+    out[(size_t)i * n + j] = j <= i ? 2.f * ((acc[0] + acc[1]) + (acc[2] + acc[3])) : 0.f;
+  }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
@@ -614,12 +645,12 @@ extern "C" int tce_seglik_chol(const tce_tables_t *t, const void *work, void *ad
   return TCE_OK;
 }
 
-extern "C" int tce_seglik_bwd(const tce_tables_t *t, const void *work, const float *L, int64_t ldb_L,
-                              const float *times, const float *init_time, const int64_t *pred_pairs,
-                              const float *upstream, float *grad_mean, float *grad_L, int64_t B, int64_t T,
-                              int64_t P, void *stream) {
+template <bool DSIGMA>
+static int seglik_bwd_launch(const tce_tables_t *t, const void *work, const float *L, int64_t ldb_L, const float *times,
+                             const float *init_time, const int64_t *pred_pairs, const float *upstream,
+                             float *grad_mean, float *grad_out, int64_t B, int64_t T, int64_t P, void *stream) {
   if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
-  if (!t || !work || !L || !times || !init_time || !pred_pairs || B < 0 || T < 1 || P < 1)
+  if (!t || !work || (!DSIGMA && !L) || !times || !init_time || !pred_pairs || B < 0 || T < 1 || P < 1)
     return TCE_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
   const double *G = (const double *)work, *A = work_R(t, const_cast<void *>(work), B, P);
@@ -627,16 +658,41 @@ extern "C" int tce_seglik_bwd(const tce_tables_t *t, const void *work, const flo
   if (t->D == Dv && t->K1 == Kv) {                                                                               \
     const size_t smem = bwd_smem<Dv, Kv>((int)P);                                                                \
     if (smem > 200 * 1024) return TCE_ERR_UNSUPPORTED_SHAPE;                                                     \
-    TCE_CUDA(cudaFuncSetAttribute(seglik_bwd_kernel<Dv, Kv>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+    TCE_CUDA(cudaFuncSetAttribute(seglik_bwd_kernel<Dv, Kv, DSIGMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)smem), "bwd smem attr");                                                  \
-    cudaFuncSetAttribute(seglik_bwd_kernel<Dv, Kv>, cudaFuncAttributePreferredSharedMemoryCarveout,              \
+    cudaFuncSetAttribute(seglik_bwd_kernel<Dv, Kv, DSIGMA>, cudaFuncAttributePreferredSharedMemoryCarveout,      \
                          cudaSharedmemCarveoutMaxShared);                                                        \
-    seglik_bwd_kernel<Dv, Kv><<<(unsigned)B, SL_THREADS, smem, st>>>(tab_dev(t), G, A, L, ldb_L, times, init_time, \
-                                                                    pred_pairs, upstream, grad_mean, grad_L, (int)T, (int)P); \
+    seglik_bwd_kernel<Dv, Kv, DSIGMA><<<(unsigned)B, SL_THREADS, smem, st>>>(                                     \
+        tab_dev(t), G, A, L, ldb_L, times, init_time, pred_pairs, upstream, grad_mean, grad_out, (int)T, (int)P); \
     TCE_CHECK_LAUNCH("seglik_bwd_kernel");                                                                       \
     return TCE_OK;                                                                                               \
   }
   TCE_FOR_SHAPES(X)
 #undef X
   return TCE_ERR_UNSUPPORTED_SHAPE;
+}
+
+extern "C" int tce_seglik_bwd(const tce_tables_t *t, const void *work, const float *L, int64_t ldb_L,
+                              const float *times, const float *init_time, const int64_t *pred_pairs,
+                              const float *upstream, float *grad_mean, float *grad_L, int64_t B, int64_t T,
+                              int64_t P, void *stream) {
+  return seglik_bwd_launch<false>(t, work, L, ldb_L, times, init_time, pred_pairs, upstream, grad_mean, grad_L, B, T,
+                                  P, stream);
+}
+
+extern "C" int tce_seglik_bwd_dsigma(const tce_tables_t *t, const void *work, const float *times,
+                                     const float *init_time, const int64_t *pred_pairs, const float *upstream,
+                                     float *grad_mean, float *grad_sigma, int64_t B, int64_t T, int64_t P,
+                                     void *stream) {
+  if (B != 0 && !grad_sigma) return TCE_ERR_INVALID_ARGUMENT;
+  return seglik_bwd_launch<true>(t, work, nullptr, 0, times, init_time, pred_pairs, upstream, grad_mean, grad_sigma,
+                                 B, T, P, stream);
+}
+
+extern "C" int tce_dsigma_to_dl(const float *grad_sigma, const float *L, float *grad_L, int n, void *stream) {
+  if (!grad_sigma || !L || !grad_L || n < 1 || n > 128) return TCE_ERR_INVALID_ARGUMENT;
+  dsigma_to_dl_kernel<<<(unsigned)n, n <= 64 ? 64 : 128, sizeof(float) * (size_t)n, (cudaStream_t)stream>>>(grad_sigma, L,
+                                                                                                       grad_L, n);
+  TCE_CHECK_LAUNCH("dsigma_to_dl_kernel");
+  return TCE_OK;
 }
