@@ -218,12 +218,12 @@ int tce_seglik_bwd(const tce_tables_t *tables, const void *work, const float *L,
                    const float *upstream, float *grad_mean, float *grad_L, int64_t B, int64_t T, int64_t P,
                    void *stream);
 /* ONE covariance for the batch (ldb_L = 0): grad_L = 2 tril(dSigma L) is linear in dSigma, so stage 3 can write
- * upstream * d logp / d Sigma [B, Dp, Dp] (symmetric) without touching L, the caller sums over the batch and
- * tce_dsigma_to_dl applies the product once: grad_L [n, n] = 2 tril(grad_sigma L).                        */
+ * upstream * d logp / d Sigma [B, Dp, Dp] (symmetric) without touching L; tce_dsigma_to_dl sums it over the
+ * batch (fixed order) and applies the product once: grad_L [n, n] = 2 tril((sum_b grad_sigma_b) L).       */
 int tce_seglik_bwd_dsigma(const tce_tables_t *tables, const void *work, const float *times,
                           const float *init_time, const int64_t *pred_pairs, const float *upstream,
                           float *grad_mean, float *grad_sigma, int64_t B, int64_t T, int64_t P, void *stream);
-int tce_dsigma_to_dl(const float *grad_sigma, const float *L, float *grad_L, int n, void *stream);
+int tce_dsigma_to_dl(const float *grad_sigma, int64_t B, const float *L, float *grad_L, int n, void *stream);
 
 /* ---- (4b) GAE and segment advantages ------------------------------------------------------------------
  * TemporalCorrelatedAgent.get_advantage_return (temporal_correlated_agent.py:118-181).

@@ -70,7 +70,7 @@ SIGNATURES = {
     "tce_seglik_chol": (C.c_int, [_P, _P, _P, _P, _D, _P, _P, _P, _D, _P, _P, _P, _I64, _I64, _P]),
     "tce_seglik_bwd": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
     "tce_seglik_bwd_dsigma": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
-    "tce_dsigma_to_dl": (C.c_int, [_P, _P, _P, _I32, _P]),
+    "tce_dsigma_to_dl": (C.c_int, [_P, _I64, _P, _P, _I32, _P]),
     "tce_gae": (C.c_int, [_P, _P, _P, _P, _F, _F, _I32, _P, _P, _I64, _I64, _P]),
     "tce_segment_advantage_raw": (C.c_int, [_I32, _P, _P, _P, _P, _F, _P, _P, _I64, _I64, _I64, _P]),
     "tce_sum_stats": (C.c_int, [_P, _P, _I64, _P]),

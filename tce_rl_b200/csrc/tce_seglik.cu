@@ -526,24 +526,48 @@ seglik_bwd_kernel(TabDev tb, const double *__restrict__ Gmat, const double *__re
   SL_STAMP(21);
 }
 
-// grad_L = 2 tril(dSigma L) for ONE [n, n] pair (fp32, as the per-episode product it replaces): CTA per row i,
-// thread per column j; L is read coalesced straight from L2, eight loads in flight per thread.
-__global__ void __launch_bounds__(128)
-dsigma_to_dl_kernel(const float *__restrict__ dS, const float *__restrict__ L, float *__restrict__ out, int n) {
-  extern __shared__ float srow[];
-  const int i = blockIdx.x;
-  for (int k = threadIdx.x; k < n; k += blockDim.x) srow[k] = dS[(size_t)i * n + k];
-  __syncthreads();
+// grad_L = 2 tril((sum_b dSigma_b) L): CTA per row i.  Stage 1: the row of the batch sum (B x n values, four
+// interleaved partial sums per column, fixed order -> deterministic); stage 2: thread per column j, fp32 as the
+// per-episode product it replaces, L read coalesced straight from L2 with eight loads in flight.
+constexpr int DS_PARTS = 16;                                      // 1024 threads = 16 batch slices x 64 columns
+__global__ void __launch_bounds__(DS_PARTS * 64)
+dsigma_to_dl_kernel(const float *__restrict__ dS, long long B, const float *__restrict__ L, float *__restrict__ out,
+                    int n) {
+  extern __shared__ float sm_f[];
+  float *part = sm_f, *srow = sm_f + DS_PARTS * 64;               // [16][64] partial sums, [n] row
+  const int i = blockIdx.x, k = threadIdx.x & 63, q = threadIdx.x >> 6;
+  const size_t nn = (size_t)n * n;
+  for (int k0 = 0; k0 < n; k0 += 64) {                              // n <= 128: at most two passes
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};          // eight loads in flight per thread
+    if (k0 + k < n) {
+      const float *src = dS + (size_t)i * n + k0 + k;
+      long long b = q;
+      for (; b + 7 * DS_PARTS < B; b += 8 * DS_PARTS) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] += src[(size_t)(b + u * DS_PARTS) * nn];
+      }
+      for (; b < B; b += DS_PARTS) a[0] += src[(size_t)b * nn];
+    }
+    part[q * 64 + k] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    __syncthreads();
+    if (threadIdx.x < 64 && k0 + k < n) {
+      float t = 0.f;
+#pragma unroll
+      for (int u = 0; u < DS_PARTS; ++u) t += part[u * 64 + k];
+      srow[k0 + k] = t;
+    }
+    __syncthreads();
+  }
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (j <= i) {
-      int k = j;                                                   // L[k][j] = 0 for k < j
+      int kk = j;                                                   // L[k][j] = 0 for k < j
 #pragma unroll 2
-      for (; k + 3 < n; k += 4) {
+      for (; kk + 3 < n; kk += 4) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] = fmaf(srow[k + u], L[(size_t)(k + u) * n + j], acc[u]);
+        for (int u = 0; u < 4; ++u) acc[u] = fmaf(srow[kk + u], L[(size_t)(kk + u) * n + j], acc[u]);
       }
-      for (; k < n; ++k) acc[0] = fmaf(srow[k], L[(size_t)k * n + j], acc[0]);
+      for (; kk < n; ++kk) acc[0] = fmaf(srow[kk], L[(size_t)kk * n + j], acc[0]);
     }
     out[(size_t)i * n + j] = j <= i ? 2.f * ((acc[0] + acc[1]) + (acc[2] + acc[3])) : 0.f;
   }
@@ -689,10 +713,11 @@ extern "C" int tce_seglik_bwd_dsigma(const tce_tables_t *t, const void *work, co
                                  B, T, P, stream);
 }
 
-extern "C" int tce_dsigma_to_dl(const float *grad_sigma, const float *L, float *grad_L, int n, void *stream) {
-  if (!grad_sigma || !L || !grad_L || n < 1 || n > 128) return TCE_ERR_INVALID_ARGUMENT;
-  dsigma_to_dl_kernel<<<(unsigned)n, n <= 64 ? 64 : 128, sizeof(float) * (size_t)n, (cudaStream_t)stream>>>(grad_sigma, L,
-                                                                                                       grad_L, n);
+extern "C" int tce_dsigma_to_dl(const float *grad_sigma, int64_t B, const float *L, float *grad_L, int n,
+                                void *stream) {
+  if (!grad_sigma || !L || !grad_L || n < 1 || n > 128 || B < 1) return TCE_ERR_INVALID_ARGUMENT;
+  dsigma_to_dl_kernel<<<(unsigned)n, DS_PARTS * 64, sizeof(float) * (DS_PARTS * 64 + 128), (cudaStream_t)stream>>>(
+      grad_sigma, (long long)B, L, grad_L, n);
   TCE_CHECK_LAUNCH("dsigma_to_dl_kernel");
   return TCE_OK;
 }

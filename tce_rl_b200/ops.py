@@ -429,12 +429,11 @@ def seglik_surrogate_bwd(upstream: Tensor, adj: Tensor, L: Tensor, times: Tensor
     g_L = torch.empty(B, dim_params, dim_params, device=times.device, dtype=torch.float32)
     if single:
         # grad_L = 2 tril(dSigma L) is linear in dSigma: stage 3 writes dSigma per episode (no L, no product),
-        # the batch sum is one library GEMV (ones^T G) and the product is applied once
+        # one small kernel sums over the batch and applies the product once
         _lib.call("tce_seglik_bwd_dsigma", tables, _p(adj), _p(times), _p(init_time), _p(pairs), _p(up), _p(g_mean),
                   _p(g_L), B, T, P, _stream())
-        g_S = torch.mv(g_L.view(B, -1).t(), _ones(B, times.device))
         out = torch.empty(1, dim_params, dim_params, device=times.device, dtype=torch.float32)
-        _lib.call("tce_dsigma_to_dl", _p(g_S), _p(L), _p(out), dim_params, _stream())
+        _lib.call("tce_dsigma_to_dl", _p(g_L), B, _p(L), _p(out), dim_params, _stream())
         return g_mean, out
     _lib.call("tce_seglik_bwd", tables, _p(adj), _p(L), ldb, _p(times), _p(init_time), _p(pairs), _p(up), _p(g_mean),
               _p(g_L), B, T, P, _stream())
