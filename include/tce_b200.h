@@ -149,8 +149,8 @@ int tce_proj_entropy_bwd(const float *L, const double *beta, int64_t ldb_beta, i
                          const float *grad_out, float *grad_L, int64_t B, int n, void *stream);
 /* KL covariance projection: min KL(N(.,S)||N(.,S~)) s.t. KL_cov(S||S_old) <= eps_cov, solved exactly on
  * the generalised eigenvalues (CTA-per-matrix one-sided Jacobi + Newton for eta); proj_L = chol(S_proj).
- * `save` (tce_proj_kl_save_doubles(B, n) doubles) carries M = L_old Q, U = L~^-1 M, L~^-1, lambda, eta to
- * the backward (implicit differentiation of eta*).  warm_start != 0: `save` still holds the state of a previous call;
+ * `save` (tce_proj_kl_save_doubles(B, n) doubles) carries M = L_old Q, U = L~^-1 M, L~^-1, Sigma_proj, lambda,
+ * {eta, active, kl0, fingerprint, alpha, ent_active, alpha^2, -} to the backward (implicit differentiation of eta*).  warm_start != 0: `save` still holds the state of a previous call;
  * it is used to start the eigen-solve when it was produced with the same L_o (checked by a fingerprint),
  * e.g. across the epochs of one update_policy.  info [B]: non positive pivot of the final Cholesky.     */
 size_t tce_proj_kl_save_doubles(int64_t B, int n);
@@ -209,6 +209,14 @@ int tce_seglik_gram(const tce_tables_t *tables, const float *smp_traj, const flo
                     int64_t ldb_L, const float *times, const float *init_time, const float *init_pos,
                     const float *init_vel, const int64_t *pred_pairs, void *work, double *diag_max,
                     int64_t B, int64_t T, int64_t P, void *stream);
+/* Stage 1 for ONE covariance shared by the batch, given as Sigma = (*sigma_scale) * Sigma0 [Dp, Dp] fp64 (device
+ * pointers; sigma_scale may be NULL = 1) instead of its factor -- e.g. straight out of tce_proj_kl_entropy_fwd's
+ * state: no L load and no L L^T per episode.                                                              */
+int tce_seglik_gram_sigma(const tce_tables_t *tables, const float *smp_traj, const float *mean,
+                          const double *Sigma0, const double *sigma_scale, const float *times,
+                          const float *init_time, const float *init_pos, const float *init_vel,
+                          const int64_t *pred_pairs, void *work, double *diag_max, int64_t B, int64_t T, int64_t P,
+                          void *stream);
 int tce_seglik_chol(const tce_tables_t *tables, const void *work, void *adj, const double *diag_max, double reg_rel,
                     const float *grad_logp, const float *logp_old, const float *advantage,
                     double grad_scale, double *loss_acc, float *logp, int32_t *info, int64_t B,

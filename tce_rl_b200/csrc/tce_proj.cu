@@ -462,14 +462,16 @@ __device__ inline double kl_solve_eta(const double *lam, int n, double eps, doub
 // Forward.  With W = Lt^-1 Lo, one-sided Jacobi rotates the columns of W into U~ = W Q (orthogonal columns,
 // |U~_j|^2 = lam_j = eigenvalues of W^T W); then M := Lo Q = Lt U~ and
 //   Sigma_proj = Lo Q diag((1+eta)/(lam+eta)) Q^T Lo^T = M D M^T ,   proj_L = chol(Sigma_proj).
-// `save` = { M, U~, Lt^-1 [n,n each], lam [n], {eta, active, kl0, fingerprint(Lo)} } per matrix: state for the backward AND a
+// `save` = { M, U~, Lt^-1, Sigma_proj [n,n each], lam [n], {eta, active, kl0, fingerprint(Lo), alpha, ent_active, alpha^2, -} }:
+// state for the backward AND a
 // warm start for the next call with the same Lo (the 50 epochs of one update_policy): starting Jacobi from
 // Lt^-1 M_prev = W Q_prev is an orthogonal change of basis of the same problem, so 2-3 sweeps suffice.
 __global__ void __launch_bounds__(KL_THREADS)
 proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_o, double eps_cov,
                        float *__restrict__ proj_L, double *__restrict__ save_M, double *__restrict__ save_U,
-                       double *__restrict__ save_Li, double *__restrict__ save_lam, double *__restrict__ save_sc,
-                       int32_t *__restrict__ info, int n, int warm_start, const double *__restrict__ beta,
+                       double *__restrict__ save_Li, double *__restrict__ save_Sig, double *__restrict__ save_lam,
+                       double *__restrict__ save_sc, int32_t *__restrict__ info, int n, int warm_start,
+                       const double *__restrict__ beta,
                        long long ldb_beta, int entropy_eq, float *__restrict__ out_L) {
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
@@ -514,6 +516,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   la_gemm(b2, b0, b3, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // M = Lt U~
   if (threadIdx.x == 0) {
     save_sc[b * KL_SC + 0] = eta; save_sc[b * KL_SC + 1] = active ? 1.0 : 0.0; save_sc[b * KL_SC + 2] = kl0; save_sc[b * KL_SC + 3] = fp;
+    save_sc[b * KL_SC + 6] = 1.0;                                  // alpha^2 (overwritten by the fused entropy control)
     if (blockIdx.x == 0) g_kl_prof[15] = sweeps;
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) save_lam[b * n + i] = lam[i];
@@ -534,10 +537,22 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
     const double H = 0.5 * n * (1.0 + LOG_2PI) + sl, bt = beta[b * ldb_beta];
     const bool ent_active = entropy_eq || (H < bt);
     const double alpha = ent_active ? exp((bt - H) / n) : 1.0;
-    if (threadIdx.x == 0) { save_sc[b * KL_SC + 4] = alpha; save_sc[b * KL_SC + 5] = ent_active ? 1.0 : 0.0; }
+    if (threadIdx.x == 0) {
+      save_sc[b * KL_SC + 4] = alpha; save_sc[b * KL_SC + 5] = ent_active ? 1.0 : 0.0; save_sc[b * KL_SC + 6] = alpha * alpha;
+    }
     return alpha;
   };
+  // Sigma of the (pre-entropy) result goes to the state as well: with ONE covariance for the batch the
+  // likelihood's stage 1 takes alpha^2 * Sigma from there instead of re-forming L L^T per episode.
+  auto save_sigma = [&](Mat S) {
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e - i * n;
+      save_Sig[off + e] = S(i, j);
+    }
+  };
   if (!active) {                                                                    // identity
+    la_gemm(b1, b0, b0.T(), n, n, n, TRI_LOWER, TRI_UPPER, TRI_FULL, 1.0, 0.0);      // Sigma = Lt Lt^T
+    save_sigma(b1);
     const double alpha = entropy_scale(b0);
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
       const float v = (e % n <= e / n) ? Lt[e] : 0.f;
@@ -553,7 +568,9 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   }
   __syncthreads();
   KL_STAMP(6);
-  la_gemm(b1, b2, b2.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_LOWER, 1.0, 0.0);       // Sigma_proj (lower)
+  la_gemm(b1, b2, b2.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_LOWER, 1.0, 0.0);       // Sigma_proj (all of it is written)
+  save_sigma(b1);
+  __syncthreads();                                                                  // ... before chol overwrites it
   KL_STAMP(7);
   la_chol(b1, n, &s_bad);
   KL_STAMP(8);
@@ -1027,7 +1044,7 @@ extern "C" int tce_debug_kl_phase_cycles(long long *out16) {
   return TCE_OK;
 }
 
-extern "C" size_t tce_proj_kl_save_doubles(int64_t B, int n) { return (size_t)B * (3 * (size_t)n * n + n + KL_SC); }
+extern "C" size_t tce_proj_kl_save_doubles(int64_t B, int n) { return (size_t)B * (4 * (size_t)n * n + n + KL_SC); }
 
 static int kl_fwd_launch(const float *L, const float *L_o, double eps_cov, const double *beta, int64_t ldb_beta,
                          int equality, float *proj_L, float *out_L, double *save, int32_t *info, int warm_start,
@@ -1039,9 +1056,9 @@ static int kl_fwd_launch(const float *L, const float *L_o, double eps_cov, const
   int rc = set_smem(proj_kl_cov_fwd_kernel, smem);
   if (rc) return rc;
   const size_t nn = (size_t)B * n * n;
-  double *M = save, *U = M + nn, *Li = U + nn, *lam = Li + nn, *sc = lam + (size_t)B * n;
+  double *M = save, *U = M + nn, *Li = U + nn, *Sig = Li + nn, *lam = Sig + nn, *sc = lam + (size_t)B * n;
   proj_kl_cov_fwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(
-      L, L_o, eps_cov, proj_L, M, U, Li, lam, sc, info, n, warm_start, beta, (long long)ldb_beta, equality, out_L);
+      L, L_o, eps_cov, proj_L, M, U, Li, Sig, lam, sc, info, n, warm_start, beta, (long long)ldb_beta, equality, out_L);
   TCE_CHECK_LAUNCH("proj_kl_cov_fwd_kernel");
   return TCE_OK;
 }
@@ -1055,7 +1072,7 @@ static int kl_bwd_launch(const float *L, const float *proj_L, const float *grad_
   int rc = set_smem(proj_kl_cov_bwd_kernel, smem);
   if (rc) return rc;
   const size_t nn = (size_t)B * n * n;
-  const double *M = save, *U = M + nn, *Li = U + nn, *lam = Li + nn, *sc = lam + (size_t)B * n;
+  const double *M = save, *U = M + nn, *Li = U + nn, *lam = Li + 2 * nn, *sc = lam + (size_t)B * n;
   proj_kl_cov_bwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, proj_L, grad_out, M, U, Li, lam, sc, grad_L,
                                                                                  n, fused_entropy);
   TCE_CHECK_LAUNCH("proj_kl_cov_bwd_kernel");

@@ -92,10 +92,13 @@ __device__ void load_lower(const float *__restrict__ L, float *Ls, int n, int NR
 // =====================================================================================================
 // Stage 1: gram.  One CTA per episode.
 // =====================================================================================================
-template <int D, int K1>
+// SIGMA_IN: the covariance Sigma = scale * Sigma0 ([Dp, Dp] fp64, ONE matrix for the batch, e.g. straight out of the
+// KL projection) is given instead of its factor: no L load and no L L^T per episode.
+template <int D, int K1, bool SIGMA_IN>
 __global__ void __launch_bounds__(SL_THREADS, 4)
 seglik_gram_kernel(TabDev tb, const float *__restrict__ smp_traj, const float *__restrict__ mean,
-                   const float *__restrict__ L, long long ldb_L, const float *__restrict__ times,
+                   const float *__restrict__ L, long long ldb_L, const double *__restrict__ Sigma0,
+                   const double *__restrict__ sigma_scale, const float *__restrict__ times,
                    const float *__restrict__ init_time, const float *__restrict__ init_pos,
                    const float *__restrict__ init_vel, const int64_t *__restrict__ pairs, double *__restrict__ Cmat,
                    double *__restrict__ Rres, double *__restrict__ diag_max, int T, int P) {
@@ -116,7 +119,23 @@ seglik_gram_kernel(TabDev tb, const float *__restrict__ smp_traj, const float *_
   const float *times_b = times + b * T;
 
   SL_STAMP(0);
-  load_lower(L + b * ldb_L, Ls, Dp, NR4, LD);
+  if (SIGMA_IN) {
+    const double sc = sigma_scale ? *sigma_scale : 1.0;
+    for (int e0 = threadIdx.x; e0 < Dp * Dp; e0 += 4 * SL_THREADS) {     // four loads in flight per thread
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (e0 + u * SL_THREADS < Dp * Dp) ? Sigma0[e0 + u * SL_THREADS] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * SL_THREADS;
+        if (e < Dp * Dp) Sg[(e / Dp) * SD + (e % Dp)] = sc * v[u];
+      }
+    }
+    if (NR > Dp)                                                          // zero padding row / column
+      for (int t = threadIdx.x; t < NR; t += blockDim.x) { Sg[Dp * SD + t] = 0.0; Sg[t * SD + Dp] = 0.0; }
+  } else {
+    load_lower(L + b * ldb_L, Ls, Dp, NR4, LD);
+  }
   __syncthreads();
   SL_STAMP(1);
   basis_points<K1>(tb, (double)init_time[b], times_b, pairs, P, hs, xi, init_row);   // ends with a barrier
@@ -124,7 +143,7 @@ seglik_gram_kernel(TabDev tb, const float *__restrict__ smp_traj, const float *_
 
   // ---- Sigma = L L^T (fp32 FFMA, 4x4 register tiles over the lower triangle: 8 LDS per 16 FFMA) -> Sg (fp64,
   //      mirrored).  Rows/cols are padded to NR4 (multiple of 4) with zeros.
-  {
+  if (!SIGMA_IN) {
     constexpr int NT4 = NR4 / 4;
     for (int t = threadIdx.x; t < tri(NT4); t += blockDim.x) {
       int I, J;
@@ -611,13 +630,15 @@ static inline double *work_R(const tce_tables_t *t, void *work, int64_t B, int64
   return (double *)work + (size_t)B * (size_t)P * (N * (N + 1) / 2);
 }
 
-extern "C" int tce_seglik_gram(const tce_tables_t *t, const float *smp_traj, const float *mean, const float *L,
-                               int64_t ldb_L, const float *times, const float *init_time, const float *init_pos,
-                               const float *init_vel, const int64_t *pred_pairs, void *work, double *diag_max,
-                               int64_t B, int64_t T, int64_t P, void *stream) {
+template <bool SIGMA_IN>
+static int seglik_gram_launch(const tce_tables_t *t, const float *smp_traj, const float *mean, const float *L,
+                              int64_t ldb_L, const double *Sigma0, const double *sigma_scale, const float *times,
+                              const float *init_time, const float *init_pos, const float *init_vel,
+                              const int64_t *pred_pairs, void *work, double *diag_max, int64_t B, int64_t T, int64_t P,
+                              void *stream) {
   if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
-  if (!t || !smp_traj || !mean || !L || !times || !init_time || !init_pos || !init_vel || !pred_pairs || !work ||
-      !diag_max || B < 0 || T < 1 || P < 1 || P > 4096)
+  if (!t || !smp_traj || !mean || (SIGMA_IN ? !Sigma0 : !L) || !times || !init_time || !init_pos || !init_vel ||
+      !pred_pairs || !work || !diag_max || B < 0 || T < 1 || P < 1 || P > 4096)
     return TCE_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
   double *Cmat = (double *)work, *R = work_R(t, work, B, P);
@@ -625,19 +646,36 @@ extern "C" int tce_seglik_gram(const tce_tables_t *t, const float *smp_traj, con
   if (t->D == Dv && t->K1 == Kv) {                                                                                \
     const size_t smem = gram_smem<Dv, Kv>((int)P);                                                                \
     if (smem > 200 * 1024) return TCE_ERR_UNSUPPORTED_SHAPE;                                                      \
-    TCE_CUDA(cudaFuncSetAttribute(seglik_gram_kernel<Dv, Kv>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+    TCE_CUDA(cudaFuncSetAttribute(seglik_gram_kernel<Dv, Kv, SIGMA_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)smem), "gram smem attr");                                                  \
-    cudaFuncSetAttribute(seglik_gram_kernel<Dv, Kv>, cudaFuncAttributePreferredSharedMemoryCarveout,              \
+    cudaFuncSetAttribute(seglik_gram_kernel<Dv, Kv, SIGMA_IN>, cudaFuncAttributePreferredSharedMemoryCarveout,    \
                          cudaSharedmemCarveoutMaxShared);                                                         \
-    seglik_gram_kernel<Dv, Kv><<<(unsigned)B, SL_THREADS, smem, st>>>(tab_dev(t), smp_traj, mean, L, ldb_L, times, \
-                                                                     init_time, init_pos, init_vel, pred_pairs,  \
-                                                                     Cmat, R, diag_max, (int)T, (int)P);          \
+    seglik_gram_kernel<Dv, Kv, SIGMA_IN><<<(unsigned)B, SL_THREADS, smem, st>>>(                                   \
+        tab_dev(t), smp_traj, mean, L, ldb_L, Sigma0, sigma_scale, times, init_time, init_pos, init_vel, pred_pairs, \
+        Cmat, R, diag_max, (int)T, (int)P);                                                                       \
     TCE_CHECK_LAUNCH("seglik_gram_kernel");                                                                       \
     return TCE_OK;                                                                                                \
   }
   TCE_FOR_SHAPES(X)
 #undef X
   return TCE_ERR_UNSUPPORTED_SHAPE;
+}
+
+extern "C" int tce_seglik_gram(const tce_tables_t *t, const float *smp_traj, const float *mean, const float *L,
+                               int64_t ldb_L, const float *times, const float *init_time, const float *init_pos,
+                               const float *init_vel, const int64_t *pred_pairs, void *work, double *diag_max,
+                               int64_t B, int64_t T, int64_t P, void *stream) {
+  return seglik_gram_launch<false>(t, smp_traj, mean, L, ldb_L, nullptr, nullptr, times, init_time, init_pos, init_vel,
+                                   pred_pairs, work, diag_max, B, T, P, stream);
+}
+
+extern "C" int tce_seglik_gram_sigma(const tce_tables_t *t, const float *smp_traj, const float *mean,
+                                     const double *Sigma0, const double *sigma_scale, const float *times,
+                                     const float *init_time, const float *init_pos, const float *init_vel,
+                                     const int64_t *pred_pairs, void *work, double *diag_max, int64_t B, int64_t T,
+                                     int64_t P, void *stream) {
+  return seglik_gram_launch<true>(t, smp_traj, mean, nullptr, 0, Sigma0, sigma_scale, times, init_time, init_pos,
+                                  init_vel, pred_pairs, work, diag_max, B, T, P, stream);
 }
 
 extern "C" int tce_seglik_chol(const tce_tables_t *t, const void *work, void *adj, const double *diag_max, double reg_rel,

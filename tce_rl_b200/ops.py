@@ -379,7 +379,8 @@ def seg_logprob(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pa
 @torch.library.custom_op("tce::seglik_surrogate_fwd", mutates_args=())
 def seglik_surrogate_fwd(smp_traj: Tensor, mean: Tensor, L: Tensor, times: Tensor, init_time: Tensor,
                          init_pos: Tensor, init_vel: Tensor, pred_pairs: Tensor, logp_old: Tensor, advantage: Tensor,
-                         tables: int, reg_rel: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+                         tables: int, reg_rel: float, sigma: Optional[Tensor] = None,
+                         sigma_scale: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """Fused segment likelihood + importance-sampling surrogate (temporal_correlated_agent.py:718-739).
 
     -> (stats [2] fp64 = {-mean(ratio * adv), mean(ratio)}, logp [B,P], adj (per-segment adjoints for the
@@ -399,8 +400,15 @@ def seglik_surrogate_fwd(smp_traj: Tensor, mean: Tensor, L: Tensor, times: Tenso
     logp = torch.empty(B, P, device=dev, dtype=torch.float32)
     info = torch.empty(B, P, device=dev, dtype=torch.int32)
     st = _stream()
-    _lib.call("tce_seglik_gram", tables, _p(smp_traj), _p(mean), _p(L), ldb, _p(times), _p(init_time), _p(init_pos),
-              _p(init_vel), _p(pairs), _p(work), _p(diag_max), B, T, P, st)
+    if sigma is not None:          # ONE covariance for the batch, given as sigma_scale * sigma [Dp, Dp] fp64
+        n = mean.shape[-1]
+        if sigma.dtype != torch.float64 or not sigma.is_cuda or not sigma.is_contiguous() or sigma.numel() != n * n:
+            raise TceError("sigma must be a contiguous CUDA float64 [Dp, Dp] tensor")
+        _lib.call("tce_seglik_gram_sigma", tables, _p(smp_traj), _p(mean), _p(sigma), _p(sigma_scale), _p(times),
+                  _p(init_time), _p(init_pos), _p(init_vel), _p(pairs), _p(work), _p(diag_max), B, T, P, st)
+    else:
+        _lib.call("tce_seglik_gram", tables, _p(smp_traj), _p(mean), _p(L), ldb, _p(times), _p(init_time),
+                  _p(init_pos), _p(init_vel), _p(pairs), _p(work), _p(diag_max), B, T, P, st)
     _reduce_diag_max(diag_max)
     _lib.call("tce_seglik_chol", tables, _p(work), _p(work), _p(diag_max), float(reg_rel), None, _p(logp_old),
               _p(advantage), 1.0 / (B * P), _p(stats), _p(logp), _p(info), B, P, st)
@@ -408,7 +416,8 @@ def seglik_surrogate_fwd(smp_traj: Tensor, mean: Tensor, L: Tensor, times: Tenso
 
 
 @seglik_surrogate_fwd.register_fake
-def _(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, logp_old, advantage, tables, reg_rel):
+def _(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, logp_old, advantage, tables, reg_rel,
+      sigma=None, sigma_scale=None):
     B, P = times.shape[0], pred_pairs.shape[0]
     n = smp_traj.shape[-1]
     return (mean.new_empty(2, dtype=torch.float64), mean.new_empty(B, P),
@@ -458,7 +467,7 @@ def _(upstream, adj, L, times, init_time, pred_pairs, tables, dim_params):
 
 
 def _sur_setup(ctx, inputs, output):
-    (smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, logp_old, advantage, tables, reg_rel) = inputs
+    (smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, logp_old, advantage, tables, reg_rel) = inputs[:12]
     ctx.save_for_backward(output[2], L, times, init_time, pred_pairs)
     ctx.tables, ctx.dim_params = tables, mean.shape[-1]
     ctx.set_materialize_grads(False)
@@ -466,7 +475,7 @@ def _sur_setup(ctx, inputs, output):
 
 def _sur_backward(ctx, g_stats, g_logp, g_adj, g_info):
     adj, L, times, init_time, pred_pairs = ctx.saved_tensors
-    none = (None,) * 12
+    none = (None,) * 14
     if g_stats is None:
         return none
     if g_stats is _E0.get(str(g_stats.device)):            # unit seed (see unit_seed): d total / d surrogate = 1
@@ -474,7 +483,7 @@ def _sur_backward(ctx, g_stats, g_logp, g_adj, g_info):
     else:
         up = g_stats[0].to(torch.float32).reshape(1)       # d total / d surrogate loss (device scalar, no sync)
     g_mean, g_L = seglik_surrogate_bwd(up, adj, L, times, init_time, pred_pairs, ctx.tables, ctx.dim_params)
-    return None, g_mean, g_L, None, None, None, None, None, None, None, None, None
+    return None, g_mean, g_L, None, None, None, None, None, None, None, None, None, None, None
 
 
 seglik_surrogate_fwd.register_autograd(_sur_backward, setup_context=_sur_setup)
@@ -484,10 +493,14 @@ def seg_surrogate(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_
                   tables: Tables, reg_rel: float = 1e-4):
     """-> (surrogate loss = -mean(exp(lp - lp_old) * adv) [fp32 scalar, differentiable], mean ratio, logp)."""
     first = getattr(L, "_tce_first", None)       # a broadcast factor: differentiate w.r.t. the ONE matrix behind it
+    sig = getattr(L, "_tce_sigma", None)          # (Sigma0 [Dp, Dp] fp64, scale [1] fp64): Sigma = scale * Sigma0 = L L^T
     if first is not None and first.shape[0] == 1:
         L = first
+    else:
+        sig = None
     stats, logp, _adj, _info = seglik_surrogate_fwd(smp_traj, mean, L, times, init_time, init_pos, init_vel,
-                                                    pred_pairs, logp_old, advantage, tables.handle, reg_rel)
+                                                    pred_pairs, logp_old, advantage, tables.handle, reg_rel,
+                                                    None if sig is None else sig[0], None if sig is None else sig[1])
     loss, ratio = _StatsToFloat.apply(stats)
     return loss, ratio.detach(), logp.detach()
 
@@ -856,6 +869,14 @@ proj_entropy.register_autograd(_pe_backward, setup_context=_pe_setup)
 
 def kl_state_size(batch: int, n: int) -> int:
     return _lib.load().tce_proj_kl_save_doubles(batch, n)
+
+
+def kl_state_sigma(state: Tensor, batch: int, n: int) -> Tuple[Tensor, Tensor]:
+    """Views into a KL state buffer: (Sigma of the projected covariance before the entropy control [batch, n, n],
+    alpha^2 of the fused entropy control [batch]) -- Sigma of the layer's output is alpha^2 * Sigma."""
+    nn = batch * n * n
+    sc = state[4 * nn + batch * n:].view(batch, 8)
+    return state[3 * nn:4 * nn].view(batch, n, n), sc[:, 6]
 
 
 def kl_state(batch: int, n: int, device) -> Tensor:

@@ -213,6 +213,9 @@ class BaseProjectionLayer:
         """Covariance projection and entropy control as one op, or None if the layer has no fused kernel."""
         return None
 
+    def _shared_sigma(self, proj_L1):
+        return None
+
     def _trust_region_projection(self, policy, p, q):
         if not self.projects:
             return p
@@ -270,7 +273,10 @@ class BaseProjectionLayer:
             proj_L1.record_stream(main)
             # broadcast here: the backward of the expand (a [B, n, n] -> [n, n] reduction) then runs on the side
             # stream in front of the covariance backward instead of delaying the mean chain on the main stream
-            return _expand_first(proj_L1, L.shape[0])
+            out = _expand_first(proj_L1, L.shape[0])
+            if fused is not None:
+                out._tce_sigma = self._shared_sigma(proj_L1)       # Sigma for the likelihood's stage 1 (or None)
+            return out
 
     def _call_overlapped(self, policy, p, q, step, cov_projected=None):
         mean, L = p
@@ -346,6 +352,16 @@ class KLProjectionLayer(BaseProjectionLayer):
         self._kl_state = None
 
     fuse_entropy = True      # KL projection + entropy control in one launch (start_cov_projection)
+    sigma_to_likelihood = True   # hand Sigma (already formed inside the projection kernel) to the likelihood
+
+    def _shared_sigma(self, proj_L1):
+        """(Sigma0 [n, n] fp64, alpha^2 [1]) views of the state written by the fused kernel: the covariance of the
+        layer's output is alpha^2 * Sigma0.  Valid until the next forward of this layer."""
+        state = getattr(self, "_last_state", None)
+        if not self.sigma_to_likelihood or state is None or proj_L1.shape[0] != 1:
+            return None
+        Sigma, scale = ops.kl_state_sigma(state, 1, proj_L1.shape[-1])
+        return Sigma[0], scale
 
     def _state_for(self, Lc):
         state = self._kl_state
@@ -373,6 +389,7 @@ class KLProjectionLayer(BaseProjectionLayer):
             return None
         Lc = L.contiguous()
         state = self._state_for(Lc)
+        self._last_state = state
         return ops.proj_kl_entropy(Lc, L_old.contiguous(), self.cov_bound, state, self.warm_start, beta,
                                    self.entropy_eq)[0]
 
