@@ -159,6 +159,11 @@ def build_gpu_workload(device, rank, world):
     return agent, dataset, times, pairs
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full, box pushing B = 1024, P = 24)
+NCU_TRAFFIC_TABLE = {"seglik_chol": 23564288 + 39680, "seglik_gram_sigma": 4078080 + 3328,
+                     "seglik_bwd_dsigma": 23839488 + 0, "dsigma_to_dl": 16293376 + 0}
+
+
 def roofline_numbers(agent, dataset, times, pairs, device, peaks):
     """Time the three stages of the segment likelihood alone (CUDA events, L2 flushed) and the FMA pipes."""
     import ctypes
@@ -207,8 +212,30 @@ def roofline_numbers(agent, dataset, times, pairs, device, peaks):
             total += a.elapsed_time(b)
         return total / reps * 1e-3                     # seconds
 
+    # the variants the timed epoch really runs for this (non-contextual) configuration: Sigma of the ONE projected
+    # covariance in, dSigma out, the product with L applied once to the batch sum
+    L1 = L[:1].contiguous()
+    Sigma = (L1[0].double() @ L1[0].double().T).contiguous()
+    one = torch.ones(1, device=device, dtype=torch.float64)
+    gS, gL1 = torch.empty(B, DP, DP, device=device), torch.empty(1, DP, DP, device=device)
+
+    def gram_sigma():
+        _lib.call("tce_seglik_gram_sigma", tabs.handle, p(ds["step_actions"]), p(mean), p(Sigma), p(one), p(times),
+                  p(ds["segment_init_time"]), p(ds["segment_init_pos"]), p(ds["segment_init_vel"]), p(pairs), p(work),
+                  p(dmax), B, T_STEPS, P, st)
+
+    def bwd_dsigma():
+        _lib.call("tce_seglik_bwd_dsigma", tabs.handle, p(adj), p(times), p(ds["segment_init_time"]), p(pairs), None,
+                  p(gm), p(gS), B, T_STEPS, P, st)
+
+    def dsigma_to_dl():
+        _lib.call("tce_dsigma_to_dl", p(gS), B, p(L1), p(gL1), DP, st)
+
     gram(); chol()
-    t = {"seglik_gram": timed(gram), "seglik_chol": timed(chol), "seglik_bwd": timed(bwd)}
+    t_general = {"seglik_gram": timed(gram), "seglik_chol": timed(chol), "seglik_bwd": timed(bwd)}
+    gram_sigma(); chol()
+    t = {"seglik_gram_sigma": timed(gram_sigma), "seglik_chol": timed(chol), "seglik_bwd_dsigma": timed(bwd_dsigma),
+         "dsigma_to_dl": timed(dsigma_to_dl)}
     scratch = torch.empty(16, device=device, dtype=torch.float64)
     pipes = {}
     for name, fp64 in (("fp32", 0), ("fp64", 1)):
@@ -227,11 +254,14 @@ def roofline_numbers(agent, dataset, times, pairs, device, peaks):
         + n ** 3 // 6 + n * n // 2 + n * K1
     fwd_flops = P * 2 * mac_seg
     dom = max(t, key=t.get)
-    alg = {"seglik_gram": (fwd_bytes, fwd_flops), "seglik_chol": (8 * P * (n * (n + 1) // 2 + n), P * 2 * (n ** 3 // 2)),
-           "seglik_bwd": (bwd_bytes, 2 * fwd_flops)}[dom]
+    shared_in = 4 * (DP + (P + 1) * D + (1 + 2 * D) + P)        # per episode without the (shared) covariance
+    alg = {"seglik_gram_sigma": (shared_in, fwd_flops),
+           "seglik_chol": (8 * P * (n * (n + 1) // 2 + n), P * 2 * (n ** 3 // 2)),
+           "seglik_bwd_dsigma": (shared_in + 4 * (P + DP), 2 * fwd_flops),
+           "dsigma_to_dl": (4 * DP * DP, 2 * DP * DP)}[dom]
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
-    # exact configuration (profiles/r01_seglik_full_summary.txt); refreshed whenever the kernels change
-    NCU_TRAFFIC = {"seglik_gram": 18276608 + 4352, "seglik_chol": 23564288 + 39680, "seglik_bwd": 38071552 + 48896}
+    # exact configuration (profiles/r01_seglik_full_final_summary.txt); refreshed whenever the kernels change
+    NCU_TRAFFIC = dict(NCU_TRAFFIC_TABLE)
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg[0] * B / t[dom] / 1e9
     roof = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
@@ -240,6 +270,7 @@ def roofline_numbers(agent, dataset, times, pairs, device, peaks):
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst, kernel timed alone)" if "hbm_gbs" in peaks
             else "fallback 6650 GB/s (B200_PROFILING.md)",
             "algorithmic_bytes_per_launch": alg[0] * B, "kernel_us": {k: round(v * 1e6, 2) for k, v in t.items()},
+            "kernel_us_per_episode_covariance": {k: round(v * 1e6, 2) for k, v in t_general.items()},
             "compute": {"note": "this kernel is FMA-pipe bound (SURVEY 8(d)): mixed fp32 FFMA + fp64 DFMA",
                         "achieved_tflops": round(alg[1] * B / t[dom] / 1e12, 3),
                         "measured_fp32_fma_tflops": round(pipes["fp32"], 2),
