@@ -254,10 +254,11 @@ def roofline_numbers(agent, dataset, times, pairs, device, peaks):
         + n ** 3 // 6 + n * n // 2 + n * K1
     fwd_flops = P * 2 * mac_seg
     dom = max(t, key=t.get)
-    shared_in = 4 * (DP + (P + 1) * D + (1 + 2 * D) + P)        # per episode without the (shared) covariance
-    alg = {"seglik_gram_sigma": (shared_in, fwd_flops),
+    # SURVEY 8(d)'s per-episode figures (they count the covariance factor per episode, as the reference stores it; the
+    # shared-covariance variants move less: see `traffic`)
+    alg = {"seglik_gram_sigma": (fwd_bytes, fwd_flops),
            "seglik_chol": (8 * P * (n * (n + 1) // 2 + n), P * 2 * (n ** 3 // 2)),
-           "seglik_bwd_dsigma": (shared_in + 4 * (P + DP), 2 * fwd_flops),
+           "seglik_bwd_dsigma": (bwd_bytes, 2 * fwd_flops),
            "dsigma_to_dl": (4 * DP * DP, 2 * DP * DP)}[dom]
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
     # exact configuration (profiles/r01_seglik_full_final_summary.txt); refreshed whenever the kernels change
