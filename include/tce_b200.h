@@ -167,6 +167,15 @@ int tce_proj_kl_entropy_fwd(const float *L, const float *L_o, double eps_cov, co
                             int32_t *info, int warm_start, int64_t B, int n, void *stream);
 int tce_proj_kl_entropy_bwd(const float *L, const float *proj_L, const float *grad_out, const double *save,
                             float *grad_L, int64_t B, int n, void *stream);
+/* tce_proj_kl_entropy_fwd in two launches: _sigma writes the state (Sigma_proj, alpha = entropy scale from the
+ * closed-form log-determinant, ...; for an inactive projection also the outputs); _chol forms
+ * proj_L = chol(Sigma_proj) and out_L = alpha proj_L from the state.  What only needs the covariance
+ * (tce_seglik_gram_sigma) can be ordered after the first launch alone.                                    */
+int tce_proj_kl_entropy_fwd_sigma(const float *L, const float *L_o, double eps_cov, const double *beta,
+                                  int64_t ldb_beta, int equality, float *proj_L, float *out_L, double *save,
+                                  int32_t *info, int warm_start, int64_t B, int n, void *stream);
+int tce_proj_kl_entropy_fwd_chol(const double *save, float *proj_L, float *out_L, int32_t *info, int64_t B, int n,
+                                 void *stream);
 /* Frobenius: S_new = (S + eta S_old) / (1 + eta), eta = sqrt(|S_old - S|_F^2 / eps_cov) - 1; save_sc [B,4] */
 int tce_proj_frob_cov_fwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov, float *proj_L,
                           double *save_sc, int32_t *info, int64_t B, int n, void *stream);

@@ -472,7 +472,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
                        double *__restrict__ save_Li, double *__restrict__ save_Sig, double *__restrict__ save_lam,
                        double *__restrict__ save_sc, int32_t *__restrict__ info, int n, int warm_start,
                        const double *__restrict__ beta,
-                       long long ldb_beta, int entropy_eq, float *__restrict__ out_L) {
+                       long long ldb_beta, int entropy_eq, float *__restrict__ out_L, int split) {
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
   Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
@@ -516,7 +516,8 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   la_gemm(b2, b0, b3, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // M = Lt U~
   if (threadIdx.x == 0) {
     save_sc[b * KL_SC + 0] = eta; save_sc[b * KL_SC + 1] = active ? 1.0 : 0.0; save_sc[b * KL_SC + 2] = kl0; save_sc[b * KL_SC + 3] = fp;
-    save_sc[b * KL_SC + 6] = 1.0;                                  // alpha^2 (overwritten by the fused entropy control)
+    save_sc[b * KL_SC + 4] = 1.0; save_sc[b * KL_SC + 5] = 0.0;    // alpha, ent_active, alpha^2: overwritten by the fused
+    save_sc[b * KL_SC + 6] = 1.0;                                  // entropy control
     if (blockIdx.x == 0) g_kl_prof[15] = sweeps;
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) save_lam[b * n + i] = lam[i];
@@ -529,10 +530,12 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   float *out = proj_L + off;
   // Fused entropy control (optional, `beta` != NULL): out_L = alpha * proj_L with
   // alpha = exp((beta - H(proj_L)) / n) where H < beta (or always: equality variant), as proj_entropy_kernel.
-  auto entropy_scale = [&](Mat P) -> double {
+  // `half_logdet(i)`: the i-th term of 1/2 logdet of the projected covariance (log of the Cholesky diagonal, or its
+  // closed form 1/2 logdet(Sigma_o) + 1/2 sum log((1+eta)/(lam+eta)) when the factor is not formed here: `split`)
+  auto entropy_scale = [&](auto half_logdet) -> double {
     if (!beta) return 1.0;
     double sl = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sl += log(P(i, i));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sl += half_logdet(i);
     sl = block_sum(sl, red);
     const double H = 0.5 * n * (1.0 + LOG_2PI) + sl, bt = beta[b * ldb_beta];
     const bool ent_active = entropy_eq || (H < bt);
@@ -553,7 +556,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   if (!active) {                                                                    // identity
     la_gemm(b1, b0, b0.T(), n, n, n, TRI_LOWER, TRI_UPPER, TRI_FULL, 1.0, 0.0);      // Sigma = Lt Lt^T
     save_sigma(b1);
-    const double alpha = entropy_scale(b0);
+    const double alpha = entropy_scale([&](int i) { return log(b0(i, i)); });
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
       const float v = (e % n <= e / n) ? Lt[e] : 0.f;
       out[e] = v;
@@ -570,15 +573,39 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   KL_STAMP(6);
   la_gemm(b1, b2, b2.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_LOWER, 1.0, 0.0);       // Sigma_proj (all of it is written)
   save_sigma(b1);
+  if (split) {        // the factor is formed by kl_chol_kernel; consumers of Sigma (likelihood stage 1) need not wait
+    entropy_scale([&](int i) { return log((double)Lo[(size_t)i * n + i]) + 0.5 * log((1.0 + eta) / (lam[i] + eta)); });
+    KL_STAMP(7); KL_STAMP(8); KL_STAMP(9);
+    return;
+  }
   __syncthreads();                                                                  // ... before chol overwrites it
   KL_STAMP(7);
   la_chol(b1, n, &s_bad);
   KL_STAMP(8);
-  const double alpha = entropy_scale(b1);
+  const double alpha = entropy_scale([&](int i) { return log(b1(i, i)); });
   store_lower_f(out, b1, n, 1.0);
   if (out_L) store_lower_f(out_L + off, b1, n, alpha);
   if (info && threadIdx.x == 0) info[b] = s_bad;
   KL_STAMP(9);
+}
+
+// Second half of a `split` forward: proj_L = chol(Sigma_proj) from the state, out_L = alpha * proj_L.
+__global__ void __launch_bounds__(KL_THREADS)
+kl_chol_kernel(const double *__restrict__ save_Sig, const double *__restrict__ save_sc, float *__restrict__ proj_L,
+               float *__restrict__ out_L, int32_t *__restrict__ info, int n) {
+  extern __shared__ double sd[];
+  const int m = pad_even(n), LD = m + 1;
+  Mat b0{sd, LD, 1};
+  __shared__ int s_bad;
+  const long long b = blockIdx.x;
+  const size_t off = (size_t)b * n * n;
+  if (save_sc[b * KL_SC + 1] == 0.0) return;          // inactive projection: the first half wrote the identity result
+  if (threadIdx.x == 0) s_bad = 0;
+  load_full_d(b0, save_Sig + off, n, m);
+  la_chol(b0, n, &s_bad);
+  store_lower_f(proj_L + off, b0, n, 1.0);
+  if (out_L) store_lower_f(out_L + off, b0, n, save_sc[b * KL_SC + 4]);
+  if (info && threadIdx.x == 0) info[b] = s_bad;
 }
 
 // Backward (implicit differentiation of eta*, no eigen-derivative singularities).  With P = proj_L, G the
@@ -1048,7 +1075,7 @@ extern "C" size_t tce_proj_kl_save_doubles(int64_t B, int n) { return (size_t)B 
 
 static int kl_fwd_launch(const float *L, const float *L_o, double eps_cov, const double *beta, int64_t ldb_beta,
                          int equality, float *proj_L, float *out_L, double *save, int32_t *info, int warm_start,
-                         int64_t B, int n, void *stream) {
+                         int64_t B, int n, void *stream, int split = 0) {
   if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!L || !L_o || !proj_L || !save || B < 0 || !(eps_cov > 0)) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
@@ -1058,7 +1085,8 @@ static int kl_fwd_launch(const float *L, const float *L_o, double eps_cov, const
   const size_t nn = (size_t)B * n * n;
   double *M = save, *U = M + nn, *Li = U + nn, *Sig = Li + nn, *lam = Sig + nn, *sc = lam + (size_t)B * n;
   proj_kl_cov_fwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(
-      L, L_o, eps_cov, proj_L, M, U, Li, Sig, lam, sc, info, n, warm_start, beta, (long long)ldb_beta, equality, out_L);
+      L, L_o, eps_cov, proj_L, M, U, Li, Sig, lam, sc, info, n, warm_start, beta, (long long)ldb_beta, equality, out_L,
+      split);
   TCE_CHECK_LAUNCH("proj_kl_cov_fwd_kernel");
   return TCE_OK;
 }
@@ -1094,6 +1122,33 @@ extern "C" int tce_proj_kl_entropy_fwd(const float *L, const float *L_o, double 
                                        int32_t *info, int warm_start, int64_t B, int n, void *stream) {
   if (B != 0 && (!beta || !out_L)) return TCE_ERR_INVALID_ARGUMENT;
   return kl_fwd_launch(L, L_o, eps_cov, beta, ldb_beta, equality, proj_L, out_L, save, info, warm_start, B, n, stream);
+}
+
+/* The forward in two launches: _sigma writes the state (Sigma_proj, alpha, ...; for an inactive projection also the
+ * outputs), _chol forms proj_L = chol(Sigma_proj) and out_L = alpha proj_L from it.  What only needs Sigma (stage 1
+ * of the likelihood) can start after the first.                                                           */
+extern "C" int tce_proj_kl_entropy_fwd_sigma(const float *L, const float *L_o, double eps_cov, const double *beta,
+                                             int64_t ldb_beta, int equality, float *proj_L, float *out_L,
+                                             double *save, int32_t *info, int warm_start, int64_t B, int n,
+                                             void *stream) {
+  if (B != 0 && (!beta || !out_L)) return TCE_ERR_INVALID_ARGUMENT;
+  return kl_fwd_launch(L, L_o, eps_cov, beta, ldb_beta, equality, proj_L, out_L, save, info, warm_start, B, n, stream,
+                       1);
+}
+
+extern "C" int tce_proj_kl_entropy_fwd_chol(const double *save, float *proj_L, float *out_L, int32_t *info, int64_t B,
+                                            int n, void *stream) {
+  if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
+  if (!save || !proj_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
+  PJ_CHECK_N(n);
+  const size_t smem = pj_smem_exclusive(pj_smem(n, 1), B);
+  int rc = set_smem(kl_chol_kernel, smem);
+  if (rc) return rc;
+  const size_t nn = (size_t)B * n * n;
+  const double *Sig = save + 3 * nn, *sc = save + 4 * nn + (size_t)B * n;
+  kl_chol_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(Sig, sc, proj_L, out_L, info, n);
+  TCE_CHECK_LAUNCH("kl_chol_kernel");
+  return TCE_OK;
 }
 
 extern "C" int tce_proj_kl_entropy_bwd(const float *L, const float *proj_L, const float *grad_out, const double *save,

@@ -932,10 +932,14 @@ class _ProjKLCov(torch.autograd.Function):
         return proj_kl_cov_bwd(g.contiguous(), L, proj_L, ctx.state), None, None, None, None
 
 
+SIGMA_READY = {}       # id(state) -> CUDA event recorded after the first half of a split forward
+
+
 @torch.library.custom_op("tce::proj_kl_entropy_fwd", mutates_args=("state",))
 def proj_kl_entropy_fwd(L: Tensor, L_o: Tensor, eps_cov: float, state: Tensor, warm: bool, beta: Tensor,
-                        equality: bool) -> Tuple[Tensor, Tensor, Tensor]:
-    """KL covariance projection + entropy control in one launch -> (out_L, proj_L (pre-entropy), info)."""
+                        equality: bool, split: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+    """KL covariance projection + entropy control -> (out_L, proj_L (pre-entropy), info).  ``split``: two launches
+    (state incl. Sigma first, Cholesky second) with an event in ``SIGMA_READY[id(state)]`` between them."""
     L, L_o = _chk(L, name="L"), _chk(L_o, name="L_o")
     beta = _chk(beta, torch.float64, "beta")
     Bc, n = L.shape[0], L.shape[-1]
@@ -943,13 +947,22 @@ def proj_kl_entropy_fwd(L: Tensor, L_o: Tensor, eps_cov: float, state: Tensor, w
         raise TceError("state must come from ops.kl_state(batch, n, device)")
     out, proj = torch.empty_like(L), torch.empty_like(L)
     info = torch.empty(Bc, device=L.device, dtype=torch.int32)
+    if split:
+        _lib.call("tce_proj_kl_entropy_fwd_sigma", _p(L), _p(L_o), float(eps_cov), _p(beta),
+                  0 if beta.numel() == 1 else 1, int(equality), _p(proj), _p(out), _p(state), _p(info), int(warm), Bc, n,
+                  _stream())
+        ev = torch.cuda.Event()
+        ev.record()
+        SIGMA_READY[id(state)] = ev
+        _lib.call("tce_proj_kl_entropy_fwd_chol", _p(state), _p(proj), _p(out), _p(info), Bc, n, _stream())
+        return out, proj, info
     _lib.call("tce_proj_kl_entropy_fwd", _p(L), _p(L_o), float(eps_cov), _p(beta), 0 if beta.numel() == 1 else 1,
               int(equality), _p(proj), _p(out), _p(state), _p(info), int(warm), Bc, n, _stream())
     return out, proj, info
 
 
 @proj_kl_entropy_fwd.register_fake
-def _(L, L_o, eps_cov, state, warm, beta, equality):
+def _(L, L_o, eps_cov, state, warm, beta, equality, split=False):
     return torch.empty_like(L), torch.empty_like(L), L.new_empty(L.shape[0], dtype=torch.int32)
 
 
@@ -969,8 +982,8 @@ def _(grad_out, L, proj_L, state):
 
 class _ProjKLEntropy(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, L, L_o, eps_cov, state, warm, beta, equality):
-        out, proj_L, info = proj_kl_entropy_fwd(L, L_o, eps_cov, state, warm, beta, equality)
+    def forward(ctx, L, L_o, eps_cov, state, warm, beta, equality, split):
+        out, proj_L, info = proj_kl_entropy_fwd(L, L_o, eps_cov, state, warm, beta, equality, split)
         ctx.save_for_backward(L, proj_L)
         ctx.state = state
         ctx.mark_non_differentiable(proj_L, info)
@@ -979,14 +992,16 @@ class _ProjKLEntropy(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g, g_proj, g_info):
         L, proj_L = ctx.saved_tensors
-        return proj_kl_entropy_bwd(g.contiguous(), L, proj_L, ctx.state), None, None, None, None, None, None
+        return proj_kl_entropy_bwd(g.contiguous(), L, proj_L, ctx.state), None, None, None, None, None, None, None
 
 
 def proj_kl_entropy(L: Tensor, L_o: Tensor, eps_cov: float, state: Tensor, warm: bool, beta: Tensor,
-                    equality: bool) -> Tuple[Tensor, Tensor, Tensor]:
+                    equality: bool, split: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     """``proj_entropy(proj_kl_cov(L, L_o, ...)[0], beta, equality)[0]`` as ONE forward and ONE backward kernel
-    -> (out_L, proj_L before the entropy control [not differentiable], info)."""
-    return _ProjKLEntropy.apply(L, L_o, eps_cov, state, warm, beta, equality)
+    -> (out_L, proj_L before the entropy control [not differentiable], info).  ``split``: the forward is two
+    launches (state with Sigma_proj and alpha first, the Cholesky factor second) and ``SIGMA_READY[id(state)]``
+    holds an event recorded between them, for consumers of ``kl_state_sigma(state, ...)``."""
+    return _ProjKLEntropy.apply(L, L_o, eps_cov, state, warm, beta, equality, split)
 
 
 def proj_kl_cov(L: Tensor, L_o: Tensor, eps_cov: float, state: Tensor, warm: bool) -> Tuple[Tensor, Tensor]:

@@ -373,7 +373,9 @@ class TemporalCorrelatedAgent:
             if zeroed_early:
                 self._zero_policy_grads()
             new = self.policy.policy(obs)
-        proj = self.projection(self.policy, new, old, self.num_iterations, cov_projected=pre)
+        proj = self.projection(self.policy, new, old, self.num_iterations, cov_projected=pre,
+                               defer_factor=bool(self.fused_surrogate and hasattr(self.policy, "segment_surrogate")))
+        cov_pending = getattr(self.projection, "_cov_pending", False)
         # trust-region loss: small (partly single-CTA) kernels that only need `new` and `proj` -- a parallel
         # branch next to the segment likelihood, forward and (autograd replays the streams) backward
         tr_stream = None
@@ -393,7 +395,11 @@ class TemporalCorrelatedAgent:
                 dataset["segment_init_pos"], dataset["segment_init_vel"], pred_pairs,
                 dataset["segment_log_prob_estimate"], dataset["segment_advantage"])
             sur_stats = {"imp_smp_ratio": ratio}
+            if cov_pending:        # stage 1 ran on Sigma alone; everything after this reads the projected factor
+                self.projection.join_covariance()
         else:
+            if cov_pending:
+                self.projection.join_covariance()
             log_prob_new = self.policy.log_prob(dataset["step_actions"], params_mean=proj[0], params_L=proj[1],
                                                 times=times, init_time=dataset["segment_init_time"],
                                                 init_pos=dataset["segment_init_pos"],
@@ -409,6 +415,8 @@ class TemporalCorrelatedAgent:
             # backward stage) but ordered on the device only after `proj_ready`, i.e. next to the likelihood.
             cur = torch.cuda.current_stream()
             tr_stream.wait_event(proj_ready)
+            if cov_pending:
+                self.projection.join_covariance(tr_stream)
             with torch.cuda.stream(tr_stream):
                 tr_loss = self.projection.get_trust_region_loss(self.policy, new, proj, set_variance=self.set_variance)
                 tr_loss.record_stream(cur)

@@ -239,9 +239,11 @@ class BaseProjectionLayer:
         return (self.projects and self.overlap and not policy.contextual_std and not self.entropy_first
                 and L.is_cuda)
 
-    def __call__(self, policy, p, q, step, *args, cov_projected=None, **kwargs):
+    def __call__(self, policy, p, q, step, *args, cov_projected=None, defer_factor=False, **kwargs):
+        """``defer_factor``: return as soon as the covariance ITSELF (``_tce_sigma``) is available; the caller then
+        calls ``join_covariance`` on every stream that reads the projected factor."""
         if self._overlappable(policy, p[1]):
-            return self._call_overlapped(policy, p, q, step, cov_projected)
+            return self._call_overlapped(policy, p, q, step, cov_projected, defer_factor)
         beta = self._entropy_bound(step, p[0].device)
         if self.entropy_first:
             p = self._entropy_projection(policy, p, beta)
@@ -278,15 +280,31 @@ class BaseProjectionLayer:
                 out._tce_sigma = self._shared_sigma(proj_L1)       # Sigma for the likelihood's stage 1 (or None)
             return out
 
-    def _call_overlapped(self, policy, p, q, step, cov_projected=None):
+    def _call_overlapped(self, policy, p, q, step, cov_projected=None, defer_factor=False):
         mean, L = p
         old_mean, old_L = q
         proj_L = cov_projected if cov_projected is not None else self.start_cov_projection(policy, L, old_L, step)
         mean_part = self._mean_part(policy, p, q)
         self.cache = {"new_old_mean": mean_part.detach()}
         proj_mean = ops.proj_mean(mean, old_mean, mean_part, self.mean_bound)
-        torch.cuda.current_stream().wait_stream(self._side_stream(mean.device))
+        sig = getattr(proj_L, "_tce_sigma", None)
+        if defer_factor and sig is not None and sig[2] is not None:
+            # the likelihood's first stage only needs Sigma: wait for the first half of the covariance forward; whoever
+            # reads the FACTOR on another stream joins the covariance stream first (`join_covariance`)
+            torch.cuda.current_stream().wait_event(sig[2])
+            self._cov_pending = True
+        else:
+            torch.cuda.current_stream().wait_stream(self._side_stream(mean.device))
+            self._cov_pending = False
         return proj_mean, proj_L
+
+    _cov_pending = False
+
+    def join_covariance(self, stream=None):
+        """Order ``stream`` (default: the current one) after the covariance chain of the last ``__call__`` (needed
+        before the projected FACTOR is read when the call returned after the Sigma half of a split forward)."""
+        if self._side is not None:
+            (stream or torch.cuda.current_stream()).wait_stream(self._side)
 
     def trust_region_value(self, policy, p, q):
         return gaussian_kl(policy, p, q)
@@ -361,7 +379,7 @@ class KLProjectionLayer(BaseProjectionLayer):
         if not self.sigma_to_likelihood or state is None or proj_L1.shape[0] != 1:
             return None
         Sigma, scale = ops.kl_state_sigma(state, 1, proj_L1.shape[-1])
-        return Sigma[0], scale
+        return Sigma[0], scale, ops.SIGMA_READY.get(id(state))
 
     def _state_for(self, Lc):
         state = self._kl_state
@@ -391,7 +409,7 @@ class KLProjectionLayer(BaseProjectionLayer):
         state = self._state_for(Lc)
         self._last_state = state
         return ops.proj_kl_entropy(Lc, L_old.contiguous(), self.cov_bound, state, self.warm_start, beta,
-                                   self.entropy_eq)[0]
+                                   self.entropy_eq, bool(self.sigma_to_likelihood and Lc.shape[0] == 1))[0]
 
 
 class FrobeniusProjectionLayer(BaseProjectionLayer):
