@@ -16,7 +16,8 @@ with torch.cuda.stream(side):
 torch.cuda.current_stream().wait_stream(side)
 torch.cuda.synchronize()
 g = torch.cuda.CUDAGraph()
-with torch.cuda.graph(g):
+hi = torch.cuda.Stream(priority=-1) if os.environ.get("TCE_HIGH_PRIO") else None
+with torch.cuda.graph(g, stream=hi):
     agent.policy_epoch(dataset, times, pairs)
 for _ in range(5):
     g.replay()

@@ -259,13 +259,16 @@ maha_shared_kernel(const float *__restrict__ mean, const float *__restrict__ mea
     double maha = 0.0;
 #pragma unroll 1
     for (int i = lane; i < n; i += 32) {                 // z = Linv d (rows of different lanes: stride LD is odd)
-      double z0 = 0.0, z1 = 0.0;
+      double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;      // four chains: eight shared-memory loads in flight
       const double *row = sA + i * LD;
       int j = 0;
 #pragma unroll 1
-      for (; j + 1 <= i; j += 2) { z0 = fma(row[j], dv[j], z0); z1 = fma(row[j + 1], dv[j + 1], z1); }
-      if (j <= i) z0 = fma(row[j], dv[j], z0);
-      const double z = z0 + z1;
+      for (; j + 3 <= i; j += 4) {
+        z0 = fma(row[j], dv[j], z0); z1 = fma(row[j + 1], dv[j + 1], z1);
+        z2 = fma(row[j + 2], dv[j + 2], z2); z3 = fma(row[j + 3], dv[j + 3], z3);
+      }
+      for (; j <= i; ++j) z0 = fma(row[j], dv[j], z0);
+      const double z = (z0 + z1) + (z2 + z3);
       zv[i] = z;
       maha = fma(z, z, maha);
     }
@@ -276,12 +279,16 @@ maha_shared_kernel(const float *__restrict__ mean, const float *__restrict__ mea
       const double g2 = gout ? 2.0 * gout[b] : 2.0;      // gout == NULL: d maha / d mean, saved for the backward
 #pragma unroll 1
       for (int j = lane; j < n; j += 32) {
-        double u0 = 0.0, u1 = 0.0;
+        double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
         const double *colp = sA + j;
         int i = j;
 #pragma unroll 1
-        for (; i + 1 < n; i += 2) { u0 = fma(colp[i * LD], zv[i], u0); u1 = fma(colp[(i + 1) * LD], zv[i + 1], u1); }
-        if (i < n) u0 = fma(colp[i * LD], zv[i], u0);
+        for (; i + 3 < n; i += 4) {
+          u0 = fma(colp[i * LD], zv[i], u0); u1 = fma(colp[(i + 1) * LD], zv[i + 1], u1);
+          u2 = fma(colp[(i + 2) * LD], zv[i + 2], u2); u3 = fma(colp[(i + 3) * LD], zv[i + 3], u3);
+        }
+        for (; i < n; ++i) u0 = fma(colp[i * LD], zv[i], u0);
+        u0 += u2; u1 += u3;
         grad_mean[b * n + j] = (float)(g2 * (u0 + u1));
       }
     }
@@ -941,6 +948,8 @@ template <typename K>
 int set_smem(K kernel, size_t smem) {
   if (smem > 220 * 1024) return TCE_ERR_UNSUPPORTED_SHAPE;
   TCE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "proj smem attr");
+  // same carve-out preference as the likelihood kernels these run beside (no measurable effect either way)
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   return TCE_OK;
 }
 

@@ -232,7 +232,7 @@ class BaseProjectionLayer:
 
     def _side_stream(self, device):
         if self._side is None:
-            self._side = torch.cuda.Stream(device=device)
+            self._side = torch.cuda.Stream(device=device, priority=-1)     # the covariance chain is the critical path
         return self._side
 
     def _overlappable(self, policy, L):
@@ -371,6 +371,10 @@ class KLProjectionLayer(BaseProjectionLayer):
 
     fuse_entropy = True      # KL projection + entropy control in one launch (start_cov_projection)
     sigma_to_likelihood = True   # hand Sigma (already formed inside the projection kernel) to the likelihood
+    # Forward in two launches (Sigma / Cholesky) so that the likelihood's stage 1 starts ~20 us earlier.  Measured
+    # at B = 1024: no net gain -- the trust-region branch, which needs the factor, then collides with stage 3 of the
+    # likelihood instead of stage 1 (profiles/README.md) -- so it is off by default.
+    split_forward = False
 
     def _shared_sigma(self, proj_L1):
         """(Sigma0 [n, n] fp64, alpha^2 [1]) views of the state written by the fused kernel: the covariance of the
@@ -379,7 +383,7 @@ class KLProjectionLayer(BaseProjectionLayer):
         if not self.sigma_to_likelihood or state is None or proj_L1.shape[0] != 1:
             return None
         Sigma, scale = ops.kl_state_sigma(state, 1, proj_L1.shape[-1])
-        return Sigma[0], scale, ops.SIGMA_READY.get(id(state))
+        return Sigma[0], scale, (ops.SIGMA_READY.get(id(state)) if self.split_forward else None)
 
     def _state_for(self, Lc):
         state = self._kl_state
@@ -409,7 +413,8 @@ class KLProjectionLayer(BaseProjectionLayer):
         state = self._state_for(Lc)
         self._last_state = state
         return ops.proj_kl_entropy(Lc, L_old.contiguous(), self.cov_bound, state, self.warm_start, beta,
-                                   self.entropy_eq, bool(self.sigma_to_likelihood and Lc.shape[0] == 1))[0]
+                                   self.entropy_eq, bool(self.split_forward and self.sigma_to_likelihood
+                                                         and Lc.shape[0] == 1))[0]
 
 
 class FrobeniusProjectionLayer(BaseProjectionLayer):

@@ -283,3 +283,12 @@ def test_fused_kl_entropy_equals_the_two_separate_ops(beta_shift, equality):
     assert torch.equal(p1, p2)
     assert (o1 - o2).abs().max() <= 2e-7 * o2.abs().max()
     assert (g1 - g2).abs().max() <= 2e-6 * g2.abs().max()
+    # the same forward as two launches (state with Sigma first, Cholesky second; alpha from the closed-form logdet)
+    state = ops.kl_state(L0.shape[0], n, DEV)
+    o3, p3, info3 = ops.proj_kl_entropy(L0.clone(), Lo, 5e-4, state, False, beta, equality, True)
+    assert int(info3.abs().max()) == 0 and id(state) in ops.SIGMA_READY
+    assert (p3 - p1).abs().max() <= 2e-7 * p1.abs().max() and (o3 - o1).abs().max() <= 2e-7 * o1.abs().max()
+    Sigma, scale = ops.kl_state_sigma(state, L0.shape[0], n)
+    ref = scale[:, None, None] * Sigma
+    got = o3.double() @ o3.double().transpose(-1, -2)
+    assert (got - ref).abs().max() <= 1e-6 * ref.abs().max()                  # fp32 rounding of the factor
