@@ -106,3 +106,61 @@ def test_ops_reject_cpu_tensors():
                 0.95, True)
     with pytest.raises(TceError):
         ops.gauss_maha(torch.zeros(2, 3), torch.zeros(2, 3), torch.eye(3).expand(2, 3, 3))
+
+
+def test_shared_kl_loss_node_matches_the_plain_formula():
+    """``_SharedKLLoss`` (one autograd node, constant gradients) == coeff * (mean 1/2 maha + shape + volume) written with
+    plain torch ops: values, detached pieces and gradients, with the cached unit seed and with a general seed."""
+    from tce_rl_b200 import ops
+    from tce_rl_b200.rl.projection import _SharedKLLoss
+    torch.manual_seed(0)
+    B, k, coeff = 17, 6, 0.8
+    for with_cov in (True, False):
+        for seed_scale in (None, 2.5):
+            maha = torch.rand(B, dtype=torch.float64).requires_grad_(True)
+            st = torch.rand(1, 5, dtype=torch.float64).requires_grad_(True)
+            loss, mean_diff, cov_diff, shape, volume = _SharedKLLoss.apply(maha, st, coeff, with_cov, k, torch.float32)
+            m2, s2 = maha.detach().clone().requires_grad_(True), st.detach().clone().requires_grad_(True)
+            sh, vo = 0.5 * (s2[:, 1] - k), 0.5 * (s2[:, 3] - s2[:, 2])
+            ref = ((0.5 * m2 + (sh + vo if with_cov else 0.0)).mean() * coeff).to(torch.float32)
+            assert loss.dtype == torch.float32 and abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item())
+            assert torch.allclose(mean_diff, 0.5 * m2.detach()) and torch.allclose(cov_diff, (sh + vo).detach())
+            assert torch.allclose(shape, sh.detach()) and torch.allclose(volume, vo.detach())
+            if seed_scale is None:
+                loss.backward(ops.unit_seed(loss.device, loss.dtype))
+                ref.backward()
+            else:
+                loss.backward(torch.tensor(seed_scale))
+                ref.backward(torch.tensor(seed_scale))
+            assert torch.allclose(maha.grad, m2.grad, rtol=1e-6, atol=0)
+            if with_cov:
+                assert torch.allclose(st.grad, s2.grad, rtol=1e-6, atol=1e-12)
+            else:
+                assert float(st.grad.abs().max()) == 0.0 and s2.grad is None or float(s2.grad.abs().max()) == 0.0
+
+
+def test_stats_to_float_node():
+    from tce_rl_b200 import ops
+    stats = torch.tensor([0.25, 1.5], dtype=torch.float64, requires_grad=True)
+    loss, ratio = ops._StatsToFloat.apply(stats)
+    assert loss.dtype == torch.float32 and float(loss.detach()) == 0.25 and float(ratio.detach()) == 1.5
+    loss.backward(ops.unit_seed(loss.device, loss.dtype))
+    assert stats.grad.tolist() == [1.0, 0.0]
+    stats.grad = None
+    loss2, _ = ops._StatsToFloat.apply(stats)
+    (3.0 * loss2).backward()
+    assert stats.grad.tolist() == [3.0, 0.0]
+
+
+def test_flat_adam_and_loader_guard_rails():
+    from tce_rl_b200._lib import TceError
+    from tce_rl_b200.rl.optim import FlatAdam
+    p = torch.nn.Parameter(torch.zeros(4))
+    with pytest.raises(TceError):
+        FlatAdam([p], torch.zeros(4))                       # CPU buffers: there is no CPU path
+    from tce_rl_b200.rl import projection as pj
+    L1 = torch.eye(3).reshape(1, 3, 3)
+    e = pj._expand_first(L1, 5)
+    assert e.shape == (5, 3, 3) and e.stride(0) == 0 and pj._first(e) is L1
+    dense = torch.eye(3).expand(5, 3, 3).contiguous()
+    assert pj._first(dense).shape == (1, 3, 3)
