@@ -167,6 +167,11 @@ int tce_proj_kl_entropy_fwd(const float *L, const float *L_o, double eps_cov, co
                             int32_t *info, int warm_start, int64_t B, int n, void *stream);
 int tce_proj_kl_entropy_bwd(const float *L, const float *proj_L, const float *grad_out, const double *save,
                             float *grad_L, int64_t B, int n, void *stream);
+/* tce_proj_kl_entropy_bwd when out_inv [B,n,n] = out_L^-1 (fp64, lower) is already known -- the trust-region loss
+ * inverts the layer's output for its Mahalanobis term (tce_tri_inverse) -- so that the backward need not invert
+ * proj_L itself (the largest single phase of that kernel).                                                */
+int tce_proj_kl_entropy_bwd_inv(const float *L, const float *proj_L, const float *grad_out, const double *save,
+                                const double *out_inv, float *grad_L, int64_t B, int n, void *stream);
 /* tce_proj_kl_entropy_fwd in two launches: _sigma writes the state (Sigma_proj, alpha = entropy scale from the
  * closed-form log-determinant, ...; for an inactive projection also the outputs); _chol forms
  * proj_L = chol(Sigma_proj) and out_L = alpha proj_L from the state.  What only needs the covariance

@@ -627,7 +627,8 @@ __global__ void __launch_bounds__(KL_THREADS)
 proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ proj_L, const float *__restrict__ gout,
                        const double *__restrict__ save_M, const double *__restrict__ save_U,
                        const double *__restrict__ save_Li, const double *__restrict__ save_lam,
-                       const double *__restrict__ save_sc, float *__restrict__ grad_L, int n, int fused_entropy) {
+                       const double *__restrict__ save_sc, float *__restrict__ grad_L, int n, int fused_entropy,
+                       const double *__restrict__ out_inv) {
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
   Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
@@ -673,7 +674,16 @@ proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ pr
     if (j > i) b2(i, j) = 0.0; else if (i == j) b2(i, j) *= 0.5;                   // Phi
   }
   load_full_d(b1, save_M + off, n, m);                                             // M (G is consumed)
-  la_tri_inverse(b0, b3, dinv, n);                                                 // P^-1
+  if (out_inv) {     // (alpha P)^-1 is already known (the trust-region loss inverts the layer's output): P^-1 = alpha (.)
+    const double alpha = fused_entropy ? save_sc[b * KL_SC + 4] : 1.0;
+    batched_load(out_inv + off, n * n, [&](int e, double v) {
+      const int i = e / n, j = e - i * n;
+      b3(i, j) = j <= i ? alpha * v : 0.0;
+    });
+    __syncthreads();
+  } else {
+    la_tri_inverse(b0, b3, dinv, n);                                               // P^-1
+  }
   la_gemm(b0, b3, b1, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // Y = P^-1 M (P is consumed)
   la_gemm(b3, b2, b0, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // Phi Y
   la_gemm(b1, b0.T(), b3, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // F' = Y^T Phi Y ; Ft = sym(F')
@@ -1101,7 +1111,7 @@ static int kl_fwd_launch(const float *L, const float *L_o, double eps_cov, const
 }
 
 static int kl_bwd_launch(const float *L, const float *proj_L, const float *grad_out, const double *save, float *grad_L,
-                         int64_t B, int n, int fused_entropy, void *stream) {
+                         int64_t B, int n, int fused_entropy, void *stream, const double *out_inv = nullptr) {
   if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!L || !proj_L || !grad_out || !save || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
@@ -1111,7 +1121,7 @@ static int kl_bwd_launch(const float *L, const float *proj_L, const float *grad_
   const size_t nn = (size_t)B * n * n;
   const double *M = save, *U = M + nn, *Li = U + nn, *lam = Li + 2 * nn, *sc = lam + (size_t)B * n;
   proj_kl_cov_bwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, proj_L, grad_out, M, U, Li, lam, sc, grad_L,
-                                                                                 n, fused_entropy);
+                                                                                 n, fused_entropy, out_inv);
   TCE_CHECK_LAUNCH("proj_kl_cov_bwd_kernel");
   return TCE_OK;
 }
@@ -1163,6 +1173,13 @@ extern "C" int tce_proj_kl_entropy_fwd_chol(const double *save, float *proj_L, f
 extern "C" int tce_proj_kl_entropy_bwd(const float *L, const float *proj_L, const float *grad_out, const double *save,
                                        float *grad_L, int64_t B, int n, void *stream) {
   return kl_bwd_launch(L, proj_L, grad_out, save, grad_L, B, n, 1, stream);
+}
+
+extern "C" int tce_proj_kl_entropy_bwd_inv(const float *L, const float *proj_L, const float *grad_out,
+                                           const double *save, const double *out_inv, float *grad_L, int64_t B, int n,
+                                           void *stream) {
+  if (B != 0 && !out_inv) return TCE_ERR_INVALID_ARGUMENT;
+  return kl_bwd_launch(L, proj_L, grad_out, save, grad_L, B, n, 1, stream, out_inv);
 }
 
 extern "C" int tce_proj_frob_cov_fwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov, float *proj_L,

@@ -967,41 +967,59 @@ def _(L, L_o, eps_cov, state, warm, beta, equality, split=False):
 
 
 @torch.library.custom_op("tce::proj_kl_entropy_bwd", mutates_args=())
-def proj_kl_entropy_bwd(grad_out: Tensor, L: Tensor, proj_L: Tensor, state: Tensor) -> Tensor:
+def proj_kl_entropy_bwd(grad_out: Tensor, L: Tensor, proj_L: Tensor, state: Tensor,
+                        out_inv: Optional[Tensor] = None) -> Tensor:
+    """``out_inv``: inverse [Bc, n, n] fp64 of the layer's OUTPUT factor if somebody already formed it."""
     g, L, proj_L = _chk(grad_out), _chk(L), _chk(proj_L)
     out = torch.empty_like(L)
-    _lib.call("tce_proj_kl_entropy_bwd", _p(L), _p(proj_L), _p(g), _p(state), _p(out), L.shape[0], L.shape[-1],
-              _stream())
+    if out_inv is not None:
+        inv = _chk(out_inv, torch.float64, "out_inv")
+        if inv.numel() != L.numel():
+            raise TceError("out_inv must have the shape of L")
+        _lib.call("tce_proj_kl_entropy_bwd_inv", _p(L), _p(proj_L), _p(g), _p(state), _p(inv), _p(out), L.shape[0],
+                  L.shape[-1], _stream())
+    else:
+        _lib.call("tce_proj_kl_entropy_bwd", _p(L), _p(proj_L), _p(g), _p(state), _p(out), L.shape[0], L.shape[-1],
+                  _stream())
     return out
 
 
 @proj_kl_entropy_bwd.register_fake
-def _(grad_out, L, proj_L, state):
+def _(grad_out, L, proj_L, state, out_inv=None):
     return torch.empty_like(L)
 
 
 class _ProjKLEntropy(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, L, L_o, eps_cov, state, warm, beta, equality, split):
+    def forward(ctx, L, L_o, eps_cov, state, warm, beta, equality, split, holder):
         out, proj_L, info = proj_kl_entropy_fwd(L, L_o, eps_cov, state, warm, beta, equality, split)
         ctx.save_for_backward(L, proj_L)
         ctx.state = state
+        ctx.holder, ctx.out_ptr = holder, out.data_ptr()
         ctx.mark_non_differentiable(proj_L, info)
         return out, proj_L, info
 
     @staticmethod
     def backward(ctx, g, g_proj, g_info):
         L, proj_L = ctx.saved_tensors
-        return proj_kl_entropy_bwd(g.contiguous(), L, proj_L, ctx.state), None, None, None, None, None, None, None
+        # somebody (the trust-region loss) may have inverted this call's output factor: (inverse, event, data_ptr)
+        known = getattr(ctx.holder, "_output_inverse", None) if ctx.holder is not None else None
+        inv = None
+        if known is not None and known[2] == ctx.out_ptr and known[0].numel() == L.numel():
+            torch.cuda.current_stream().wait_event(known[1])
+            inv = known[0].reshape(L.shape)
+        return (proj_kl_entropy_bwd(g.contiguous(), L, proj_L, ctx.state, inv),) + (None,) * 8
 
 
 def proj_kl_entropy(L: Tensor, L_o: Tensor, eps_cov: float, state: Tensor, warm: bool, beta: Tensor,
-                    equality: bool, split: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+                    equality: bool, split: bool = False, holder=None) -> Tuple[Tensor, Tensor, Tensor]:
     """``proj_entropy(proj_kl_cov(L, L_o, ...)[0], beta, equality)[0]`` as ONE forward and ONE backward kernel
     -> (out_L, proj_L before the entropy control [not differentiable], info).  ``split``: the forward is two
     launches (state with Sigma_proj and alpha first, the Cholesky factor second) and ``SIGMA_READY[id(state)]``
-    holds an event recorded between them, for consumers of ``kl_state_sigma(state, ...)``."""
-    return _ProjKLEntropy.apply(L, L_o, eps_cov, state, warm, beta, equality, split)
+    holds an event recorded between them, for consumers of ``kl_state_sigma(state, ...)``.  ``holder``: an object
+    whose attribute ``_output_inverse = (inverse of out_L [.., n, n] fp64, CUDA event, out_L.data_ptr())`` -- if set
+    by the time of the backward and matching this call -- saves the backward its own triangular inverse."""
+    return _ProjKLEntropy.apply(L, L_o, eps_cov, state, warm, beta, equality, split, holder)
 
 
 def proj_kl_cov(L: Tensor, L_o: Tensor, eps_cov: float, state: Tensor, warm: bool) -> Tuple[Tensor, Tensor]:

@@ -334,7 +334,12 @@ class BaseProjectionLayer:
         cur, helper = torch.cuda.current_stream(), _helper_stream(p[0].device)
         helper.wait_stream(cur)
         with torch.cuda.stream(helper):                                    # mean part beside the covariance part
-            maha = _maha(policy, p[0], target[0], target[1])
+            linv = shared_inverse(target[1])
+            ready = torch.cuda.Event()
+            ready.record()
+            # the KL layer's backward needs the inverse of exactly this factor (its own output): hand it over
+            self._output_inverse = (linv, ready, _first(target[1]).data_ptr())
+            maha = _maha(policy, p[0], target[0], target[1], linv=linv)
             maha.record_stream(cur)
         L1, Lt1 = _first(p[1]), _first(target[1])
         zeros = torch.zeros(1, L1.shape[-1], device=L1.device)
@@ -412,9 +417,10 @@ class KLProjectionLayer(BaseProjectionLayer):
         Lc = L.contiguous()
         state = self._state_for(Lc)
         self._last_state = state
+        self._output_inverse = None            # only an inverse formed AFTER this forward can belong to it
         return ops.proj_kl_entropy(Lc, L_old.contiguous(), self.cov_bound, state, self.warm_start, beta,
                                    self.entropy_eq, bool(self.split_forward and self.sigma_to_likelihood
-                                                         and Lc.shape[0] == 1))[0]
+                                                         and Lc.shape[0] == 1), self)[0]
 
 
 class FrobeniusProjectionLayer(BaseProjectionLayer):
