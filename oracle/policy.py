@@ -131,7 +131,7 @@ class TemporalCorrelatedPolicy(BlackBoxPolicy):
         self.mp.update_inputs(times=time_pairs, params=mean_e, params_L=L_e,
                               init_time=it, init_pos=ip, init_vel=iv)
         traj_mean = self.mp.get_traj_pos(flat_shape=True)
-        traj_cov, reg = self.mp.get_traj_pos_cov(return_reg=True)
+        traj_cov, reg = self.mp.get_traj_pos_cov(return_reg=True, reg_override=kwargs.get("reg_override"))
         mvn = MultivariateNormal(loc=traj_mean, covariance_matrix=traj_cov, validate_args=False)
         lp = mvn.log_prob(x)
         return (lp, traj_mean, traj_cov, reg) if return_parts else lp

@@ -210,13 +210,17 @@ class ProDMP:
         return H
 
     def get_traj_pos_cov(self, times=None, params_L=None, init_time=None, init_pos=None, init_vel=None,
-                         reg: float = 1e-4, return_reg=False):
-        """H (L L^T) H^T + reg * max(diag over the WHOLE batch) * I   (App. A.5)."""
+                         reg: float = 1e-4, return_reg=False, reg_override=None):
+        """H (L L^T) H^T + reg * max(diag over the WHOLE batch) * I   (App. A.5).
+        ``reg_override`` (tests only): use this regulariser term instead -- lets a large batch be evaluated in
+        chunks with the batch-global term computed once."""
         self.update_inputs(times, None, params_L, init_time, init_pos, init_vel)
         H = self.basis_multi_dof()
         Sigma = torch.einsum('...ij,...kj->...ik', self.params_L, self.params_L)
         cov = torch.einsum('...ik,...kl,...jl->...ij', H, Sigma, H)
         reg_term = torch.max(torch.einsum('...ii->...i', cov)).item() * reg
+        if reg_override is not None:
+            reg_term = float(reg_override)
         cov = cov + torch.eye(cov.shape[-1], dtype=cov.dtype) * reg_term
         return (cov, reg_term) if return_reg else cov
 

@@ -269,19 +269,10 @@ def _(mean, L, mean_o, L_o):
 # --------------------------------------------------------------------------------------------------
 # (3) segment-wise trajectory likelihood
 # --------------------------------------------------------------------------------------------------
-_REG_GROUP = None   # torch.distributed process group over which the regulariser max is reduced
-
-
-def set_regulariser_group(group) -> None:
-    """At >1 GPU, all-reduce(MAX) the batch-global regulariser seed over ``group``."""
-    global _REG_GROUP
-    _REG_GROUP = group
-
-
-def _reduce_diag_max(diag_max: Tensor) -> None:
-    if _REG_GROUP is not None:
-        import torch.distributed as dist
-        dist.all_reduce(diag_max, op=dist.ReduceOp.MAX, group=None if _REG_GROUP is True else _REG_GROUP)
+# The product path of the likelihood is the fused implementation in ops_seglik.py (re-exported at the end of this
+# module); the STAGED ops below (gram / chol / bwd with an fp64 HBM workspace) are kept as an independent
+# implementation for cross-checks (tests) and for mp.ProDMP.get_traj_pos_cov.
+from .ops_seglik import set_regulariser_group, _reduce_diag_max, unit_seed  # noqa: E402
 
 
 def _work(tables: int, B: int, P: int, device) -> Tensor:
@@ -368,9 +359,9 @@ def _seglik_backward(ctx, g_logp, g_work, g_diag, g_info):
 seglik_fwd.register_autograd(_seglik_backward, setup_context=_seglik_setup)
 
 
-def seg_logprob(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, tables: Tables,
-                reg_rel: float = 1e-4, return_info: bool = False):
-    """Segment-wise log-likelihood [B, P] (differentiable w.r.t. ``mean`` and ``L``)."""
+def seg_logprob_staged(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, tables: Tables,
+                       reg_rel: float = 1e-4, return_info: bool = False):
+    """Segment-wise log-likelihood [B, P] (differentiable w.r.t. ``mean`` and ``L``), staged kernels."""
     logp, _work_, diag_max, info = seglik_fwd(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs,
                                               tables.handle, reg_rel)
     return (logp, info, diag_max) if return_info else logp
@@ -489,9 +480,9 @@ def _sur_backward(ctx, g_stats, g_logp, g_adj, g_info):
 seglik_surrogate_fwd.register_autograd(_sur_backward, setup_context=_sur_setup)
 
 
-def seg_surrogate(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, logp_old, advantage,
-                  tables: Tables, reg_rel: float = 1e-4):
-    """-> (surrogate loss = -mean(exp(lp - lp_old) * adv) [fp32 scalar, differentiable], mean ratio, logp)."""
+def seg_surrogate_staged(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, logp_old, advantage,
+                         tables: Tables, reg_rel: float = 1e-4):
+    """Staged kernels -> (surrogate loss = -mean(exp(lp - lp_old) * adv) [fp32 scalar, differentiable], mean ratio, logp)."""
     first = getattr(L, "_tce_first", None)       # a broadcast factor: differentiate w.r.t. the ONE matrix behind it
     sig = getattr(L, "_tce_sigma", None)          # (Sigma0 [Dp, Dp] fp64, scale [1] fp64): Sigma = scale * Sigma0 = L L^T
     if first is not None and first.shape[0] == 1:
@@ -529,18 +520,6 @@ class _StatsToFloat(torch.autograd.Function):
         if g_loss is unit_seed(g_loss.device, g_loss.dtype):   # seeded with the cached 1: no kernel at all
             return ctx.e0
         return ctx.e0 * g_loss                            # fp64 [2] = {d/d loss, 0}
-
-
-_UNIT = {}
-
-
-def unit_seed(device, dtype) -> Tensor:
-    """A cached 0-dim 1.0: pass it as the gradient of a loss term to ``torch.autograd.backward`` -- the likelihood
-    ops recognise it (by identity) and skip the scalar bookkeeping kernels in front of their backward stage."""
-    key = (str(device), dtype)
-    if key not in _UNIT:
-        _UNIT[key] = torch.ones((), device=device, dtype=dtype)
-    return _UNIT[key]
 
 
 # --------------------------------------------------------------------------------------------------
@@ -1165,3 +1144,10 @@ def _cd_backward(ctx, g):
 
 
 cov_distance.register_autograd(_cd_backward, setup_context=_cd_setup)
+
+
+# --------------------------------------------------------------------------------------------------
+# (3) product path of the segment likelihood: fused kernels
+# --------------------------------------------------------------------------------------------------
+from .ops_seglik import (seg_logprob, seg_surrogate, seglik, pairs_chained, times_uniform, declare_uniform,  # noqa: E402,F401
+                         shared_factor)
