@@ -248,48 +248,52 @@ int tce_seglik_bwd_dsigma(const tce_tables_t *tables, const void *work, const fl
 int tce_dsigma_to_dl(const float *grad_sigma, int64_t B, const float *L, float *grad_L, int n, void *stream);
 
 /* ---- (3') the same likelihood, fused: product path of TemporalCorrelatedPolicy.log_prob / segment_surrogate --------
- * (temporal_correlated_policy.py:104-203 + temporal_correlated_agent.py:718-739).  No HBM workspace.
+ * (temporal_correlated_policy.py:104-203 + temporal_correlated_agent.py:718-739).
  *
- * tce_seglik_diagmax : diagonal-only pre-pass, folds max_{b,p,i} C_bp[i,i] into *diag_max (caller zeroes it; at >1 GPU
- *                      the caller all-reduces(MAX) it before the next call).  Covariance either as factors L
- *                      (batch stride ldb_L, 0 = one shared factor) or as Sigma = (*sigma_scale) * Sigma0 [Dp,Dp] fp64
- *                      (Sigma0 != NULL; sigma_scale may be NULL = 1).
+ * tce_seglik_prepass : per episode the basis rows of its distinct time points and the residuals r = x - mu into `pre`
+ *                      (tce_seglik_fused_config: pre_doubles_per_episode doubles per episode, ~5 KB for box pushing --
+ *                      the only HBM intermediate of the path), and max_{b,p,i} C_bp[i,i] folded into *diag_max (caller
+ *                      zeroes it; at >1 GPU the caller all-reduces(MAX) it before the next call).  Covariance either
+ *                      as factors L (batch stride ldb_L, 0 = one shared factor) or as Sigma = (*sigma_scale) * Sigma0
+ *                      [Dp,Dp] fp64 (Sigma0 != NULL; sigma_scale may be NULL = 1).
  * tce_seglik_fused   : ONE persistent kernel: gram, per-segment Cholesky, log-prob, and for grad_mode != 0 the whole
  *                      backward.  grad_mode 0: logp / info only.  1: upstream gradient grad_logp [B,P].  2: fused
  *                      surrogate: g = -exp(lp - logp_old) * advantage * grad_scale, loss_acc[0] += sum g,
  *                      loss_acc[1] += sum ratio * grad_scale (loss_acc: 2 device doubles, caller zeroes).
  *                      Outputs (any may be NULL): logp [B,P], info [B,P] (first non-positive pivot + 1), grad_mean
  *                      [B,Dp]; per-episode factors: grad_L [B,Dp,Dp] (lower, upper = 0); shared covariance:
- *                      dsigma_part [grid][D(D+1)/2][K1][K1] fp32 = one partial d loss / d Sigma per CTA in DoF-block
- *                      layout (grid and the partial size from tce_seglik_fused_config), to be finished by
- *                      tce_seglik_dsigma_reduce: grad_L [Dp,Dp] = 2 tril((sum partials) L) * (*upstream) and / or
- *                      grad_sigma [Dp,Dp] (dense symmetric).
+ *                      dsigma_part (part_floats floats from tce_seglik_fused_config: one partial d loss / d Sigma per
+ *                      CTA in DoF-block layout, then the reduce kernel's sum and ticket), to be finished by
+ *                      tce_seglik_dsigma_reduce(nparts = grid): grad_L [Dp,Dp] = 2 tril((sum partials) L) * (*upstream)
+ *                      and / or grad_sigma [Dp,Dp] (dense symmetric).
  *                      `chained` != 0 claims pred_pairs[p][1] == pred_pairs[p+1][0] for all p (the fixed-interval
  *                      selection of every TCE config: P + 1 distinct time points instead of 2 P); a wrong claim is
- *                      refused (info[0] = -7, nothing computed).
+ *                      refused (info[0] = -7, nothing computed).  The same value must be given to both calls.
  * Uniform time grid (every episode has the same init_time and times row) + shared covariance: C_p, its Cholesky
  * factor and its inverse are identical for all episodes.  tce_seglik_uniform_prep (what & 1: basis rows + C_p + diag
  * max from episode 0's grid; what & 2: factor / inverse / logdet per segment; a multi-GPU caller may all-reduce
- * *diag_max between two calls), tce_seglik_uniform_main (per episode: residual, log-prob, gradient pieces into `red`,
- * grad_mean) and tce_seglik_uniform_finish (batch reduction -> ONE dsigma partial for tce_seglik_dsigma_reduce)
- * replace the fused kernel in that case.
- * ws: tce_seglik_uniform_ws_doubles(P) doubles, red: tce_seglik_uniform_red_doubles(B, P) doubles.              */
+ * *diag_max between two calls), tce_seglik_uniform_main (per episode: residual, log-prob, grad_mean; per CTA the sums
+ * of g alpha alpha^T into `apart`, sizes from tce_seglik_uniform_parts) and tce_seglik_uniform_finish (one CTA:
+ * adjoints -> dSigma -> grad_L / grad_sigma) replace pre-pass + fused kernel + reduce in that case.
+ * ws: tce_seglik_uniform_ws_doubles(P) doubles.                                                                 */
 int tce_seglik_fused_config(const tce_tables_t *tables, int64_t B, int64_t P, int chained, int32_t *episodes_per_iter,
-                            int32_t *grid, int64_t *part_floats);
-int tce_seglik_diagmax(const tce_tables_t *tables, const float *L, int64_t ldb_L, const double *Sigma0,
-                       const double *sigma_scale, const float *times, const float *init_time,
-                       const int64_t *pred_pairs, double *diag_max, int64_t B, int64_t T, int64_t P, void *stream);
-int tce_seglik_fused(const tce_tables_t *tables, const float *smp_traj, const float *mean, const float *L,
-                     int64_t ldb_L, const double *Sigma0, const double *sigma_scale, const float *times,
-                     const float *init_time, const float *init_pos, const float *init_vel,
-                     const int64_t *pred_pairs, const double *diag_max, double reg_rel, int grad_mode,
-                     const float *grad_logp, const float *logp_old, const float *advantage, double grad_scale,
-                     double *loss_acc, float *logp, int32_t *info, float *grad_mean, float *grad_L,
-                     float *dsigma_part, int chained, int64_t B, int64_t T, int64_t P, void *stream);
-int tce_seglik_dsigma_reduce(const tce_tables_t *tables, const float *dsigma_part, int nparts, const float *L,
+                            int32_t *grid, int64_t *part_floats, int64_t *pre_doubles_per_episode);
+int tce_seglik_prepass(const tce_tables_t *tables, const float *smp_traj, const float *mean, const float *L,
+                       int64_t ldb_L, const double *Sigma0, const double *sigma_scale, const float *times,
+                       const float *init_time, const float *init_pos, const float *init_vel,
+                       const int64_t *pred_pairs, double *pre, double *diag_max, int chained, int64_t B, int64_t T,
+                       int64_t P, void *stream);
+int tce_seglik_fused(const tce_tables_t *tables, const double *pre, const float *L, int64_t ldb_L,
+                     const double *Sigma0, const double *sigma_scale, const int64_t *pred_pairs,
+                     const double *diag_max, double reg_rel, int grad_mode, const float *grad_logp,
+                     const float *logp_old, const float *advantage, double grad_scale, double *loss_acc, float *logp,
+                     int32_t *info, float *grad_mean, float *grad_L, float *dsigma_part, int chained, int64_t B,
+                     int64_t P, void *stream);
+int tce_seglik_dsigma_reduce(const tce_tables_t *tables, float *dsigma_part, int nparts, const float *L,
                              const float *upstream, float *grad_L, float *grad_sigma, void *stream);
 size_t tce_seglik_uniform_ws_doubles(const tce_tables_t *tables, int64_t P);
-size_t tce_seglik_uniform_red_doubles(const tce_tables_t *tables, int64_t B, int64_t P);
+int tce_seglik_uniform_parts(const tce_tables_t *tables, int64_t B, int64_t P, int32_t *nparts,
+                             int64_t *apart_doubles);
 int tce_seglik_uniform_prep(const tce_tables_t *tables, const float *L, const double *Sigma0,
                             const double *sigma_scale, const float *times, const float *init_time,
                             const int64_t *pred_pairs, double *ws, double *diag_max, double reg_rel, int what,
@@ -298,9 +302,10 @@ int tce_seglik_uniform_main(const tce_tables_t *tables, const double *ws, const 
                             const float *init_pos, const float *init_vel, const int64_t *pred_pairs, int grad_mode,
                             const float *grad_logp, const float *logp_old, const float *advantage,
                             double grad_scale, double *loss_acc, float *logp, int32_t *info, float *grad_mean,
-                            double *red, int64_t B, int64_t T, int64_t P, void *stream);
-int tce_seglik_uniform_finish(const tce_tables_t *tables, double *ws, const double *red, float *dsigma_part,
-                              int64_t B, int64_t P, void *stream);
+                            double *apart, int64_t B, int64_t T, int64_t P, void *stream);
+int tce_seglik_uniform_finish(const tce_tables_t *tables, double *ws, const double *apart, int nparts,
+                              const float *L, const float *upstream, float *grad_L, float *grad_sigma, int64_t P,
+                              void *stream);
 
 /* ---- (4b) GAE and segment advantages ------------------------------------------------------------------
  * TemporalCorrelatedAgent.get_advantage_return (temporal_correlated_agent.py:118-181).

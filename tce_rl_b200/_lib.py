@@ -76,17 +76,17 @@ SIGNATURES = {
     "tce_seglik_bwd_dsigma": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
     "tce_dsigma_to_dl": (C.c_int, [_P, _I64, _P, _P, _I32, _P]),
     "tce_seglik_fused_config": (C.c_int, [_P, _I64, _I64, _I32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
-                                          C.POINTER(C.c_int64)]),
-    "tce_seglik_diagmax": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
-    "tce_seglik_fused": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _D, _I32, _P, _P, _P, _D, _P,
-                                   _P, _P, _P, _P, _P, _I32, _I64, _I64, _I64, _P]),
+                                          C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "tce_seglik_prepass": (C.c_int, [_P] * 4 + [_I64] + [_P] * 9 + [_I32, _I64, _I64, _I64, _P]),
+    "tce_seglik_fused": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _D, _I32, _P, _P, _P, _D, _P, _P, _P, _P, _P, _P,
+                                   _I32, _I64, _I64, _P]),
     "tce_seglik_dsigma_reduce": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P]),
     "tce_seglik_uniform_ws_doubles": (C.c_size_t, [_P, _I64]),
-    "tce_seglik_uniform_red_doubles": (C.c_size_t, [_P, _I64, _I64]),
+    "tce_seglik_uniform_parts": (C.c_int, [_P, _I64, _I64, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "tce_seglik_uniform_prep": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _D, _I32, _I64, _P]),
     "tce_seglik_uniform_main": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _D, _P, _P, _P, _P, _P, _I64,
                                           _I64, _I64, _P]),
-    "tce_seglik_uniform_finish": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P]),
+    "tce_seglik_uniform_finish": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P, _I64, _P]),
     "tce_gae": (C.c_int, [_P, _P, _P, _P, _F, _F, _I32, _P, _P, _I64, _I64, _P]),
     "tce_segment_advantage_raw": (C.c_int, [_I32, _P, _P, _P, _P, _F, _P, _P, _I64, _I64, _I64, _P]),
     "tce_sum_stats": (C.c_int, [_P, _P, _I64, _P]),
@@ -124,7 +124,7 @@ def check(status: int, what: str = "") -> None:
 
 
 LAUNCHES = 0          # kernel launches issued through the C ABI (bench.py reports them as gpu_launches)
-_NO_KERNEL = {"tce_seglik_fused_config", "tce_prodmp_tables_export", "tce_prodmp_tables_create", "tce_debug_kl_phase_cycles", "tce_debug_seglik_phase_cycles"}
+_NO_KERNEL = {"tce_seglik_fused_config", "tce_seglik_uniform_parts", "tce_prodmp_tables_export", "tce_prodmp_tables_create", "tce_debug_kl_phase_cycles", "tce_debug_seglik_phase_cycles"}
 
 
 def call(name: str, *args) -> None:

@@ -135,23 +135,25 @@ def shared_factor(L: Tensor, batch: int) -> Optional[Tensor]:
     return None
 
 
-class _Scratch:
-    """Per (tables, B, P, device) buffers of the likelihood ops (static addresses: CUDA-graph friendly)."""
-    _cache = {}
+_CONFIG = {}
 
-    @classmethod
-    def get(cls, tables: int, B: int, P: int, chained: bool, device) -> dict:
-        key = (tables, B, P, chained, str(device))
-        buf = cls._cache.get(key)
-        if buf is None:
-            lib = _lib.load()
-            E, grid, part = C.c_int32(), C.c_int32(), C.c_int64()
-            _lib.check(lib.tce_seglik_fused_config(tables, max(B, 1), P, int(chained), C.byref(E), C.byref(grid),
-                                                   C.byref(part)), "tce_seglik_fused_config")
-            buf = {"E": E.value, "grid": grid.value, "part": part.value,
-                   "ws_doubles": lib.tce_seglik_uniform_ws_doubles(tables, P)}
-            cls._cache[key] = buf
-        return buf
+
+def fused_config(tables: int, B: int, P: int, chained: bool) -> dict:
+    """Launch geometry / buffer sizes of the fused path for these shapes (host integers, cached)."""
+    key = (tables, B, P, chained)
+    cfg = _CONFIG.get(key)
+    if cfg is None:
+        lib = _lib.load()
+        E, grid, part, pre = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
+        _lib.check(lib.tce_seglik_fused_config(tables, max(B, 1), P, int(chained), C.byref(E), C.byref(grid),
+                                               C.byref(part), C.byref(pre)), "tce_seglik_fused_config")
+        nparts, apart = C.c_int32(), C.c_int64()
+        rc = lib.tce_seglik_uniform_parts(tables, max(B, 1), P, C.byref(nparts), C.byref(apart))
+        cfg = {"E": E.value, "grid": grid.value, "part_floats": part.value, "pre_doubles": pre.value,
+               "ws_doubles": lib.tce_seglik_uniform_ws_doubles(tables, P),
+               "uni_parts": nparts.value if rc == 0 else 0, "apart_doubles": apart.value if rc == 0 else 0}
+        _CONFIG[key] = cfg
+    return cfg
 
 
 @torch.library.custom_op("tce::seglik", mutates_args=())
@@ -202,51 +204,49 @@ def seglik(smp_traj: Tensor, mean: Tensor, L: Optional[Tensor], sigma: Optional[
     if need_L and shared and L is None:
         raise TceError("grad_L of a shared covariance needs its factor L")
     st = _stream()
-    scr = _Scratch.get(tables, B, P, chained, dev)
+    cfg = fused_config(tables, B, P, chained)
     scale = 1.0 / (B * P)
+    if uniform and cfg["uni_parts"] == 0:
+        uniform = False                                      # shape outside the uniform kernels: general path
     if uniform:
-        ws = torch.empty(scr["ws_doubles"], device=dev, dtype=torch.float64)
+        ws = torch.empty(cfg["ws_doubles"], device=dev, dtype=torch.float64)
+        Lp = None if sigma is not None else _p(L)
         if _REG_GROUP is None:
-            _lib.call("tce_seglik_uniform_prep", tables, None if sigma is not None else _p(L), _p(sigma),
-                      _p(sigma_scale), _p(times), _p(init_time), _p(pairs), _p(ws), _p(diag_max), float(reg_rel), 3, P,
-                      st)
+            _lib.call("tce_seglik_uniform_prep", tables, Lp, _p(sigma), _p(sigma_scale), _p(times), _p(init_time),
+                      _p(pairs), _p(ws), _p(diag_max), float(reg_rel), 3, P, st)
         else:
-            for what in (1, 2):
-                _lib.call("tce_seglik_uniform_prep", tables, None if sigma is not None else _p(L), _p(sigma),
-                          _p(sigma_scale), _p(times), _p(init_time), _p(pairs), _p(ws), _p(diag_max), float(reg_rel),
-                          what, P, st)
-                if what == 1:
-                    _reduce_diag_max(diag_max)
-        red = None
-        if want:
-            red = torch.empty(_lib.load().tce_seglik_uniform_red_doubles(tables, B, P), device=dev,
-                              dtype=torch.float64)
+            _lib.call("tce_seglik_uniform_prep", tables, Lp, _p(sigma), _p(sigma_scale), _p(times), _p(init_time),
+                      _p(pairs), _p(ws), _p(diag_max), float(reg_rel), 1, P, st)
+            _reduce_diag_max(diag_max)
+            _lib.call("tce_seglik_uniform_prep", tables, Lp, _p(sigma), _p(sigma_scale), _p(times), _p(init_time),
+                      _p(pairs), _p(ws), _p(diag_max), float(reg_rel), 2, P, st)
+        apart = torch.empty(cfg["apart_doubles"], device=dev, dtype=torch.float64) if need_L else None
         _lib.call("tce_seglik_uniform_main", tables, _p(ws), _p(smp_traj), _p(mean), _p(init_pos), _p(init_vel),
                   _p(pairs), int(grad_mode), _p(grad_logp), _p(logp_old), _p(advantage), scale, _p(stats), _p(logp),
-                  _p(info), _p(g_mean) if want else None, _p(red), B, T, P, st)
+                  _p(info), _p(g_mean) if want else None, _p(apart), B, T, P, st)
         if need_L:
-            part = torch.empty(scr["part"], device=dev, dtype=torch.float32)
-            _lib.call("tce_seglik_uniform_finish", tables, _p(ws), _p(red), _p(part), B, P, st)
             g_L = torch.empty(1, Dp, Dp, device=dev, dtype=torch.float32)
-            _lib.call("tce_seglik_dsigma_reduce", tables, _p(part), 1, _p(L), None, _p(g_L), None, st)
+            _lib.call("tce_seglik_uniform_finish", tables, _p(ws), _p(apart), cfg["uni_parts"], _p(L), None, _p(g_L),
+                      None, P, st)
         return logp, info, acc, g_mean, g_L
-    _lib.call("tce_seglik_diagmax", tables, None if sigma is not None else _p(L), ldb, _p(sigma), _p(sigma_scale),
-              _p(times), _p(init_time), _p(pairs), _p(diag_max), B, T, P, st)
+    pre = torch.empty(B * cfg["pre_doubles"], device=dev, dtype=torch.float64)
+    _lib.call("tce_seglik_prepass", tables, _p(smp_traj), _p(mean), None if sigma is not None else _p(L), ldb,
+              _p(sigma), _p(sigma_scale), _p(times), _p(init_time), _p(init_pos), _p(init_vel), _p(pairs), _p(pre),
+              _p(diag_max), int(chained), B, T, P, st)
     _reduce_diag_max(diag_max)
     part = None
     if need_L:
         if shared:
-            part = torch.empty(scr["grid"] * scr["part"], device=dev, dtype=torch.float32)
+            part = torch.empty(cfg["part_floats"], device=dev, dtype=torch.float32)
         else:
             g_L = torch.empty(B, Dp, Dp, device=dev, dtype=torch.float32)
-    _lib.call("tce_seglik_fused", tables, _p(smp_traj), _p(mean), None if sigma is not None else _p(L), ldb,
-              _p(sigma), _p(sigma_scale), _p(times), _p(init_time), _p(init_pos), _p(init_vel), _p(pairs),
-              _p(diag_max), float(reg_rel), int(grad_mode), _p(grad_logp), _p(logp_old), _p(advantage), scale,
-              _p(stats), _p(logp), _p(info), _p(g_mean) if want else None,
-              _p(g_L) if (need_L and not shared) else None, _p(part), int(chained), B, T, P, st)
+    _lib.call("tce_seglik_fused", tables, _p(pre), None if sigma is not None else _p(L), ldb, _p(sigma),
+              _p(sigma_scale), _p(pairs), _p(diag_max), float(reg_rel), int(grad_mode), _p(grad_logp), _p(logp_old),
+              _p(advantage), scale, _p(stats), _p(logp), _p(info), _p(g_mean) if want else None,
+              _p(g_L) if (need_L and not shared) else None, _p(part), int(chained), B, P, st)
     if need_L and shared:
         g_L = torch.empty(1, Dp, Dp, device=dev, dtype=torch.float32)
-        _lib.call("tce_seglik_dsigma_reduce", tables, _p(part), scr["grid"], _p(L), None, _p(g_L), None, st)
+        _lib.call("tce_seglik_dsigma_reduce", tables, _p(part), cfg["grid"], _p(L), None, _p(g_L), None, st)
     return logp, info, acc, g_mean, g_L
 
 

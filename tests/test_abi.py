@@ -34,6 +34,20 @@ def test_binding_covers_header(lib):
     assert sorted(_lib.SIGNATURES) == declared_symbols()
 
 
+def test_binding_argument_counts_match_header():
+    """Every ctypes signature has exactly as many arguments as the declaration in the header (a short argtypes list
+    makes ctypes silently pass garbage)."""
+    from tce_rl_b200 import _lib
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    seen = 0
+    for m in re.finditer(r"\b(?:int|size_t|void|const char \*)\s*\**(tce_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        n = 0 if args in ("void", "") else len(args.split(","))
+        assert len(_lib.SIGNATURES[name][1]) == n, name
+        seen += 1
+    assert seen == len(_lib.SIGNATURES)
+
+
 def test_version_and_errors(lib):
     assert lib.tce_version() >= 100
     assert lib.tce_strerror(0) == b"ok"
