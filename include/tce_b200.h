@@ -172,6 +172,16 @@ int tce_proj_kl_entropy_bwd(const float *L, const float *proj_L, const float *gr
  * proj_L itself (the largest single phase of that kernel).                                                */
 int tce_proj_kl_entropy_bwd_inv(const float *L, const float *proj_L, const float *grad_out, const double *save,
                                 const double *out_inv, float *grad_L, int64_t B, int n, void *stream);
+/* Backward of tce_proj_kl_cov_fwd (fused_entropy = 0) / tce_proj_kl_entropy_fwd* (fused_entropy = 1) when the consumer
+ * returns the gradient w.r.t. the output COVARIANCE Sigma_out = alpha^2 Sigma_proj [B,n,n] (symmetric, fp64) -- e.g.
+ * grad_sigma of tce_seglik_uniform_finish / tce_seglik_dsigma_reduce -- instead of w.r.t. the factor: no Cholesky
+ * adjoint, and the forward's factor (tce_proj_kl_entropy_fwd_chol) is off the critical path.
+ * tr_coeff != 0 additionally adds the gradient of tr_coeff * KL_cov(N(., L L^T) || N(., Sigma_out)) with Sigma_out
+ * DETACHED -- the covariance term of the trust-region regression loss (get_trust_region_loss,
+ * temporal_correlated_agent.py:561-567), whose VALUE the forward leaves in the state (scalar 7 of a matrix): both
+ * are closed forms on the saved eigen-system, so the loss term needs no kernel of its own.                      */
+int tce_proj_kl_bwd_sigma(const float *L, const double *grad_sigma, const double *save, int fused_entropy,
+                          double tr_coeff, float *grad_L, int64_t B, int n, void *stream);
 /* tce_proj_kl_entropy_fwd in two launches: _sigma writes the state (Sigma_proj, alpha = entropy scale from the
  * closed-form log-determinant, ...; for an inactive projection also the outputs); _chol forms
  * proj_L = chol(Sigma_proj) and out_L = alpha proj_L from the state.  What only needs the covariance
@@ -179,8 +189,9 @@ int tce_proj_kl_entropy_bwd_inv(const float *L, const float *proj_L, const float
 int tce_proj_kl_entropy_fwd_sigma(const float *L, const float *L_o, double eps_cov, const double *beta,
                                   int64_t ldb_beta, int equality, float *proj_L, float *out_L, double *save,
                                   int32_t *info, int warm_start, int64_t B, int n, void *stream);
-int tce_proj_kl_entropy_fwd_chol(const double *save, float *proj_L, float *out_L, int32_t *info, int64_t B, int n,
-                                 void *stream);
+/* out_inv (optional) [B,n,n] fp64: inverse of out_L (lower), for the Mahalanobis term of the trust-region loss   */
+int tce_proj_kl_entropy_fwd_chol(const double *save, float *proj_L, float *out_L, double *out_inv, int32_t *info,
+                                 int64_t B, int n, void *stream);
 /* Frobenius: S_new = (S + eta S_old) / (1 + eta), eta = sqrt(|S_old - S|_F^2 / eps_cov) - 1; save_sc [B,4] */
 int tce_proj_frob_cov_fwd(const float *L, const float *L_o, int64_t ldb_Lo, double eps_cov, float *proj_L,
                           double *save_sc, int32_t *info, int64_t B, int n, void *stream);
@@ -290,7 +301,7 @@ int tce_seglik_fused(const tce_tables_t *tables, const double *pre, const float 
                      int32_t *info, float *grad_mean, float *grad_L, float *dsigma_part, int chained, int64_t B,
                      int64_t P, void *stream);
 int tce_seglik_dsigma_reduce(const tce_tables_t *tables, float *dsigma_part, int nparts, const float *L,
-                             const float *upstream, float *grad_L, float *grad_sigma, void *stream);
+                             const float *upstream, float *grad_L, double *grad_sigma, void *stream);
 size_t tce_seglik_uniform_ws_doubles(const tce_tables_t *tables, int64_t P);
 int tce_seglik_uniform_parts(const tce_tables_t *tables, int64_t B, int64_t P, int32_t *nparts,
                              int64_t *apart_doubles);
@@ -304,7 +315,7 @@ int tce_seglik_uniform_main(const tce_tables_t *tables, const double *ws, const 
                             double grad_scale, double *loss_acc, float *logp, int32_t *info, float *grad_mean,
                             double *apart, int64_t B, int64_t T, int64_t P, void *stream);
 int tce_seglik_uniform_finish(const tce_tables_t *tables, double *ws, const double *apart, int nparts,
-                              const float *L, const float *upstream, float *grad_L, float *grad_sigma, int64_t P,
+                              const float *L, const float *upstream, float *grad_L, double *grad_sigma, int64_t P,
                               void *stream);
 
 /* ---- (4b) GAE and segment advantages ------------------------------------------------------------------

@@ -58,9 +58,10 @@ SIGNATURES = {
     "tce_proj_kl_cov_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
     "tce_proj_kl_entropy_fwd": (C.c_int, [_P, _P, _D, _P, _I64, _I32, _P, _P, _P, _P, _I32, _I64, _I32, _P]),
     "tce_proj_kl_entropy_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "tce_proj_kl_bwd_sigma": (C.c_int, [_P, _P, _P, _I32, _D, _P, _I64, _I32, _P]),
     "tce_proj_kl_entropy_bwd_inv": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "tce_proj_kl_entropy_fwd_sigma": (C.c_int, [_P, _P, _D, _P, _I64, _I32, _P, _P, _P, _P, _I32, _I64, _I32, _P]),
-    "tce_proj_kl_entropy_fwd_chol": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
+    "tce_proj_kl_entropy_fwd_chol": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
     "tce_grad_sumsq": (C.c_int, [_P, _I64, _P, _P]),
     "tce_adam_step": (C.c_int, [_I32, _P, _P, _P, _P, _P, _P, _D, _D, _D, _D, _D, _D, _P]),
     "tce_proj_frob_cov_fwd": (C.c_int, [_P, _P, _I64, _D, _P, _P, _P, _I64, _I32, _P]),

@@ -16,7 +16,8 @@ namespace {
 constexpr int PJ_THREADS = 512;
 constexpr int KL_THREADS = 512;   // 128 registers per thread: 4x4 fp64 GEMM tiles and the register-resident Jacobi
 constexpr double LOG_2PI = 1.8378770664093453;
-constexpr int KL_SC = 8;      // scalars saved per matrix by the KL projection: eta, active, kl0, fingerprint, alpha, ent_active
+constexpr int KL_SC = 10;     // scalars saved per matrix by the KL projection: eta, active, kl0, fingerprint, alpha, ent_active,
+                              // alpha^2, trust-region shape part, trust-region volume part, (spare)
 
 __device__ inline int pad_even(int n) { return (n + 1) & ~1; }
 
@@ -552,6 +553,25 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
     }
     return alpha;
   };
+  // Covariance part of KL(N(., Sigma) || N(., Sigma_out)), Sigma = Lt Lt^T the UNPROJECTED covariance and
+  // Sigma_out = alpha^2 Sigma_proj the layer's output -- the covariance term of the trust-region regression loss
+  // (get_trust_region_loss, temporal_correlated_agent.py:561-567) -- in closed form on the eigen-system:
+  //   tr(Sigma_out^-1 Sigma) = alpha^-2 sum_i 1 / (D_ii lam_i),  logdet Sigma_out - logdet Sigma = 2 n ln alpha + sum_i ln(D_ii lam_i)
+  // with D_ii = (1 + eta) / (lam_i + eta)  (identity step: D_ii lam_i = 1).  -> save_sc[7] (1/2 (tr - n)) and save_sc[8] (1/2 logdet difference)
+  auto save_tr_value = [&](double alpha, bool act) {
+    double tr = 0.0, ld = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double dl = act ? (1.0 + eta) * lam[i] / (lam[i] + eta) : 1.0;      // D_ii lam_i
+      tr += 1.0 / dl;
+      ld += log(dl);
+    }
+    tr = block_sum(tr, red);
+    ld = block_sum(ld, red);
+    if (threadIdx.x == 0) {
+      save_sc[b * KL_SC + 7] = 0.5 * (tr / (alpha * alpha) - (double)n);            // "shape" part  1/2 (tr - n)
+      save_sc[b * KL_SC + 8] = 0.5 * (2.0 * n * log(alpha) + ld);                  // "volume" part 1/2 (logdet_t - logdet)
+    }
+  };
   // Sigma of the (pre-entropy) result goes to the state as well: with ONE covariance for the batch the
   // likelihood's stage 1 takes alpha^2 * Sigma from there instead of re-forming L L^T per episode.
   auto save_sigma = [&](Mat S) {
@@ -564,6 +584,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
     la_gemm(b1, b0, b0.T(), n, n, n, TRI_LOWER, TRI_UPPER, TRI_FULL, 1.0, 0.0);      // Sigma = Lt Lt^T
     save_sigma(b1);
     const double alpha = entropy_scale([&](int i) { return log(b0(i, i)); });
+    save_tr_value(alpha, false);
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
       const float v = (e % n <= e / n) ? Lt[e] : 0.f;
       out[e] = v;
@@ -581,7 +602,9 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   la_gemm(b1, b2, b2.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_LOWER, 1.0, 0.0);       // Sigma_proj (all of it is written)
   save_sigma(b1);
   if (split) {        // the factor is formed by kl_chol_kernel; consumers of Sigma (likelihood stage 1) need not wait
-    entropy_scale([&](int i) { return log((double)Lo[(size_t)i * n + i]) + 0.5 * log((1.0 + eta) / (lam[i] + eta)); });
+    const double alpha_s =
+        entropy_scale([&](int i) { return log((double)Lo[(size_t)i * n + i]) + 0.5 * log((1.0 + eta) / (lam[i] + eta)); });
+    save_tr_value(alpha_s, true);
     KL_STAMP(7); KL_STAMP(8); KL_STAMP(9);
     return;
   }
@@ -590,6 +613,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   la_chol(b1, n, &s_bad);
   KL_STAMP(8);
   const double alpha = entropy_scale([&](int i) { return log(b1(i, i)); });
+  save_tr_value(alpha, true);
   store_lower_f(out, b1, n, 1.0);
   if (out_L) store_lower_f(out_L + off, b1, n, alpha);
   if (info && threadIdx.x == 0) info[b] = s_bad;
@@ -599,20 +623,35 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
 // Second half of a `split` forward: proj_L = chol(Sigma_proj) from the state, out_L = alpha * proj_L.
 __global__ void __launch_bounds__(KL_THREADS)
 kl_chol_kernel(const double *__restrict__ save_Sig, const double *__restrict__ save_sc, float *__restrict__ proj_L,
-               float *__restrict__ out_L, int32_t *__restrict__ info, int n) {
+               float *__restrict__ out_L, double *__restrict__ out_inv, int32_t *__restrict__ info, int n) {
   extern __shared__ double sd[];
-  const int m = pad_even(n), LD = m + 1;
-  Mat b0{sd, LD, 1};
+  const int m = pad_even(n), LD = m + 1, MS = m * LD;
+  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1};
+  double *dinv = sd + 2 * MS;
   __shared__ int s_bad;
   const long long b = blockIdx.x;
   const size_t off = (size_t)b * n * n;
-  if (save_sc[b * KL_SC + 1] == 0.0) return;          // inactive projection: the first half wrote the identity result
-  if (threadIdx.x == 0) s_bad = 0;
-  load_full_d(b0, save_Sig + off, n, m);
-  la_chol(b0, n, &s_bad);
-  store_lower_f(proj_L + off, b0, n, 1.0);
-  if (out_L) store_lower_f(out_L + off, b0, n, save_sc[b * KL_SC + 4]);
-  if (info && threadIdx.x == 0) info[b] = s_bad;
+  const double alpha = save_sc[b * KL_SC + 4];
+  if (save_sc[b * KL_SC + 1] == 0.0) {                // inactive projection: the first half wrote the identity result
+    if (!out_inv) return;
+    load_lower_d(b0, proj_L + off, n, m);             // proj_L = Lt
+  } else {
+    if (threadIdx.x == 0) s_bad = 0;
+    load_full_d(b0, save_Sig + off, n, m);
+    la_chol(b0, n, &s_bad);
+    store_lower_f(proj_L + off, b0, n, 1.0);
+    if (out_L) store_lower_f(out_L + off, b0, n, alpha);
+    if (info && threadIdx.x == 0) info[b] = s_bad;
+  }
+  if (out_inv) {                                      // (alpha P)^-1, fp64 lower: the trust-region loss's Mahalanobis term
+    __syncthreads();
+    la_tri_inverse(b0, b1, dinv, n);
+    const double ia = 1.0 / alpha;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e - i * n;
+      out_inv[off + e] = j <= i ? ia * b1(i, j) : 0.0;
+    }
+  }
 }
 
 // Backward (implicit differentiation of eta*, no eigen-derivative singularities).  With P = proj_L, G the
@@ -706,6 +745,92 @@ proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ pr
   load_full_d(b2, save_Li + off, n, m);                                            // Lt^-1 (Nt is consumed)
   la_gemm(b3, b2.T(), b1, n, n, n, TRI_UPPER, TRI_FULL, TRI_LOWER, 1.0, 0.0);      // Lt^-T (.)
   store_lower_f(gl, b3, n, -2.0);
+}
+
+// Backward in COVARIANCE space: the consumer of the projected covariance (the segment likelihood, which reads
+// Sigma_out = alpha^2 Sigma_proj straight from the state) hands back Sbar_out = d loss / d Sigma_out (symmetric, fp64)
+// instead of a gradient w.r.t. the Cholesky factor.  Then M^T Sbar_proj M is formed directly:
+//   F0 = M^T Sbar_out M ;  fused entropy control (alpha = exp((beta - H) / n), H = const + 1/2 logdet Sigma_proj):
+//   Sbar_proj = alpha^2 (Sbar_out - c / n Sigma_proj^-1),  c = <Sbar_out, Sigma_proj> = sum_i D_ii F0_ii,
+//   M^T Sigma_proj^-1 M = D^-1,  D = diag((1 + eta) / (lam + eta))   =>   Ft = alpha^2 (F0 - c / n D^-1)
+// and the rest is the implicit differentiation of proj_kl_cov_bwd_kernel.  Neither the factor P, nor P^-1, nor the
+// Cholesky adjoint appear: 5 GEMMs instead of 7 + a triangular inverse, and the forward need not form P on the
+// critical path at all (tce_proj_kl_entropy_fwd_sigma).
+__global__ void __launch_bounds__(KL_THREADS)
+proj_kl_cov_bwd_sigma_kernel(const float *__restrict__ L, const double *__restrict__ gsig,
+                             const double *__restrict__ save_M, const double *__restrict__ save_U,
+                             const double *__restrict__ save_Li, const double *__restrict__ save_Sig,
+                             const double *__restrict__ save_lam, const double *__restrict__ save_sc,
+                             float *__restrict__ grad_L, int n, int fused_entropy, double tr_coeff) {
+  extern __shared__ double sd[];
+  const int m = pad_even(n), LD = m + 1, MS = m * LD;
+  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
+  double *dinv = sd + 4 * MS, *lam = dinv + LA_DINV_DOUBLES, *rho = lam + m, *red = rho + m;
+  const long long b = blockIdx.x;
+  const size_t off = (size_t)b * n * n;
+  float *gl = grad_L + off;
+  const double eta = save_sc[b * KL_SC + 0];
+  const bool kl_active = save_sc[b * KL_SC + 1] != 0.0;
+  const double alpha = fused_entropy ? save_sc[b * KL_SC + 4] : 1.0, a2 = alpha * alpha;
+  const bool ent_active = fused_entropy && save_sc[b * KL_SC + 5] != 0.0;
+  load_full_d(b0, gsig + off, n, m);                                               // Sbar_out
+  if (!kl_active) {
+    // identity KL step: Sigma_proj = Lt Lt^T, grad_Lt = 2 alpha^2 tril(Sbar_out Lt) - (2 alpha^2 c / n) diag(1 / Lt_ii)
+    load_lower_d(b1, L + off, n, m);                                               // Lt
+    double c = 0.0;
+    if (ent_active) {
+      for (int e = threadIdx.x; e < n * n; e += blockDim.x) c = fma(b0(e / n, e % n), save_Sig[off + e], c);
+      c = block_sum(c, red);
+    }
+    la_gemm(b2, b0, b1, n, n, n, TRI_FULL, TRI_LOWER, TRI_LOWER, 1.0, 0.0);
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int i = e / n, j = e - i * n;
+      double v = j <= i ? 2.0 * a2 * b2(i, j) : 0.0;
+      if (i == j && ent_active) v -= 2.0 * a2 * c / (n * b1(i, i));
+      if (i == j) v += tr_coeff * (1.0 / a2 - 1.0) / b1(i, i);      // trust-region term: Sigma_t = alpha^2 Sigma
+      gl[e] = (float)v;
+    }
+    return;
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { lam[i] = save_lam[b * n + i]; rho[i] = 1.0 / (lam[i] + eta); }
+  load_full_d(b1, save_M + off, n, m);                                             // M
+  la_gemm(b2, b0, b1, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);            // Sbar_out M
+  la_gemm(b3, b1.T(), b2, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // F0 = M^T Sbar_out M
+  double c = 0.0;
+  if (ent_active) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) c += (1.0 + eta) * rho[i] * b3(i, i);
+    c = block_sum(c, red);
+  }
+  double eb = 0.0, dfe = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double ft = a2 * (b3(i, i) - (ent_active ? c / (n * (1.0 + eta) * rho[i]) : 0.0));
+    eb += ft * (rho[i] - (1.0 + eta) * rho[i] * rho[i]);
+    dfe += 2.0 * rho[i] - (1.0 + eta) * rho[i] * rho[i] - 1.0 / (1.0 + eta);
+  }
+  eb = block_sum(eb, red);
+  dfe = 0.5 * block_sum(dfe, red);
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    double ft = a2 * 0.5 * (b3(i, j) + b3(j, i));
+    if (i == j && ent_active) ft -= a2 * c / (n * (1.0 + eta) * rho[i]);
+    double v = -(1.0 + eta) * rho[i] * rho[j] * ft;
+    if (i == j) v -= eb * (0.5 * (rho[i] - (1.0 + eta) * rho[i] * rho[i])) / dfe;
+    // trust-region regression term tr_coeff * KL_cov(N(Sigma) || N(Sigma_t)), Sigma_t = alpha^2 Sigma_proj DETACHED:
+    // d / d Lt = tr_coeff (Sigma_t^-1 Lt - Lt^-T), Sigma_t^-1 Lt = Lt^-T U~ diag(1 / (alpha^2 lam_i^2 D_ii)) U~^T
+    if (i == j) v -= 0.5 * tr_coeff / (a2 * (1.0 + eta) * rho[i] * lam[i] * lam[i]);
+    b2(i, j) = v;                                                                  // Nt
+  }
+  load_full_d(b0, save_U + off, n, m);                                             // U~
+  la_gemm(b3, b0, b2, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);            // U~ Nt
+  la_gemm(b1, b3, b0.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // U~ Nt U~^T
+  load_full_d(b2, save_Li + off, n, m);                                            // Lt^-1
+  la_gemm(b3, b2.T(), b1, n, n, n, TRI_UPPER, TRI_FULL, TRI_LOWER, 1.0, 0.0);      // Lt^-T (.)
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    double v = j <= i ? -2.0 * b3(i, j) : 0.0;
+    if (i == j && tr_coeff != 0.0) v -= tr_coeff / (double)L[off + e];              // - tr_coeff (Lt^-T)_ii
+    gl[e] = (float)v;
+  }
 }
 
 // =====================================================================================================
@@ -1155,17 +1280,17 @@ extern "C" int tce_proj_kl_entropy_fwd_sigma(const float *L, const float *L_o, d
                        1);
 }
 
-extern "C" int tce_proj_kl_entropy_fwd_chol(const double *save, float *proj_L, float *out_L, int32_t *info, int64_t B,
-                                            int n, void *stream) {
+extern "C" int tce_proj_kl_entropy_fwd_chol(const double *save, float *proj_L, float *out_L, double *out_inv,
+                                            int32_t *info, int64_t B, int n, void *stream) {
   if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!save || !proj_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
-  const size_t smem = pj_smem_exclusive(pj_smem(n, 1), B);
+  const size_t smem = pj_smem_exclusive(pj_smem(n, 2), B);
   int rc = set_smem(kl_chol_kernel, smem);
   if (rc) return rc;
   const size_t nn = (size_t)B * n * n;
   const double *Sig = save + 3 * nn, *sc = save + 4 * nn + (size_t)B * n;
-  kl_chol_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(Sig, sc, proj_L, out_L, info, n);
+  kl_chol_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(Sig, sc, proj_L, out_L, out_inv, info, n);
   TCE_CHECK_LAUNCH("kl_chol_kernel");
   return TCE_OK;
 }
@@ -1173,6 +1298,24 @@ extern "C" int tce_proj_kl_entropy_fwd_chol(const double *save, float *proj_L, f
 extern "C" int tce_proj_kl_entropy_bwd(const float *L, const float *proj_L, const float *grad_out, const double *save,
                                        float *grad_L, int64_t B, int n, void *stream) {
   return kl_bwd_launch(L, proj_L, grad_out, save, grad_L, B, n, 1, stream);
+}
+
+/* Backward of tce_proj_kl_cov_fwd (fused_entropy = 0) / tce_proj_kl_entropy_fwd* (fused_entropy = 1) given the gradient
+ * w.r.t. the OUTPUT COVARIANCE Sigma_out = alpha^2 Sigma_proj [B,n,n] (symmetric, fp64) instead of w.r.t. its factor.  */
+extern "C" int tce_proj_kl_bwd_sigma(const float *L, const double *grad_sigma, const double *save, int fused_entropy,
+                                     double tr_coeff, float *grad_L, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;
+  if (!L || !grad_sigma || !save || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
+  PJ_CHECK_N(n);
+  const size_t smem = pj_smem_exclusive(pj_smem(n, 4), B);
+  int rc = set_smem(proj_kl_cov_bwd_sigma_kernel, smem);
+  if (rc) return rc;
+  const size_t nn = (size_t)B * n * n;
+  const double *M = save, *U = M + nn, *Li = U + nn, *Sig = Li + nn, *lam = Sig + nn, *sc = lam + (size_t)B * n;
+  proj_kl_cov_bwd_sigma_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, grad_sigma, M, U, Li, Sig, lam,
+                                                                                       sc, grad_L, n, fused_entropy, tr_coeff);
+  TCE_CHECK_LAUNCH("proj_kl_cov_bwd_sigma_kernel");
+  return TCE_OK;
 }
 
 extern "C" int tce_proj_kl_entropy_bwd_inv(const float *L, const float *proj_L, const float *grad_out,

@@ -916,7 +916,7 @@ constexpr int RT = 256;
 template <int D, int K1>
 __global__ void __launch_bounds__(RT)
 dsigma_reduce_kernel(float *part, int nparts, const float *__restrict__ L, const float *__restrict__ upstream,
-                     float *__restrict__ grad_L, float *__restrict__ grad_sigma) {
+                     float *__restrict__ grad_L, double *__restrict__ grad_sigma) {
   using FL = FusedLayout<D, K1>;
   constexpr int Dp = FL::Dp, NB = FL::NB, NR4 = FL::NR4, LD = FL::LD, NE = NB * K1 * K1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -960,7 +960,7 @@ dsigma_reduce_kernel(float *part, int nparts, const float *__restrict__ L, const
   unpack_blocks<D, K1>(dsum, up, M);
   __syncthreads();
   if (grad_sigma)
-    for (int t = threadIdx.x; t < Dp * Dp; t += RT) grad_sigma[t] = M[(t / Dp) * LD + (t % Dp)];
+    for (int t = threadIdx.x; t < Dp * Dp; t += RT) grad_sigma[t] = (double)M[(t / Dp) * LD + (t % Dp)];
   if (grad_L) dl_from_dsigma<D, K1>(M, Ls, grad_L);
 }
 
@@ -1424,7 +1424,7 @@ uniform_main_kernel(TabDev tb, const double *__restrict__ ws, const float *__res
 template <int D, int K1>
 __global__ void __launch_bounds__(UT)
 uniform_finish_kernel(double *ws, const double *__restrict__ apart, int nparts, const float *__restrict__ L,
-                      const float *__restrict__ upstream, float *__restrict__ grad_L, float *__restrict__ grad_sigma,
+                      const float *__restrict__ upstream, float *__restrict__ grad_L, double *__restrict__ grad_sigma,
                       int P) {
   using FL = FusedLayout<D, K1>;
   using UL = UniLayout<D, K1>;
@@ -1522,7 +1522,7 @@ uniform_finish_kernel(double *ws, const double *__restrict__ apart, int nparts, 
   }
   __syncthreads();
   if (grad_sigma)
-    for (int e = threadIdx.x; e < Dp * Dp; e += UT) grad_sigma[e] = M[(e / Dp) * LD + (e % Dp)];
+    for (int e = threadIdx.x; e < Dp * Dp; e += UT) grad_sigma[e] = (double)M[(e / Dp) * LD + (e % Dp)];
   if (grad_L) dl_from_dsigma<D, K1>(M, Ls, grad_L);
 }
 
@@ -1676,7 +1676,7 @@ extern "C" int tce_seglik_fused(const tce_tables_t *t, const double *pre, const 
 }
 
 extern "C" int tce_seglik_dsigma_reduce(const tce_tables_t *t, float *dsigma_part, int nparts, const float *L,
-                                        const float *upstream, float *grad_L, float *grad_sigma, void *stream) {
+                                        const float *upstream, float *grad_L, double *grad_sigma, void *stream) {
   if (!t || !dsigma_part || nparts < 1 || (!grad_L && !grad_sigma) || (grad_L && !L)) return TCE_ERR_INVALID_ARGUMENT;
 #define X(Dv, Kv)                                                                                               \
   if (t->D == Dv && t->K1 == Kv) {                                                                              \
@@ -1800,7 +1800,7 @@ extern "C" int tce_seglik_uniform_main(const tce_tables_t *t, const double *ws, 
 }
 
 extern "C" int tce_seglik_uniform_finish(const tce_tables_t *t, double *ws, const double *apart, int nparts,
-                                         const float *L, const float *upstream, float *grad_L, float *grad_sigma,
+                                         const float *L, const float *upstream, float *grad_L, double *grad_sigma,
                                          int64_t P, void *stream) {
   if (!t || !ws || !apart || nparts < 1 || (!grad_L && !grad_sigma) || (grad_L && !L) || P < 1)
     return TCE_ERR_INVALID_ARGUMENT;

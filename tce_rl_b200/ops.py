@@ -854,8 +854,17 @@ def kl_state_sigma(state: Tensor, batch: int, n: int) -> Tuple[Tensor, Tensor]:
     """Views into a KL state buffer: (Sigma of the projected covariance before the entropy control [batch, n, n],
     alpha^2 of the fused entropy control [batch]) -- Sigma of the layer's output is alpha^2 * Sigma."""
     nn = batch * n * n
-    sc = state[4 * nn + batch * n:].view(batch, 8)
+    sc = kl_state_scalars(state, batch, n)
     return state[3 * nn:4 * nn].view(batch, n, n), sc[:, 6]
+
+
+KL_STATE_SCALARS = 10
+
+
+def kl_state_scalars(state: Tensor, batch: int, n: int) -> Tensor:
+    """[batch, 10] view: eta, KL step active, KL before the projection, fingerprint(L_old), alpha, entropy control
+    active, alpha^2, shape and volume part of KL_cov(N(Sigma_in) || N(Sigma_out)) (the trust-region loss), spare."""
+    return state[4 * batch * n * n + batch * n:].view(batch, KL_STATE_SCALARS)
 
 
 def kl_state(batch: int, n: int, device) -> Tensor:
@@ -894,21 +903,36 @@ def _(grad_out, L, proj_L, state):
     return torch.empty_like(L)
 
 
+def _check_generation(ctx):
+    """The state buffer of a warm-started layer is overwritten by its NEXT forward; a backward that runs after that
+    would silently read the wrong eigen-system (two projections in one graph, micro-batch accumulation, ...)."""
+    h = ctx.holder
+    if h is not None and getattr(h, "_kl_generation", None) != ctx.generation:
+        raise RuntimeError("KL projection: backward() after a later forward() of the same layer overwrote its state "
+                           "buffer; run backward before projecting again, or use warm_start=False (fresh state "
+                           "per call)")
+
+
 class _ProjKLCov(torch.autograd.Function):
     """Autograd wrapper (a mutating custom op cannot carry an autograd formula itself)."""
 
     @staticmethod
-    def forward(ctx, L, L_o, eps_cov, state, warm):
+    def forward(ctx, L, L_o, eps_cov, state, warm, holder):
         proj_L, info = proj_kl_cov_fwd(L, L_o, eps_cov, state, warm)
         ctx.save_for_backward(L, proj_L)
-        ctx.state = state        # overwritten by the NEXT forward only (after this backward has run)
+        ctx.state = state        # overwritten by the NEXT forward of a warm-started layer: guarded by a generation
+        ctx.holder, ctx.generation = holder, None
+        if holder is not None:
+            holder._kl_generation = getattr(holder, "_kl_generation", 0) + 1
+            ctx.generation = holder._kl_generation
         ctx.mark_non_differentiable(info)
         return proj_L, info
 
     @staticmethod
     def backward(ctx, g, g_info):
         L, proj_L = ctx.saved_tensors
-        return proj_kl_cov_bwd(g.contiguous(), L, proj_L, ctx.state), None, None, None, None
+        _check_generation(ctx)
+        return proj_kl_cov_bwd(g.contiguous(), L, proj_L, ctx.state), None, None, None, None, None
 
 
 SIGMA_READY = {}       # id(state) -> CUDA event recorded after the first half of a split forward
@@ -916,7 +940,7 @@ SIGMA_READY = {}       # id(state) -> CUDA event recorded after the first half o
 
 @torch.library.custom_op("tce::proj_kl_entropy_fwd", mutates_args=("state",))
 def proj_kl_entropy_fwd(L: Tensor, L_o: Tensor, eps_cov: float, state: Tensor, warm: bool, beta: Tensor,
-                        equality: bool, split: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+                        equality: bool, split: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """KL covariance projection + entropy control -> (out_L, proj_L (pre-entropy), info).  ``split``: two launches
     (state incl. Sigma first, Cholesky second) with an event in ``SIGMA_READY[id(state)]`` between them."""
     L, L_o = _chk(L, name="L"), _chk(L_o, name="L_o")
@@ -933,16 +957,18 @@ def proj_kl_entropy_fwd(L: Tensor, L_o: Tensor, eps_cov: float, state: Tensor, w
         ev = torch.cuda.Event()
         ev.record()
         SIGMA_READY[id(state)] = ev
-        _lib.call("tce_proj_kl_entropy_fwd_chol", _p(state), _p(proj), _p(out), _p(info), Bc, n, _stream())
-        return out, proj, info
+        out_inv = torch.empty(Bc, n, n, device=L.device, dtype=torch.float64)     # (out_L)^-1 for the trust-region loss
+        _lib.call("tce_proj_kl_entropy_fwd_chol", _p(state), _p(proj), _p(out), _p(out_inv), _p(info), Bc, n, _stream())
+        return out, proj, info, out_inv
     _lib.call("tce_proj_kl_entropy_fwd", _p(L), _p(L_o), float(eps_cov), _p(beta), 0 if beta.numel() == 1 else 1,
               int(equality), _p(proj), _p(out), _p(state), _p(info), int(warm), Bc, n, _stream())
-    return out, proj, info
+    return out, proj, info, L.new_empty(0, dtype=torch.float64)
 
 
 @proj_kl_entropy_fwd.register_fake
 def _(L, L_o, eps_cov, state, warm, beta, equality, split=False):
-    return torch.empty_like(L), torch.empty_like(L), L.new_empty(L.shape[0], dtype=torch.int32)
+    return (torch.empty_like(L), torch.empty_like(L), L.new_empty(L.shape[0], dtype=torch.int32),
+            L.new_empty(L.shape if split else (0,), dtype=torch.float64))
 
 
 @torch.library.custom_op("tce::proj_kl_entropy_bwd", mutates_args=())
@@ -968,44 +994,90 @@ def _(grad_out, L, proj_L, state, out_inv=None):
     return torch.empty_like(L)
 
 
+@torch.library.custom_op("tce::proj_kl_bwd_sigma", mutates_args=())
+def proj_kl_bwd_sigma(grad_sigma: Tensor, L: Tensor, state: Tensor, fused_entropy: bool, tr_coeff: float = 0.0) -> Tensor:
+    """Backward of the KL covariance projection given d loss / d Sigma_out [Bc, n, n] fp64 (symmetric); ``tr_coeff``:
+    also add the gradient of tr_coeff * KL_cov(N(L L^T) || N(Sigma_out detached)) (trust-region regression loss)."""
+    L = _chk(L)
+    g = _chk(grad_sigma, torch.float64, "grad_sigma")
+    if g.numel() != L.numel():
+        raise TceError("grad_sigma must have the shape of L")
+    out = torch.empty_like(L)
+    _lib.call("tce_proj_kl_bwd_sigma", _p(L), _p(g), _p(state), int(fused_entropy), float(tr_coeff), _p(out),
+              L.shape[0], L.shape[-1], _stream())
+    return out
+
+
+@proj_kl_bwd_sigma.register_fake
+def _(grad_sigma, L, state, fused_entropy, tr_coeff=0.0):
+    return torch.empty_like(L)
+
+
 class _ProjKLEntropy(torch.autograd.Function):
+    """-> (out_L, proj_L, info, Sigma0 [Bc,n,n] fp64 (a view of the state), alpha^2 [Bc]): the output covariance is
+    alpha^2 * Sigma0.  Sigma0 is a DIFFERENTIABLE output: a consumer that works on the covariance (the segment
+    likelihood) returns d loss / d (alpha^2 Sigma0) as its gradient and the backward then runs in covariance space
+    (no Cholesky adjoint); gradients w.r.t. out_L take the factor path; both may arrive."""
+
     @staticmethod
     def forward(ctx, L, L_o, eps_cov, state, warm, beta, equality, split, holder):
-        out, proj_L, info = proj_kl_entropy_fwd(L, L_o, eps_cov, state, warm, beta, equality, split)
+        out, proj_L, info, out_inv = proj_kl_entropy_fwd(L, L_o, eps_cov, state, warm, beta, equality, split)
+        sigma, scale = kl_state_sigma(state, L.shape[0], L.shape[-1])
         ctx.save_for_backward(L, proj_L)
         ctx.state = state
         ctx.holder, ctx.out_ptr = holder, out.data_ptr()
-        ctx.mark_non_differentiable(proj_L, info)
-        return out, proj_L, info
+        ctx.generation = None
+        if holder is not None:
+            holder._kl_generation = getattr(holder, "_kl_generation", 0) + 1
+            ctx.generation = holder._kl_generation
+        ctx.mark_non_differentiable(proj_L, info, scale, out_inv)
+        ctx.set_materialize_grads(False)
+        return out, proj_L, info, sigma, scale, out_inv
 
     @staticmethod
-    def backward(ctx, g, g_proj, g_info):
+    def backward(ctx, g, g_proj, g_info, g_sigma, g_scale, g_inv):
         L, proj_L = ctx.saved_tensors
-        # somebody (the trust-region loss) may have inverted this call's output factor: (inverse, event, data_ptr)
-        known = getattr(ctx.holder, "_output_inverse", None) if ctx.holder is not None else None
-        inv = None
-        if known is not None and known[2] == ctx.out_ptr and known[0].numel() == L.numel():
-            torch.cuda.current_stream().wait_event(known[1])
-            inv = known[0].reshape(L.shape)
-        return (proj_kl_entropy_bwd(g.contiguous(), L, proj_L, ctx.state, inv),) + (None,) * 8
+        _check_generation(ctx)
+        res = None
+        # a trust-region loss whose covariance gradient was folded into this backward (rl.projection, fold=True)
+        fold = float(getattr(ctx.holder, "_tr_fold", 0.0) or 0.0) if ctx.holder is not None else 0.0
+        if ctx.holder is not None:
+            ctx.holder._tr_fold = 0.0
+        if g_sigma is None and fold != 0.0:
+            g_sigma = torch.zeros(L.shape, device=L.device, dtype=torch.float64)
+        if g_sigma is not None:
+            res = proj_kl_bwd_sigma(g_sigma.contiguous(), L, ctx.state, True, fold)
+        if g is not None:
+            # somebody (the trust-region loss) may have inverted this call's output factor: (inverse, event, data_ptr)
+            known = getattr(ctx.holder, "_output_inverse", None) if ctx.holder is not None else None
+            inv = None
+            if known is not None and known[2] == ctx.out_ptr and known[0].numel() == L.numel():
+                torch.cuda.current_stream().wait_event(known[1])
+                inv = known[0].reshape(L.shape)
+            r2 = proj_kl_entropy_bwd(g.contiguous(), L, proj_L, ctx.state, inv)
+            res = r2 if res is None else res + r2
+        return (res,) + (None,) * 8
 
 
 def proj_kl_entropy(L: Tensor, L_o: Tensor, eps_cov: float, state: Tensor, warm: bool, beta: Tensor,
-                    equality: bool, split: bool = False, holder=None) -> Tuple[Tensor, Tensor, Tensor]:
+                    equality: bool, split: bool = False, holder=None, return_sigma: bool = False):
     """``proj_entropy(proj_kl_cov(L, L_o, ...)[0], beta, equality)[0]`` as ONE forward and ONE backward kernel
-    -> (out_L, proj_L before the entropy control [not differentiable], info).  ``split``: the forward is two
-    launches (state with Sigma_proj and alpha first, the Cholesky factor second) and ``SIGMA_READY[id(state)]``
-    holds an event recorded between them, for consumers of ``kl_state_sigma(state, ...)``.  ``holder``: an object
-    whose attribute ``_output_inverse = (inverse of out_L [.., n, n] fp64, CUDA event, out_L.data_ptr())`` -- if set
-    by the time of the backward and matching this call -- saves the backward its own triangular inverse."""
-    return _ProjKLEntropy.apply(L, L_o, eps_cov, state, warm, beta, equality, split, holder)
+    -> (out_L, proj_L before the entropy control [not differentiable], info [, Sigma0, alpha^2, out_L^-1 (split only)]).
+    ``split``: the
+    forward is two launches (state with Sigma_proj and alpha first, the Cholesky factor second) and
+    ``SIGMA_READY[id(state)]`` holds an event recorded between them, for consumers of the covariance.  ``holder``:
+    the owning layer: guards the state against a second forward before this call's backward, and its attribute
+    ``_output_inverse = (inverse of out_L [.., n, n] fp64, CUDA event, out_L.data_ptr())`` -- if set by the time of the
+    backward and matching this call -- saves the factor-path backward its own triangular inverse."""
+    res = _ProjKLEntropy.apply(L, L_o, eps_cov, state, warm, beta, equality, split, holder)
+    return res if return_sigma else res[:3]
 
 
-def proj_kl_cov(L: Tensor, L_o: Tensor, eps_cov: float, state: Tensor, warm: bool) -> Tuple[Tensor, Tensor]:
+def proj_kl_cov(L: Tensor, L_o: Tensor, eps_cov: float, state: Tensor, warm: bool, holder=None) -> Tuple[Tensor, Tensor]:
     """-> (proj_L [Bc,n,n], info [Bc]); ``state`` (``kl_state``) is overwritten with {M = L_o Q, lambda, eta, ...}:
     it feeds the backward and, with ``warm``, the next call with the same ``L_o`` starts its eigen-solve from it
     (2-3 Jacobi sweeps instead of ~9; guarded by a fingerprint of ``L_o`` inside the kernel)."""
-    return _ProjKLCov.apply(L, L_o, eps_cov, state, warm)
+    return _ProjKLCov.apply(L, L_o, eps_cov, state, warm, holder)
 
 
 @torch.library.custom_op("tce::proj_frob_cov", mutates_args=())

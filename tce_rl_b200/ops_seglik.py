@@ -135,25 +135,18 @@ def shared_factor(L: Tensor, batch: int) -> Optional[Tensor]:
     return None
 
 
-_CONFIG = {}
-
-
 def fused_config(tables: int, B: int, P: int, chained: bool) -> dict:
-    """Launch geometry / buffer sizes of the fused path for these shapes (host integers, cached)."""
-    key = (tables, B, P, chained)
-    cfg = _CONFIG.get(key)
-    if cfg is None:
-        lib = _lib.load()
-        E, grid, part, pre = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
-        _lib.check(lib.tce_seglik_fused_config(tables, max(B, 1), P, int(chained), C.byref(E), C.byref(grid),
-                                               C.byref(part), C.byref(pre)), "tce_seglik_fused_config")
-        nparts, apart = C.c_int32(), C.c_int64()
-        rc = lib.tce_seglik_uniform_parts(tables, max(B, 1), P, C.byref(nparts), C.byref(apart))
-        cfg = {"E": E.value, "grid": grid.value, "part_floats": part.value, "pre_doubles": pre.value,
-               "ws_doubles": lib.tce_seglik_uniform_ws_doubles(tables, P),
-               "uni_parts": nparts.value if rc == 0 else 0, "apart_doubles": apart.value if rc == 0 else 0}
-        _CONFIG[key] = cfg
-    return cfg
+    """Launch geometry / buffer sizes of the fused path for these shapes (host integers; NOT cached by handle: a
+    freed tables handle can be re-issued for another MP shape)."""
+    lib = _lib.load()
+    E, grid, part, pre = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
+    _lib.check(lib.tce_seglik_fused_config(tables, max(B, 1), P, int(chained), C.byref(E), C.byref(grid),
+                                           C.byref(part), C.byref(pre)), "tce_seglik_fused_config")
+    nparts, apart = C.c_int32(), C.c_int64()
+    rc = lib.tce_seglik_uniform_parts(tables, max(B, 1), P, C.byref(nparts), C.byref(apart))
+    return {"E": E.value, "grid": grid.value, "part_floats": part.value, "pre_doubles": pre.value,
+            "ws_doubles": lib.tce_seglik_uniform_ws_doubles(tables, P),
+            "uni_parts": nparts.value if rc == 0 else 0, "apart_doubles": apart.value if rc == 0 else 0}
 
 
 @torch.library.custom_op("tce::seglik", mutates_args=())
@@ -161,14 +154,15 @@ def seglik(smp_traj: Tensor, mean: Tensor, L: Optional[Tensor], sigma: Optional[
            sigma_scale: Optional[Tensor], times: Tensor, init_time: Tensor, init_pos: Tensor, init_vel: Tensor,
            pred_pairs: Tensor, tables: int, reg_rel: float, grad_mode: int, grad_logp: Optional[Tensor],
            logp_old: Optional[Tensor], advantage: Optional[Tensor], chained: bool, uniform: bool,
-           want_grad_L: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+           want_grad_L: bool, want_grad_sigma: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """The whole likelihood in one op.
 
     ``L``: [B, n, n] per-episode factors or [1, n, n] = one shared factor; ``sigma`` (+ optional ``sigma_scale`` [1]):
     the shared covariance itself as fp64 [n, n] (then ``L`` is only used for grad_L = 2 tril(dSigma L)).
     grad_mode 0: log-probs; 1: backward for ``grad_logp``; 2: fused surrogate with ``logp_old`` / ``advantage``.
     -> (logp [B,P], info [B,P] int32, acc [3] fp64 {regulariser seed max diag C, -mean(ratio adv), mean ratio},
-        grad_mean [B,Dp] or empty, grad_L [B or 1, Dp, Dp] or empty)
+        grad_mean [B,Dp] or empty, grad_L [B or 1, Dp, Dp] or empty,
+        grad_sigma [Dp, Dp] fp64 = d loss / d (sigma_scale * sigma) (shared covariance, ``want_grad_sigma``) or empty)
     """
     smp_traj, mean, times = _chk(smp_traj, name="smp_traj"), _chk(mean, name="mean"), _chk(times, name="times")
     init_time, init_pos, init_vel = _chk(init_time), _chk(init_pos), _chk(init_vel)
@@ -196,11 +190,17 @@ def seglik(smp_traj: Tensor, mean: Tensor, L: Optional[Tensor], sigma: Optional[
     want = grad_mode != 0
     g_mean = torch.empty(B, Dp, device=dev, dtype=torch.float32) if want else mean.new_empty(0)
     need_L = want and want_grad_L
+    need_S = want and want_grad_sigma
+    if need_S and not shared:
+        raise TceError("grad_sigma exists for a shared covariance only")
     g_L = mean.new_empty(0)
+    g_S = mean.new_empty(0, dtype=torch.float64)
     if B == 0:
         if need_L:
             g_L = torch.zeros(1 if shared else 0, Dp, Dp, device=dev, dtype=torch.float32)
-        return logp, info, acc, g_mean, g_L
+        if need_S:
+            g_S = torch.zeros(Dp, Dp, device=dev, dtype=torch.float64)
+        return logp, info, acc, g_mean, g_L, g_S
     if need_L and shared and L is None:
         raise TceError("grad_L of a shared covariance needs its factor L")
     st = _stream()
@@ -220,22 +220,25 @@ def seglik(smp_traj: Tensor, mean: Tensor, L: Optional[Tensor], sigma: Optional[
             _reduce_diag_max(diag_max)
             _lib.call("tce_seglik_uniform_prep", tables, Lp, _p(sigma), _p(sigma_scale), _p(times), _p(init_time),
                       _p(pairs), _p(ws), _p(diag_max), float(reg_rel), 2, P, st)
-        apart = torch.empty(cfg["apart_doubles"], device=dev, dtype=torch.float64) if need_L else None
+        apart = torch.empty(cfg["apart_doubles"], device=dev, dtype=torch.float64) if (need_L or need_S) else None
         _lib.call("tce_seglik_uniform_main", tables, _p(ws), _p(smp_traj), _p(mean), _p(init_pos), _p(init_vel),
                   _p(pairs), int(grad_mode), _p(grad_logp), _p(logp_old), _p(advantage), scale, _p(stats), _p(logp),
                   _p(info), _p(g_mean) if want else None, _p(apart), B, T, P, st)
-        if need_L:
-            g_L = torch.empty(1, Dp, Dp, device=dev, dtype=torch.float32)
-            _lib.call("tce_seglik_uniform_finish", tables, _p(ws), _p(apart), cfg["uni_parts"], _p(L), None, _p(g_L),
-                      None, P, st)
-        return logp, info, acc, g_mean, g_L
+        if need_L or need_S:
+            if need_L:
+                g_L = torch.empty(1, Dp, Dp, device=dev, dtype=torch.float32)
+            if need_S:
+                g_S = torch.empty(Dp, Dp, device=dev, dtype=torch.float64)
+            _lib.call("tce_seglik_uniform_finish", tables, _p(ws), _p(apart), cfg["uni_parts"],
+                      _p(L) if need_L else None, None, _p(g_L) if need_L else None, _p(g_S) if need_S else None, P, st)
+        return logp, info, acc, g_mean, g_L, g_S
     pre = torch.empty(B * cfg["pre_doubles"], device=dev, dtype=torch.float64)
     _lib.call("tce_seglik_prepass", tables, _p(smp_traj), _p(mean), None if sigma is not None else _p(L), ldb,
               _p(sigma), _p(sigma_scale), _p(times), _p(init_time), _p(init_pos), _p(init_vel), _p(pairs), _p(pre),
               _p(diag_max), int(chained), B, T, P, st)
     _reduce_diag_max(diag_max)
     part = None
-    if need_L:
+    if need_L or need_S:
         if shared:
             part = torch.empty(cfg["part_floats"], device=dev, dtype=torch.float32)
         else:
@@ -244,21 +247,27 @@ def seglik(smp_traj: Tensor, mean: Tensor, L: Optional[Tensor], sigma: Optional[
               _p(sigma_scale), _p(pairs), _p(diag_max), float(reg_rel), int(grad_mode), _p(grad_logp), _p(logp_old),
               _p(advantage), scale, _p(stats), _p(logp), _p(info), _p(g_mean) if want else None,
               _p(g_L) if (need_L and not shared) else None, _p(part), int(chained), B, P, st)
-    if need_L and shared:
-        g_L = torch.empty(1, Dp, Dp, device=dev, dtype=torch.float32)
-        _lib.call("tce_seglik_dsigma_reduce", tables, _p(part), cfg["grid"], _p(L), None, _p(g_L), None, st)
-    return logp, info, acc, g_mean, g_L
+    if (need_L or need_S) and shared:
+        if need_L:
+            g_L = torch.empty(1, Dp, Dp, device=dev, dtype=torch.float32)
+        if need_S:
+            g_S = torch.empty(Dp, Dp, device=dev, dtype=torch.float64)
+        _lib.call("tce_seglik_dsigma_reduce", tables, _p(part), cfg["grid"], _p(L) if need_L else None, None,
+                  _p(g_L) if need_L else None, _p(g_S) if need_S else None, st)
+    return logp, info, acc, g_mean, g_L, g_S
 
 
 @seglik.register_fake
 def _(smp_traj, mean, L, sigma, sigma_scale, times, init_time, init_pos, init_vel, pred_pairs, tables, reg_rel,
-      grad_mode, grad_logp, logp_old, advantage, chained, uniform, want_grad_L):
+      grad_mode, grad_logp, logp_old, advantage, chained, uniform, want_grad_L, want_grad_sigma=False):
     B, P, Dp = times.shape[0], pred_pairs.shape[0], mean.shape[-1]
     shared = sigma is not None or L.shape[0] == 1
     want = grad_mode != 0
     return (mean.new_empty(B, P), mean.new_empty(B, P, dtype=torch.int32), mean.new_empty(3, dtype=torch.float64),
             mean.new_empty(B, Dp) if want else mean.new_empty(0),
-            mean.new_empty(1 if shared else B, Dp, Dp) if (want and want_grad_L) else mean.new_empty(0))
+            mean.new_empty(1 if shared else B, Dp, Dp) if (want and want_grad_L) else mean.new_empty(0),
+            mean.new_empty(Dp, Dp, dtype=torch.float64) if (want and want_grad_sigma) else
+            mean.new_empty(0, dtype=torch.float64))
 
 
 def _resolve(L: Tensor, B: int, sigma):
@@ -277,8 +286,8 @@ class _SegLogProb(torch.autograd.Function):
     @staticmethod
     def forward(ctx, smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, tables, reg_rel, chained,
                 uniform, sigma, sigma_scale):
-        logp, info, acc, _, _ = seglik(smp_traj, mean, L, sigma, sigma_scale, times, init_time, init_pos, init_vel,
-                                       pred_pairs, tables, reg_rel, 0, None, None, None, chained, uniform, False)
+        logp, info, acc, _, _, _ = seglik(smp_traj, mean, L, sigma, sigma_scale, times, init_time, init_pos, init_vel,
+                                          pred_pairs, tables, reg_rel, 0, None, None, None, chained, uniform, False)
         diag_max = acc[:1]
         ctx.save_for_backward(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs)
         ctx.sig = (sigma, sigma_scale)
@@ -293,11 +302,13 @@ class _SegLogProb(torch.autograd.Function):
             return (None,) * 14
         smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs = ctx.saved_tensors
         tables, reg_rel, chained, uniform = ctx.args
-        need_L = ctx.needs_input_grad[2]
-        _, _, _, g_mean, g_L = seglik(smp_traj, mean, L, ctx.sig[0], ctx.sig[1], times, init_time, init_pos,
-                                      init_vel, pred_pairs, tables, reg_rel, 1, g_logp.contiguous(), None, None,
-                                      chained, uniform, need_L)
-        return (None, g_mean if ctx.needs_input_grad[1] else None, g_L if need_L else None) + (None,) * 11
+        need_S = ctx.sig[0] is not None and ctx.needs_input_grad[12]      # the gradient flows through Sigma when it can
+        need_L = ctx.needs_input_grad[2] and not need_S
+        _, _, _, g_mean, g_L, g_S = seglik(smp_traj, mean, L, ctx.sig[0], ctx.sig[1], times, init_time, init_pos,
+                                           init_vel, pred_pairs, tables, reg_rel, 1, g_logp.contiguous(), None, None,
+                                           chained, uniform, need_L, need_S)
+        return (None, g_mean if ctx.needs_input_grad[1] else None, g_L if need_L else None) + (None,) * 9 + (
+            g_S.view_as(ctx.sig[0]) if need_S else None, None)
 
 
 _UNIT = {}
@@ -318,13 +329,14 @@ class _SegSurrogate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, logp_old, advantage, tables,
                 reg_rel, chained, uniform, sigma, sigma_scale):
-        need_L = bool(ctx.needs_input_grad[2])
-        logp, info, acc, g_mean, g_L = seglik(smp_traj, mean, L, sigma, sigma_scale, times, init_time, init_pos,
-                                              init_vel, pred_pairs, tables, reg_rel, 2, None, logp_old, advantage,
-                                              chained, uniform, need_L)
+        need_S = sigma is not None and bool(ctx.needs_input_grad[14])     # the gradient flows through Sigma when it can
+        need_L = bool(ctx.needs_input_grad[2]) and not need_S
+        logp, info, acc, g_mean, g_L, g_S = seglik(smp_traj, mean, L, sigma, sigma_scale, times, init_time, init_pos,
+                                                   init_vel, pred_pairs, tables, reg_rel, 2, None, logp_old, advantage,
+                                                   chained, uniform, need_L, need_S)
         s32 = acc[1:].to(torch.float32)
-        ctx.save_for_backward(g_mean, g_L)
-        ctx.need_L = need_L
+        ctx.save_for_backward(g_mean, g_L, g_S.view_as(sigma) if need_S else g_S)
+        ctx.need_L, ctx.need_S = need_L, need_S
         ctx.mark_non_differentiable(logp, info)
         ctx.set_materialize_grads(False)
         return s32[0], s32[1], logp, info
@@ -333,11 +345,13 @@ class _SegSurrogate(torch.autograd.Function):
     def backward(ctx, g_loss, g_ratio, g_logp, g_info):
         if g_loss is None:
             return (None,) * 16
-        g_mean, g_L = ctx.saved_tensors
+        g_mean, g_L, g_S = ctx.saved_tensors
         if g_loss is not unit_seed(g_loss.device, g_loss.dtype):
             g_mean = g_mean * g_loss
             g_L = g_L * g_loss if ctx.need_L else g_L
-        return (None, g_mean if ctx.needs_input_grad[1] else None, g_L if ctx.need_L else None) + (None,) * 13
+            g_S = g_S * g_loss if ctx.need_S else g_S
+        return (None, g_mean if ctx.needs_input_grad[1] else None, g_L if ctx.need_L else None) + (None,) * 11 + (
+            g_S if ctx.need_S else None, None)
 
 
 def _facts(pred_pairs, init_time, times, shared, uniform):
@@ -361,7 +375,10 @@ def seg_logprob(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pa
 
 def seg_surrogate(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, logp_old, advantage, tables,
                   reg_rel: float = 1e-4, uniform: Optional[bool] = None, sigma=None):
-    """-> (surrogate loss = -mean(exp(lp - lp_old) * adv) [fp32 scalar, differentiable], mean ratio, logp)."""
+    """-> (surrogate loss = -mean(exp(lp - lp_old) * adv) [fp32 scalar, differentiable], mean ratio, logp).
+    ``sigma`` = (Sigma0 [n,n] or [1,n,n] fp64, scale [1] fp64 or None): the shared covariance scale * Sigma0 itself; when
+    Sigma0 requires grad the gradient is returned w.r.t. the covariance (d loss / d (scale * Sigma0)) and not w.r.t. ``L``
+    (contract with the KL projection layer, whose backward consumes it: ops._ProjKLEntropy)."""
     if sigma is None:
         sigma = getattr(L, "_tce_sigma", None)
         if sigma is not None:

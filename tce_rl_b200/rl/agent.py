@@ -406,6 +406,11 @@ class TemporalCorrelatedAgent:
                                                 init_vel=dataset["segment_init_vel"], pred_pairs=pred_pairs)
             surrogate, sur_stats = self.surrogate_loss(dataset["segment_advantage"], log_prob_new,
                                                        dataset["segment_log_prob_estimate"])
+        # the trust-region loss is back-propagated exactly once with a unit seed next to the projection when the two
+        # loss terms are separate autograd roots (below): its covariance gradient may then be folded into the
+        # projection's backward kernel (no kernels of its own)
+        fold = dict(fold=True) if (defer_entropy and tr_stream is not None
+                                   and isinstance(self.projection, KLProjectionLayer)) else {}
         if tr_stream is None:
             ent_loss, ent_stats = self._entropy_term(proj)
             tr_loss = self.projection.get_trust_region_loss(self.policy, new, proj, set_variance=self.set_variance)
@@ -418,7 +423,8 @@ class TemporalCorrelatedAgent:
             if cov_pending:
                 self.projection.join_covariance(tr_stream)
             with torch.cuda.stream(tr_stream):
-                tr_loss = self.projection.get_trust_region_loss(self.policy, new, proj, set_variance=self.set_variance)
+                tr_loss = self.projection.get_trust_region_loss(self.policy, new, proj, set_variance=self.set_variance,
+                                                                **fold)
                 tr_loss.record_stream(cur)
                 if not defer_entropy:
                     ent_loss, ent_stats = self._entropy_term(proj)

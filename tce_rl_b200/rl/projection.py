@@ -110,6 +110,17 @@ def gaussian_kl(policy, p, q):
 _KL_LOSS_CONST = {}
 
 
+def _kl_loss_consts(B, coeff, with_cov, dev):
+    """Cached constant gradients of the shared-covariance KL trust-region loss: (w [1,5], d loss / d maha [B],
+    d loss / d stats [1,5])."""
+    key = (B, coeff, with_cov, str(dev))
+    if key not in _KL_LOSS_CONST:
+        w = torch.tensor([[0.0, 0.5, -0.5, 0.5, 0.0]], dtype=torch.float64, device=dev)
+        _KL_LOSS_CONST[key] = (w, torch.full((B,), 0.5 * coeff / B, dtype=torch.float64, device=dev),
+                               w * (coeff if with_cov else 0.0))
+    return _KL_LOSS_CONST[key]
+
+
 class _SharedKLLoss(torch.autograd.Function):
     """loss = coeff * (mean_b 1/2 maha_b + [with_cov] (shape + volume)),  shape = 1/2 (tr - k),
     volume = 1/2 (logdet_q - logdet_p), from maha [B] and the five scalars st [1, 5] of ``gauss_stats``.
@@ -118,12 +129,7 @@ class _SharedKLLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, maha, st, coeff, with_cov, k, out_dtype):
         B, dev = maha.shape[0], maha.device
-        key = (B, coeff, with_cov, str(dev))
-        if key not in _KL_LOSS_CONST:
-            w = torch.tensor([[0.0, 0.5, -0.5, 0.5, 0.0]], dtype=torch.float64, device=dev)
-            _KL_LOSS_CONST[key] = (w, torch.full((B,), 0.5 * coeff / B, dtype=torch.float64, device=dev),
-                                   w * (coeff if with_cov else 0.0))
-        w, ctx.g_maha, ctx.g_st = _KL_LOSS_CONST[key]
+        w, ctx.g_maha, ctx.g_st = _kl_loss_consts(B, coeff, with_cov, dev)
         mean_diff = 0.5 * maha
         shape, volume = 0.5 * (st[:, 1] - k), 0.5 * (st[:, 3] - st[:, 2])
         cov_diff = shape + volume
@@ -137,6 +143,29 @@ class _SharedKLLoss(torch.autograd.Function):
             return ctx.g_maha, ctx.g_st, None, None, None, None
         g = g.to(torch.float64)
         return ctx.g_maha * g, ctx.g_st * g, None, None, None, None
+
+
+class _FoldedKLLoss(torch.autograd.Function):
+    """loss = coeff * (mean_b 1/2 maha_b + [with_cov] (shape + volume)) with shape / volume read from the KL state
+    scalars [1, 10] (slots 7, 8; constants for autograd: their gradient is applied by the projection's backward)."""
+
+    @staticmethod
+    def forward(ctx, maha, sc, coeff, with_cov, out_dtype):
+        B = maha.shape[0]
+        _, ctx.g_maha, _ = _kl_loss_consts(B, coeff, with_cov, maha.device)
+        mean_diff = 0.5 * maha
+        shape, volume = sc[:, 7].expand(B), sc[:, 8].expand(B)
+        cov_diff = shape + volume
+        loss = mean_diff.mean() + cov_diff[0] if with_cov else mean_diff.mean()
+        ctx.mark_non_differentiable(mean_diff, cov_diff, shape, volume)
+        return (loss * coeff).to(out_dtype), mean_diff, cov_diff, shape, volume
+
+    @staticmethod
+    def backward(ctx, g, *_unused):
+        if g is ops.unit_seed(g.device, g.dtype):
+            return ctx.g_maha, None, None, None, None
+        raise RuntimeError("a folded trust-region loss must be back-propagated with the unit seed "
+                           "(ops.unit_seed): its covariance gradient was added to the projection's backward")
 
 
 def _entropy_schedule(kind, total_train_steps, dim):
@@ -312,11 +341,17 @@ class BaseProjectionLayer:
     def _with_cov(self, policy, set_variance):
         return policy.contextual_std or (set_variance is not None and not set_variance)
 
-    def get_trust_region_loss(self, policy, p, proj_p, set_variance=None):
-        """coeff * mean(mean_diff [+ cov_diff]) between p and the DETACHED projection."""
+    def get_trust_region_loss(self, policy, p, proj_p, set_variance=None, fold=False):
+        """coeff * mean(mean_diff [+ cov_diff]) between p and the DETACHED projection.
+        ``fold`` (KL layer, one shared covariance, ``proj_p`` = the output of the last projection of ``p``): the
+        covariance term is taken in closed form from the projection's eigen-system and its GRADIENT is added inside
+        the projection's own backward kernel; valid when the loss is back-propagated exactly once with unit weight
+        together with that projection (TemporalCorrelatedAgent.policy_epoch does) -- otherwise leave it False."""
         target = (proj_p[0].detach(), proj_p[1].detach())
         kl_metric = type(self).trust_region_value is BaseProjectionLayer.trust_region_value
         if kl_metric and p[0].is_cuda and _shared(policy, p[1]):
+            if fold and self._can_fold(p, proj_p):
+                return self._folded_kl_trust_region_loss(policy, p, target, set_variance)
             return self._shared_kl_trust_region_loss(policy, p, target, set_variance)
         if kl_metric:      # KL metric
             mean_diff, cov_diff, shape, volume = gaussian_kl_details(policy, p, target)
@@ -325,6 +360,9 @@ class BaseProjectionLayer:
             mean_diff, cov_diff = self.trust_region_value(policy, p, target)
         loss = (mean_diff + cov_diff if self._with_cov(policy, set_variance) else mean_diff).mean()
         return (loss * self.trust_region_coeff).to(p[0].dtype)
+
+    def _can_fold(self, p, proj_p):
+        return False
 
     def _shared_kl_trust_region_loss(self, policy, p, target, set_variance):
         """KL metric, ONE covariance for the batch: same value as the generic path, but the loss arithmetic is one
@@ -342,10 +380,10 @@ class BaseProjectionLayer:
             maha = _maha(policy, p[0], target[0], target[1], linv=linv)
             maha.record_stream(cur)
         L1, Lt1 = _first(p[1]), _first(target[1])
+        with_cov = self._with_cov(policy, set_variance)
         zeros = torch.zeros(1, L1.shape[-1], device=L1.device)
         st = ops.gauss_stats(zeros, L1.contiguous(), zeros, Lt1)          # [1, 5]
         cur.wait_stream(helper)
-        with_cov = self._with_cov(policy, set_variance)
         loss, mean_diff, cov_diff, shape, volume = _SharedKLLoss.apply(
             maha, st, float(self.trust_region_coeff), bool(with_cov), int(p[0].shape[-1]), p[0].dtype)
         self.cache["new_proj"] = (mean_diff, cov_diff, shape, volume)
@@ -379,16 +417,18 @@ class KLProjectionLayer(BaseProjectionLayer):
     # Forward in two launches (Sigma / Cholesky) so that the likelihood's stage 1 starts ~20 us earlier.  Measured
     # at B = 1024: no net gain -- the trust-region branch, which needs the factor, then collides with stage 3 of the
     # likelihood instead of stage 1 (profiles/README.md) -- so it is off by default.
-    split_forward = False
+    split_forward = True     # (round 2: the uniform-grid likelihood leaves most SMs free, the collision is gone, and the
+    #                          gradient returns in covariance space, so nothing on the critical path needs the factor)
 
     def _shared_sigma(self, proj_L1):
         """(Sigma0 [n, n] fp64, alpha^2 [1]) views of the state written by the fused kernel: the covariance of the
         layer's output is alpha^2 * Sigma0.  Valid until the next forward of this layer."""
         state = getattr(self, "_last_state", None)
-        if not self.sigma_to_likelihood or state is None or proj_L1.shape[0] != 1:
+        sig = getattr(self, "_last_sigma", None)
+        if not self.sigma_to_likelihood or state is None or sig is None or proj_L1.shape[0] != 1:
             return None
-        Sigma, scale = ops.kl_state_sigma(state, 1, proj_L1.shape[-1])
-        return Sigma[0], scale, (ops.SIGMA_READY.get(id(state)) if self.split_forward else None)
+        # sig[0]: Sigma0 [1, n, n] fp64, a DIFFERENTIABLE output of the projection op (gradient in covariance space)
+        return sig[0], sig[1], (ops.SIGMA_READY.get(id(state)) if self.split_forward else None)
 
     def _state_for(self, Lc):
         state = self._kl_state
@@ -398,6 +438,28 @@ class KLProjectionLayer(BaseProjectionLayer):
             if self.warm_start:
                 self._kl_state = state
         return state
+
+    def _can_fold(self, p, proj_p):
+        last = getattr(self, "_last_call", None)
+        return (last is not None and last["out_inv"] is not None and _first(p[1]) is last["L_in"]
+                and _first(proj_p[1]) is last["out"])
+
+    def _folded_kl_trust_region_loss(self, policy, p, target, set_variance):
+        """Shared covariance, target = this layer's last output: Mahalanobis term with the inverse the forward's
+        second launch already formed; covariance term = two scalars of the state (closed form on the eigen-system),
+        its gradient is added by the projection's backward kernel (``_tr_fold``)."""
+        last = self._last_call
+        n = p[0].shape[-1]
+        linv = last["out_inv"][0]
+        self._output_inverse = None
+        maha = _maha(policy, p[0], target[0], target[1], linv=linv)
+        with_cov = self._with_cov(policy, set_variance)
+        sc = ops.kl_state_scalars(last["state"], 1, n)
+        self._tr_fold = float(self.trust_region_coeff) if with_cov else 0.0
+        loss, mean_diff, cov_diff, shape, volume = _FoldedKLLoss.apply(
+            maha, sc, float(self.trust_region_coeff), bool(with_cov), p[0].dtype)
+        self.cache["new_proj"] = (mean_diff, cov_diff, shape, volume)
+        return loss
 
     def _mean_part(self, policy, p, q):
         linv = shared_inverse(q[1]) if (_shared(policy, q[1]) and q[1].is_cuda) else None
@@ -409,7 +471,7 @@ class KLProjectionLayer(BaseProjectionLayer):
             raise NotImplementedError("diagonal KL projection is outside the TCE configs")
         Lc = L.contiguous()
         state = self._state_for(Lc)
-        return ops.proj_kl_cov(Lc, L_old.contiguous(), self.cov_bound, state, self.warm_start)[0]
+        return ops.proj_kl_cov(Lc, L_old.contiguous(), self.cov_bound, state, self.warm_start, self)[0]
 
     def _cov_projection_with_entropy(self, policy, L, L_old, beta):
         if policy.is_diag or not self.fuse_entropy:
@@ -418,9 +480,15 @@ class KLProjectionLayer(BaseProjectionLayer):
         state = self._state_for(Lc)
         self._last_state = state
         self._output_inverse = None            # only an inverse formed AFTER this forward can belong to it
-        return ops.proj_kl_entropy(Lc, L_old.contiguous(), self.cov_bound, state, self.warm_start, beta,
-                                   self.entropy_eq, bool(self.split_forward and self.sigma_to_likelihood
-                                                         and Lc.shape[0] == 1), self)[0]
+        split = bool(self.split_forward and self.sigma_to_likelihood and Lc.shape[0] == 1)
+        out, _proj, _info, sigma, scale, out_inv = ops.proj_kl_entropy(
+            Lc, L_old.contiguous(), self.cov_bound, state, self.warm_start, beta, self.entropy_eq, split, self,
+            return_sigma=True)
+        self._last_sigma = (sigma, scale)
+        # what a folded trust-region loss (get_trust_region_loss(..., fold=True)) needs from THIS forward
+        self._last_call = dict(L_in=L, out=out, out_inv=out_inv if split else None, state=state)
+        self._tr_fold = 0.0
+        return out
 
 
 class FrobeniusProjectionLayer(BaseProjectionLayer):

@@ -292,3 +292,64 @@ def test_fused_kl_entropy_equals_the_two_separate_ops(beta_shift, equality):
     ref = scale[:, None, None] * Sigma
     got = o3.double() @ o3.double().transpose(-1, -2)
     assert (got - ref).abs().max() <= 1e-6 * ref.abs().max()                  # fp32 rounding of the factor
+
+
+@pytest.mark.parametrize("beta_shift,equality,kl_active", [(+0.5, False, True), (-0.5, False, True), (-0.5, True, True),
+                                                         (+0.5, False, False), (-0.5, False, False)])
+@pytest.mark.parametrize("split", [False, True])
+def test_kl_backward_in_covariance_space_equals_factor_path(beta_shift, equality, kl_active, split):
+    """tce_proj_kl_bwd_sigma (gradient w.r.t. Sigma_out = alpha^2 Sigma0, as the likelihood returns it) == the factor
+    path (gradient w.r.t. out_L through the Cholesky adjoint) for a loss that depends on the covariance only;
+    KL step active / inactive (identity), entropy control active / inactive / equality."""
+    inp = synthetic_inputs("box", 2, dtype=torch.float32)
+    L0 = inp["L"].to(DEV)
+    Lo = inp["L_old"].to(DEV) if kl_active else (L0 * 1.0001).contiguous()
+    n = L0.shape[-1]
+    H = 0.5 * n * (1.0 + 1.8378770664093453) + torch.diagonal(Lo, dim1=-2, dim2=-1).double().log().sum(-1)
+    beta = (H.mean() + beta_shift).reshape(1).to(torch.float64)
+    g = torch.Generator().manual_seed(1)
+    W = torch.randn(L0.shape, generator=g, dtype=torch.float64)
+    W = (W + W.transpose(-1, -2)).to(DEV)                                      # d loss / d Sigma_out, symmetric
+
+    class Holder:
+        pass
+    res = []
+    for path in ("factor", "sigma"):
+        L = L0.clone().requires_grad_(True)
+        state = ops.kl_state(L.shape[0], n, DEV)
+        out, proj, info, sigma, scale, _inv = ops.proj_kl_entropy(L, Lo, 5e-4, state, False, beta, equality, split, Holder(),
+                                                            return_sigma=True)
+        active = ops.kl_state(L.shape[0], n, DEV)                              # (placeholder to keep allocator busy)
+        del active
+        if path == "factor":
+            S = out.double() @ out.double().transpose(-1, -2)
+            (S * W).sum().backward()
+        else:
+            assert sigma.requires_grad and sigma.shape == L.shape and sigma.dtype == torch.float64
+            (sigma * W).sum().backward()               # contract: the gradient of `sigma` IS d loss / d Sigma_out
+        sc = ops.kl_state_scalars(state, L.shape[0], n)
+        assert bool((sc[:, 1] != 0).all()) == kl_active
+        res.append(L.grad.clone())
+    gf, gs = res
+    assert (gf - gs).abs().max() <= 2e-5 * gf.abs().max()
+
+
+def test_kl_state_generation_guard():
+    """A second forward of a warm-started layer before the first one's backward must not silently use the
+    overwritten state: backward raises."""
+    inp = synthetic_inputs("box", 1, dtype=torch.float32)
+    L0, Lo = inp["L"].to(DEV), inp["L_old"].to(DEV)
+    n = L0.shape[-1]
+    beta = torch.zeros(1, device=DEV, dtype=torch.float64)
+
+    class Holder:
+        pass
+    h = Holder()
+    state = ops.kl_state(1, n, DEV)
+    La = L0.clone().requires_grad_(True)
+    out_a = ops.proj_kl_entropy(La, Lo, 5e-4, state, True, beta, False, False, h)[0]
+    Lb = (L0 * 1.01).requires_grad_(True)
+    out_b = ops.proj_kl_entropy(Lb, Lo, 5e-4, state, True, beta, False, False, h)[0]
+    out_b.sum().backward()                                                     # the latest forward: fine
+    with pytest.raises(RuntimeError, match="overwrote its state"):
+        out_a.sum().backward()
