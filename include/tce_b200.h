@@ -341,12 +341,39 @@ int tce_normalize_by_stats(float *x, const double *stats, int64_t N, void *strea
  * tce_grad_sumsq: state[0] += 1 (step counter), state[1] += sum g^2 (caller zeroes state[1] beforehand).
  * tce_adam_step : torch.optim.Adam (L2 weight decay, bias correction with t = state[0], no amsgrad) on the
  *                 gradient scaled by min(1, max_norm / (sqrt(state[1]) + 1e-6)) (max_norm <= 0: no clipping).
+ *                 A non-finite gradient norm skips the update (parameters and moments stay intact: the reference
+ *                 raises BEFORE backward/step on a NaN loss, temporal_correlated_agent.py:569-577).
  * `params` / `sizes` are HOST arrays (count <= 32) of device pointers and element counts; m, v are flat fp32
  * moment buffers of sum(sizes) elements.                                                                   */
 int tce_grad_sumsq(const float *grad_flat, int64_t n, double *state, void *stream);
 int tce_adam_step(int count, float *const *params, const int64_t *sizes, const float *grad_flat, float *m,
                   float *v, const double *state, double max_norm, double lr, double beta1, double beta2,
                   double eps, double weight_decay, void *stream);
+
+/* ---- mean chain of a policy epoch with ONE shared covariance (csrc/tce_epoch.cu) -----------------------------
+ * Replaces, for the non-contextual policies of every shipped config, the per-episode pieces between the policy
+ * network and the segment likelihood: the mean part of the KL metric and the mean projection
+ * (trust_region_projections mean_projection via temporal_correlated_agent.py:530-533), its backward, the mean part of
+ * the trust-region regression loss with its gradient (get_trust_region_loss, :561-567) and the batch means of the
+ * logging decomposition (:641-686).
+ * tce_epoch_mean_fwd : Linv_old = L_old^-1 [n,n] fp64 (tce_tri_inverse) -> proj_mean [B,n], maha_old [B] =
+ *                      |L_old^-1 (mean - mean_old)|^2, u_old [B,n] = Sigma_old^-1 (mean - mean_old);
+ *                      acc[0] += sum_b 1/2 maha_old, acc[1] += sum_b 1/2 maha(proj_mean, mean_old).
+ * tce_epoch_mean_bwd : g_proj_mean = d loss / d proj_mean [B,n]; Linv_new = L~^-1 [n,n] fp64 and kl_scalars [16] as
+ *                      left in the state by tce_proj_kl_entropy_fwd(_sigma) -> grad_mean [B,n] = mean-projection
+ *                      adjoint + tr_coeff / B * Sigma_out^-1 (mean - proj_mean), Sigma_out^-1 = (Sigma~^-1 + eta
+ *                      Sigma_old^-1) / (alpha^2 (1 + eta));  acc[2] += sum_b 1/2 maha(mean, proj_mean; Sigma_out).
+ * tce_epoch_metrics  : out19 = the 7 loss values + 12 KL logging means of one epoch (rl/agent.py key order) from
+ *                      acc[3], lik_stats {surrogate, mean ratio}, kl_scalars, adam_stats {step, sum g^2} (may be NULL).
+ * acc is zero-initialised by the caller; everything is asynchronous on `stream`.                                */
+int tce_epoch_mean_fwd(const float *mean, const float *mean_old, const double *Linv_old, double eps_mean,
+                       float *proj_mean, double *maha_old, float *u_old, double *acc, int64_t B, int n,
+                       void *stream);
+int tce_epoch_mean_bwd(const float *g_proj_mean, const float *mean, const float *mean_old, const double *maha_old,
+                       const float *u_old, const double *Linv_new, const double *kl_scalars, double eps_mean,
+                       double tr_coeff, float *grad_mean, double *acc, int64_t B, int n, void *stream);
+int tce_epoch_metrics(const double *acc, const double *lik_stats, const double *kl_scalars, const double *adam_stats,
+                      int64_t B, double tr_coeff, int with_cov, double ent_coef, double *out19, void *stream);
 
 /* ---- measurement helper ---------------------------------------------------------------------------------
  * One register-resident FMA-chain kernel (fp32 or fp64) over the whole chip; *flops (host) receives the

@@ -88,6 +88,9 @@ SIGNATURES = {
     "tce_seglik_uniform_main": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _D, _P, _P, _P, _P, _P, _I64,
                                           _I64, _I64, _P]),
     "tce_seglik_uniform_finish": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P, _I64, _P]),
+    "tce_epoch_mean_fwd": (C.c_int, [_P, _P, _P, _D, _P, _P, _P, _P, _I64, _I32, _P]),
+    "tce_epoch_mean_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _D, _D, _P, _P, _I64, _I32, _P]),
+    "tce_epoch_metrics": (C.c_int, [_P, _P, _P, _P, _I64, _D, _I32, _D, _P, _P]),
     "tce_gae": (C.c_int, [_P, _P, _P, _P, _F, _F, _I32, _P, _P, _I64, _I64, _P]),
     "tce_segment_advantage_raw": (C.c_int, [_I32, _P, _P, _P, _P, _F, _P, _P, _I64, _I64, _I64, _P]),
     "tce_sum_stats": (C.c_int, [_P, _P, _I64, _P]),
@@ -128,8 +131,24 @@ LAUNCHES = 0          # kernel launches issued through the C ABI (bench.py repor
 _NO_KERNEL = {"tce_seglik_fused_config", "tce_seglik_uniform_parts", "tce_prodmp_tables_export", "tce_prodmp_tables_create", "tce_debug_kl_phase_cycles", "tce_debug_seglik_phase_cycles"}
 
 
+# Optional per-launch timing (bench.py's roofline report): when TIMING is a list, every kernel-launching ABI call is
+# bracketed by CUDA events on ITS launching stream (the `stream` argument, always the last one) and
+# (name, start_event, stop_event) is appended.  None = off (the default: no overhead on the product path).
+TIMING = None
+
+
 def call(name: str, *args) -> None:
     global LAUNCHES
+    if TIMING is not None and name not in _NO_KERNEL:
+        import torch
+        st = torch.cuda.ExternalStream(args[-1]) if args[-1] else torch.cuda.default_stream()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        check(getattr(load(), name)(*args), name)
+        b.record(st)
+        TIMING.append((name, a, b))
+        LAUNCHES += 1
+        return
     check(getattr(load(), name)(*args), name)
     if name not in _NO_KERNEL:
         LAUNCHES += 1

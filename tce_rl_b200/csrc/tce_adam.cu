@@ -50,6 +50,7 @@ adam_kernel(ParamTable tab, const float *__restrict__ grad, float *__restrict__ 
             double weight_decay) {
   const long long n = tab.offset[tab.count];
   const double t = state[0];
+  if (!(state[1] < INFINITY)) return;        // NaN / Inf gradient: leave parameters and moments untouched
   double coef = 1.0;
   if (max_norm > 0.0) coef = fmin(1.0, max_norm / (sqrt(state[1]) + 1e-6));      // clip_grad_norm_
   const double bc1 = 1.0 - pow(beta1, t), bc2 = 1.0 - pow(beta2, t);

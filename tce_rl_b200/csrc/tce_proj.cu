@@ -16,8 +16,10 @@ namespace {
 constexpr int PJ_THREADS = 512;
 constexpr int KL_THREADS = 512;   // 128 registers per thread: 4x4 fp64 GEMM tiles and the register-resident Jacobi
 constexpr double LOG_2PI = 1.8378770664093453;
-constexpr int KL_SC = 10;     // scalars saved per matrix by the KL projection: eta, active, kl0, fingerprint, alpha, ent_active,
-                              // alpha^2, trust-region shape part, trust-region volume part, (spare)
+constexpr int KL_SC = 16;     // scalars saved per matrix by the KL projection: eta, active, kl0, fingerprint, alpha, ent_active,
+                              // alpha^2, [7] trust-region shape part, [8] trust-region volume part (KL(new || out)),
+                              // [9] entropy of the output, [10] / [11] shape / volume part of KL(new || old),
+                              // [12] / [13] shape / volume part of KL(out || old), (2 spare)
 
 __device__ inline int pad_even(int n) { return (n + 1) & ~1; }
 
@@ -541,15 +543,20 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   // `half_logdet(i)`: the i-th term of 1/2 logdet of the projected covariance (log of the Cholesky diagonal, or its
   // closed form 1/2 logdet(Sigma_o) + 1/2 sum log((1+eta)/(lam+eta)) when the factor is not formed here: `split`)
   auto entropy_scale = [&](auto half_logdet) -> double {
-    if (!beta) return 1.0;
     double sl = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) sl += half_logdet(i);
     sl = block_sum(sl, red);
-    const double H = 0.5 * n * (1.0 + LOG_2PI) + sl, bt = beta[b * ldb_beta];
+    const double H = 0.5 * n * (1.0 + LOG_2PI) + sl;
+    if (!beta) {
+      if (threadIdx.x == 0) save_sc[b * KL_SC + 9] = H;
+      return 1.0;
+    }
+    const double bt = beta[b * ldb_beta];
     const bool ent_active = entropy_eq || (H < bt);
     const double alpha = ent_active ? exp((bt - H) / n) : 1.0;
     if (threadIdx.x == 0) {
       save_sc[b * KL_SC + 4] = alpha; save_sc[b * KL_SC + 5] = ent_active ? 1.0 : 0.0; save_sc[b * KL_SC + 6] = alpha * alpha;
+      save_sc[b * KL_SC + 9] = ent_active ? bt : H;             // entropy of the output: H + n ln alpha
     }
     return alpha;
   };
@@ -558,18 +565,35 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   // (get_trust_region_loss, temporal_correlated_agent.py:561-567) -- in closed form on the eigen-system:
   //   tr(Sigma_out^-1 Sigma) = alpha^-2 sum_i 1 / (D_ii lam_i),  logdet Sigma_out - logdet Sigma = 2 n ln alpha + sum_i ln(D_ii lam_i)
   // with D_ii = (1 + eta) / (lam_i + eta)  (identity step: D_ii lam_i = 1).  -> save_sc[7] (1/2 (tr - n)) and save_sc[8] (1/2 logdet difference)
+  // The logging decompositions of temporal_correlated_agent.py:641-686 in the same closed form (no extra kernels):
+  //   KL(new || old):  tr(Sigma_o^-1 Sigma) = sum_i 1 / lam_i,  logdet Sigma_o - logdet Sigma = sum_i ln lam_i
+  //   KL(out || old):  tr(Sigma_o^-1 Sigma_out) = alpha^2 sum_i D_ii,  logdet Sigma_o - logdet Sigma_out = -2 n ln alpha - sum_i ln D_ii
+  // (identity step: D_ii = 1 / lam_i).  -> save_sc[10..13]
   auto save_tr_value = [&](double alpha, bool act) {
-    double tr = 0.0, ld = 0.0;
+    double tr = 0.0, ld = 0.0, il = 0.0, ll = 0.0, sd = 0.0, ldd = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const double dl = act ? (1.0 + eta) * lam[i] / (lam[i] + eta) : 1.0;      // D_ii lam_i
+      const double dii = act ? (1.0 + eta) / (lam[i] + eta) : 1.0 / lam[i];
+      const double dl = act ? dii * lam[i] : 1.0;                                // D_ii lam_i
       tr += 1.0 / dl;
       ld += log(dl);
+      il += 1.0 / lam[i];
+      ll += log(lam[i]);
+      sd += dii;
+      ldd += log(dii);
     }
     tr = block_sum(tr, red);
     ld = block_sum(ld, red);
+    il = block_sum(il, red);
+    ll = block_sum(ll, red);
+    sd = block_sum(sd, red);
+    ldd = block_sum(ldd, red);
     if (threadIdx.x == 0) {
       save_sc[b * KL_SC + 7] = 0.5 * (tr / (alpha * alpha) - (double)n);            // "shape" part  1/2 (tr - n)
       save_sc[b * KL_SC + 8] = 0.5 * (2.0 * n * log(alpha) + ld);                  // "volume" part 1/2 (logdet_t - logdet)
+      save_sc[b * KL_SC + 10] = 0.5 * (il - (double)n);
+      save_sc[b * KL_SC + 11] = 0.5 * ll;
+      save_sc[b * KL_SC + 12] = 0.5 * (alpha * alpha * sd - (double)n);
+      save_sc[b * KL_SC + 13] = -(double)n * log(alpha) - 0.5 * ldd;
     }
   };
   // Sigma of the (pre-entropy) result goes to the state as well: with ONE covariance for the batch the
@@ -1275,7 +1299,7 @@ extern "C" int tce_proj_kl_entropy_fwd_sigma(const float *L, const float *L_o, d
                                              int64_t ldb_beta, int equality, float *proj_L, float *out_L,
                                              double *save, int32_t *info, int warm_start, int64_t B, int n,
                                              void *stream) {
-  if (B != 0 && (!beta || !out_L)) return TCE_ERR_INVALID_ARGUMENT;
+  if (B != 0 && !out_L) return TCE_ERR_INVALID_ARGUMENT;        /* beta == NULL: no entropy control (bound -inf) */
   return kl_fwd_launch(L, L_o, eps_cov, beta, ldb_beta, equality, proj_L, out_L, save, info, warm_start, B, n, stream,
                        1);
 }

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS)
 traj_fwd_kernel(TabDev tb, const float *__restrict__ params, const float *__restrict__ times,
                 const float *__restrict__ init_time, const float *__restrict__ init_pos,
                 const float *__restrict__ init_vel, float *__restrict__ traj, long long B, int T,
-                int staged_rows) {
+                int staged_rows, int chunk) {
   extern __shared__ __align__(16) float smem[];
   const int D = tb.D, D2 = 2 * D, Dp = D * K1, stride = tb.row32_stride;
   const int ep_floats = Dp + D2;                                  // theta | y0 | v0 * tau  per episode
@@ -57,9 +57,11 @@ traj_fwd_kernel(TabDev tb, const float *__restrict__ params, const float *__rest
   const float tau = (float)tb.tau, inv_tau_f = 1.0f / tau;
   const double inv_tau = 1.0 / tb.tau;
   const float goal_shift_scale = tb.relative_goal ? (tb.relative_goal_scaled ? 1.0f : 1.0f / s_scale[K1 - 1]) : 0.0f;
-  for (long long g0 = (long long)blockIdx.x * TRAJ_THREADS; g0 < total; g0 += (long long)gridDim.x * TRAJ_THREADS) {
+  // chunk = time points per CTA iteration: TRAJ_THREADS, or fewer for very short trajectories (T < 9: the time
+  // PAIRS of the mp_pytorch surface) so that a chunk never spans more than MAX_EP_PER_CHUNK episodes
+  for (long long g0 = (long long)blockIdx.x * chunk; g0 < total; g0 += (long long)gridDim.x * chunk) {
     const long long b_first = g0 / T;
-    long long g_last = g0 + TRAJ_THREADS - 1;
+    long long g_last = g0 + chunk - 1;
     if (g_last >= total) g_last = total - 1;
     const int n_ep = (int)(g_last / T - b_first) + 1;
     // per-episode data: initial-condition basis values, parameters, y0, v0 * tau
@@ -88,7 +90,7 @@ traj_fwd_kernel(TabDev tb, const float *__restrict__ params, const float *__rest
     }
     __syncthreads();
     const long long g = g0 + threadIdx.x;
-    if (g < total) {
+    if (g < total && (int)threadIdx.x < chunk) {
       const int e = (int)(g / T - b_first);
       const EpInit &E = eps[e];
       const float *ed = epd + e * ep_floats;
@@ -225,7 +227,9 @@ int launch_traj_fwd(const tce_tables *t, const float *params, const float *times
   }
   const int stride = t->row32_stride;
   const size_t row_bytes = (size_t)stride * sizeof(float);
-  const long long chunks = (B * T + TRAJ_THREADS - 1) / TRAJ_THREADS;
+  int chunk = TRAJ_THREADS;
+  if ((TRAJ_THREADS + T - 1) / T + 2 > MAX_EP_PER_CHUNK) chunk = (int)((MAX_EP_PER_CHUNK - 2) * T);   // T < 9
+  const long long chunks = (B * T + chunk - 1) / chunk;
   // Staging the rows pays only when a persistent CTA reuses them over several chunks; short-lived
   // CTAs read the (few, hot) rows through L1 instead.
   int staged = (int)((64 * 1024) / row_bytes);
@@ -241,7 +245,6 @@ int launch_traj_fwd(const tce_tables *t, const float *params, const float *times
   }
   if (grid > chunks) grid = chunks;
   const size_t smem = base_smem + (size_t)staged * row_bytes;
-  if ((TRAJ_THREADS + T - 1) / T + 2 > MAX_EP_PER_CHUNK) return TCE_ERR_INVALID_ARGUMENT;  // T < 9
   static bool attr_set = false;
   if (!attr_set) {
     TCE_CUDA(cudaFuncSetAttribute(traj_fwd_kernel<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024),
@@ -251,7 +254,7 @@ int launch_traj_fwd(const tce_tables *t, const float *params, const float *times
     attr_set = true;
   }
   traj_fwd_kernel<K1><<<(unsigned)grid, TRAJ_THREADS, smem, st>>>(tab_dev(t), params, times, init_time, init_pos,
-                                                                  init_vel, traj, B, (int)T, staged);
+                                                                  init_vel, traj, B, (int)T, staged, chunk);
   TCE_CHECK_LAUNCH("traj_fwd_kernel");
   return TCE_OK;
 }

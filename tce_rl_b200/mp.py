@@ -30,11 +30,29 @@ class ProDMP:
             if val is not None:
                 setattr(self, name, val)
                 self._traj = None
+                if name == "times":
+                    self._check_range(val)
+
+    strict_range = True      # raise like mp_pytorch as soon as a time lies beyond the pre-computed range
 
     def _check_range(self, times):
-        # mp_pytorch raises when a time lies beyond the pre-computed range; checked lazily on the host
-        # only when explicitly requested (no device sync on the hot path)
-        pass
+        """mp_pytorch raises ``RuntimeError`` when a scaled time exceeds the pre-computed range (``factor`` = 5
+        periods, util_mp.py:33).  The kernels clamp the table index (no device-side exception), so the shim keeps a
+        lazy device flag ``range_flag`` (1 = some time was out of range since the last ``check_range()``) and, with
+        ``strict_range`` (default), reads it right away -- one host synchronisation, as in the reference; under CUDA-
+        graph capture or with ``strict_range = False`` call ``check_range()`` when convenient."""
+        if times is None or times.numel() == 0:
+            return
+        over = ((times.detach().amax() - self.tables.delay) / self.tables.tau > self.tables.factor).to(torch.int32)
+        self.range_flag = over if getattr(self, "range_flag", None) is None else torch.maximum(self.range_flag, over)
+        if self.strict_range and not (times.is_cuda and torch.cuda.is_current_stream_capturing()):
+            self.check_range()
+
+    def check_range(self):
+        flag = getattr(self, "range_flag", None)
+        self.range_flag = None
+        if flag is not None and bool(flag.item()):
+            raise RuntimeError("Time is beyond the pre-computation range.")
 
     def _flat(self, t, trailing):
         lead = t.shape[:t.ndim - trailing]

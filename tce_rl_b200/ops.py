@@ -858,12 +858,13 @@ def kl_state_sigma(state: Tensor, batch: int, n: int) -> Tuple[Tensor, Tensor]:
     return state[3 * nn:4 * nn].view(batch, n, n), sc[:, 6]
 
 
-KL_STATE_SCALARS = 10
+KL_STATE_SCALARS = 16
 
 
 def kl_state_scalars(state: Tensor, batch: int, n: int) -> Tensor:
-    """[batch, 10] view: eta, KL step active, KL before the projection, fingerprint(L_old), alpha, entropy control
-    active, alpha^2, shape and volume part of KL_cov(N(Sigma_in) || N(Sigma_out)) (the trust-region loss), spare."""
+    """[batch, 16] view: eta, KL step active, KL before the projection, fingerprint(L_old), alpha, entropy control
+    active, alpha^2, [7:9] shape and volume part of KL_cov(N(Sigma_in) || N(Sigma_out)) (the trust-region loss),
+    [9] entropy of the output, [10:12] shape / volume of KL(in || old), [12:14] shape / volume of KL(out || old)."""
     return state[4 * batch * n * n + batch * n:].view(batch, KL_STATE_SCALARS)
 
 

@@ -361,11 +361,22 @@ def _facts(pred_pairs, init_time, times, shared, uniform):
     return chained, bool(uniform and shared)
 
 
+# Per-episode covariance factors (contextual layout): measured on B200 the staged kernels (4 CTAs per SM, fp64
+# workspace in HBM) beat the one-CTA-per-SM fused kernel, whose register-resident design pays off only when the
+# covariance -- and with a uniform time grid the factorisations -- are shared: B = 1024 x 24: 146 vs 248 us forward +
+# backward, B = 16384: 1.60 vs 2.75 ms (scripts/perf_seglik.py).  False = fused kernel for every layout.
+PER_EPISODE_STAGED = True
+
+
 def seg_logprob(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, tables, reg_rel: float = 1e-4,
                 return_info: bool = False, uniform: Optional[bool] = None, sigma=None):
     """Segment-wise log-likelihood [B, P], differentiable w.r.t. ``mean`` and ``L``.  ``uniform``: None = decide from
     the data (one cached device read), True / False = the caller knows.  ``sigma`` = (Sigma0 [n,n] fp64, scale [1])."""
     Lr, shared = _resolve(L, times.shape[0], sigma)
+    if not shared and PER_EPISODE_STAGED and times.shape[0] > 0:
+        from . import ops
+        return ops.seg_logprob_staged(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs, tables,
+                                      reg_rel, return_info)
     chained, uni = _facts(pred_pairs, init_time, times, shared, uniform)
     logp, info, diag_max = _SegLogProb.apply(smp_traj, mean, Lr, times, init_time, init_pos, init_vel, pred_pairs,
                                              tables.handle, float(reg_rel), chained, uni,
@@ -386,6 +397,11 @@ def seg_surrogate(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_
     Lr, shared = _resolve(L, times.shape[0], sigma)
     if not shared:
         sigma = None
+        if PER_EPISODE_STAGED and times.shape[0] > 0:
+            from . import ops
+            return ops.seg_surrogate_staged(smp_traj, mean, L, times, init_time, init_pos, init_vel, pred_pairs,
+                                            _chk(logp_old, name="logp_old"), _chk(advantage, name="advantage"),
+                                            tables, reg_rel)
     chained, uni = _facts(pred_pairs, init_time, times, shared, uniform)
     loss, ratio, logp, _ = _SegSurrogate.apply(smp_traj, mean, Lr, times, init_time, init_pos, init_vel, pred_pairs,
                                                _chk(logp_old, name="logp_old"), _chk(advantage, name="advantage"),

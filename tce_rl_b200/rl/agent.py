@@ -82,6 +82,10 @@ class TemporalCorrelatedAgent:
         self.fused_surrogate = bool(kwargs.get("fused_surrogate", True))
         self.overlap_logging = bool(kwargs.get("overlap_logging", True))
         self.use_flat_adam = bool(kwargs.get("flat_adam", True))
+        # hand-scheduled epoch for the shipped configuration (shared covariance + KL projection), rl/fast_epoch.py;
+        # False = always the generic autograd-driven epoch below (any policy / projection layer)
+        self.fast_epoch = bool(kwargs.get("fast_epoch", True))
+        self._fast = None
         if self.overlap_logging and hasattr(policy, "mean_net") and hasattr(policy.mean_net, "side_wgrad"):
             policy.mean_net.side_wgrad = True              # joined after every backward of policy_epoch
         self._log_stream = None
@@ -90,6 +94,12 @@ class TemporalCorrelatedAgent:
         self._flat_grad = None
         self._flat_adam_tried = False
         self.process_group = kwargs.get("process_group", None)      # torch.distributed group (None = single GPU)
+        if self.process_group is not None:
+            # the batch-global quantities of the path are global over the SAME group as the gradients: the
+            # likelihood regulariser (MAX over all episodes, mp_pytorch get_traj_pos_cov) and the advantage
+            # normalisation statistics (temporal_correlated_agent.py:281-284)
+            ops.set_regulariser_group(self.process_group)
+            ops.set_stats_group(self.process_group)
         self.policy_net_params = policy.parameters
         self.critic_net_params = critic.parameters if critic is not None else []
         capt = dict(capturable=True, fused=True) if self.device.type == "cuda" else {}   # one multi-tensor kernel
@@ -354,6 +364,12 @@ class TemporalCorrelatedAgent:
     def policy_epoch(self, dataset, times, pred_pairs):
         """One epoch body of ``update_policy`` (temporal_correlated_agent.py:524-589): returns the metrics
         vector [7 + 12] (``_LOSS_KEYS`` then ``_KL_KEYS``) living on the device."""
+        if self.fast_epoch:
+            from .fast_epoch import SharedCovKLEpoch
+            if SharedCovKLEpoch.applicable(self, dataset):
+                if self._fast is None:
+                    self._fast = SharedCovKLEpoch(self)
+                return self._fast.run(dataset, times, pred_pairs)
         D2 = self.policy.num_dof * 2
         old = (dataset["segment_params_mean"], dataset["segment_params_L"])
         obs = dataset["segment_state"][..., :-D2]

@@ -139,6 +139,15 @@ _ACT = {"tanh": torch.tanh, "relu": nn.functional.relu, "leaky_relu": nn.functio
 
 
 _SIDE_GRAD_STREAMS = set()          # streams with parameter-gradient work still to be joined
+_LAYER_STREAMS = {}                 # id(nn.Linear) -> its side stream (kept OFF the module: deepcopy / pickle of an MLP
+#                                     must not meet CUDA stream objects)
+
+
+def _layer_stream(lin, device):
+    st = _LAYER_STREAMS.get(id(lin))
+    if st is None:
+        st = _LAYER_STREAMS[id(lin)] = torch.cuda.Stream(device=device)
+    return st
 
 
 def join_side_grads():
@@ -168,9 +177,7 @@ class _SideGradLinear(torch.autograd.Function):
         owner = ctx.owner
         g = g.contiguous()
         main = torch.cuda.current_stream()
-        if owner._side_stream is None:
-            owner._side_stream = torch.cuda.Stream(device=g.device)
-        side = owner._side_stream
+        side = _layer_stream(owner, g.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             g2, x2 = g.reshape(-1, g.shape[-1]), x.reshape(-1, x.shape[-1])
@@ -211,8 +218,6 @@ class MLP(nn.Module):
     def _linear(self, lin, x):
         if (self.side_wgrad and x.is_cuda and torch.is_grad_enabled() and lin.weight.grad is not None
                 and lin.bias.grad is not None):
-            if not hasattr(lin, "_side_stream"):
-                lin._side_stream = None
             return _SideGradLinear.apply(x, lin.weight, lin.bias, lin)
         return lin(x)
 

@@ -106,6 +106,7 @@ def test_overlapped_epoch_equals_serial_epoch():
     res = []
     for overlap in (True, False):
         agent, dataset = build(epochs=2)
+        agent.fast_epoch = False                                   # this test is about the generic epoch's streams
         agent.num_iterations = 1
         dataset = agent.process_dataset(dataset)
         agent.ensure_flat_grads(agent.policy_net_params)
@@ -124,6 +125,38 @@ def test_overlapped_epoch_equals_serial_epoch():
     assert (m1 - m2).abs().max().item() <= 1e-6 * max(1.0, m2.abs().max().item())
     for a, b in zip(p1, p2):
         assert (a - b).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("name,B", [("box", 64), ("box", 1024), ("metaworld", 200), ("table_tennis", 33)])
+def test_fast_epoch_equals_generic_epoch(name, B):
+    """The hand-scheduled shared-covariance epoch (rl/fast_epoch.py: closed-form trust-region / logging terms, mean
+    chain in two kernels) against the generic autograd-driven epoch: metrics of three consecutive epochs (incl. warm-
+    started projections and Adam steps in between) and the updated parameters."""
+    res = []
+    for fast in (True, False):
+        agent, dataset = build(name=name, B=B, epochs=3)
+        agent.fast_epoch = fast
+        agent.num_iterations = 1
+        dataset = agent.process_dataset(dataset)
+        with torch.no_grad():                                     # away from old == new: both projection branches
+            for p in agent.policy.mean_net.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+            agent.policy.variance_net.variable.add_(0.02 * torch.randn_like(agent.policy.variance_net.variable))
+        agent.ensure_flat_grads(agent.policy_net_params)
+        old = [dataset["segment_params_mean"], dataset["segment_params_L"]]
+        agent.projection.initial_entropy = agent.policy.entropy(old).mean()
+        times = agent.sampler.get_times(dataset["segment_init_time"], agent.sampler.num_times)
+        rows = [agent.policy_epoch(dataset, times, agent.sampler.pred_pairs).clone() for _ in range(3)]
+        torch.cuda.synchronize()
+        assert (agent._fast is not None) == fast
+        res.append((torch.stack(rows).cpu(), [p.detach().clone().cpu() for p in agent.policy.parameters]))
+    (m1, p1), (m2, p2) = res
+    assert torch.isfinite(m1).all()
+    assert (m2[:, 7] > 0.05).any() or (m2[:, 8] > 5e-4).any()     # the trust region was active
+    err = (m1 - m2).abs() / m2.abs().clamp_min(1.0)
+    assert err.max().item() <= 2e-5, err
+    for a, b in zip(p1, p2):
+        assert (a - b).abs().max().item() <= 2e-6
 
 
 def test_dataset_to_device_broadcasts_the_shared_old_factor():

@@ -116,13 +116,17 @@ def test_kl_projection_constraint_satisfied_on_gpu():
     assert ((ck - 5e-4).abs() <= 2e-6).all()        # fp32 storage of proj_L limits this, not the solver
 
 
-@pytest.mark.parametrize("name,typ,contextual", [("box", "KLProjectionLayer", False),
-                                                  ("box", "KLProjectionLayer", True),
-                                                  ("metaworld", "KLProjectionLayer", False),
-                                                  ("table_tennis", "WassersteinProjectionLayer", False),
-                                                  ("box", "FrobeniusProjectionLayer", True)])
-def test_policy_epoch_matches_oracle(name, typ, contextual):
-    """Loss and parameter gradients of one update_policy epoch (temporal_correlated_agent.py:524-589)."""
+@pytest.mark.parametrize("name,typ,contextual,fast", [("box", "KLProjectionLayer", False, False),
+                                                       ("box", "KLProjectionLayer", False, True),
+                                                       ("box", "KLProjectionLayer", True, False),
+                                                       ("metaworld", "KLProjectionLayer", False, False),
+                                                       ("metaworld", "KLProjectionLayer", False, True),
+                                                       ("table_tennis", "KLProjectionLayer", False, True),
+                                                       ("table_tennis", "WassersteinProjectionLayer", False, False),
+                                                       ("box", "FrobeniusProjectionLayer", True, False)])
+def test_policy_epoch_matches_oracle(name, typ, contextual, fast):
+    """Loss, logging KLs and parameter gradients of one update_policy epoch (temporal_correlated_agent.py:524-589);
+    ``fast``: through the hand-scheduled shared-covariance epoch (rl/fast_epoch.py), else the generic one."""
     torch.manual_seed(0)
     B = 24
     cfg = MP_CONFIGS[name]
@@ -149,7 +153,9 @@ def test_policy_epoch_matches_oracle(name, typ, contextual):
                                     lr_critic=1e-3, wd_policy=5e-5, wd_critic=5e-5, discount_factor=1.0,
                                     epochs_policy=1, epochs_critic=1, norm_advantages=True,
                                     segment_advantage="value_subtraction", set_variance=False,
-                                    fused_surrogate=(name != "metaworld"))
+                                    fused_surrogate=(name != "metaworld" or fast), fast_epoch=fast)
+    if fast:
+        agent.ensure_flat_grads(agent.policy_net_params)          # FlatAdam: the fast epoch's optimiser
     obs = torch.randn(B, obs_dim + 2 * D)
     c = lambda t: t.to(DEV)
     init_time = inp["init_time"]
@@ -175,6 +181,7 @@ def test_policy_epoch_matches_oracle(name, typ, contextual):
     params0 = [p.detach().clone() for p in policy.parameters]
     metrics = agent.policy_epoch(dataset, times, pairs).cpu()
     grads = [p.grad.detach().double().cpu() for p in policy.parameters]
+    assert (agent._fast is not None) == fast
 
     # --- oracle side: same parameters / data in fp64 -------------------------------------------------
     import copy
@@ -190,13 +197,18 @@ def test_policy_epoch_matches_oracle(name, typ, contextual):
     olayer = oproj.projection_factory(typ, dtype=torch.float64, **layer_kwargs(typ, mb, cb, Dp))
     olayer.initial_entropy = f64(layer.initial_entropy)
     odata = {k: (f64(v) if v.is_floating_point() else v.cpu()) for k, v in dataset.items()}
-    loss, parts = oa.policy_epoch(opolicy, olayer, odata, f64(times), pairs.cpu(), 0, set_variance=False)
+    loss, parts = oa.policy_epoch(opolicy, olayer, odata, f64(times), pairs.cpu(), 0, set_variance=False,
+                                  with_metrics=True)
     oparams = list(mean_net.parameters()) + (list(var_net.parameters()) if contextual else [cov_vec])
     ograds = torch.autograd.grad(loss, oparams)
     assert abs(metrics[0].item() - parts["surrogate_loss"].item()) <= 1e-4
     assert abs(metrics[2].item() - parts["trust_region_loss"].item()) <= 1e-4
     assert abs(metrics[3].item() - loss.item()) <= 2e-4
     assert abs(metrics[4].item() - parts["entropy"].item()) <= 1e-4
+    assert abs(metrics[5].item() - parts["imp_smp_ratio"].item()) <= 1e-4
+    from tce_rl_b200.rl.agent import _KL_KEYS
+    for i, key in enumerate(_KL_KEYS):                           # the 12 logging means of :641-686
+        assert abs(metrics[7 + i].item() - parts["kl"][key].item()) <= 1e-4, key
     for g, og in zip(grads, ograds):
         assert (g - og).abs().max() <= 1e-3 * max(1e-3, og.abs().max().item())
     # seg-advantage and old log-probs that fed the epoch agree with the oracle too

@@ -20,6 +20,17 @@ if CUDA:
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True, params=[False, True], ids=["fused", "routed"])
+def per_episode_route(request):
+    """Per-episode covariance factors are routed to the staged kernels by default (ops_seglik.PER_EPISODE_STAGED:
+    they are faster for that layout); every test here runs both ways so the fused kernel keeps its coverage."""
+    from tce_rl_b200 import ops_seglik
+    old = ops_seglik.PER_EPISODE_STAGED
+    ops_seglik.PER_EPISODE_STAGED = request.param
+    yield request.param
+    ops_seglik.PER_EPISODE_STAGED = old
+
+
 def literal_pairs(T, P):
     """The synthetic P-pair index set of SURVEY 8(d) config 2 ("25 segments": {0, 4, ..., 96, 99})."""
     step = T // (P + 1) if P + 1 <= T else 1
