@@ -205,6 +205,9 @@ def build_gpu_workload(device, rank, world, shape="box", B=B_PER_GPU, pairs_mode
     dataset = agent.dataset_to_device(host_dataset)
     agent.host_dataset = host_dataset
     projection.initial_entropy = agent._global_mean(policy.entropy([mean_old, L_old]))
+    if dist_on:                                                  # as update_policy does once per dataset
+        from tce_rl_b200 import ops
+        ops.sync_uniform(dataset["segment_init_time"], times)
     agent.num_iterations = 100
     agent.ensure_flat_grads(agent.policy_net_params)
     return agent, dataset, times, pairs
@@ -633,7 +636,7 @@ def run_ours(args):
         variants["contextual_P24"], ctx = epoch_point(timer, device, rank, world, Kv, Wv, contextual=True)
         variants["contextual_P24"]["note"] = ("per-episode covariance factors [B, 63, 63] (variance NET, contextual "
                                               "layout): 1024 KL projections per step, nothing broadcast")
-        if rank == 0 and not args.no_roofline:
+        if not args.no_roofline:                 # every rank: the timed eager epochs contain the collectives
             try:
                 r = roofline_numbers(ctx[0], ctx[1], ctx[2], ctx[3], timer, peaks, variants["contextual_P24"]["ms_per_step"],
                                      contextual=True)
@@ -667,7 +670,7 @@ def run_ours(args):
         _mark("also epochs done")
 
     roof = None
-    if rank == 0 and not args.no_roofline:
+    if not args.no_roofline:                         # every rank (collectives inside the eager epochs); rank 0 reports
         roof = roofline_numbers(agent, dataset, times, pairs, timer, peaks, ms_per_step)
         if world == 1 and not args.no_also:
             pipes = {"fp32": roof["compute"]["measured_fp32_fma_tflops"], "fp64": roof["compute"]["measured_fp64_fma_tflops"]}

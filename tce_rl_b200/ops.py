@@ -272,7 +272,7 @@ def _(mean, L, mean_o, L_o):
 # The product path of the likelihood is the fused implementation in ops_seglik.py (re-exported at the end of this
 # module); the STAGED ops below (gram / chol / bwd with an fp64 HBM workspace) are kept as an independent
 # implementation for cross-checks (tests) and for mp.ProDMP.get_traj_pos_cov.
-from .ops_seglik import set_regulariser_group, _reduce_diag_max, unit_seed  # noqa: E402
+from .ops_seglik import set_regulariser_group, _reduce_diag_max, unit_seed, sync_uniform  # noqa: E402
 
 
 def _work(tables: int, B: int, P: int, device) -> Tensor:

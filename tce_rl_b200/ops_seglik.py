@@ -27,13 +27,44 @@ Tensor = torch.Tensor
 
 # torch.distributed group over which the batch-global regulariser seed is MAX-reduced (None: single GPU)
 _REG_GROUP = None
+# True: every rank is known to hold the SAME time grid for all its episodes (``sync_uniform``).  With a shared
+# covariance the gram matrices -- and hence the regulariser seed -- are then identical on all ranks by construction
+# and the uniform path skips the all-reduce(MAX).
+_GLOBAL_UNIFORM = False
 
 
 def set_regulariser_group(group) -> None:
     """At >1 GPU, all-reduce(MAX) the batch-global regulariser seed over ``group``; ``True`` = the
     default group, ``None`` = no reduction."""
-    global _REG_GROUP
+    global _REG_GROUP, _GLOBAL_UNIFORM
     _REG_GROUP = group
+    _GLOBAL_UNIFORM = False
+
+
+def sync_uniform(init_time: Tensor, times: Tensor) -> bool:
+    """Collective (call on every rank of the regulariser group, outside graph capture): do ALL ranks hold one and the
+    same time grid?  One all-reduce of four floats per dataset; the answer lets the uniform likelihood path drop its
+    per-epoch all-reduce(MAX) (see ``_GLOBAL_UNIFORM``).  Returns the answer and remembers it."""
+    global _GLOBAL_UNIFORM
+    _GLOBAL_UNIFORM = False
+    if _REG_GROUP is None:
+        return False
+    import torch.distributed as dist
+    group = None if _REG_GROUP is True else _REG_GROUP
+    local = times.shape[0] > 0 and times_uniform(init_time, times)
+    if times.shape[0] > 0:
+        row, t0 = times[0].double(), init_time[0].double().reshape(1)
+        sig = torch.cat([t0, row.sum().reshape(1), (row * torch.arange(1, row.numel() + 1, device=row.device)).sum()
+                         .reshape(1), torch.full((1,), float(local), device=row.device, dtype=torch.float64)])
+    else:                                                # an empty shard constrains nothing
+        sig = None
+    big = 1e300
+    lo = sig.clone() if sig is not None else torch.full((4,), big, device=times.device, dtype=torch.float64)
+    hi = sig.clone() if sig is not None else torch.full((4,), -big, device=times.device, dtype=torch.float64)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    _GLOBAL_UNIFORM = bool(torch.equal(lo, hi) and lo[3].item() == 1.0)
+    return _GLOBAL_UNIFORM
 
 
 def _reduce_diag_max(diag_max: Tensor) -> None:
@@ -211,7 +242,7 @@ def seglik(smp_traj: Tensor, mean: Tensor, L: Optional[Tensor], sigma: Optional[
     if uniform:
         ws = torch.empty(cfg["ws_doubles"], device=dev, dtype=torch.float64)
         Lp = None if sigma is not None else _p(L)
-        if _REG_GROUP is None:
+        if _REG_GROUP is None or (_GLOBAL_UNIFORM and shared):
             _lib.call("tce_seglik_uniform_prep", tables, Lp, _p(sigma), _p(sigma_scale), _p(times), _p(init_time),
                       _p(pairs), _p(ws), _p(diag_max), float(reg_rel), 3, P, st)
         else:

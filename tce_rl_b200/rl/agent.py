@@ -518,8 +518,10 @@ class TemporalCorrelatedAgent:
         if self.projection.initial_entropy is None:
             self.projection.initial_entropy = self._global_mean(self.policy.entropy(list(old)))
         self.ensure_flat_grads(self.policy_net_params)
+        if self._distributed:
+            ops.sync_uniform(init_time, times)       # same time grid on all ranks: no per-epoch all-reduce(MAX)
         rows = []
-        if self.use_cuda_graph and not self._distributed:
+        if self.use_cuda_graph:                      # NCCL all-reduces are captured with the epoch
             metrics = self._graphed_epochs(dataset, times, pred_pairs, rows)
         else:
             for _ in range(self.epochs_policy):
