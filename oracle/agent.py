@@ -72,6 +72,49 @@ def value_loss(values, returns, old_vs, clip_critic=0.0):
     return loss.mean()
 
 
+def generate_minibatches(n, n_minibatches):
+    """mprl/util/util_data_structure.py:378-391 -- the GLOBAL numpy generator, shuffle of arange(n), array_split."""
+    import numpy as np
+    idx = np.arange(n)
+    np.random.shuffle(idx)
+    return np.array_split(idx, n_minibatches)
+
+
+def grad_norm_clip(bound, params):
+    """mprl/util/util_numerical.py:244-275: (norm before, norm after clip_grad_norm_)."""
+    params = [p for p in params if p.grad is not None]
+    norm = torch.linalg.vector_norm(torch.stack([p.grad.norm(2) for p in params]))
+    if bound > 0:
+        torch.nn.utils.clip_grad_norm_(params, bound)
+        clipped = torch.linalg.vector_norm(torch.stack([p.grad.norm(2) for p in params]))
+    else:
+        clipped = norm
+    return norm.item(), clipped.item()
+
+
+def update_critic(critic_net, optimizer, dataset, epochs_critic, num_minibatchs, num_dof, clip_critic=0.0,
+                  clip_grad_norm=0.0):
+    """TemporalCorrelatedAgent.update_critic (temporal_correlated_agent.py:323-379) -> (losses, grad norms, clipped
+    grad norms), one entry per optimiser step."""
+    states = dataset["step_states"].flatten(0, 1)
+    old_values = dataset["step_values"][:, :-1].flatten(0, 1)
+    returns = dataset["step_returns"].flatten(0, 1)
+    losses, norms, clipped = [], [], []
+    for _ in range(epochs_critic):
+        for idx in generate_minibatches(states.shape[0], num_minibatchs):
+            sel = torch.as_tensor(idx)
+            values_new = critic_net(states[sel][..., :-num_dof * 2]).squeeze(-1)
+            loss = value_loss(values_new, returns[sel], old_values[sel], clip_critic)
+            optimizer.zero_grad(set_to_none=True)
+            loss.backward()
+            n0, n1 = grad_norm_clip(clip_grad_norm, [p for g in optimizer.param_groups for p in g["params"]])
+            optimizer.step()
+            losses.append(loss.item())
+            norms.append(n0)
+            clipped.append(n1)
+    return losses, norms, clipped
+
+
 def surrogate_loss(advantages, log_prob_new, log_prob_old):
     ratio = (log_prob_new - log_prob_old).exp()
     return -(ratio * advantages).mean(), {"imp_smp_ratio": ratio.mean()}

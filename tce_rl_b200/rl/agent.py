@@ -296,27 +296,145 @@ class TemporalCorrelatedAgent:
             return torch.stack([x.expand(new[0].shape[0]) for x in parts]).mean(dim=1)    # one reduction
 
     # ---- critic ---------------------------------------------------------------------------------------------
-    def update_critic(self, dataset):
+    def _flat_buffer(self, params):
+        """Give every parameter a ``.grad`` view into ONE new flat buffer (see ``ensure_flat_grads``)."""
+        flat = torch.zeros(sum(p.numel() for p in params), dtype=params[0].dtype, device=params[0].device)
+        off = 0
+        for p in params:
+            view = flat[off:off + p.numel()].view_as(p)
+            if p.grad is not None:
+                view.copy_(p.grad)
+            p.grad = view
+            off += p.numel()
+        return flat
+
+    def _critic_flat_adam(self):
+        """Flat gradient buffer + ``FlatAdam`` for the critic (same maths as torch Adam + clip_grad_norm_)."""
+        from .optim import FlatAdam
+        if getattr(self, "_critic_flat", None) is not None or isinstance(self.critic_optimizer, FlatAdam):
+            return isinstance(self.critic_optimizer, FlatAdam)
+        params = self.critic_net_params
+        if (self.device.type != "cuda" or not self.use_flat_adam or self.critic_optimizer.state
+                or len(params) > 32):
+            self._critic_flat = False
+            return False
+        self._critic_flat = self._flat_buffer(params)
+        g = self.critic_optimizer.param_groups[0]
+        opt = FlatAdam(params, self._critic_flat, lr=g["lr"], betas=g["betas"], eps=g["eps"],
+                       weight_decay=g["weight_decay"])
+        if "initial_lr" in g:
+            opt.param_groups[0]["initial_lr"] = g["initial_lr"]
+        if self.critic_lr_scheduler is not None:
+            sched = LinearLR(opt, start_factor=1, end_factor=0.01, total_iters=self.total_iterations)
+            sched.load_state_dict(self.critic_lr_scheduler.state_dict())
+            opt.param_groups[0]["lr"] = g["lr"]
+            self.critic_lr_scheduler = sched
+        self.critic_optimizer = opt
+        return True
+
+    def _critic_step(self, states, returns, old_values, sel, row):
+        """One optimiser step of update_critic on the minibatch ``sel`` (None: the whole batch in its own order);
+        writes {loss, grad norm, clipped grad norm} into ``row`` [3] on the device."""
         D2 = self.policy.num_dof * 2
-        states = dataset["step_states"].flatten(0, 1)
-        old_values = dataset["step_values"][:, :-1].flatten(0, 1)
-        returns = dataset["step_returns"].flatten(0, 1)
-        losses, norms = [], []
-        for _ in range(self.epochs_critic):
-            perm = np.random.permutation(states.shape[0])          # util_data_structure.py:378-391 (numpy RNG)
-            for idx in np.array_split(perm, self.num_minibatchs):
-                sel = torch.as_tensor(idx, device=states.device)
-                values_new = self.critic.critic(states[sel][..., :-D2]).squeeze(-1)
-                loss = self.value_loss(values_new, returns[sel], old_values[sel])
-                self.critic_optimizer.zero_grad(set_to_none=True)
-                loss.backward()
+        flat = isinstance(getattr(self, "_critic_flat", None), torch.Tensor)
+        if sel is None:
+            st, rt, ov = states, returns, old_values
+        else:
+            st, rt, ov = states.index_select(0, sel), returns.index_select(0, sel), old_values.index_select(0, sel)
+        values_new = self.critic.critic(st[..., :-D2]).squeeze(-1)
+        loss = self.value_loss(values_new, rt, ov)
+        if flat:
+            self.critic_optimizer.begin()
+        else:
+            self.critic_optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        util.join_side_grads()
+        if self._distributed:
+            if flat:
+                buf = self._critic_flat
+                if dist.get_backend(self._group()) == "nccl":
+                    dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self._group())
+                else:
+                    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self._group())
+                    buf.div_(self.world_size)
+            else:
                 self._allreduce_grads(self.critic_net_params)
-                norms.append(self._grad_norm_clip(self.critic_net_params))
-                self.critic_optimizer.step()
-                losses.append(loss.detach())
-        losses = torch.stack(losses).cpu().numpy()
-        norms = torch.stack(norms).cpu().numpy()
-        return {**_stats(losses, "critic_loss"), **_stats(norms, "critic_grad_norm")}
+        if flat:
+            self.critic_optimizer.step(max_norm=float(self.clip_grad_norm))
+            norm = self.critic_optimizer.grad_norm()
+        else:
+            norm = self._grad_norm_clip(self.critic_net_params)
+            self.critic_optimizer.step()
+        clipped = torch.clamp(norm, max=self.clip_grad_norm) if self.clip_grad_norm > 0 else norm
+        row[0].copy_(loss.detach())
+        row[1].copy_(norm.detach())
+        row[2].copy_(clipped.detach())
+
+    def update_critic(self, dataset):
+        """temporal_correlated_agent.py:323-379: ``epochs_critic`` passes over the flattened step states in
+        ``num_minibatchs`` shuffled minibatches (numpy GLOBAL generator, util_data_structure.py:378-391), value loss,
+        gradient-norm clipping, Adam.  All permutations of the update are drawn up front (same generator sequence as
+        the reference: nothing else consumes numpy's generator in between) and uploaded once; the per-step losses and
+        norms stay on the device and are read back once.  With ``use_cuda_graph`` the minibatch step (gather, MLP
+        forward/backward, all-reduce, norm + Adam in two launches) is captured once per minibatch size and replayed.
+        ``num_minibatchs == 1`` (every shipped config): the full-batch mean does not depend on the order, so the
+        gather is skipped."""
+        states = dataset["step_states"].flatten(0, 1)
+        old_values = dataset["step_values"][:, :-1].flatten(0, 1).contiguous()
+        returns = dataset["step_returns"].flatten(0, 1)
+        n, E, M = states.shape[0], int(self.epochs_critic), int(self.num_minibatchs)
+        self._critic_flat_adam()
+        splits = []
+        for _ in range(E):
+            idx = np.arange(n)
+            np.random.shuffle(idx)                                   # reference RNG call sequence
+            splits.append(np.array_split(idx, M))
+        gather = M > 1
+        if gather:
+            perm = torch.as_tensor(np.concatenate([np.concatenate(sp) for sp in splits])).to(states.device)
+        out = torch.zeros(E * M, 3, device=states.device, dtype=torch.float64)
+        graphs = getattr(self, "_critic_graphs", None)
+        key = (states.data_ptr(), returns.data_ptr(), old_values.data_ptr(), n, M,
+               float(self.critic_optimizer.param_groups[0]["lr"]))   # the learning rate is baked into a captured step
+        if self.use_cuda_graph and states.is_cuda and (graphs is None or graphs["key"] != key):
+            graphs = self._critic_graphs = {"key": key, "by_size": {}}
+        k = 0
+        off = 0
+        for e in range(E):
+            for m in range(M):
+                size = len(splits[e][m])
+                sel = perm[off:off + size] if gather else None
+                off += size
+                if self.use_cuda_graph and states.is_cuda:
+                    ent = graphs["by_size"].get(size)
+                    if ent is None:
+                        sel_static = torch.empty(size, device=states.device, dtype=torch.long) if gather else None
+                        row_static = torch.zeros(3, device=states.device, dtype=torch.float64)
+                        if gather:
+                            sel_static.copy_(sel)
+                        side = torch.cuda.Stream()
+                        side.wait_stream(torch.cuda.current_stream())
+                        with torch.cuda.stream(side):                # warm-up outside the capture (lazy inits)
+                            self._critic_step(states, returns, old_values, sel_static, row_static)
+                        torch.cuda.current_stream().wait_stream(side)
+                        out[k].copy_(row_static)
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            self._critic_step(states, returns, old_values, sel_static, row_static)
+                        graphs["by_size"][size] = (g, sel_static, row_static)
+                        k += 1
+                        continue
+                    g, sel_static, row_static = ent
+                    if gather:
+                        sel_static.copy_(sel)
+                    g.replay()
+                    out[k].copy_(row_static)
+                else:
+                    self._critic_step(states, returns, old_values, sel, out[k])
+                k += 1
+        res = out.cpu().numpy()                                      # the ONE synchronisation of the update
+        return {**_stats(res[:, 0], "critic_loss"), **_stats(res[:, 1], "critic_grad_norm"),
+                **_stats(res[:, 2], "clipped_critic_grad_norm")}
 
     def _zero_policy_grads(self):
         from .optim import FlatAdam

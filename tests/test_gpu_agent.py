@@ -98,6 +98,37 @@ def test_update_critic_and_projection_bounds_hold():
         agent.step()                     # environment rollout is outside the B200 path
 
 
+@pytest.mark.parametrize("use_graph,minibatches,clip", [(False, 3, 0.0), (True, 3, 0.5), (True, 1, 0.0), (False, 1, 0.0)])
+def test_update_critic_matches_oracle(use_graph, minibatches, clip):
+    """update_critic (temporal_correlated_agent.py:323-379) against the oracle restatement with the SAME numpy
+    permutations: per-step losses, gradient norms and the updated critic weights."""
+    import numpy as np
+    from oracle import agent as oa
+    agent, dataset = build(B=16, use_graph=use_graph)
+    agent.epochs_critic, agent.num_minibatchs, agent.clip_grad_norm = 3, minibatches, clip
+    agent.num_iterations = 1
+    dataset = agent.process_dataset(dataset)
+    net = copy.deepcopy(agent.critic.net).cpu().double()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=5e-5)
+    odata = {k: (v.detach().double().cpu() if v.is_floating_point() else v.cpu()) for k, v in dataset.items()
+             if torch.is_tensor(v)}
+    np.random.seed(123)
+    losses, norms, clipped = oa.update_critic(net, opt, odata, 3, minibatches, agent.policy.num_dof, 0.0, clip)
+    np.random.seed(123)
+    out = agent.update_critic(dataset)
+    assert abs(out["critic_loss_mean"] - np.mean(losses)) <= 1e-4 * np.mean(losses)
+    assert abs(out["critic_loss_min"] - np.min(losses)) <= 1e-4 * np.mean(losses)
+    assert abs(out["critic_grad_norm_max"] - np.max(norms)) <= 1e-4 * np.max(norms)
+    assert abs(out["clipped_critic_grad_norm_mean"] - np.mean(clipped)) <= 1e-4 * np.mean(clipped)
+    for p, q in zip(agent.critic.parameters, net.parameters()):
+        assert (p.detach().double().cpu() - q.detach()).abs().max().item() <= 5e-5
+    # a second call (new learning rate after a scheduler step) re-captures and keeps training
+    if agent.critic_lr_scheduler:
+        agent.critic_lr_scheduler.step()
+    out2 = agent.update_critic(dataset)
+    assert out2["critic_loss_mean"] < out["critic_loss_mean"]
+
+
 def test_overlapped_epoch_equals_serial_epoch():
     """Side streams (covariance chain first, trust-region loss / logging branches, weight gradients on per-layer
     streams, early gradient clearing) only reorder independent work: metrics and updated parameters of two epochs
