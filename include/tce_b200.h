@@ -119,6 +119,13 @@ int tce_gauss_stats_bwd(const float *mean, const float *L, int64_t ldb_L, const 
  * otherwise grad_mean [B,n] = grad_out[b] * 2 Sigma_o^-1 (mean - mean_o) (maha may also be written).      */
 int tce_gauss_maha(const float *mean, const float *mean_o, const float *L_o, int64_t ldb_Lo,
                    const double *grad_out, double *maha, float *grad_mean, int64_t B, int n, void *stream);
+/* backward of tce_gauss_maha w.r.t. ALL arguments (BlackBoxPolicy.log_prob differentiates the Mahalanobis term w.r.t.
+ * the distribution's own mean and factor, black_box_policy.py:95-128):  grad_mean [B,n] = 2 g L_o^-T L_o^-1 d
+ * (d maha / d mean_o is its negative), grad_L [B,n,n] = -2 g tril(u z^T), z = L_o^-1 d, u = L_o^-T z; either may be
+ * NULL.                                                                                                   */
+int tce_gauss_maha_bwd_full(const float *mean, const float *mean_o, const float *L_o, int64_t ldb_Lo,
+                            const double *grad_out, float *grad_mean, float *grad_L, int64_t B, int n,
+                            void *stream);
 /* Non-contextual policy: ONE L_o for all episodes (the reference repeats it B times,
  * black_box_policy.py:50-53).  tce_tri_inverse writes Linv [B,n,n] = L^-1 (fp64, B is normally 1);
  * tce_gauss_maha_shared is tce_gauss_maha with the two triangular solves per episode replaced by products

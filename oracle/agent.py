@@ -160,3 +160,35 @@ def policy_epoch(policy, projection, dataset, times, pred_pairs, num_iterations,
         with torch.no_grad():
             out["kl"] = kl_old_new_proj(policy, new, old, proj)
     return sur + ent + trl, out
+
+
+def bbrl_process_dataset(dataset, norm_advantages=True, clip_advantages=0.0):
+    """BlackBoxAgent.process_dataset (black_box_agent.py:90-103)."""
+    adv = dataset["segment_reward"] - dataset["segment_value"]
+    if norm_advantages:
+        std = adv.std() if len(adv) != 1 else 1.0
+        adv = (adv - adv.mean()) / (std + 1e-8)
+    if clip_advantages > 0:
+        adv = torch.clamp(adv, -clip_advantages, clip_advantages)
+    return adv
+
+
+def policy_epoch_bbrl(policy, projection, dataset, num_iterations, *, entropy_penalty_coef=0.0, set_variance=False,
+                      with_metrics=False):
+    """One epoch body of BlackBoxAgent.update_policy (black_box_agent.py:285-334) up to the loss."""
+    old = (dataset["segment_params_mean"], dataset["segment_params_L"])
+    if projection.initial_entropy is None:
+        projection.initial_entropy = policy.entropy(list(old)).mean()
+    new = policy.policy(dataset["segment_state"])
+    proj = projection(policy, new, old, num_iterations)
+    lp_new = policy.log_prob(dataset["segment_action"], params_mean=proj[0], params_L=proj[1])
+    sur, sur_stats = surrogate_loss(dataset["segment_advantage"], lp_new, dataset["segment_log_prob"])
+    ent, ent_stats = entropy_loss(policy, proj[0], proj[1], entropy_penalty_coef)
+    trl = projection.get_trust_region_loss(policy, new, proj, set_variance=set_variance)
+    out = {"new": new, "proj": proj, "log_prob_new": lp_new, "surrogate_loss": sur, "entropy_loss": ent,
+           "trust_region_loss": trl, **sur_stats, **ent_stats}
+    if with_metrics:
+        with torch.no_grad():
+            out["kl"] = kl_old_new_proj(policy, new, old, proj)
+            out["projection_metrics"] = projection.compute_metrics(policy, new, proj, num_iterations)
+    return sur + ent + trl, out

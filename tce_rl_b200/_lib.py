@@ -47,6 +47,7 @@ SIGNATURES = {
     "tce_gauss_stats": (C.c_int, [_P, _P, _I64, _P, _P, _I64, _P, _I64, _I32, _P]),
     "tce_gauss_stats_bwd": (C.c_int, [_P, _P, _I64, _P, _P, _I64, _P, _P, _P, _I64, _I32, _P]),
     "tce_gauss_maha": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _I64, _I32, _P]),
+    "tce_gauss_maha_bwd_full": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _I64, _I32, _P]),
     "tce_tri_inverse": (C.c_int, [_P, _I64, _P, _I64, _I32, _P]),
     "tce_gauss_maha_shared": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "tce_proj_mean_fwd": (C.c_int, [_P, _P, _P, _D, _P, _I64, _I32, _P]),

@@ -181,11 +181,11 @@ gauss_kl_kernel(const float *__restrict__ mean, const float *__restrict__ L, lon
 __global__ void __launch_bounds__(128)
 maha_kernel(const float *__restrict__ mean, const float *__restrict__ mean_o, const float *__restrict__ L_o,
             long long ldb_Lo, const double *__restrict__ gout, double *__restrict__ out,
-            float *__restrict__ grad_mean, int n) {
+            float *__restrict__ grad_mean, float *__restrict__ grad_L, int n) {
   extern __shared__ double smd[];
   const int LD = n | 1;
-  double *bv = smd, *inv = smd + n;
-  float *sL = reinterpret_cast<float *>(smd + 2 * n);
+  double *bv = smd, *inv = smd + n, *zv = smd + 2 * n;
+  float *sL = reinterpret_cast<float *>(smd + 3 * n);
   const long long b = blockIdx.x;
   const float *Lo = L_o + b * ldb_Lo;
   {
@@ -198,28 +198,40 @@ maha_kernel(const float *__restrict__ mean, const float *__restrict__ mean_o, co
     inv[i] = 1.0 / (double)Lo[(size_t)i * n + i];
   }
   __syncthreads();
-  if (threadIdx.x >= 32) return;
-  const int lane = threadIdx.x;
-  double maha = 0.0;
-  for (int j = 0; j < n; ++j) {                       // z = L_o^-1 diff
-    const double zj = bv[j] * inv[j];
-    __syncwarp();
-    for (int i = j + 1 + lane; i < n; i += 32) bv[i] = fma(-(double)sL[i * LD + j], zj, bv[i]);
-    if (lane == 0) bv[j] = zj;
-    maha = fma(zj, zj, maha);
-    __syncwarp();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    double maha = 0.0;
+    for (int j = 0; j < n; ++j) {                       // z = L_o^-1 diff
+      const double zj = bv[j] * inv[j];
+      __syncwarp();
+      for (int i = j + 1 + lane; i < n; i += 32) bv[i] = fma(-(double)sL[i * LD + j], zj, bv[i]);
+      if (lane == 0) { bv[j] = zj; zv[j] = zj; }
+      maha = fma(zj, zj, maha);
+      __syncwarp();
+    }
+    if (out && lane == 0) out[b] = maha;
+    if (gout) {
+      const double g2 = 2.0 * gout[b];
+      for (int i = n - 1; i >= 0; --i) {                  // u = L_o^-T z
+        const double ui = bv[i] * inv[i];
+        __syncwarp();
+        for (int k = lane; k < i; k += 32) bv[k] = fma(-(double)sL[i * LD + k], ui, bv[k]);
+        if (lane == 0) bv[i] = ui;
+        __syncwarp();
+      }
+      if (grad_mean)
+        for (int i = lane; i < n; i += 32) grad_mean[b * n + i] = (float)(g2 * bv[i]);
+    }
   }
-  if (out && lane == 0) out[b] = maha;
-  if (!gout) return;
+  if (!gout || !grad_L) return;
+  // d maha / d L_o = -2 tril(u z^T)   (d(L^-1) = -L^-1 dL L^-1)
+  __syncthreads();
   const double g2 = 2.0 * gout[b];
-  for (int i = n - 1; i >= 0; --i) {                  // u = L_o^-T z
-    const double ui = bv[i] * inv[i];
-    __syncwarp();
-    for (int k = lane; k < i; k += 32) bv[k] = fma(-(double)sL[i * LD + k], ui, bv[k]);
-    if (lane == 0) bv[i] = ui;
-    __syncwarp();
+  float *gl = grad_L + (size_t)b * n * n;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    gl[e] = j <= i ? (float)(-g2 * bv[i] * zv[j]) : 0.f;
   }
-  for (int i = lane; i < n; i += 32) grad_mean[b * n + i] = (float)(g2 * bv[i]);
 }
 
 // Shared-covariance variants (non-contextual policy: every episode has the same L_o).  L_o^-1 is formed once
@@ -1145,17 +1157,32 @@ extern "C" int tce_gauss_stats_bwd(const float *mean, const float *L, int64_t ld
   return TCE_OK;
 }
 
+static int maha_launch(const float *mean, const float *mean_o, const float *L_o, int64_t ldb_Lo, const double *grad_out,
+                       double *maha, float *grad_mean, float *grad_L, int64_t B, int n, void *stream) {
+  const size_t smem = 3 * (size_t)n * sizeof(double) + (size_t)n * (n | 1) * sizeof(float);
+  if (smem > 48 * 1024)
+    TCE_CUDA(cudaFuncSetAttribute(maha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "maha attr");
+  maha_kernel<<<(unsigned)B, 128, smem, (cudaStream_t)stream>>>(mean, mean_o, L_o, ldb_Lo, grad_out, maha, grad_mean,
+                                                               grad_L, n);
+  TCE_CHECK_LAUNCH("maha_kernel");
+  return TCE_OK;
+}
+
 extern "C" int tce_gauss_maha(const float *mean, const float *mean_o, const float *L_o, int64_t ldb_Lo,
                               const double *grad_out, double *maha, float *grad_mean, int64_t B, int n, void *stream) {
   if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!mean || !mean_o || !L_o || B < 0 || n < 1 || n > 128 || (grad_out && !grad_mean) || (!grad_out && !maha))
     return TCE_ERR_INVALID_ARGUMENT;
-  const size_t smem = 2 * (size_t)n * sizeof(double) + (size_t)n * (n | 1) * sizeof(float);
-  if (smem > 48 * 1024)
-    TCE_CUDA(cudaFuncSetAttribute(maha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "maha attr");
-  maha_kernel<<<(unsigned)B, 128, smem, (cudaStream_t)stream>>>(mean, mean_o, L_o, ldb_Lo, grad_out, maha, grad_mean, n);
-  TCE_CHECK_LAUNCH("maha_kernel");
-  return TCE_OK;
+  return maha_launch(mean, mean_o, L_o, ldb_Lo, grad_out, maha, grad_mean, nullptr, B, n, stream);
+}
+
+extern "C" int tce_gauss_maha_bwd_full(const float *mean, const float *mean_o, const float *L_o, int64_t ldb_Lo,
+                                       const double *grad_out, float *grad_mean, float *grad_L, int64_t B, int n,
+                                       void *stream) {
+  if (B == 0) return TCE_OK;
+  if (!mean || !mean_o || !L_o || !grad_out || (!grad_mean && !grad_L) || B < 0 || n < 1 || n > 128)
+    return TCE_ERR_INVALID_ARGUMENT;
+  return maha_launch(mean, mean_o, L_o, ldb_Lo, grad_out, nullptr, grad_mean, grad_L, B, n, stream);
 }
 
 extern "C" int tce_tri_inverse(const float *L, int64_t ldb, double *Linv, int64_t B, int n, void *stream) {

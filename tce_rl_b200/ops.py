@@ -602,7 +602,7 @@ def _(x):
 
 @torch.library.custom_op("tce::gauss_maha", mutates_args=())
 def gauss_maha(mean: Tensor, mean_o: Tensor, L_o: Tensor) -> Tensor:
-    """|L_o^-1 (mean - mean_o)|^2  [B] fp64 (``policy.maha``); differentiable w.r.t. ``mean``."""
+    """|L_o^-1 (mean - mean_o)|^2  [B] fp64 (``policy.maha``); differentiable w.r.t. all three arguments."""
     mean, mean_o = _chk(mean), _chk(mean_o)
     L_o, ldbo = _batched_matrix(L_o, "L_o")
     B, n = mean.shape
@@ -632,13 +632,39 @@ def _(grad, mean, mean_o, L_o):
     return torch.empty_like(mean)
 
 
+@torch.library.custom_op("tce::gauss_maha_bwd_full", mutates_args=())
+def gauss_maha_bwd_full(grad: Tensor, mean: Tensor, mean_o: Tensor, L_o: Tensor, need_L: bool) -> Tuple[Tensor, Tensor]:
+    """-> (d maha / d mean [B, n] (= -d maha / d mean_o), d maha / d L_o [B, n, n] or empty)."""
+    mean, mean_o = _chk(mean), _chk(mean_o)
+    Lc, ldbo = _batched_matrix(L_o, "L_o")
+    B, n = mean.shape
+    g = _chk(grad, torch.float64, "grad")
+    g_mean = torch.empty_like(mean)
+    g_L = torch.empty(B, n, n, device=mean.device, dtype=torch.float32) if need_L else mean.new_empty(0)
+    _lib.call("tce_gauss_maha_bwd_full", _p(mean), _p(mean_o), _p(Lc), ldbo, _p(g), _p(g_mean),
+              _p(g_L) if need_L else None, B, n, _stream())
+    return g_mean, g_L
+
+
+@gauss_maha_bwd_full.register_fake
+def _(grad, mean, mean_o, L_o, need_L):
+    B, n = mean.shape
+    return torch.empty_like(mean), (mean.new_empty(B, n, n) if need_L else mean.new_empty(0))
+
+
 def _gm_setup(ctx, inputs, output):
     ctx.save_for_backward(*inputs)
 
 
 def _gm_backward(ctx, g):
     mean, mean_o, L_o = ctx.saved_tensors
-    return gauss_maha_bwd(g, mean, mean_o, L_o), None, None
+    if not (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
+        return gauss_maha_bwd(g, mean, mean_o, L_o), None, None
+    g_mean, g_L = gauss_maha_bwd_full(g, mean, mean_o, L_o, bool(ctx.needs_input_grad[2]))
+    if ctx.needs_input_grad[2] and L_o.shape[0] != mean.shape[0]:      # one factor [1, n, n] for the whole batch
+        g_L = g_L.sum(dim=0, keepdim=True)
+    return (g_mean if ctx.needs_input_grad[0] else None, -g_mean if ctx.needs_input_grad[1] else None,
+            g_L if ctx.needs_input_grad[2] else None)
 
 
 gauss_maha.register_autograd(_gm_backward, setup_context=_gm_setup)

@@ -3,4 +3,4 @@ from .policy import BlackBoxPolicy, TemporalCorrelatedPolicy, policy_factory  # 
 from .projection import (BaseProjectionLayer, FrobeniusProjectionLayer, KLProjectionLayer,  # noqa: F401
                          WassersteinProjectionLayer, projection_factory)
 from .critic import ValueFunction, critic_factory  # noqa: F401
-from .agent import TemporalCorrelatedAgent, agent_factory  # noqa: F401
+from .agent import BlackBoxAgent, TemporalCorrelatedAgent, agent_factory  # noqa: F401

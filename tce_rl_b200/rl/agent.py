@@ -337,11 +337,12 @@ class TemporalCorrelatedAgent:
         writes {loss, grad norm, clipped grad norm} into ``row`` [3] on the device."""
         D2 = self.policy.num_dof * 2
         flat = isinstance(getattr(self, "_critic_flat", None), torch.Tensor)
+        keep_tail = getattr(self, "_critic_keep_tail", False)        # BBRL: the critic sees the whole state
         if sel is None:
             st, rt, ov = states, returns, old_values
         else:
             st, rt, ov = states.index_select(0, sel), returns.index_select(0, sel), old_values.index_select(0, sel)
-        values_new = self.critic.critic(st[..., :-D2]).squeeze(-1)
+        values_new = self.critic.critic(st if keep_tail else st[..., :-D2]).squeeze(-1)
         loss = self.value_loss(values_new, rt, ov)
         if flat:
             self.critic_optimizer.begin()
@@ -479,6 +480,44 @@ class TemporalCorrelatedAgent:
         return norm
 
     # ---- policy -----------------------------------------------------------------------------------------------
+    _segment_wise = True       # TCE: segment-wise trajectory likelihood; BlackBoxAgent: likelihood of the parameters
+
+    def _policy_obs(self, dataset):
+        """Network input: the observation without the desired position / velocity tail (:352, :527)."""
+        return dataset["segment_state"][..., :-self.policy.num_dof * 2]
+
+    def _log_probs(self, dataset, proj, times, pred_pairs):
+        """-> (log-prob of the data under the projected policy, log-prob recorded at sampling time)."""
+        lp = self.policy.log_prob(dataset["step_actions"], params_mean=proj[0], params_L=proj[1], times=times,
+                                  init_time=dataset["segment_init_time"], init_pos=dataset["segment_init_pos"],
+                                  init_vel=dataset["segment_init_vel"], pred_pairs=pred_pairs)
+        return lp, dataset["segment_log_prob_estimate"]
+
+    def _flat_grad_norm(self):
+        return torch.linalg.vector_norm(self._flat_grad).double()
+
+    def balance_norms(self, dataset, times, pred_pairs):
+        """The balance check of temporal_correlated_agent.py:446-522 / black_box_agent.py:221-283: the gradient norm of
+        the surrogate loss alone and of the trust-region loss alone (two extra forward + backward passes, no optimiser
+        step).  -> device tensor [2] = (surrogate_grad_norm, trust_region_grad_norm)."""
+        old = (dataset["segment_params_mean"], dataset["segment_params_L"])
+        obs = self._policy_obs(dataset)
+        norms = []
+        for which in ("surrogate", "trust_region"):
+            new = self.policy.policy(obs)
+            proj = self.projection(self.policy, new, old, self.num_iterations)
+            if which == "surrogate":
+                lp, lp_old = self._log_probs(dataset, proj, times, pred_pairs)
+                loss, _ = self.surrogate_loss(dataset["segment_advantage"], lp, lp_old)
+            else:
+                loss = self.projection.get_trust_region_loss(self.policy, new, proj, set_variance=self.set_variance)
+            self._zero_policy_grads()
+            loss.backward()
+            util.join_side_grads()
+            self._allreduce_grads(self.policy_net_params)
+            norms.append(self._flat_grad_norm())
+        return torch.stack(norms)
+
     def policy_epoch(self, dataset, times, pred_pairs):
         """One epoch body of ``update_policy`` (temporal_correlated_agent.py:524-589): returns the metrics
         vector [7 + 12] (``_LOSS_KEYS`` then ``_KL_KEYS``) living on the device."""
@@ -488,9 +527,8 @@ class TemporalCorrelatedAgent:
                 if self._fast is None:
                     self._fast = SharedCovKLEpoch(self)
                 return self._fast.run(dataset, times, pred_pairs)
-        D2 = self.policy.num_dof * 2
         old = (dataset["segment_params_mean"], dataset["segment_params_L"])
-        obs = dataset["segment_state"][..., :-D2]
+        obs = self._policy_obs(dataset)
         # gradients are cleared early (after the covariance chain is launched, while this stream has slack), not in
         # front of backward()
         zeroed_early = self._flat_grad is not None and self._flat_grad_ok(self.policy_net_params)
@@ -508,7 +546,8 @@ class TemporalCorrelatedAgent:
                 self._zero_policy_grads()
             new = self.policy.policy(obs)
         proj = self.projection(self.policy, new, old, self.num_iterations, cov_projected=pre,
-                               defer_factor=bool(self.fused_surrogate and hasattr(self.policy, "segment_surrogate")))
+                               defer_factor=bool(self.fused_surrogate and self._segment_wise
+                                                 and hasattr(self.policy, "segment_surrogate")))
         cov_pending = getattr(self.projection, "_cov_pending", False)
         # trust-region loss: small (partly single-CTA) kernels that only need `new` and `proj` -- a parallel
         # branch next to the segment likelihood, forward and (autograd replays the streams) backward
@@ -523,7 +562,7 @@ class TemporalCorrelatedAgent:
             tr_stream = self._tr_stream
             proj_ready = torch.cuda.Event()                # everything the trust-region branch reads exists here
             proj_ready.record()
-        if self.fused_surrogate and hasattr(self.policy, "segment_surrogate"):
+        if self.fused_surrogate and self._segment_wise and hasattr(self.policy, "segment_surrogate"):
             surrogate, ratio, _ = self.policy.segment_surrogate(
                 dataset["step_actions"], proj[0], proj[1], times, dataset["segment_init_time"],
                 dataset["segment_init_pos"], dataset["segment_init_vel"], pred_pairs,
@@ -534,12 +573,8 @@ class TemporalCorrelatedAgent:
         else:
             if cov_pending:
                 self.projection.join_covariance()
-            log_prob_new = self.policy.log_prob(dataset["step_actions"], params_mean=proj[0], params_L=proj[1],
-                                                times=times, init_time=dataset["segment_init_time"],
-                                                init_pos=dataset["segment_init_pos"],
-                                                init_vel=dataset["segment_init_vel"], pred_pairs=pred_pairs)
-            surrogate, sur_stats = self.surrogate_loss(dataset["segment_advantage"], log_prob_new,
-                                                       dataset["segment_log_prob_estimate"])
+            log_prob_new, log_prob_old = self._log_probs(dataset, proj, times, pred_pairs)
+            surrogate, sur_stats = self.surrogate_loss(dataset["segment_advantage"], log_prob_new, log_prob_old)
         # the trust-region loss is back-propagated exactly once with a unit seed next to the projection when the two
         # loss terms are separate autograd roots (below): its covariance gradient may then be folded into the
         # projection's backward kernel (no kernels of its own)
@@ -628,23 +663,31 @@ class TemporalCorrelatedAgent:
                             sur_stats["imp_smp_ratio"].detach(), grad_norm.detach()])
         return torch.cat([head.double(), kl.double()])
 
-    def update_policy(self, dataset):
+    def _update_inputs(self, dataset):
         init_time = dataset["segment_init_time"]
-        times = self.sampler.get_times(init_time, self.sampler.num_times)
-        pred_pairs = self.sampler.pred_pairs
+        return init_time, self.sampler.get_times(init_time, self.sampler.num_times), self.sampler.pred_pairs
+
+    def update_policy(self, dataset):
+        init_time, times, pred_pairs = self._update_inputs(dataset)
         old = (dataset["segment_params_mean"], dataset["segment_params_L"])
         if self.projection.initial_entropy is None:
             self.projection.initial_entropy = self._global_mean(self.policy.entropy(list(old)))
         self.ensure_flat_grads(self.policy_net_params)
-        if self._distributed:
+        if self._distributed and times is not None:
             ops.sync_uniform(init_time, times)       # same time grid on all ranks: no per-epoch all-reduce(MAX)
-        rows = []
-        if self.use_cuda_graph:                      # NCCL all-reduces are captured with the epoch
+        check_balance = isinstance(self.balance_check, int) and self.balance_check > 0 \
+            and self.num_iterations % self.balance_check == 1
+        rows, balance_rows = [], []
+        if self.use_cuda_graph and not check_balance:   # NCCL all-reduces are captured with the epoch
             metrics = self._graphed_epochs(dataset, times, pred_pairs, rows)
         else:
             for _ in range(self.epochs_policy):
+                if check_balance:
+                    balance_rows.append(self.balance_norms(dataset, times, pred_pairs))
                 rows.append(self.policy_epoch(dataset, times, pred_pairs))
             metrics = torch.stack(rows)
+        if balance_rows:
+            metrics = torch.cat([metrics, torch.stack(balance_rows).to(metrics.dtype)], dim=1)
         metrics = metrics.cpu().numpy()                      # the ONE synchronisation of the update
         if not np.isfinite(metrics[:, :4]).all():
             raise Exception("NAN loss detected")           # temporal_correlated_agent.py:569-577
@@ -653,13 +696,24 @@ class TemporalCorrelatedAgent:
             out.update(_stats(metrics[:, i], k))
         for i, k in enumerate(_KL_KEYS):
             out.update(_stats(metrics[:, len(_LOSS_KEYS) + i], "projection_" + k))
+        gn = metrics[:, _LOSS_KEYS.index("policy_grad_norm")]
+        out.update(_stats(np.minimum(gn, self.clip_grad_norm) if self.clip_grad_norm > 0 else gn,
+                          "clipped_policy_grad_norm"))
+        if balance_rows:                                     # temporal_correlated_agent.py:601-612
+            nb = len(_LOSS_KEYS) + len(_KL_KEYS)
+            out.update(_stats(metrics[:, nb], "surrogate_grad_norm"))
+            out.update(_stats(metrics[:, nb + 1], "trust_region_grad_norm"))
+            out["balance_ratio"] = out["surrogate_grad_norm_mean"] / out["trust_region_grad_norm_mean"]
+        out.update(self._after_update_metrics(dataset, old))
         if self.set_variance and not self.policy.contextual_cov:
-            D2 = self.policy.num_dof * 2
             with torch.no_grad():
-                new = self.policy.policy(dataset["segment_state"][..., :-D2])
+                new = self.policy.policy(self._policy_obs(dataset))
                 proj = self.projection(self.policy, new, old, self.num_iterations)
             self.policy.set_cov_variable(proj[1][0].detach())
         return out
+
+    def _after_update_metrics(self, dataset, old):
+        return {}
 
     def _graphed_epochs(self, dataset, times, pred_pairs, rows):
         """Capture one epoch (forward, backward, Adam) in a CUDA graph and replay it ``epochs_policy`` times."""
@@ -694,8 +748,62 @@ class TemporalCorrelatedAgent:
         return out
 
 
+class BlackBoxAgent(TemporalCorrelatedAgent):
+    """The BBRL baseline agent on the same kernels (mprl/rl/agent/black_box_agent.py): one Gaussian over the whole
+    ProDMP parameter vector, episode-level advantage ``segment_reward - segment_value`` (:90-103), critic on the
+    episode's initial state (:105-158), ``update_policy`` with ``BlackBoxPolicy.log_prob`` (63-dim MVN through
+    ``tce_gauss_maha``), the same projections / trust-region loss / logging and ``projection.compute_metrics``
+    (:159-389).  Dataset keys: segment_state, segment_action, segment_log_prob, segment_params_mean, segment_params_L,
+    segment_reward, segment_value."""
+    _segment_wise = False
+
+    def __init__(self, *args, **kwargs):
+        kwargs.setdefault("discount_factor", 1.0)
+        super().__init__(*args, **kwargs)
+        self.fast_epoch = False                        # the hand-scheduled epoch is the TCE likelihood's
+
+    def process_dataset(self, dataset):
+        adv = dataset["segment_reward"] - dataset["segment_value"]
+        if self.norm_advantages:
+            if adv.numel() == 1 and not self._distributed:          # black_box_agent.py:95: std := 1 for one episode
+                adv = (adv - adv.mean()) / (1.0 + 1e-8)
+            else:
+                adv = ops.normalize(adv.contiguous())               # global mean / unbiased std (all ranks)
+        if self.clip_advantages > 0:
+            adv = torch.clamp(adv, -self.clip_advantages, self.clip_advantages)
+        dataset["segment_advantage"] = adv
+        return dataset
+
+    def _policy_obs(self, dataset):
+        return dataset["segment_state"]
+
+    def _log_probs(self, dataset, proj, times, pred_pairs):
+        return (self.policy.log_prob(dataset["segment_action"], params_mean=proj[0], params_L=proj[1]),
+                dataset["segment_log_prob"])
+
+    def _update_inputs(self, dataset):
+        return None, None, None
+
+    def update_critic(self, dataset):
+        flat = dict(step_states=dataset["segment_state"][:, None], step_returns=dataset["segment_reward"][:, None],
+                    step_values=torch.stack([dataset["segment_value"], dataset["segment_value"]], dim=1))
+        self._critic_keep_tail = True
+        return super().update_critic(flat)
+
+    def _after_update_metrics(self, dataset, old):
+        """projection.compute_metrics(policy, new, proj, step) after the last epoch (black_box_agent.py:359-363)."""
+        with torch.no_grad():
+            new = self.policy.policy(self._policy_obs(dataset))
+            proj = self.projection(self.policy, new, old, self.num_iterations)
+            met = self.projection.compute_metrics(self.policy, new, proj, self.num_iterations)
+            keys = sorted(met)
+            vals = torch.stack([met[k].double() for k in keys]).cpu().numpy()
+        return {"projection_" + k: float(v) for k, v in zip(keys, vals)}
+
+
 def agent_factory(typ: str, **kwargs):
-    """mprl/rl/agent/__init__.py:8-19 (only the TCE agent is on the B200 path)."""
-    if typ != "TemporalCorrelatedAgent":
-        raise NotImplementedError(f"{typ}: only TemporalCorrelatedAgent is built (SURVEY section 8(f))")
-    return TemporalCorrelatedAgent(**kwargs)
+    """mprl/rl/agent/__init__.py:8-19."""
+    agents = {"TemporalCorrelatedAgent": TemporalCorrelatedAgent, "BlackBoxAgent": BlackBoxAgent}
+    if typ not in agents:
+        raise NotImplementedError(f"{typ}: not on the B200 path (SURVEY section 8(f))")
+    return agents[typ](**kwargs)
