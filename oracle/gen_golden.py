@@ -245,6 +245,104 @@ def gen_oracle_path():
     return out
 
 
+def gen_ref_glue(mprl):
+    """Rollout-side glue and agent pieces from the REAL reference: RunningMeanStd, make_mdp_reward, checkpoint paths and
+    file contents of ``MLP.save`` / ``TrainableVariable.save``, ``generate_minibatches`` (numpy global generator),
+    ``BlackBoxAgent.process_dataset`` and ``TemporalCorrelatedAgent.update_critic`` (run unbound on a stand-in self)."""
+    import tempfile
+    import types
+    import numpy as np
+    import mprl.util as util
+    from mprl.rl.agent.black_box_agent import BlackBoxAgent
+    from mprl.rl.agent.temporal_correlated_agent import TemporalCorrelatedAgent
+    g = {}
+    gen = torch.Generator().manual_seed(11)
+    # ---- RunningMeanStd ------------------------------------------------------------------------------------------------
+    rms = util.RunningMeanStd(name="obs", shape=(5,), dtype="torch.float64", device="cpu")
+    batches = [torch.randn(n, 5, generator=gen, dtype=torch.float64) * (i + 1) + i for i, n in enumerate((7, 1000, 3))]
+    hist = []
+    for b in batches[:2]:
+        rms.update(b)
+        hist.append(dict(mean=rms.mean.clone(), var=rms.var.clone(), count=float(rms.count)))
+    other = util.RunningMeanStd(shape=(5,), dtype="torch.float64", device="cpu")
+    other.update(batches[2])
+    rms.combine(other)
+    hist.append(dict(mean=rms.mean.clone(), var=rms.var.clone(), count=float(rms.count)))
+    g["rms"] = dict(batches=batches, hist=hist)
+    # ---- make_mdp_reward -----------------------------------------------------------------------------------------------
+    E, T = 6, 9
+    rewards = torch.randn(E, T, generator=gen, dtype=torch.float64)
+    first = [4, 0, 8, 1, -1, 3]                       # -1: never; 0: event from the very first step (argmax 0 -> "not happened")
+    event = np.zeros((E, T), dtype=bool)
+    for e, f in enumerate(first):
+        if f >= 0:
+            event[e, f:] = True
+    infos_hit = [{"hit_ball": event[e].tolist(), "has_left_floor": event[e][::-1].tolist()} for e in range(E)]
+    g["mdp"] = dict(rewards=rewards.clone(), event=torch.as_tensor(event),
+                    table_tennis=util.make_mdp_reward("TableTennis4D-v0", rewards.clone(), infos_hit, torch.float64, "cpu"),
+                    hopper=util.make_mdp_reward("HopperJumpSparse", rewards.clone(), infos_hit, torch.float64, "cpu"),
+                    other=util.make_mdp_reward("BoxPushingDense", rewards.clone(), infos_hit, torch.float64, "cpu"))
+    # ---- checkpoint paths and file contents --------------------------------------------------------------------------
+    g["paths"] = dict(nn=util.get_nn_save_paths("/log", "policy_mean_mlp", 12), nn_none=util.get_nn_save_paths("/log", "x", None),
+                      state=util.get_training_state_save_path("/log", "policy_optimizer", 3),
+                      state_none=util.get_training_state_save_path("/log", "obs", None))
+    torch.manual_seed(3)
+    mlp = util.MLP(name="critic_net", dim_in=4, dim_out=1, hidden_layers=[8, 6], init_method="orthogonal",
+                   out_layer_gain=1.0, act_func_hidden="leaky_relu", act_func_last=None, dtype=torch.float64,
+                   device=torch.device("cpu"))
+    var = util.TrainableVariable("cov", torch.arange(5, dtype=torch.float64))
+    with tempfile.TemporaryDirectory() as d:
+        mlp.save(d, 7)
+        var.save(d, 7)
+        files = sorted(os.listdir(d))
+        import pickle as pkl
+        with open(os.path.join(d, "critic_net_mlp_parameters.pkl"), "rb") as f:
+            structure = pkl.load(f)
+        weights = torch.load(os.path.join(d, "critic_net_mlp_weights_7"), weights_only=False)
+        with open(os.path.join(d, "cov_variable_parameters.pkl"), "rb") as f:
+            var_structure = pkl.load(f)
+        var_saved = torch.load(os.path.join(d, "cov_variable_weights_7"), weights_only=False)
+    x = torch.randn(3, 4, generator=gen, dtype=torch.float64)
+    g["ckpt"] = dict(files=files, structure={k: (str(v) if k in ("dtype", "device") else v) for k, v in structure.items()},
+                     weights={k: v.clone() for k, v in weights.items()}, x=x, y=mlp(x).detach(),
+                     var_structure={k: (str(v) if k in ("dtype", "device") else (tuple(v) if k == "variable_shape" else v))
+                                    for k, v in var_structure.items()}, var_saved=var_saved.detach().clone())
+    # ---- generate_minibatches ------------------------------------------------------------------------------------------
+    np.random.seed(7)
+    g["minibatches"] = [[torch.as_tensor(s) for s in util.generate_minibatches(23, 4)] for _ in range(2)]
+    # ---- BlackBoxAgent.process_dataset -------------------------------------------------------------------------------
+    for n in (9, 1):
+        fake = types.SimpleNamespace(norm_advantages=True, clip_advantages=1.5)
+        ds = dict(segment_reward=torch.randn(n, generator=gen, dtype=torch.float64) * 3,
+                  segment_value=torch.randn(n, generator=gen, dtype=torch.float64))
+        out = BlackBoxAgent.process_dataset(fake, {k: v.clone() for k, v in ds.items()})
+        g[f"bbrl_process_{n}"] = dict(inputs=ds, advantage=out["segment_advantage"].clone())
+    # ---- TemporalCorrelatedAgent.update_critic -----------------------------------------------------------------------
+    torch.manual_seed(5)
+    critic_net = util.MLP(name="ValueFunction", dim_in=6, dim_out=1, hidden_layers=[16, 16], init_method="orthogonal",
+                          out_layer_gain=1.0, act_func_hidden="leaky_relu", act_func_last=None, dtype=torch.float64,
+                          device=torch.device("cpu"))
+    w0 = {k: v.clone() for k, v in critic_net.state_dict().items()}
+    D = 2
+    ds = dict(step_states=torch.randn(5, 12, 6 + 2 * D, generator=gen, dtype=torch.float64),
+              step_values=torch.randn(5, 13, generator=gen, dtype=torch.float64),
+              step_returns=torch.randn(5, 12, generator=gen, dtype=torch.float64))
+    for clip_critic, clip_norm in ((0.0, 0.0), (0.2, 0.5)):
+        critic_net.load_state_dict(w0)
+        opt = torch.optim.Adam(critic_net.parameters(), lr=1e-3, weight_decay=5e-5)
+        fake = types.SimpleNamespace(epochs_critic=3, num_minibatchs=4, clip_grad_norm=clip_norm, clip_critic=clip_critic,
+                                     critic=types.SimpleNamespace(critic=critic_net), policy=types.SimpleNamespace(num_dof=D),
+                                     critic_optimizer=opt, critic_net_params=list(critic_net.parameters()))
+        fake.value_loss = types.MethodType(TemporalCorrelatedAgent.value_loss, fake)
+        np.random.seed(99)
+        stats = TemporalCorrelatedAgent.update_critic(fake, ds)
+        g[f"update_critic_{clip_critic}_{clip_norm}"] = dict(
+            stats={k: float(v) for k, v in stats.items()},
+            weights={k: v.clone() for k, v in critic_net.state_dict().items()})
+    g["update_critic_inputs"] = dict(dataset=ds, w0=w0, num_dof=D)
+    return g
+
+
 def main():
     from . import ref_loader
     os.makedirs(OUT, exist_ok=True)
@@ -254,6 +352,7 @@ def main():
     torch.save(gen_ref_agent(mprl), os.path.join(OUT, "ref_agent.pt"))
     torch.save(gen_ref_policy(mprl), os.path.join(OUT, "ref_policy.pt"))
     torch.save(gen_oracle_path(), os.path.join(OUT, "oracle_path.pt"))
+    torch.save(gen_ref_glue(mprl), os.path.join(OUT, "ref_glue.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -731,6 +731,38 @@ class TemporalCorrelatedAgent:
         self._graph = graph
         return torch.stack(rows)
 
+    # ---- checkpoints (abstract_agent.py:109-174) ---------------------------------------------------------------
+    def save_agent(self, log_dir: str, epoch: int):
+        """Policy / critic weights and both optimiser states in the reference's files
+        (``*_parameters.pkl``, ``*_weights_<epoch>``, ``{policy,critic}_optimizer_state_<epoch>``)."""
+        from .. import rollout
+        self.policy.save_weights(log_dir, epoch)
+        if self.critic is not None:
+            self.critic.save_weights(log_dir, epoch)
+        for name, opt in (("policy_optimizer", self.policy_optimizer), ("critic_optimizer", self.critic_optimizer)):
+            if opt is not None:
+                with open(rollout.get_training_state_save_path(log_dir, name, epoch), "wb") as f:
+                    torch.save(opt.state_dict(), f)
+
+    def load_agent(self, log_dir: str, epoch: int):
+        """Inverse of ``save_agent``: weights are copied INTO the existing parameters (the flat gradient buffers and
+        ``FlatAdam`` keep referring to them), the Adam moments and step counters are restored, the LR schedulers are
+        re-created and ``num_iterations = epoch`` as in the reference."""
+        from .. import rollout
+        self.policy.load_weights(log_dir, epoch)
+        if self.critic is not None:
+            self.critic.load_weights(log_dir, epoch)
+        for name, opt in (("policy_optimizer", self.policy_optimizer), ("critic_optimizer", self.critic_optimizer)):
+            if opt is not None:
+                sd = torch.load(rollout.get_training_state_save_path(log_dir, name, epoch), map_location=self.device,
+                                weights_only=False)
+                opt.load_state_dict(sd)
+        mk = lambda opt: LinearLR(opt, start_factor=1, end_factor=0.01, total_iters=self.total_iterations)
+        self.policy_lr_scheduler = mk(self.policy_optimizer) if self.schedule_lr_policy else None
+        self.critic_lr_scheduler = (mk(self.critic_optimizer)
+                                    if self.schedule_lr_critic and self.critic_optimizer else None)
+        self.num_iterations = epoch
+
     def step(self):
         if not hasattr(self.sampler, "run"):
             raise NotImplementedError("environment rollout is outside the B200 hot path: provide a sampler with "

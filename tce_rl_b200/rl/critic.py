@@ -21,6 +21,15 @@ class ValueFunction:
     def critic(self, state):
         return self.net(state)
 
+    def save_weights(self, log_dir: str, epoch: int):
+        """abstract_critic.py:83-105, files in the reference's layout."""
+        from .. import rollout
+        rollout.save_net(self.net, log_dir, epoch)
+
+    def load_weights(self, log_dir: str, epoch: int):
+        from .. import rollout
+        rollout.load_net(self.net, log_dir, epoch)
+
 
 def critic_factory(typ: str, **kwargs):
     return {"ValueFunction": ValueFunction}[typ](**kwargs)

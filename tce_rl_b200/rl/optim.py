@@ -41,6 +41,42 @@ class FlatAdam(torch.optim.Optimizer):
                 raise TceError("FlatAdam: parameter gradients must be views of the flat buffer (ensure_flat_grads)")
             off += p.numel()
 
+    # ---- checkpoints in torch.optim.Adam's format (abstract_agent.py:109-174 saves / loads optimizer.state_dict()) ----
+    def state_dict(self):
+        """Same layout as ``torch.optim.Adam.state_dict()``: per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq`` (views
+        of the flat moment buffers are cloned), so a checkpoint moves freely between the two optimisers."""
+        if float(self.stats[0].item()) > 0:
+            off = 0
+            for p in self._params:
+                n = p.numel()
+                self.state[p] = {"step": self.stats[0].detach().to(torch.float32).clone(),
+                                 "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
+                                 "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
+                off += n
+        try:
+            return super().state_dict()
+        finally:
+            self.state.clear()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        off = 0
+        step = 0.0
+        for p in self._params:
+            n = p.numel()
+            st = self.state.get(p)
+            if st:
+                self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                step = float(st["step"])
+            else:
+                self.exp_avg[off:off + n].zero_()
+                self.exp_avg_sq[off:off + n].zero_()
+            off += n
+        self.stats.zero_()
+        self.stats[0] = step
+        self.state.clear()
+
     def begin(self):
         """Clear the gradients and the norm accumulator (call before backward; cheap, can be issued early)."""
         self.flat_grad.zero_()

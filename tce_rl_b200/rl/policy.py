@@ -71,6 +71,17 @@ class AbstractGaussianPolicy:
     def is_diag(self):
         return self.std_only
 
+    def save_weights(self, log_dir: str, epoch: int):
+        """abstract_policy.py:140-151, files in the reference's layout (rollout.save_mlp / save_variable)."""
+        from .. import rollout
+        rollout.save_net(self.mean_net, log_dir, epoch)
+        rollout.save_net(self.variance_net, log_dir, epoch)
+
+    def load_weights(self, log_dir: str, epoch: int):
+        from .. import rollout
+        rollout.load_net(self.mean_net, log_dir, epoch)
+        rollout.load_net(self.variance_net, log_dir, epoch)
+
     def _vector_to_cholesky(self, cov_val: torch.Tensor, batch: int | None = None):
         """softplus(diag) + min_std, strictly-lower row-major fill -- one fused kernel (``tce::policy_head``)."""
         if cov_val.dim() == 1:

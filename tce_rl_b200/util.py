@@ -203,6 +203,7 @@ class MLP(nn.Module):
         dims = [dim_in, *hidden_layers, dim_out]
         self.layers = nn.ModuleList(nn.Linear(a, b, dtype=dtype, device=device) for a, b in zip(dims[:-1], dims[1:]))
         self.act_hidden, self.act_last = _ACT[act_func_hidden], _ACT[act_func_last]
+        self.act_hidden_name, self.act_last_name = act_func_hidden, act_func_last
         for i, lin in enumerate(self.layers):
             gain = out_layer_gain if i == len(self.layers) - 1 else math.sqrt(2)
             if init_method == "orthogonal":

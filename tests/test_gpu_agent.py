@@ -190,6 +190,44 @@ def test_fast_epoch_equals_generic_epoch(name, B):
         assert (a - b).abs().max().item() <= 2e-6
 
 
+def test_save_and_load_agent_resume_training(tmp_path):
+    """save_agent / load_agent (abstract_agent.py:109-174) in the reference's file layout: a resumed agent continues
+    exactly like the uninterrupted one (weights, Adam moments and step counters of BOTH FlatAdam optimisers)."""
+    import os
+    agent, dataset = build(epochs=2)
+    agent.num_iterations = 1
+    dataset = agent.process_dataset(dataset)
+    agent.update_critic(dataset)
+    agent.update_policy(dataset)
+    agent.save_agent(str(tmp_path), 1)
+    files = set(os.listdir(tmp_path))
+    assert {"policy_optimizer_state_1", "critic_optimizer_state_1", "ValueFunction_mlp_weights_1",
+            "ValueFunction_mlp_parameters.pkl", "TemporalCorrelatedPolicy_mean_mlp_weights_1",
+            "TemporalCorrelatedPolicy_variance_variable_weights_1"} <= files, files
+    sd = agent.policy_optimizer.state_dict()                   # torch.optim.Adam layout
+    assert set(sd) == {"state", "param_groups"} and set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    assert float(sd["state"][0]["step"]) == 2.0
+    import numpy as np
+    np.random.seed(5)                                          # the critic's minibatch shuffles (numpy global generator)
+    agent.update_critic(dataset)
+    out_a = agent.update_policy(dataset)
+    want = [p.detach().clone() for p in agent.policy.parameters + agent.critic.parameters]
+    # a fresh agent (different weights), resumed from the checkpoint
+    agent2, _ = build(epochs=2, seed=123)
+    agent2.ensure_flat_grads(agent2.policy_net_params)
+    agent2._critic_flat_adam()
+    agent2.load_agent(str(tmp_path), 1)
+    assert agent2.num_iterations == 1
+    agent2.projection.initial_entropy = agent.projection.initial_entropy
+    np.random.seed(5)
+    agent2.update_critic(dataset)
+    out_b = agent2.update_policy(dataset)
+    got = [p.detach() for p in agent2.policy.parameters + agent2.critic.parameters]
+    for a, b in zip(want, got):
+        assert (a - b).abs().max().item() <= 1e-6
+    assert abs(out_a["policy_loss_mean"] - out_b["policy_loss_mean"]) <= 1e-5 * max(1.0, abs(out_a["policy_loss_mean"]))
+
+
 def test_dataset_to_device_broadcasts_the_shared_old_factor():
     agent, dataset = build()
     host = {k: v.cpu().pin_memory() for k, v in dataset.items()}
