@@ -86,7 +86,9 @@ def test_factories_refuse_what_is_out_of_scope():
     with pytest.raises(NotImplementedError):
         projection_factory("KLProjectionLayer", device="cpu", dtype="float32")          # no CPU path
     with pytest.raises(NotImplementedError):
-        agent_factory("BlackBoxAgent")
+        agent_factory("SomeOtherAgent")
+    from tce_rl_b200.rl import BlackBoxAgent, TemporalCorrelatedAgent          # both agents of the reference are built
+    assert issubclass(BlackBoxAgent, TemporalCorrelatedAgent)
     layer = projection_factory("KLProjectionLayer", device="cuda", dtype="float32", mean_bound=0.05, cov_bound=5e-4,
                                entropy_schedule="linear", action_dim=63, total_train_steps=7500)
     layer.initial_entropy = torch.tensor(3.0)
