@@ -488,6 +488,36 @@ __device__ inline double kl_solve_eta(const double *lam, int n, double eps, doub
 // state for the backward AND a
 // warm start for the next call with the same Lo (the 50 epochs of one update_policy): starting Jacobi from
 // Lt^-1 M_prev = W Q_prev is an orthogonal change of basis of the same problem, so 2-3 sweeps suffice.
+// sum NV values over the CTA at once (scratch: >= 32 * NV + NV doubles); every thread receives all sums in v[]
+template <int NV>
+__device__ inline void block_sum_n(double (&v)[NV], double *scratch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (int)(blockDim.x >> 5);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) scratch[warp * NV + k] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += scratch[w * NV + threadIdx.x];
+    scratch[32 * NV + threadIdx.x] = t;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = scratch[32 * NV + k];
+  __syncthreads();
+}
+
+// dense row-major [n, n] global <- shared matrix, one row per warp pass (no index divisions, coalesced rows)
+__device__ __forceinline__ void store_full_rows(double *__restrict__ dst, Mat M, int n, int t, int nt) {
+  const int w = t >> 5, lane = t & 31, nw = nt >> 5;
+  for (int i = w; i < n; i += nw)
+    for (int j = lane; j < n; j += 32) dst[(size_t)i * n + j] = M(i, j);
+}
+
 __global__ void __launch_bounds__(KL_THREADS)
 proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_o, double eps_cov,
                        float *__restrict__ proj_L, double *__restrict__ save_M, double *__restrict__ save_U,
@@ -505,23 +535,60 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   const float *Lt = L + off, *Lo = L_o + off;
   if (threadIdx.x == 0) s_bad = 0;
   KL_STAMP(0);
-  load_lower_d(b0, Lt, n, m);
-  // fingerprint of Lo (position weighted sum, deterministic order): guards the warm start
+  // All three input matrices are requested before anything is consumed (EIGHT global loads in flight per thread: the
+  // kernel starts with cold caches and every dependent round trip costs ~2 k cycles): Lt -> b0, Lo -> b3 (with its
+  // fingerprint: position weighted sum, deterministic order; guards the warm start), and -- speculatively -- the
+  // previous call's M = Lo Q_prev -> b1.
   double fp = 0.0;
-  batched_load(Lo, n * n, [&](int e, float v) { fp = fma((double)(e % 251 + 1), (double)v, fp); });
+  {
+    const int total = n * n, step = (int)blockDim.x;
+    for (int e0 = threadIdx.x; e0 < total; e0 += 4 * step) {
+      float vt[4], vo[4];
+      double vm[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * step;
+        vt[u] = e < total ? Lt[e] : 0.f;
+        vo[u] = e < total ? Lo[e] : 0.f;
+        vm[u] = (e < total && warm_start) ? save_M[off + e] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * step;
+        if (e < total) {
+          const int i = e / n, j = e - i * n;
+          b0(i, j) = j <= i ? (double)vt[u] : 0.0;
+          b3(i, j) = j <= i ? (double)vo[u] : 0.0;
+          b1(i, j) = vm[u];
+          fp = fma((double)(e % 251 + 1), (double)vo[u], fp);
+        }
+      }
+    }
+    zero_padding(b0, n, m);
+    zero_padding(b1, n, m);
+    zero_padding(b3, n, m);
+  }
   fp = block_sum(fp, red);
   const bool warm = warm_start && save_sc[b * KL_SC + 3] == fp;
-  if (warm) load_full_d(b1, save_M + off, n, m); else load_lower_d(b1, Lo, n, m);
+  if (!warm) {                                                                      // cold: b1 = Lo (lower)
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) b1(e / m, e % m) = b3(e / m, e % m);
+    __syncthreads();
+  }
   KL_STAMP(1);
   la_tri_inverse(b0, b2, dinv, n);                                                 // Lt^-1 (kept for the backward)
+  KL_STAMP(10);
   zero_padding(b3, n, m);
   la_gemm(b3, b2, b1, n, n, n, TRI_LOWER, warm ? TRI_FULL : TRI_LOWER, TRI_FULL, 1.0, 0.0);   // W (or W Q_prev)
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-    const int i = e / n, j = e - i * n;
-    save_Li[off + e] = b2(i, j);
-  }
+  KL_STAMP(11);
   KL_STAMP(2);
-  const int sweeps = la_jacobi_onesided(b3, lam, nrm, n);                          // b3 = U~
+  // the warps that hold no rows of the register-resident iteration write Lt^-1 to the state meanwhile
+  const int sweeps = la_jacobi_onesided(b3, lam, nrm, n, [&](int t, int nt) {
+    if (nt >= 32) store_full_rows(save_Li + off, b2, n, t, nt);
+  });                                                                               // b3 = U~
+  if ((int)blockDim.x - 32 * ((n + LA_JACOBI_ROWS - 1) / LA_JACOBI_ROWS) < 32) {    // (no idle warp: all of them do it now)
+    store_full_rows(save_Li + off, b2, n, threadIdx.x, blockDim.x);
+    __syncthreads();
+  }
   KL_STAMP(3);
   const double kl0 = [&] {
     double v = 0.0;
@@ -542,85 +609,73 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
     save_sc[b * KL_SC + 6] = 1.0;                                  // entropy control
     if (blockIdx.x == 0) g_kl_prof[15] = sweeps;
   }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) save_lam[b * n + i] = lam[i];
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-    const int i = e / n, j = e - i * n;
-    save_M[off + e] = b2(i, j);
-    save_U[off + e] = b3(i, j);                                                     // U~ = Lt^-1 M for the backward
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    save_lam[b * n + i] = lam[i];
+    nrm[i] = active ? sqrt((1.0 + eta) / (lam[i] + eta)) : 1.0;                     // sqrt(D_ii): column scale of M
   }
+  store_full_rows(save_M + off, b2, n, threadIdx.x, blockDim.x);
+  store_full_rows(save_U + off, b3, n, threadIdx.x, blockDim.x);                   // U~ = Lt^-1 M for the backward
+  __syncthreads();
   KL_STAMP(5);
   float *out = proj_L + off;
-  // Fused entropy control (optional, `beta` != NULL): out_L = alpha * proj_L with
-  // alpha = exp((beta - H(proj_L)) / n) where H < beta (or always: equality variant), as proj_entropy_kernel.
-  // `half_logdet(i)`: the i-th term of 1/2 logdet of the projected covariance (log of the Cholesky diagonal, or its
-  // closed form 1/2 logdet(Sigma_o) + 1/2 sum log((1+eta)/(lam+eta)) when the factor is not formed here: `split`)
-  auto entropy_scale = [&](auto half_logdet) -> double {
-    double sl = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sl += half_logdet(i);
-    sl = block_sum(sl, red);
-    const double H = 0.5 * n * (1.0 + LOG_2PI) + sl;
-    if (!beta) {
-      if (threadIdx.x == 0) save_sc[b * KL_SC + 9] = H;
-      return 1.0;
+  // Everything that is a sum over the eigenvalues, in ONE reduction:
+  //  * fused entropy control (optional, `beta` != NULL): out_L = alpha * proj_L with alpha = exp((beta - H(proj_L)) / n)
+  //    where H < beta (or always: equality variant), as proj_entropy_kernel.  `half_logdet(i)`: the i-th term of
+  //    1/2 logdet of the projected covariance (log of the Cholesky diagonal, or its closed form 1/2 logdet(Sigma_o) +
+  //    1/2 sum log((1+eta)/(lam+eta)) when the factor is not formed here: `split`)
+  //  * covariance part of KL(N(., Sigma) || N(., Sigma_out)), Sigma = Lt Lt^T the UNPROJECTED covariance and
+  //    Sigma_out = alpha^2 Sigma_proj the layer's output -- the covariance term of the trust-region regression loss
+  //    (get_trust_region_loss, temporal_correlated_agent.py:561-567) -- in closed form on the eigen-system:
+  //      tr(Sigma_out^-1 Sigma) = alpha^-2 sum_i 1 / (D_ii lam_i),  logdet Sigma_out - logdet Sigma = 2 n ln alpha + sum_i ln(D_ii lam_i)
+  //    with D_ii = (1 + eta) / (lam_i + eta)  (identity step: D_ii lam_i = 1).  -> save_sc[7] (1/2 (tr - n)), save_sc[8]
+  //  * the logging decompositions of temporal_correlated_agent.py:641-686 in the same closed form (no extra kernels):
+  //      KL(new || old):  tr(Sigma_o^-1 Sigma) = sum_i 1 / lam_i,  logdet Sigma_o - logdet Sigma = sum_i ln lam_i
+  //      KL(out || old):  tr(Sigma_o^-1 Sigma_out) = alpha^2 sum_i D_ii,  logdet Sigma_o - logdet Sigma_out = -2 n ln alpha - sum_i ln D_ii
+  //    (identity step: D_ii = 1 / lam_i).  -> save_sc[10..13];  save_sc[9] = entropy of the output
+  auto tail_scalars = [&](auto half_logdet, bool act) -> double {
+    double v[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};              // sl, tr, ld, il, ll, sd, ldd
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double li = lam[i], dii = act ? (1.0 + eta) / (li + eta) : 1.0 / li;
+      const double llog = log(li), dlog = log(dii);
+      const double dl = act ? dii * li : 1.0;                       // D_ii lam_i
+      v[0] += half_logdet(i, dlog);
+      v[1] += 1.0 / dl;
+      v[2] += act ? dlog + llog : 0.0;
+      v[3] += 1.0 / li;
+      v[4] += llog;
+      v[5] += dii;
+      v[6] += dlog;
     }
-    const double bt = beta[b * ldb_beta];
-    const bool ent_active = entropy_eq || (H < bt);
-    const double alpha = ent_active ? exp((bt - H) / n) : 1.0;
+    block_sum_n<7>(v, nrm + 64);
+    const double H = 0.5 * n * (1.0 + LOG_2PI) + v[0];
+    double alpha = 1.0, Hout = H;
+    bool ent_active = false;
+    if (beta) {
+      const double bt = beta[b * ldb_beta];
+      ent_active = entropy_eq || (H < bt);
+      alpha = ent_active ? exp((bt - H) / n) : 1.0;
+      Hout = ent_active ? bt : H;                                   // H + n ln alpha
+    }
     if (threadIdx.x == 0) {
-      save_sc[b * KL_SC + 4] = alpha; save_sc[b * KL_SC + 5] = ent_active ? 1.0 : 0.0; save_sc[b * KL_SC + 6] = alpha * alpha;
-      save_sc[b * KL_SC + 9] = ent_active ? bt : H;             // entropy of the output: H + n ln alpha
+      double *sc = save_sc + b * KL_SC;
+      if (beta) { sc[4] = alpha; sc[5] = ent_active ? 1.0 : 0.0; sc[6] = alpha * alpha; }
+      const double la = log(alpha);
+      sc[7] = 0.5 * (v[1] / (alpha * alpha) - (double)n);           // "shape" part  1/2 (tr - n)
+      sc[8] = 0.5 * (2.0 * n * la + v[2]);                          // "volume" part 1/2 (logdet_t - logdet)
+      sc[9] = Hout;
+      sc[10] = 0.5 * (v[3] - (double)n);
+      sc[11] = 0.5 * v[4];
+      sc[12] = 0.5 * (alpha * alpha * v[5] - (double)n);
+      sc[13] = -(double)n * la - 0.5 * v[6];
     }
     return alpha;
   };
-  // Covariance part of KL(N(., Sigma) || N(., Sigma_out)), Sigma = Lt Lt^T the UNPROJECTED covariance and
-  // Sigma_out = alpha^2 Sigma_proj the layer's output -- the covariance term of the trust-region regression loss
-  // (get_trust_region_loss, temporal_correlated_agent.py:561-567) -- in closed form on the eigen-system:
-  //   tr(Sigma_out^-1 Sigma) = alpha^-2 sum_i 1 / (D_ii lam_i),  logdet Sigma_out - logdet Sigma = 2 n ln alpha + sum_i ln(D_ii lam_i)
-  // with D_ii = (1 + eta) / (lam_i + eta)  (identity step: D_ii lam_i = 1).  -> save_sc[7] (1/2 (tr - n)) and save_sc[8] (1/2 logdet difference)
-  // The logging decompositions of temporal_correlated_agent.py:641-686 in the same closed form (no extra kernels):
-  //   KL(new || old):  tr(Sigma_o^-1 Sigma) = sum_i 1 / lam_i,  logdet Sigma_o - logdet Sigma = sum_i ln lam_i
-  //   KL(out || old):  tr(Sigma_o^-1 Sigma_out) = alpha^2 sum_i D_ii,  logdet Sigma_o - logdet Sigma_out = -2 n ln alpha - sum_i ln D_ii
-  // (identity step: D_ii = 1 / lam_i).  -> save_sc[10..13]
-  auto save_tr_value = [&](double alpha, bool act) {
-    double tr = 0.0, ld = 0.0, il = 0.0, ll = 0.0, sd = 0.0, ldd = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const double dii = act ? (1.0 + eta) / (lam[i] + eta) : 1.0 / lam[i];
-      const double dl = act ? dii * lam[i] : 1.0;                                // D_ii lam_i
-      tr += 1.0 / dl;
-      ld += log(dl);
-      il += 1.0 / lam[i];
-      ll += log(lam[i]);
-      sd += dii;
-      ldd += log(dii);
-    }
-    tr = block_sum(tr, red);
-    ld = block_sum(ld, red);
-    il = block_sum(il, red);
-    ll = block_sum(ll, red);
-    sd = block_sum(sd, red);
-    ldd = block_sum(ldd, red);
-    if (threadIdx.x == 0) {
-      save_sc[b * KL_SC + 7] = 0.5 * (tr / (alpha * alpha) - (double)n);            // "shape" part  1/2 (tr - n)
-      save_sc[b * KL_SC + 8] = 0.5 * (2.0 * n * log(alpha) + ld);                  // "volume" part 1/2 (logdet_t - logdet)
-      save_sc[b * KL_SC + 10] = 0.5 * (il - (double)n);
-      save_sc[b * KL_SC + 11] = 0.5 * ll;
-      save_sc[b * KL_SC + 12] = 0.5 * (alpha * alpha * sd - (double)n);
-      save_sc[b * KL_SC + 13] = -(double)n * log(alpha) - 0.5 * ldd;
-    }
-  };
   // Sigma of the (pre-entropy) result goes to the state as well: with ONE covariance for the batch the
   // likelihood's stage 1 takes alpha^2 * Sigma from there instead of re-forming L L^T per episode.
-  auto save_sigma = [&](Mat S) {
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-      const int i = e / n, j = e - i * n;
-      save_Sig[off + e] = S(i, j);
-    }
-  };
   if (!active) {                                                                    // identity
     la_gemm(b1, b0, b0.T(), n, n, n, TRI_LOWER, TRI_UPPER, TRI_FULL, 1.0, 0.0);      // Sigma = Lt Lt^T
-    save_sigma(b1);
-    const double alpha = entropy_scale([&](int i) { return log(b0(i, i)); });
-    save_tr_value(alpha, false);
+    store_full_rows(save_Sig + off, b1, n, threadIdx.x, blockDim.x);
+    const double alpha = tail_scalars([&](int i, double) { return log(b0(i, i)); }, false);
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
       const float v = (e % n <= e / n) ? Lt[e] : 0.f;
       out[e] = v;
@@ -629,18 +684,17 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
     if (info && threadIdx.x == 0) info[b] = 0;
     return;
   }
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-    const int j = e % n;
-    b2(e / n, j) *= sqrt((1.0 + eta) / (lam[j] + eta));
+  {                                                                                 // M sqrt(D)
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (int)(blockDim.x >> 5);
+    for (int i = w; i < n; i += nw)
+      for (int j = lane; j < n; j += 32) b2(i, j) *= nrm[j];
   }
   __syncthreads();
   KL_STAMP(6);
   la_gemm(b1, b2, b2.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_LOWER, 1.0, 0.0);       // Sigma_proj (all of it is written)
-  save_sigma(b1);
+  store_full_rows(save_Sig + off, b1, n, threadIdx.x, blockDim.x);
   if (split) {        // the factor is formed by kl_chol_kernel; consumers of Sigma (likelihood stage 1) need not wait
-    const double alpha_s =
-        entropy_scale([&](int i) { return log((double)Lo[(size_t)i * n + i]) + 0.5 * log((1.0 + eta) / (lam[i] + eta)); });
-    save_tr_value(alpha_s, true);
+    tail_scalars([&](int i, double dlog) { return log((double)Lo[(size_t)i * n + i]) + 0.5 * dlog; }, true);
     KL_STAMP(7); KL_STAMP(8); KL_STAMP(9);
     return;
   }
@@ -648,8 +702,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   KL_STAMP(7);
   la_chol(b1, n, &s_bad);
   KL_STAMP(8);
-  const double alpha = entropy_scale([&](int i) { return log(b1(i, i)); });
-  save_tr_value(alpha, true);
+  const double alpha = tail_scalars([&](int i, double) { return log(b1(i, i)); }, true);
   store_lower_f(out, b1, n, 1.0);
   if (out_L) store_lower_f(out_L + off, b1, n, alpha);
   if (info && threadIdx.x == 0) info[b] = s_bad;
@@ -1258,6 +1311,9 @@ extern "C" int tce_debug_kl_phase_cycles(long long *out16) {
   if (!out16) return TCE_ERR_INVALID_ARGUMENT;
   TCE_CUDA(cudaDeviceSynchronize(), "kl prof sync");
   TCE_CUDA(cudaMemcpyFromSymbol(out16, g_kl_prof, 16 * sizeof(long long)), "kl prof copy");
+  float diag[8];
+  TCE_CUDA(cudaMemcpyFromSymbol(diag, g_jac_diag, sizeof(diag)), "jacobi diag copy");
+  for (int i = 0; i < 3; ++i) out16[12 + i] = (long long)(1e12 * (double)diag[i]);     // max cos^2 met in sweep i, x 1e12
 #ifdef JAC_PROF
   unsigned int jp[8];
   TCE_CUDA(cudaMemcpyFromSymbol(jp, g_jac_prof, sizeof jp), "jac prof copy");
