@@ -366,19 +366,24 @@ int tce_adam_step(int count, float *const *params, const int64_t *sizes, const f
  * tce_epoch_mean_fwd : Linv_old = L_old^-1 [n,n] fp64 (tce_tri_inverse) -> proj_mean [B,n], maha_old [B] =
  *                      |L_old^-1 (mean - mean_old)|^2, u_old [B,n] = Sigma_old^-1 (mean - mean_old);
  *                      acc[0] += sum_b 1/2 maha_old, acc[1] += sum_b 1/2 maha(proj_mean, mean_old).
- * tce_epoch_mean_bwd : g_proj_mean = d loss / d proj_mean [B,n]; Linv_new = L~^-1 [n,n] fp64 and kl_scalars [16] as
- *                      left in the state by tce_proj_kl_entropy_fwd(_sigma) -> grad_mean [B,n] = mean-projection
- *                      adjoint + tr_coeff / B * Sigma_out^-1 (mean - proj_mean), Sigma_out^-1 = (Sigma~^-1 + eta
- *                      Sigma_old^-1) / (alpha^2 (1 + eta));  acc[2] += sum_b 1/2 maha(mean, proj_mean; Sigma_out).
+ * tce_epoch_tr_mean  : Linv_new = L~^-1 [n,n] fp64 and kl_scalars [16] as left in the state by
+ *                      tce_proj_kl_entropy_fwd(_sigma) -> tr_grad [B,n] = tr_coeff / B * Sigma_out^-1 (mean - proj_mean),
+ *                      Sigma_out^-1 = (Sigma~^-1 + eta Sigma_old^-1) / (alpha^2 (1 + eta));  acc[2] += sum_b 1/2
+ *                      maha(mean, proj_mean; Sigma_out).  Needs nothing of the likelihood: runs beside it.
+ * tce_epoch_mean_combine : g_proj_mean = d loss / d proj_mean [B,n] -> grad_mean [B,n] = mean-projection adjoint of g
+ *                      + tr_grad (may be NULL).
  * tce_epoch_metrics  : out19 = the 7 loss values + 12 KL logging means of one epoch (rl/agent.py key order) from
  *                      acc[3], lik_stats {surrogate, mean ratio}, kl_scalars, adam_stats {step, sum g^2} (may be NULL).
  * acc is zero-initialised by the caller; everything is asynchronous on `stream`.                                */
 int tce_epoch_mean_fwd(const float *mean, const float *mean_old, const double *Linv_old, double eps_mean,
                        float *proj_mean, double *maha_old, float *u_old, double *acc, int64_t B, int n,
                        void *stream);
-int tce_epoch_mean_bwd(const float *g_proj_mean, const float *mean, const float *mean_old, const double *maha_old,
-                       const float *u_old, const double *Linv_new, const double *kl_scalars, double eps_mean,
-                       double tr_coeff, float *grad_mean, double *acc, int64_t B, int n, void *stream);
+int tce_epoch_tr_mean(const float *mean, const float *mean_old, const double *maha_old, const float *u_old,
+                      const double *Linv_new, const double *kl_scalars, double eps_mean, double tr_coeff,
+                      float *tr_grad, double *acc, int64_t B, int n, void *stream);
+int tce_epoch_mean_combine(const float *g_proj_mean, const float *mean, const float *mean_old, const double *maha_old,
+                           const float *u_old, const float *tr_grad, double eps_mean, float *grad_mean, int64_t B,
+                           int n, void *stream);
 int tce_epoch_metrics(const double *acc, const double *lik_stats, const double *kl_scalars, const double *adam_stats,
                       int64_t B, double tr_coeff, int with_cov, double ent_coef, double *out19, void *stream);
 

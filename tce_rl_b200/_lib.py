@@ -90,7 +90,8 @@ SIGNATURES = {
                                           _I64, _I64, _P]),
     "tce_seglik_uniform_finish": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P, _I64, _P]),
     "tce_epoch_mean_fwd": (C.c_int, [_P, _P, _P, _D, _P, _P, _P, _P, _I64, _I32, _P]),
-    "tce_epoch_mean_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _D, _D, _P, _P, _I64, _I32, _P]),
+    "tce_epoch_tr_mean": (C.c_int, [_P, _P, _P, _P, _P, _P, _D, _D, _P, _P, _I64, _I32, _P]),
+    "tce_epoch_mean_combine": (C.c_int, [_P, _P, _P, _P, _P, _P, _D, _P, _I64, _I32, _P]),
     "tce_epoch_metrics": (C.c_int, [_P, _P, _P, _P, _I64, _D, _I32, _D, _P, _P]),
     "tce_gae": (C.c_int, [_P, _P, _P, _P, _F, _F, _I32, _P, _P, _I64, _I64, _P]),
     "tce_segment_advantage_raw": (C.c_int, [_I32, _P, _P, _P, _P, _F, _P, _P, _I64, _I64, _I64, _P]),

@@ -35,6 +35,7 @@ class SharedCovKLEpoch:
     def __init__(self, agent):
         self.agent = agent
         self._cov_stream = None
+        self._tr_stream = None
 
     # ---- when the hand-scheduled epoch applies ------------------------------------------------------------------
     @staticmethod
@@ -100,10 +101,17 @@ class SharedCovKLEpoch:
         _lib.call("tce_epoch_mean_fwd", _p(mean_d), _p(mean_old), _p(Linv_old), float(proj.mean_bound), _p(proj_mean),
                   _p(maha_old), _p(u_old), _p(acc), B, n, main.cuda_stream)
         # ---- segment likelihood + surrogate (forward + backward in one pass, gradient in covariance space) ----------
+        mean_fwd_done = torch.cuda.Event()
+        mean_fwd_done.record(main)
         main.wait_event(sigma_ready)
         nn_ = n * n
         sigma0 = state[3 * nn_:4 * nn_]
         sc = state[4 * nn_ + n:]
+        # trust-region mean term (value + gradient): needs the projection's state only -> beside the likelihood
+        if self._tr_stream is None:
+            self._tr_stream = torch.cuda.Stream(device=dev)
+        tr_stream = self._tr_stream
+        tr_grad = torch.empty(B, n, device=dev, dtype=f32)
         chained, uniform = ops_seglik._facts(pred_pairs, dataset["segment_init_time"], times, True, None)
         logp, linfo, lacc, g_pm, _, g_S = ops_seglik.seglik(
             dataset["step_actions"], proj_mean, None, sigma0, sc[6:7], times, dataset["segment_init_time"],
@@ -123,10 +131,18 @@ class SharedCovKLEpoch:
             g_S.record_stream(cov)
             g_L.record_stream(cov)
         # ---- mean chain, backward ----------------------------------------------------------------------------------------
+        tr_stream.wait_event(mean_fwd_done)          # maha_old, u_old
+        tr_stream.wait_event(sigma_ready)            # the projection's state (L~^-1, eta, alpha)
+        with torch.cuda.stream(tr_stream):
+            _lib.call("tce_epoch_tr_mean", _p(mean_d), _p(mean_old), _p(maha_old), _p(u_old),
+                      _p(state[2 * nn_:3 * nn_]), _p(sc), float(proj.mean_bound), coeff, _p(tr_grad), _p(acc), B, n,
+                      tr_stream.cuda_stream)
+            for t in (mean_d, maha_old, u_old, tr_grad, acc):
+                t.record_stream(tr_stream)
         g_mean = torch.empty(B, n, device=dev, dtype=f32)
-        _lib.call("tce_epoch_mean_bwd", _p(g_pm), _p(mean_d), _p(mean_old), _p(maha_old), _p(u_old),
-                  _p(state[2 * nn_:3 * nn_]), _p(sc), float(proj.mean_bound), coeff, _p(g_mean), _p(acc), B, n,
-                  main.cuda_stream)
+        main.wait_stream(tr_stream)
+        _lib.call("tce_epoch_mean_combine", _p(g_pm), _p(mean_d), _p(mean_old), _p(maha_old), _p(u_old), _p(tr_grad),
+                  float(proj.mean_bound), _p(g_mean), B, n, main.cuda_stream)
         torch.autograd.backward([mean], [g_mean])
         util.join_side_grads()
         main.wait_event(cov_done)
