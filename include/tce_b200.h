@@ -390,8 +390,10 @@ int tce_epoch_metrics(const double *acc, const double *lik_stats, const double *
 /* ---- measurement helper ---------------------------------------------------------------------------------
  * One register-resident FMA-chain kernel (fp32 or fp64) over the whole chip; *flops (host) receives the
  * FLOPs executed.  bench.py times it to obtain the FMA-pipe roofline denominators.                      */
-/* debugging aid: SM-clock stamps taken between the phases of the last tce_proj_kl_cov_fwd launch */
-int tce_debug_kl_phase_cycles(long long *out16);
+/* Profiling aids, functional only when the library is built with -DTCE_PROFILE (otherwise they return
+ * TCE_ERR_UNSUPPORTED_SHAPE and the kernels contain no stamps): SM-clock stamps taken between the phases of the last
+ * KL forward ([0..15]) / covariance-space backward ([16..31]) launch                                              */
+int tce_debug_kl_phase_cycles(long long *out32);
 /* same for block 0 of the last tce_seglik_gram ([0..6]) / tce_seglik_bwd ([16..21]) launches */
 int tce_debug_seglik_phase_cycles(long long *out32);
 int tce_bench_fma(int fp64, int iters, void *scratch, double *flops, void *stream);

@@ -35,7 +35,7 @@ def measure(tag, mutate):
     if tag == "baseline":                      # phase clocks of the last KL forward of the replayed epoch
         import ctypes
         from tce_rl_b200 import _lib
-        buf = (ctypes.c_longlong * 16)()
+        buf = (ctypes.c_longlong * 32)()
         _lib.call("tce_debug_kl_phase_cycles", buf)
         st = list(buf)
         names = ["load", "trsm W", "jacobi", "eta solve", "gemm M + save", "scale", "gemm Sigma", "chol", "store"]

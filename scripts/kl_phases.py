@@ -11,7 +11,7 @@ state = ops.kl_state(1, 63, "cuda")
 for i in range(3):
     out = ops.proj_kl_cov(L + (1e-4 * i if warm else 0.0) * torch.tril(torch.ones_like(L)), Lo, 5e-4, state, warm)
 torch.cuda.synchronize()
-buf = (ctypes.c_longlong * 16)()
+buf = (ctypes.c_longlong * 32)()
 _lib.call("tce_debug_kl_phase_cycles", buf)
 st = list(buf)[:10]
 names = ["load", "trsm W", "jacobi", "eta solve", "save", "load+gemm M", "gemm Sigma", "chol", "store"]

@@ -44,6 +44,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(obj)
         cmd = [nvcc, *[f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")], "-c", path, "-o", obj]
+        if os.environ.get("TCE_PROFILE"):            # phase-clock stamps + tce_debug_* (scripts/kl_phases*.py); never shipped
+            cmd.insert(1, "-DTCE_PROFILE")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

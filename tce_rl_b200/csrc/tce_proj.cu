@@ -8,8 +8,16 @@
 
 #include "tce_smem_la.cuh"
 
-__device__ long long g_kl_prof[16];   // SM-clock stamps of the last KL forward kernel (block 0, thread 0)
+// Profiling scaffolding, compiled in with -DTCE_PROFILE only (TCE_PROFILE=1 python -m tce_rl_b200._build --force):
+// SM-clock stamps of block 0 / thread 0 of the last KL forward [0..15] and covariance-space backward [16..31] kernel.
+#ifdef TCE_PROFILE
+__device__ long long g_kl_prof[32];
 #define KL_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_kl_prof[i] = clock64(); } while (0)
+#define KL_PROF_SET(i, v) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_kl_prof[i] = (v); } while (0)
+#else
+#define KL_STAMP(i) do { } while (0)
+#define KL_PROF_SET(i, v) do { } while (0)
+#endif
 
 namespace {
 
@@ -607,7 +615,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
     save_sc[b * KL_SC + 0] = eta; save_sc[b * KL_SC + 1] = active ? 1.0 : 0.0; save_sc[b * KL_SC + 2] = kl0; save_sc[b * KL_SC + 3] = fp;
     save_sc[b * KL_SC + 4] = 1.0; save_sc[b * KL_SC + 5] = 0.0;    // alpha, ent_active, alpha^2: overwritten by the fused
     save_sc[b * KL_SC + 6] = 1.0;                                  // entropy control
-    if (blockIdx.x == 0) g_kl_prof[15] = sweeps;
+    KL_PROF_SET(15, sweeps);
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     save_lam[b * n + i] = lam[i];
@@ -862,7 +870,9 @@ proj_kl_cov_bwd_sigma_kernel(const float *__restrict__ L, const double *__restri
   const bool kl_active = save_sc[b * KL_SC + 1] != 0.0;
   const double alpha = fused_entropy ? save_sc[b * KL_SC + 4] : 1.0, a2 = alpha * alpha;
   const bool ent_active = fused_entropy && save_sc[b * KL_SC + 5] != 0.0;
+  KL_STAMP(16);
   load_full_d(b0, gsig + off, n, m);                                               // Sbar_out
+  KL_STAMP(17);
   if (!kl_active) {
     // identity KL step: Sigma_proj = Lt Lt^T, grad_Lt = 2 alpha^2 tril(Sbar_out Lt) - (2 alpha^2 c / n) diag(1 / Lt_ii)
     load_lower_d(b1, L + off, n, m);                                               // Lt
@@ -883,8 +893,11 @@ proj_kl_cov_bwd_sigma_kernel(const float *__restrict__ L, const double *__restri
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) { lam[i] = save_lam[b * n + i]; rho[i] = 1.0 / (lam[i] + eta); }
   load_full_d(b1, save_M + off, n, m);                                             // M
+  KL_STAMP(18);
   la_gemm(b2, b0, b1, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);            // Sbar_out M
+  KL_STAMP(19);
   la_gemm(b3, b1.T(), b2, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // F0 = M^T Sbar_out M
+  KL_STAMP(20);
   double c = 0.0;
   if (ent_active) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) c += (1.0 + eta) * rho[i] * b3(i, i);
@@ -909,17 +922,24 @@ proj_kl_cov_bwd_sigma_kernel(const float *__restrict__ L, const double *__restri
     if (i == j) v -= 0.5 * tr_coeff / (a2 * (1.0 + eta) * rho[i] * lam[i] * lam[i]);
     b2(i, j) = v;                                                                  // Nt
   }
+  KL_STAMP(21);
   load_full_d(b0, save_U + off, n, m);                                             // U~
+  KL_STAMP(22);
   la_gemm(b3, b0, b2, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);            // U~ Nt
+  KL_STAMP(23);
   la_gemm(b1, b3, b0.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // U~ Nt U~^T
+  KL_STAMP(24);
   load_full_d(b2, save_Li + off, n, m);                                            // Lt^-1
+  KL_STAMP(25);
   la_gemm(b3, b2.T(), b1, n, n, n, TRI_UPPER, TRI_FULL, TRI_LOWER, 1.0, 0.0);      // Lt^-T (.)
+  KL_STAMP(26);
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     const int i = e / n, j = e - i * n;
     double v = j <= i ? -2.0 * b3(i, j) : 0.0;
     if (i == j && tr_coeff != 0.0) v -= tr_coeff / (double)L[off + e];              // - tr_coeff (Lt^-T)_ii
     gl[e] = (float)v;
   }
+  KL_STAMP(27);
 }
 
 // =====================================================================================================
@@ -1307,19 +1327,18 @@ extern "C" int tce_proj_entropy_bwd(const float *L, const double *beta, int64_t 
 }
 
 // debugging aid: SM-clock stamps of the phases of the last KL forward kernel (synchronises)
-extern "C" int tce_debug_kl_phase_cycles(long long *out16) {
-  if (!out16) return TCE_ERR_INVALID_ARGUMENT;
+extern "C" int tce_debug_kl_phase_cycles(long long *out32) {
+  if (!out32) return TCE_ERR_INVALID_ARGUMENT;
+#ifdef TCE_PROFILE
   TCE_CUDA(cudaDeviceSynchronize(), "kl prof sync");
-  TCE_CUDA(cudaMemcpyFromSymbol(out16, g_kl_prof, 16 * sizeof(long long)), "kl prof copy");
+  TCE_CUDA(cudaMemcpyFromSymbol(out32, g_kl_prof, 32 * sizeof(long long)), "kl prof copy");
   float diag[8];
   TCE_CUDA(cudaMemcpyFromSymbol(diag, g_jac_diag, sizeof(diag)), "jacobi diag copy");
-  for (int i = 0; i < 3; ++i) out16[12 + i] = (long long)(1e12 * (double)diag[i]);     // max cos^2 met in sweep i, x 1e12
-#ifdef JAC_PROF
-  unsigned int jp[8];
-  TCE_CUDA(cudaMemcpyFromSymbol(jp, g_jac_prof, sizeof jp), "jac prof copy");
-  for (int i = 0; i < 5; ++i) out16[10 + i] = jp[i];
-#endif
+  for (int i = 0; i < 3; ++i) out32[12 + i] = (long long)(1e12 * (double)diag[i]);     // max cos^2 met in sweep i, x 1e12
   return TCE_OK;
+#else
+  return TCE_ERR_UNSUPPORTED_SHAPE;          /* library built without -DTCE_PROFILE */
+#endif
 }
 
 extern "C" size_t tce_proj_kl_save_doubles(int64_t B, int n) { return (size_t)B * (4 * (size_t)n * n + n + KL_SC); }

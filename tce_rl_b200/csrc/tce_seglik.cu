@@ -21,8 +21,13 @@
 
 #include "tce_common.cuh"
 
-__device__ long long g_sl_prof[32];   // SM-clock stamps of block 0 of the last gram [0..15] / bwd [16..31] kernel
+// profiling scaffolding (-DTCE_PROFILE only): SM-clock stamps of block 0 of the last gram [0..15] / bwd [16..31] kernel
+#ifdef TCE_PROFILE
+__device__ long long g_sl_prof[32];
 #define SL_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_sl_prof[i] = clock64(); } while (0)
+#else
+#define SL_STAMP(i) do { } while (0)
+#endif
 
 namespace {
 
@@ -614,9 +619,13 @@ size_t bwd_smem(int P) {
 // debugging aid: SM-clock stamps of block 0 of the last gram ([0..6]) and bwd ([16..21]) launches (synchronises)
 extern "C" int tce_debug_seglik_phase_cycles(long long *out32) {
   if (!out32) return TCE_ERR_INVALID_ARGUMENT;
+#ifdef TCE_PROFILE
   TCE_CUDA(cudaDeviceSynchronize(), "seglik prof sync");
   TCE_CUDA(cudaMemcpyFromSymbol(out32, g_sl_prof, 32 * sizeof(long long)), "seglik prof copy");
   return TCE_OK;
+#else
+  return TCE_ERR_UNSUPPORTED_SHAPE;          /* library built without -DTCE_PROFILE */
+#endif
 }
 
 extern "C" size_t tce_seglik_work_bytes(const tce_tables_t *t, int64_t B, int64_t P) {

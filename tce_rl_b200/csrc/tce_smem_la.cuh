@@ -362,7 +362,9 @@ __device__ unsigned int g_jac_prof[8];
 #define JP(i)
 #endif
 
+#ifdef TCE_PROFILE
 __device__ float g_jac_diag[8];       // diagnostics of the last call (block 0): max cos^2 met in sweep 0..7
+#endif
 
 __device__ __forceinline__ void la_named_barrier(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
@@ -422,8 +424,10 @@ __device__ inline int la_jacobi_onesided(Mat W, double *lam, double *scratch, in
       la_named_barrier(nbar);                          // the step buffers alias these partial sums
       if (done || sweeps == 40) break;
       float a = (float)ap, b = (float)aq;
-      int big = 0;      // some pair was still correlated above 1e-4 when it was visited in this sweep
+      int big = 0;      // some pair was still correlated above the tolerance when it was visited in this sweep
+#ifdef TCE_PROFILE
       float cmax2 = 0.f;
+#endif
       int buf = 0;                                     // double buffered partials: one barrier per step
 #ifdef JAC_PROF
       unsigned int jp[5] = {0, 0, 0, 0, 0}, jt = clock();
@@ -449,7 +453,9 @@ __device__ inline int la_jacobi_onesided(Mat W, double *lam, double *scratch, in
           float na = a, nb = b;
           const float g2 = g * g, ab = a * b;
           if (g2 > LA_JACOBI_TOL2 * ab) big = 1;
+#ifdef TCE_PROFILE
           if (ab > 0.f) cmax2 = fmaxf(cmax2, g2 / ab);
+#endif
           if (g2 > 1e-24f * ab) {
             // tan(theta) = 2g / (d + sgn(d) sqrt(d^2 + 4 g^2)), d = b - a: three MUFU ops, no IEEE fix-ups
             const float d = b - a, s4 = fmaf(d, d, 4.0f * g2);
@@ -497,11 +503,13 @@ __device__ inline int la_jacobi_onesided(Mat W, double *lam, double *scratch, in
 #ifdef JAC_PROF
       if (threadIdx.x == 0 && blockIdx.x == 0) for (int i = 0; i < 5; ++i) g_jac_prof[i] = jp[i];
 #endif
+#ifdef TCE_PROFILE
       if (blockIdx.x == 0 && warp == 0 && sweeps < 8) {
         float m = cmax2;
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         if (lane == 0) g_jac_diag[sweeps] = m;
       }
+#endif
       ++sweeps;
       la_named_barrier(nbar);                          // the last step's buffer is the next norm buffer
       // a sweep that only met cosines <= sqrt(LA_JACOBI_TOL2) is the last one (see the constant)
