@@ -417,6 +417,8 @@ def roofline_numbers(agent, dataset, times, pairs, timer, peaks, ms_per_step, sh
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
         ent = tj.get("kernels", {}).get(dom)
+        if ent is not None:                              # captures are keyed by launch grid (1 matrix / B matrices / CTAs)
+            ent = ent.get(f"grid={n_cov}") or (next(iter(ent.values())) if len(ent) == 1 else None)
         if ent is not None and tj.get("csrc_hash") == csrc_hash():
             traffic, traffic_src = ent["dram_bytes"], tj.get("source", "profiles/r02_ncu_traffic.json")
         elif ent is not None:

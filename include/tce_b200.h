@@ -187,6 +187,11 @@ int tce_proj_kl_entropy_bwd_inv(const float *L, const float *proj_L, const float
  * DETACHED -- the covariance term of the trust-region regression loss (get_trust_region_loss,
  * temporal_correlated_agent.py:561-567), whose VALUE the forward leaves in the state (scalar 7 of a matrix): both
  * are closed forms on the saved eigen-system, so the loss term needs no kernel of its own.                      */
+/* tce_proj_kl_entropy_bwd that also adds the gradient of the trust-region regression term
+ * tr_coeff * KL_cov(N(L L^T) || N(Sigma_out)), Sigma_out = the layer's own (detached) output (closed form on the saved
+ * eigen-system; get_trust_region_loss, temporal_correlated_agent.py:561-567).                              */
+int tce_proj_kl_entropy_bwd_tr(const float *L, const float *proj_L, const float *grad_out, const double *save,
+                               double tr_coeff, float *grad_L, int64_t B, int n, void *stream);
 int tce_proj_kl_bwd_sigma(const float *L, const double *grad_sigma, const double *save, int fused_entropy,
                           double tr_coeff, float *grad_L, int64_t B, int n, void *stream);
 /* tce_proj_kl_entropy_fwd in two launches: _sigma writes the state (Sigma_proj, alpha = entropy scale from the

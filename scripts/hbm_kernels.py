@@ -1,0 +1,67 @@
+"""The HBM-bound kernel family at B = 16384 (box-pushing shape): CUDA-event time per launch (L2 flushed), achieved GB/s
+on SURVEY 8(d)'s ALGORITHMIC bytes, fraction of the measured HBM peak (MEASURED_PEAKS.json).
+-> profiles/r02_hbm_kernels_summary.txt"""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from tce_rl_b200 import ops
+from oracle.gen_golden import MP_CONFIGS, NUM_TIMES, synthetic_inputs
+from oracle import util as ou
+
+dev = "cuda:0"
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+name = "box"
+cfg, T = MP_CONFIGS[name], NUM_TIMES[name]
+D, K1 = cfg["num_dof"], cfg["num_basis"] + 1
+Dp, P = D * K1, 24
+peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(
+    os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+flush = torch.empty(192 * 1024 * 1024, device=dev, dtype=torch.int32)
+
+
+def timed(fn, reps=20, warm=5):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e-3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+base = min(B, 2048)
+inp = synthetic_inputs(name, base, dtype=torch.float32)
+rep = B // base
+g = {k: v.repeat(rep, *([1] * (v.dim() - 1))).contiguous().to(dev) for k, v in inp.items()}
+times = ou.get_times(g["init_time"].double().cpu(), T, cfg["dt"]).float().to(dev)
+torch.manual_seed(0)
+pairs = ou.get_time_pairs(T, dict(num_select=25, fixed_interval=True)).to(dev)
+tabs = ops.Tables(**cfg)
+theta = ops.mvn_rsample(g["mean"], g["L"], g["eps"], 0, 0)
+vec = torch.randn(B, Dp + Dp * (Dp - 1) // 2, device=dev)
+tri = Dp * (Dp + 1) // 2
+rows = [
+    ("traj_fwd (policy.sample)", lambda: ops.prodmp_traj(theta, times, g["init_time"], g["init_pos"], g["init_vel"], tabs.handle, D),
+     4 * (Dp + (1 + 2 * D) + T + 2 * D * T)),
+    ("mvn_rsample (per-episode L)", lambda: ops.mvn_rsample(g["mean"], g["L"], g["eps"], 0, 0), 4 * (3 * Dp + tri)),
+    ("policy_head_fwd (contextual)", lambda: ops.policy_head(vec, B, Dp, 1e-4), 4 * (vec.shape[1] + Dp * Dp)),
+    ("gauss_maha (per-episode L)", lambda: ops.gauss_maha(g["mean"], g["mean_old"], g["L_old"]), 4 * (tri + 2 * Dp) + 8),
+    ("gae", lambda: ops.gae(g["rewards"], g["values"], g["dones"], g["time_limit_dones"], 1.0, 0.95, True), 18 * T + 4),
+    ("segment_advantage (value_subtraction + normalise)", lambda: ops.segment_advantage(1, g["rewards"], g["values"], g["rewards"], pairs, 1.0, True),
+     4 * (T + 2 * P)),
+]
+out = [f"# HBM-bound family, {name} shape, B = {B}; CUDA events per launch (median of 20, L2 flushed); peak = {peak:.0f} GB/s "
+       f"(MEASURED_PEAKS.json hbm_gbs); bytes = SURVEY 8(d) algorithmic bytes per episode x B",
+       f"{'kernel':52s} {'us':>9s} {'alg MB':>9s} {'GB/s':>9s} {'frac':>7s}"]
+for tag, fn, bpe in rows:
+    t = timed(fn)
+    mb = bpe * B / 1e6
+    out.append(f"{tag:52s} {t * 1e6:9.1f} {mb:9.1f} {mb / 1e3 / t:9.1f} {mb / 1e3 / t / peak:7.3f}")
+txt = "\n".join(out)
+print(txt)
+dst = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "r02_hbm_kernels_summary.txt")
+open(dst, "w").write(txt + "\n")

@@ -1,0 +1,24 @@
+"""One process that launches every kernel worth an `ncu --set full` capture: three eager headline epochs (shared
+covariance, fast epoch), two epochs of the per-episode-covariance variant, and the HBM family at B = 16384."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(0)
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+if what in ("all", "epoch"):
+    agent, dataset, times, pairs = bench.build_gpu_workload(dev, 0, 1)
+    for _ in range(3):
+        agent.policy_epoch(dataset, times, pairs)
+    torch.cuda.synchronize()
+if what in ("all", "ctx"):
+    agent, dataset, times, pairs = bench.build_gpu_workload(dev, 0, 1, contextual=True)
+    for _ in range(2):
+        agent.policy_epoch(dataset, times, pairs)
+    torch.cuda.synchronize()
+if what in ("all", "hbm"):
+    sys.argv = [sys.argv[0], "16384", "/dev/null"]
+    exec(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "hbm_kernels.py")).read())
+print("done")

@@ -764,7 +764,7 @@ proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ pr
                        const double *__restrict__ save_M, const double *__restrict__ save_U,
                        const double *__restrict__ save_Li, const double *__restrict__ save_lam,
                        const double *__restrict__ save_sc, float *__restrict__ grad_L, int n, int fused_entropy,
-                       const double *__restrict__ out_inv) {
+                       const double *__restrict__ out_inv, double tr_coeff) {
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
   Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
@@ -775,7 +775,9 @@ proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ pr
   (void)L;
   const double eta = save_sc[b * KL_SC + 0];
   const bool kl_active = save_sc[b * KL_SC + 1] != 0.0;
-  if (!kl_active && !fused_entropy) {                                              // identity
+  // tr_coeff != 0: the gradient of the trust-region regression term tr_coeff * KL_cov(N(Lt Lt^T) || N(Sigma_out DETACHED))
+  // is added (see proj_kl_cov_bwd_sigma_kernel); identity KL step: Sigma_out = alpha^2 Lt Lt^T -> tr_coeff (1 / alpha^2 - 1) / Lt_ii
+  if (!kl_active && !fused_entropy) {                                              // identity (alpha = 1: no trust-region term)
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) gl[e] = (e % n <= e / n) ? gout[off + e] : 0.f;
     return;
   }
@@ -800,6 +802,11 @@ proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ pr
     }
     __syncthreads();
     if (!kl_active) {                                                              // identity KL step
+      if (tr_coeff != 0.0) {
+        const double a2 = alpha * alpha;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) b1(i, i) += tr_coeff * (1.0 / a2 - 1.0) / (double)L[off + (size_t)i * n + i];
+        __syncthreads();
+      }
       store_lower_f(gl, b1, n, 1.0);
       return;
     }
@@ -834,6 +841,10 @@ proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ pr
     const int i = e / n, j = e - i * n;
     double v = -(1.0 + eta) * rho[i] * rho[j] * (0.5 * (b1(i, j) + b1(j, i)));
     if (i == j) v -= eb * (0.5 * (rho[i] - (1.0 + eta) * rho[i] * rho[i])) / dfe;
+    if (i == j && tr_coeff != 0.0) {                                               // trust-region term, as in the sigma kernel
+      const double a2 = fused_entropy ? save_sc[b * KL_SC + 6] : 1.0;
+      v -= 0.5 * tr_coeff / (a2 * (1.0 + eta) * rho[i] * lam[i] * lam[i]);
+    }
     b2(i, j) = v;                                                                  // Nt (Phi is consumed)
   }
   load_full_d(b0, save_U + off, n, m);                                             // U~ (Y is consumed)
@@ -841,6 +852,10 @@ proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ pr
   la_gemm(b1, b3, b0.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // U~ Nt U~^T (F' is consumed)
   load_full_d(b2, save_Li + off, n, m);                                            // Lt^-1 (Nt is consumed)
   la_gemm(b3, b2.T(), b1, n, n, n, TRI_UPPER, TRI_FULL, TRI_LOWER, 1.0, 0.0);      // Lt^-T (.)
+  if (tr_coeff != 0.0) {                                                           // - tr_coeff (Lt^-T)_ii  (scaled by -2 below)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) b3(i, i) += 0.5 * tr_coeff / (double)L[off + (size_t)i * n + i];
+    __syncthreads();
+  }
   store_lower_f(gl, b3, n, -2.0);
 }
 
@@ -1362,7 +1377,8 @@ static int kl_fwd_launch(const float *L, const float *L_o, double eps_cov, const
 }
 
 static int kl_bwd_launch(const float *L, const float *proj_L, const float *grad_out, const double *save, float *grad_L,
-                         int64_t B, int n, int fused_entropy, void *stream, const double *out_inv = nullptr) {
+                         int64_t B, int n, int fused_entropy, void *stream, const double *out_inv = nullptr,
+                         double tr_coeff = 0.0) {
   if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!L || !proj_L || !grad_out || !save || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
@@ -1372,7 +1388,7 @@ static int kl_bwd_launch(const float *L, const float *proj_L, const float *grad_
   const size_t nn = (size_t)B * n * n;
   const double *M = save, *U = M + nn, *Li = U + nn, *lam = Li + 2 * nn, *sc = lam + (size_t)B * n;
   proj_kl_cov_bwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, proj_L, grad_out, M, U, Li, lam, sc, grad_L,
-                                                                                 n, fused_entropy, out_inv);
+                                                                                 n, fused_entropy, out_inv, tr_coeff);
   TCE_CHECK_LAUNCH("proj_kl_cov_bwd_kernel");
   return TCE_OK;
 }
@@ -1424,6 +1440,12 @@ extern "C" int tce_proj_kl_entropy_fwd_chol(const double *save, float *proj_L, f
 extern "C" int tce_proj_kl_entropy_bwd(const float *L, const float *proj_L, const float *grad_out, const double *save,
                                        float *grad_L, int64_t B, int n, void *stream) {
   return kl_bwd_launch(L, proj_L, grad_out, save, grad_L, B, n, 1, stream);
+}
+
+/* tce_proj_kl_entropy_bwd + the gradient of tr_coeff * KL_cov(N(L L^T) || N(Sigma_out detached)) (trust-region loss). */
+extern "C" int tce_proj_kl_entropy_bwd_tr(const float *L, const float *proj_L, const float *grad_out, const double *save,
+                                          double tr_coeff, float *grad_L, int64_t B, int n, void *stream) {
+  return kl_bwd_launch(L, proj_L, grad_out, save, grad_L, B, n, 1, stream, nullptr, tr_coeff);
 }
 
 /* Backward of tce_proj_kl_cov_fwd (fused_entropy = 0) / tce_proj_kl_entropy_fwd* (fused_entropy = 1) given the gradient

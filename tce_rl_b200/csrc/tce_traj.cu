@@ -140,6 +140,99 @@ traj_fwd_kernel(TabDev tb, const float *__restrict__ params, const float *__rest
   }
 }
 
+
+// Warp-per-slab variant (the product path): a warp owns 32 consecutive time points of ONE episode, so everything
+// per-episode (basis values at the initial time, parameters, initial conditions) is warp-uniform: the initial-condition
+// row is built cooperatively (lane j -> basis column j) and broadcast by shuffles, the parameters are warp-uniform
+// (broadcast) loads through L1, the table rows are read through L1 as well (44 KB of fp32 rows: resident).  No shared
+// staging of parameters, no CTA barrier, no serial per-episode section; the warp's 32 x 2D results go through a private
+// shared tile so that the global stores are contiguous 128-bit.  HBM traffic = the algorithmic bytes (params, initial
+// conditions and times are read once, the trajectory is written once).
+constexpr int TW_WARPS = 8;
+template <int K1, int DMAX>
+__global__ void __launch_bounds__(TW_WARPS * 32)
+traj_fwd_warp_kernel(TabDev tb, const float *__restrict__ params, const float *__restrict__ times,
+                     const float *__restrict__ init_time, const float *__restrict__ init_pos,
+                     const float *__restrict__ init_vel, float *__restrict__ traj, long long B, int T) {
+  extern __shared__ __align__(16) float tile_all[];
+  const int D = tb.D, D2 = 2 * D, Dp = D * K1, stride = tb.row32_stride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *tile = tile_all + warp * (32 * D2 + 4);
+  const int slabs = (T + 31) >> 5;
+  const long long total = B * (long long)slabs;
+  const float tau = (float)tb.tau, inv_tau_f = 1.0f / tau;
+  const double inv_tau = 1.0 / tb.tau;
+  float sc[K1];
+#pragma unroll
+  for (int j = 0; j < K1; ++j) sc[j] = (float)tb.scale[j];
+  const float goal_shift_scale = tb.relative_goal ? (tb.relative_goal_scaled ? 1.0f : 1.0f / sc[K1 - 1]) : 0.0f;
+  for (long long w = (long long)blockIdx.x * TW_WARPS + warp; w < total; w += (long long)gridDim.x * TW_WARPS) {
+    const long long b = w / slabs;
+    const int t0 = (int)(w - b * slabs) << 5, t = t0 + lane;
+    const int nt = T - t0 < 32 ? T - t0 : 32;
+    // ---- initial-condition row of the episode: lane j < K1 -> (pb_j, vb_j), lane K1 -> y1b, y2b, dy1b, dy2b ----
+    int ib; float wb;
+    time_to_index_fast(tb, inv_tau, init_time[b], ib, wb);
+    const float *q0 = tb.row32 + (size_t)ib * stride, *q1 = q0 + stride;
+    float mine0 = 0.f, mine1 = 0.f, y1b = 0.f, y2b = 0.f, dy1b = 0.f, dy2b = 0.f;
+    if (lane < K1) {
+      mine0 = lerp_t(q0[4 + lane], q1[4 + lane], wb);
+      mine1 = lerp_t(q0[4 + K1 + lane], q1[4 + K1 + lane], wb);
+    }
+    if (lane < 4) y1b = lerp_t(q0[lane], q1[lane], wb);               // lane l < 4 holds the l-th of (y1, y2, dy1, dy2)
+    y2b = __shfl_sync(0xffffffffu, y1b, 1); dy1b = __shfl_sync(0xffffffffu, y1b, 2); dy2b = __shfl_sync(0xffffffffu, y1b, 3);
+    y1b = __shfl_sync(0xffffffffu, y1b, 0);
+    const float inv_det = 1.0f / (y1b * dy2b - y2b * dy1b);
+    // ---- this lane's time point ----
+    float hp[K1], hv[K1], xi1 = 0.f, xi2 = 0.f, xi3 = 0.f, xi4 = 0.f;
+    {
+      int i0; float wf;
+      time_to_index_fast(tb, inv_tau, lane < nt ? times[b * T + t] : times[b * T + t0], i0, wf);
+      const float *r0 = tb.row32 + (size_t)i0 * stride, *r1 = r0 + stride;
+      const float y1 = lerp_t(r0[0], r1[0], wf), y2 = lerp_t(r0[1], r1[1], wf);
+      const float dy1 = lerp_t(r0[2], r1[2], wf), dy2 = lerp_t(r0[3], r1[3], wf);
+      xi1 = (dy2b * y1 - dy1b * y2) * inv_det; xi2 = (y1b * y2 - y2b * y1) * inv_det;
+      xi3 = (dy2b * dy1 - dy1b * dy2) * inv_det; xi4 = (y1b * dy2 - y2b * dy1) * inv_det;
+#pragma unroll
+      for (int j = 0; j < K1; ++j) {
+        const float pbj = __shfl_sync(0xffffffffu, mine0, j), vbj = __shfl_sync(0xffffffffu, mine1, j);
+        const float pj = lerp_t(r0[4 + j], r1[4 + j], wf), vj = lerp_t(r0[4 + K1 + j], r1[4 + K1 + j], wf);
+        hp[j] = (pj - xi1 * pbj - xi2 * vbj) * sc[j];
+        hv[j] = (vj - xi3 * pbj - xi4 * vbj) * sc[j];
+      }
+    }
+    const float *th = params + b * Dp;
+    float *o = tile + lane * D2;
+    for (int d = 0; d < D; ++d) {
+      const float y0 = init_pos[b * D + d], v0 = init_vel[b * D + d] * tau;      // warp-uniform loads
+      float p = xi1 * y0 + xi2 * v0, v = xi3 * y0 + xi4 * v0;
+#pragma unroll
+      for (int j = 0; j < K1; ++j) {
+        const float thj = th[d * K1 + j];
+        p = fmaf(hp[j], thj, p);
+        v = fmaf(hv[j], thj, v);
+      }
+      const float shift = goal_shift_scale * y0;         // relative goal (0 otherwise)
+      p = fmaf(hp[K1 - 1], shift, p);
+      v = fmaf(hv[K1 - 1], shift, v);
+      o[d] = p;
+      o[D + d] = v * inv_tau_f;
+    }
+    __syncwarp();
+    const long long g0 = b * T + t0;
+    const int n_out = nt * D2;
+    float *dst = traj + g0 * D2;
+    if ((n_out & 3) == 0 && ((g0 * D2) & 3) == 0) {
+      const float4 *s4 = reinterpret_cast<const float4 *>(tile);
+      float4 *d4 = reinterpret_cast<float4 *>(dst);
+      for (int i = lane; i < n_out / 4; i += 32) d4[i] = s4[i];
+    } else {
+      for (int i = lane; i < n_out; i += 32) dst[i] = tile[i];
+    }
+    __syncwarp();
+  }
+}
+
 // backward: one CTA per episode, thread (d, j) reduces over time.  Low priority path (the reference
 // only ever samples under no_grad), kept simple.
 template <int K1>
@@ -215,6 +308,7 @@ int num_sms() {
   return g_num_sms;
 }
 
+bool g_traj_cta = false;
 int g_traj_stage = -1;      // TCE_TRAJ_STAGE: 0 = read the basis rows through L1, 1 = stage them in smem (default)
 
 template <int K1>
@@ -224,6 +318,19 @@ int launch_traj_fwd(const tce_tables *t, const float *params, const float *times
   if (g_traj_stage < 0) {
     const char *e = getenv("TCE_TRAJ_STAGE");
     g_traj_stage = e ? atoi(e) : 1;
+    const char *k = getenv("TCE_TRAJ_KERNEL");
+    g_traj_cta = k && k[0] == 'c';                 // "cta": the chunk-per-CTA kernel (kept for cross-checks)
+  }
+  if (!g_traj_cta) {
+    const long long slabs = B * ((T + 31) / 32);
+    long long grid = (slabs + TW_WARPS - 1) / TW_WARPS;
+    const long long cap = 8LL * num_sms();
+    if (grid > cap) grid = cap;
+    const size_t smem_w = (size_t)TW_WARPS * (32 * 2 * t->D + 4) * sizeof(float);
+    traj_fwd_warp_kernel<K1, TCE_MAX_DOF><<<(unsigned)grid, TW_WARPS * 32, smem_w, st>>>(
+        tab_dev(t), params, times, init_time, init_pos, init_vel, traj, B, (int)T);
+    TCE_CHECK_LAUNCH("traj_fwd_warp_kernel");
+    return TCE_OK;
   }
   const int stride = t->row32_stride;
   const size_t row_bytes = (size_t)stride * sizeof(float);

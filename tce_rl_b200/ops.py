@@ -1021,6 +1021,21 @@ def _(grad_out, L, proj_L, state, out_inv=None):
     return torch.empty_like(L)
 
 
+@torch.library.custom_op("tce::proj_kl_entropy_bwd_tr", mutates_args=())
+def proj_kl_entropy_bwd_tr(grad_out: Tensor, L: Tensor, proj_L: Tensor, state: Tensor, tr_coeff: float) -> Tensor:
+    """``proj_kl_entropy_bwd`` + the gradient of tr_coeff * KL_cov(N(L L^T) || N(Sigma_out detached)) per matrix."""
+    g, L, proj_L = _chk(grad_out), _chk(L), _chk(proj_L)
+    out = torch.empty_like(L)
+    _lib.call("tce_proj_kl_entropy_bwd_tr", _p(L), _p(proj_L), _p(g), _p(state), float(tr_coeff), _p(out), L.shape[0],
+              L.shape[-1], _stream())
+    return out
+
+
+@proj_kl_entropy_bwd_tr.register_fake
+def _(grad_out, L, proj_L, state, tr_coeff):
+    return torch.empty_like(L)
+
+
 @torch.library.custom_op("tce::proj_kl_bwd_sigma", mutates_args=())
 def proj_kl_bwd_sigma(grad_sigma: Tensor, L: Tensor, state: Tensor, fused_entropy: bool, tr_coeff: float = 0.0) -> Tensor:
     """Backward of the KL covariance projection given d loss / d Sigma_out [Bc, n, n] fp64 (symmetric); ``tr_coeff``:
@@ -1070,10 +1085,14 @@ class _ProjKLEntropy(torch.autograd.Function):
         fold = float(getattr(ctx.holder, "_tr_fold", 0.0) or 0.0) if ctx.holder is not None else 0.0
         if ctx.holder is not None:
             ctx.holder._tr_fold = 0.0
-        if g_sigma is None and fold != 0.0:
-            g_sigma = torch.zeros(L.shape, device=L.device, dtype=torch.float64)
         if g_sigma is not None:
             res = proj_kl_bwd_sigma(g_sigma.contiguous(), L, ctx.state, True, fold)
+            fold = 0.0
+        if g is None and fold != 0.0:
+            g = torch.zeros_like(L)
+        if g is not None and fold != 0.0:          # per-matrix (contextual) covariance: the fold rides on the factor path
+            r2 = proj_kl_entropy_bwd_tr(g.contiguous(), L, proj_L, ctx.state, fold)
+            return ((r2 if res is None else res + r2),) + (None,) * 8
         if g is not None:
             # somebody (the trust-region loss) may have inverted this call's output factor: (inverse, event, data_ptr)
             known = getattr(ctx.holder, "_output_inverse", None) if ctx.holder is not None else None

@@ -274,6 +274,15 @@ class TemporalCorrelatedAgent:
         with torch.no_grad():
             mp = cache.get("new_old_mean") if kl_metric else None
             linv = getattr(self.projection, "_old_linv", None) if kl_metric else None
+            no_cov, po_cov = cache.get("new_old_cov"), cache.get("proj_old_cov")
+            if kl_metric and no_cov is not None and po_cov is not None and mp is not None:
+                # per-episode covariances projected by the fused KL kernel: every covariance term is a closed form of
+                # the eigen-systems in the projection's state -- only the two missing mean terms are evaluated
+                parts = [mp, *no_cov]
+                parts += list(cache["new_proj"]) if "new_proj" in cache else list(
+                    gaussian_kl_details(self.policy, new, proj))
+                parts += [0.5 * ops.gauss_maha(proj[0], old[0], old[1]), *po_cov]
+                return torch.stack([x.expand(new[0].shape[0]) for x in parts]).mean(dim=1)
             second = None
             if new[0].is_cuda and self.overlap_logging:     # the two decompositions are independent chains (each
                 cur = torch.cuda.current_stream()            # has a single-CTA kernel): run them side by side

@@ -154,9 +154,9 @@ class _FoldedKLLoss(torch.autograd.Function):
         B = maha.shape[0]
         _, ctx.g_maha, _ = _kl_loss_consts(B, coeff, with_cov, maha.device)
         mean_diff = 0.5 * maha
-        shape, volume = sc[:, 7].expand(B), sc[:, 8].expand(B)
+        shape, volume = sc[:, 7].expand(B), sc[:, 8].expand(B)       # [1] (shared covariance) or [B] (per episode)
         cov_diff = shape + volume
-        loss = mean_diff.mean() + cov_diff[0] if with_cov else mean_diff.mean()
+        loss = mean_diff.mean() + cov_diff.mean() if with_cov else mean_diff.mean()
         ctx.mark_non_differentiable(mean_diff, cov_diff, shape, volume)
         return (loss * coeff).to(out_dtype), mean_diff, cov_diff, shape, volume
 
@@ -259,6 +259,10 @@ class BaseProjectionLayer:
             proj_L = self._cov_projection(policy, L, old_L)
         return proj_mean, proj_L
 
+    def _trust_region_projection_with_entropy(self, policy, p, q, beta):
+        """Trust-region step + entropy control as fused kernels, or None (then the two steps run separately)."""
+        return None
+
     def _side_stream(self, device):
         if self._side is None:
             self._side = torch.cuda.Stream(device=device, priority=-1)     # the covariance chain is the critical path
@@ -276,6 +280,10 @@ class BaseProjectionLayer:
         beta = self._entropy_bound(step, p[0].device)
         if self.entropy_first:
             p = self._entropy_projection(policy, p, beta)
+        elif beta is not None:
+            fused = self._trust_region_projection_with_entropy(policy, p, q, beta)
+            if fused is not None:
+                return fused
         proj = self._trust_region_projection(policy, p, q)
         return proj if self.entropy_first else self._entropy_projection(policy, proj, beta)
 
@@ -349,6 +357,8 @@ class BaseProjectionLayer:
         together with that projection (TemporalCorrelatedAgent.policy_epoch does) -- otherwise leave it False."""
         target = (proj_p[0].detach(), proj_p[1].detach())
         kl_metric = type(self).trust_region_value is BaseProjectionLayer.trust_region_value
+        if kl_metric and fold and p[0].is_cuda and not _shared(policy, p[1]) and self._can_fold(p, proj_p):
+            return self._folded_kl_trust_region_loss(policy, p, target, set_variance)
         if kl_metric and p[0].is_cuda and _shared(policy, p[1]):
             if fold and self._can_fold(p, proj_p):
                 return self._folded_kl_trust_region_loss(policy, p, target, set_variance)
@@ -441,8 +451,39 @@ class KLProjectionLayer(BaseProjectionLayer):
 
     def _can_fold(self, p, proj_p):
         last = getattr(self, "_last_call", None)
-        return (last is not None and last["out_inv"] is not None and _first(p[1]) is last["L_in"]
-                and _first(proj_p[1]) is last["out"])
+        if last is None:
+            return False
+        if last.get("per_episode"):
+            return p[1] is last["L_in"] and proj_p[1] is last["out"]
+        return last["out_inv"] is not None and _first(p[1]) is last["L_in"] and _first(proj_p[1]) is last["out"]
+
+    def _trust_region_projection_with_entropy(self, policy, p, q, beta):
+        """Per-episode covariance factors (contextual policy): KL projection + entropy control of all B matrices in ONE
+        kernel each way (instead of projection + entropy-scaling kernels), and the eigen-system of every matrix stays
+        in the state: the covariance terms of the trust-region loss and of the logging decomposition are closed forms
+        of it (``cache``: no gauss_stats launches), the trust-region covariance gradient is added inside the backward
+        kernel (``get_trust_region_loss(fold=True)``)."""
+        if (not policy.contextual_std or policy.is_diag or not self.fuse_entropy or not p[1].is_cuda
+                or p[1].shape[-1] > 64):
+            return None
+        mean, L = p
+        old_mean, old_L = q
+        mean_part = self._mean_part(policy, p, q)
+        proj_mean = ops.proj_mean(mean, old_mean, mean_part, self.mean_bound)
+        Lc = L.contiguous()
+        state = self._state_for(Lc)
+        self._last_state = state
+        self._output_inverse = None
+        out, _proj, _info, _sigma, _scale, _inv = ops.proj_kl_entropy(
+            Lc, old_L.contiguous(), self.cov_bound, state, self.warm_start, beta, self.entropy_eq, False, self,
+            return_sigma=True)
+        sc = ops.kl_state_scalars(state, Lc.shape[0], Lc.shape[-1]).detach()
+        self.cache = {"new_old_mean": mean_part.detach(),
+                      "new_old_cov": (sc[:, 10] + sc[:, 11], sc[:, 10], sc[:, 11]),
+                      "proj_old_cov": (sc[:, 12] + sc[:, 13], sc[:, 12], sc[:, 13])}
+        self._last_call = dict(L_in=L, out=out, out_inv=None, state=state, per_episode=True)
+        self._tr_fold = 0.0
+        return proj_mean, out
 
     def _folded_kl_trust_region_loss(self, policy, p, target, set_variance):
         """Shared covariance, target = this layer's last output: Mahalanobis term with the inverse the forward's
@@ -450,12 +491,18 @@ class KLProjectionLayer(BaseProjectionLayer):
         its gradient is added by the projection's backward kernel (``_tr_fold``)."""
         last = self._last_call
         n = p[0].shape[-1]
-        linv = last["out_inv"][0]
-        self._output_inverse = None
-        maha = _maha(policy, p[0], target[0], target[1], linv=linv)
         with_cov = self._with_cov(policy, set_variance)
-        sc = ops.kl_state_scalars(last["state"], 1, n)
-        self._tr_fold = float(self.trust_region_coeff) if with_cov else 0.0
+        if last.get("per_episode"):                        # B matrices: mean term per episode, covariance terms from the state
+            B = p[0].shape[0]
+            maha = ops.gauss_maha(p[0], target[0], target[1])
+            sc = ops.kl_state_scalars(last["state"], B, n)
+            self._tr_fold = float(self.trust_region_coeff) / B if with_cov else 0.0     # loss = mean over the B matrices
+        else:
+            linv = last["out_inv"][0]
+            self._output_inverse = None
+            maha = _maha(policy, p[0], target[0], target[1], linv=linv)
+            sc = ops.kl_state_scalars(last["state"], 1, n)
+            self._tr_fold = float(self.trust_region_coeff) if with_cov else 0.0
         loss, mean_diff, cov_diff, shape, volume = _FoldedKLLoss.apply(
             maha, sc, float(self.trust_region_coeff), bool(with_cov), p[0].dtype)
         self.cache["new_proj"] = (mean_diff, cov_diff, shape, volume)
