@@ -702,6 +702,9 @@ def run_ours(args):
                                    "are each ONE [63,63] matrix broadcast over the batch with stride 0 (the reference "
                                    "repeats them B times); the per-episode layout is config.variants.contextual_P24",
                        "kl_warm_start": True,
+                       "grad_exchange": ("none (1 GPU)" if world == 1 else
+                                         "fused NVLink peer-memory all-reduce + gradient norm (tce_p2p_allreduce_sumsq)"
+                                         if getattr(agent, "_p2p", None) is not None else "NCCL all_reduce(AVG)"),
                        "kl_warm_start_note": "every timed step projects against the same old factor, so the eigenbasis "
                                              "warm start always hits: a real update is 1 cold + 49 warm epochs per "
                                              "dataset (cold epoch: +0.1-0.2 ms once per 50)",

@@ -362,6 +362,19 @@ int tce_adam_step(int count, float *const *params, const int64_t *sizes, const f
                   float *v, const double *state, double max_norm, double lr, double beta1, double beta2,
                   double eps, double weight_decay, void *stream);
 
+/* ---- data-parallel gradient exchange fused with the gradient norm, over NVLink peer memory (csrc/tce_p2p.cu) ----
+ * Replaces ncclAllReduce(AVG) of the flat gradient + tce_grad_sumsq per optimiser step (SURVEY 8(e) collective (1)).
+ * peer_bufs[r] / peer_pads[r] (HOST arrays of `world` device pointers): rank r's flat gradient buffer (n floats,
+ * 16-byte aligned) and signal pad (>= 2 * world uint64, zero-initialised once) as mapped into THIS process
+ * (symmetric memory: torch.distributed._symmetric_memory rendezvous, or cudaIpc / cuMem mappings).
+ * avg_out [n] (local) receives (1/world) * sum_r peer_bufs[r] summed in rank order (bit-identical on all ranks);
+ * state3 = {step += 1, sum of squares of avg_out += , error flag (1 = a peer did not arrive within ~2 s)};
+ * local2 = two uint64 of local device memory, zero-initialised once (launch sequence number, block ticket).
+ * Every rank must launch it the same number of times.  On return (stream order) every peer has finished reading
+ * this rank's buffer, which may then be overwritten.                                                         */
+int tce_p2p_allreduce_sumsq(int world, int rank, const void *const *peer_bufs, void *const *peer_pads, int64_t n,
+                            float *avg_out, void *local2, double *state3, void *stream);
+
 /* ---- mean chain of a policy epoch with ONE shared covariance (csrc/tce_epoch.cu) -----------------------------
  * Replaces, for the non-contextual policies of every shipped config, the per-episode pieces between the policy
  * network and the segment likelihood: the mean part of the KL metric and the mean projection

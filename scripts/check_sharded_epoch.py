@@ -114,7 +114,7 @@ def main():
                             max_err_segment_advantage=errs[0].item(), max_err_updated_parameters=errs[1].item(),
                             max_rel_err_logging_means=errs[2].item(), parameters_moved_by=moved,
                             uniform_everywhere=bool(__import__("tce_rl_b200.ops_seglik", fromlist=["x"])._GLOBAL_UNIFORM),
-                            epochs=4))
+                            grad_exchange="p2p_fused" if agent._p2p is not None else "nccl", epochs=4))
     ok = all(r["max_err_segment_advantage"] <= 1e-5 and r["max_err_updated_parameters"] <= 1e-6
              and r["max_rel_err_logging_means"] <= 1e-5 for r in results)
     if rank == 0:

@@ -90,6 +90,7 @@ SIGNATURES = {
     "tce_seglik_uniform_main": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _D, _P, _P, _P, _P, _P, _I64,
                                           _I64, _I64, _P]),
     "tce_seglik_uniform_finish": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P, _I64, _P]),
+    "tce_p2p_allreduce_sumsq": (C.c_int, [_I32, _I32, _P, _P, _I64, _P, _P, _P, _P]),
     "tce_epoch_mean_fwd": (C.c_int, [_P, _P, _P, _D, _P, _P, _P, _P, _I64, _I32, _P]),
     "tce_epoch_tr_mean": (C.c_int, [_P, _P, _P, _P, _P, _P, _D, _D, _P, _P, _I64, _I32, _P]),
     "tce_epoch_mean_combine": (C.c_int, [_P, _P, _P, _P, _P, _P, _D, _P, _I64, _I32, _P]),

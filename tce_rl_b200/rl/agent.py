@@ -85,6 +85,9 @@ class TemporalCorrelatedAgent:
         # hand-scheduled epoch for the shipped configuration (shared covariance + KL projection), rl/fast_epoch.py;
         # False = always the generic autograd-driven epoch below (any policy / projection layer)
         self.fast_epoch = bool(kwargs.get("fast_epoch", True))
+        # data parallel: exchange the flat gradient with the fused NVLink peer-memory kernel (rl/p2p.py) instead of NCCL
+        self.p2p_allreduce = bool(kwargs.get("p2p_allreduce", True))
+        self._p2p = None
         self._fast = None
         if self.overlap_logging and hasattr(policy, "mean_net") and hasattr(policy.mean_net, "side_wgrad"):
             policy.mean_net.side_wgrad = True              # joined after every backward of policy_epoch
@@ -133,6 +136,9 @@ class TemporalCorrelatedAgent:
         if not self._distributed:
             return
         flat = self._flat_grad
+        if (getattr(self, "_p2p", None) is not None and flat is not None and params is self.policy_net_params
+                and getattr(self.policy_optimizer, "reducer", None) is self._p2p):
+            return                 # exchanged inside FlatAdam.step (fused with the gradient norm, rl/p2p.py)
         if flat is not None and self._flat_grad_ok(params):        # gradients already live in one buffer
             if dist.get_backend(self._group()) == "nccl":
                 dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self._group())
@@ -163,7 +169,14 @@ class TemporalCorrelatedAgent:
         params = list(params)
         if self._flat_grad is not None and self._flat_grad_ok(params):
             return
-        flat = torch.zeros(sum(p.numel() for p in params), dtype=params[0].dtype, device=params[0].device)
+        numel = sum(p.numel() for p in params)
+        self._p2p = None
+        if self._distributed and self.p2p_allreduce and self.use_flat_adam and params[0].is_cuda:
+            from . import p2p
+            if p2p.available(self._group()):
+                self._p2p = p2p.P2PGradBuffer(numel, params[0].device, self._group())
+        flat = self._p2p.buffer if self._p2p is not None else torch.zeros(numel, dtype=params[0].dtype,
+                                                                          device=params[0].device)
         off = 0
         for p in params:
             view = flat[off:off + p.numel()].view_as(p)
@@ -174,6 +187,8 @@ class TemporalCorrelatedAgent:
         self._flat_grad = flat
         if params and params[0] is self.policy_net_params[0] and self.use_flat_adam:
             self._use_flat_adam()
+            if self._p2p is not None and hasattr(self.policy_optimizer, "reducer"):
+                self.policy_optimizer.reducer = self._p2p
 
     def _global_mean(self, x):
         """Mean over the global batch (equal shard sizes)."""
@@ -523,8 +538,13 @@ class TemporalCorrelatedAgent:
             self._zero_policy_grads()
             loss.backward()
             util.join_side_grads()
-            self._allreduce_grads(self.policy_net_params)
-            norms.append(self._flat_grad_norm())
+            if self._p2p is not None and getattr(self.policy_optimizer, "reducer", None) is self._p2p:
+                st = torch.zeros(3, device=self._flat_grad.device, dtype=torch.float64)
+                self._p2p.allreduce_sumsq(st)                 # global gradient: averaged over the ranks
+                norms.append(st[1].sqrt())
+            else:
+                self._allreduce_grads(self.policy_net_params)
+                norms.append(self._flat_grad_norm())
         return torch.stack(norms)
 
     def policy_epoch(self, dataset, times, pred_pairs):
@@ -698,6 +718,8 @@ class TemporalCorrelatedAgent:
         if balance_rows:
             metrics = torch.cat([metrics, torch.stack(balance_rows).to(metrics.dtype)], dim=1)
         metrics = metrics.cpu().numpy()                      # the ONE synchronisation of the update
+        if self._p2p is not None and float(self.policy_optimizer.stats[2].item()) != 0.0:
+            raise RuntimeError("data-parallel gradient exchange: a peer did not arrive (tce_p2p_allreduce_sumsq timed out)")
         if not np.isfinite(metrics[:, :4]).all():
             raise Exception("NAN loss detected")           # temporal_correlated_agent.py:569-577
         out = {}

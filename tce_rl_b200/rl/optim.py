@@ -30,7 +30,8 @@ class FlatAdam(torch.optim.Optimizer):
             raise TceError("flat gradient buffer does not match the parameters")
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=flat_grad.device)
         self.exp_avg_sq = torch.zeros_like(self.exp_avg)
-        self.stats = torch.zeros(2, dtype=torch.float64, device=flat_grad.device)     # {step, sum g^2}
+        self.stats = torch.zeros(3, dtype=torch.float64, device=flat_grad.device)     # {step, sum g^2, p2p error flag}
+        self.reducer = None        # rl.p2p.P2PGradBuffer: all-reduce fused with the gradient norm (data parallel)
         self._params = params
         self._sizes = (C.c_int64 * len(params))(*[p.numel() for p in params])
 
@@ -80,7 +81,7 @@ class FlatAdam(torch.optim.Optimizer):
     def begin(self):
         """Clear the gradients and the norm accumulator (call before backward; cheap, can be issued early)."""
         self.flat_grad.zero_()
-        self.stats[1:].zero_()
+        self.stats[1:2].zero_()
 
     def zero_grad(self, set_to_none: bool = False):
         self.begin()
@@ -95,8 +96,12 @@ class FlatAdam(torch.optim.Optimizer):
         g = self.param_groups[0]
         st = torch.cuda.current_stream().cuda_stream
         ptrs = (C.c_void_p * len(self._params))(*[p.data_ptr() for p in self._params])
-        _lib.call("tce_grad_sumsq", self.flat_grad.data_ptr(), self.flat_grad.numel(), self.stats.data_ptr(), st)
+        if self.reducer is not None:           # averaged over the ranks through NVLink peer memory, norm in the same launch
+            grad = self.reducer.allreduce_sumsq(self.stats)
+        else:
+            grad = self.flat_grad
+            _lib.call("tce_grad_sumsq", grad.data_ptr(), grad.numel(), self.stats.data_ptr(), st)
         _lib.call("tce_adam_step", len(self._params), C.cast(ptrs, C.c_void_p), C.cast(self._sizes, C.c_void_p),
-                  self.flat_grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                  grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                   self.stats.data_ptr(), float(max_norm), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
                   float(g["eps"]), float(g["weight_decay"]), st)
