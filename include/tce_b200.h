@@ -194,6 +194,23 @@ int tce_proj_kl_entropy_bwd_tr(const float *L, const float *proj_L, const float 
                                double tr_coeff, float *grad_L, int64_t B, int n, void *stream);
 int tce_proj_kl_bwd_sigma(const float *L, const double *grad_sigma, const double *save, int fused_entropy,
                           double tr_coeff, float *grad_L, int64_t B, int n, void *stream);
+/* tce_proj_kl_bwd_prep: K = L~^-T U~ into the state -- the part of the covariance-space backward that does not depend
+ * on the incoming gradient; run it after the forward while the consumer of the covariance is busy.
+ * tce_proj_kl_bwd_sigma_k: tce_proj_kl_bwd_sigma using that K (4 GEMMs instead of 5, one matrix load less).    */
+/* Policy head fused into the projection (shipped configuration: one covariance vector for the batch):
+ * tce_proj_kl_entropy_fwd_sigma_vec = tce_policy_head_fwd + tce_proj_kl_entropy_fwd_sigma in one launch (the factor is
+ * also written to L_built); tce_proj_kl_bwd_sigma_k_vec = tce_proj_kl_bwd_sigma_k + tce_policy_head_bwd (gradient
+ * w.r.t. the covariance vector, overwritten).  abstract_policy.py:166-187, black_box_policy.py:30-56.           */
+int tce_proj_kl_entropy_fwd_sigma_vec(const float *vec, int64_t ldb_vec, float min_std, float *L_built,
+                                      const float *L_o, double eps_cov, const double *beta, int64_t ldb_beta,
+                                      int equality, float *proj_L, float *out_L, double *save, int32_t *info,
+                                      int warm_start, int64_t B, int n, void *stream);
+int tce_proj_kl_bwd_sigma_k_vec(const float *L, const float *vec, int64_t ldb_vec, const double *grad_sigma,
+                                const double *save, int fused_entropy, double tr_coeff, float *grad_vec, int64_t B,
+                                int n, void *stream);
+int tce_proj_kl_bwd_prep(double *save, int64_t B, int n, void *stream);
+int tce_proj_kl_bwd_sigma_k(const float *L, const double *grad_sigma, const double *save, int fused_entropy,
+                            double tr_coeff, float *grad_L, int64_t B, int n, void *stream);
 /* tce_proj_kl_entropy_fwd in two launches: _sigma writes the state (Sigma_proj, alpha = entropy scale from the
  * closed-form log-determinant, ...; for an inactive projection also the outputs); _chol forms
  * proj_L = chol(Sigma_proj) and out_L = alpha proj_L from the state.  What only needs the covariance

@@ -32,9 +32,13 @@ tmp = "/tmp/trace.json"
 prof.export_chrome_trace(tmp)
 ev = [e for e in json.load(open(tmp))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
 ev.sort(key=lambda e: e["ts"])
-# keep the last replay: it starts with the last launch of the policy head
-cut = max(i for i, e in enumerate(ev) if "head_fwd_kernel" in e["name"])
-ev = ev[cut:]
+# keep the last replay: everything after the previous epoch's last kernel (metrics assembly / policy head as markers)
+ends = [i for i, e in enumerate(ev) if "epoch_metrics_kernel" in e["name"]]
+if len(ends) >= 2:
+    ev = ev[ends[-2] + 1:]
+else:
+    cut = max(i for i, e in enumerate(ev) if "head_fwd_kernel" in e["name"])
+    ev = ev[cut:]
 t0 = ev[0]["ts"]
 with open(out, "w") as f:
     f.write(f"# {len(ev)} GPU activities, span {ev[-1]['ts'] + ev[-1]['dur'] - t0:.1f} us\n# start_us dur_us stream name\n")

@@ -61,6 +61,11 @@ SIGNATURES = {
     "tce_proj_kl_entropy_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
     "tce_proj_kl_entropy_bwd_tr": (C.c_int, [_P, _P, _P, _P, _D, _P, _I64, _I32, _P]),
     "tce_proj_kl_bwd_sigma": (C.c_int, [_P, _P, _P, _I32, _D, _P, _I64, _I32, _P]),
+    "tce_proj_kl_bwd_sigma_k": (C.c_int, [_P, _P, _P, _I32, _D, _P, _I64, _I32, _P]),
+    "tce_proj_kl_bwd_prep": (C.c_int, [_P, _I64, _I32, _P]),
+    "tce_proj_kl_entropy_fwd_sigma_vec": (C.c_int, [_P, _I64, _F, _P, _P, _D, _P, _I64, _I32, _P, _P, _P, _P, _I32, _I64,
+                                                    _I32, _P]),
+    "tce_proj_kl_bwd_sigma_k_vec": (C.c_int, [_P, _P, _I64, _P, _P, _I32, _D, _P, _I64, _I32, _P]),
     "tce_proj_kl_entropy_bwd_inv": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "tce_proj_kl_entropy_fwd_sigma": (C.c_int, [_P, _P, _D, _P, _I64, _I32, _P, _P, _P, _P, _I32, _I64, _I32, _P]),
     "tce_proj_kl_entropy_fwd_chol": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),

@@ -532,7 +532,8 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
                        double *__restrict__ save_Li, double *__restrict__ save_Sig, double *__restrict__ save_lam,
                        double *__restrict__ save_sc, int32_t *__restrict__ info, int n, int warm_start,
                        const double *__restrict__ beta,
-                       long long ldb_beta, int entropy_eq, float *__restrict__ out_L, int split) {
+                       long long ldb_beta, int entropy_eq, float *__restrict__ out_L, int split,
+                       const float *__restrict__ vec, long long ldb_vec, float min_std, float *__restrict__ L_built) {
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
   Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
@@ -540,7 +541,11 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   __shared__ int s_bad;
   const long long b = blockIdx.x;
   const size_t off = (size_t)b * n * n;
-  const float *Lt = L + off, *Lo = L_o + off;
+  // `vec` != NULL: the policy head is fused in -- Lt is built from the covariance vector (softplus(v_i) + min_std on the
+  // diagonal, strictly-lower entries row-major behind the first n: abstract_policy.py:166-187) and also written to
+  // L_built for the kernels that read the factor later.
+  const float *Lt = vec ? L_built + off : L + off, *Lo = L_o + off;
+  const float *vb = vec ? vec + b * ldb_vec : nullptr;
   if (threadIdx.x == 0) s_bad = 0;
   KL_STAMP(0);
   // All three input matrices are requested before anything is consumed (EIGHT global loads in flight per thread: the
@@ -556,7 +561,12 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int e = e0 + u * step;
-        vt[u] = e < total ? Lt[e] : 0.f;
+        if (vb) {
+          const int i = e / n, j = e - i * n;
+          vt[u] = (e < total && j <= i) ? (j == i ? vb[i] : vb[n + i * (i - 1) / 2 + j]) : 0.f;
+        } else {
+          vt[u] = e < total ? Lt[e] : 0.f;
+        }
         vo[u] = e < total ? Lo[e] : 0.f;
         vm[u] = (e < total && warm_start) ? save_M[off + e] : 0.0;
       }
@@ -565,6 +575,10 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
         const int e = e0 + u * step;
         if (e < total) {
           const int i = e / n, j = e - i * n;
+          if (vb) {
+            if (i == j) vt[u] = (vt[u] > 20.f ? vt[u] : log1pf(expf(vt[u]))) + min_std;     // head_fwd_kernel's softplus
+            L_built[off + e] = j <= i ? vt[u] : 0.f;
+          }
           b0(i, j) = j <= i ? (double)vt[u] : 0.0;
           b3(i, j) = j <= i ? (double)vo[u] : 0.0;
           b1(i, j) = vm[u];
@@ -685,7 +699,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
     store_full_rows(save_Sig + off, b1, n, threadIdx.x, blockDim.x);
     const double alpha = tail_scalars([&](int i, double) { return log(b0(i, i)); }, false);
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-      const float v = (e % n <= e / n) ? Lt[e] : 0.f;
+      const float v = (e % n <= e / n) ? (float)b0(e / n, e % n) : 0.f;          // Lt (fp32 values, exact in fp64)
       out[e] = v;
       if (out_L) out_L[off + e] = (float)(alpha * (double)v);
     }
@@ -868,28 +882,78 @@ proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ pr
 // and the rest is the implicit differentiation of proj_kl_cov_bwd_kernel.  Neither the factor P, nor P^-1, nor the
 // Cholesky adjoint appear: 5 GEMMs instead of 7 + a triangular inverse, and the forward need not form P on the
 // critical path at all (tce_proj_kl_entropy_fwd_sigma).
+// K = Lt^-T U~ : the part of the covariance-space backward that does not depend on the incoming gradient.  Launched
+// right after the forward on the covariance stream it runs while the segment likelihood is busy and takes one GEMM and
+// one matrix load off the backward's critical path.
+__global__ void __launch_bounds__(KL_THREADS)
+kl_bwd_prep_kernel(const double *__restrict__ save_U, const double *__restrict__ save_Li, const double *__restrict__ save_sc,
+                   double *__restrict__ save_K, int n) {
+  extern __shared__ double sd[];
+  const int m = pad_even(n), LD = m + 1, MS = m * LD;
+  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1};
+  const long long b = blockIdx.x;
+  const size_t off = (size_t)b * n * n;
+  if (save_sc[b * KL_SC + 1] == 0.0) return;                                        // identity step: K is not used
+  {
+    const int total = n * n, step = (int)blockDim.x;
+    for (int e0 = threadIdx.x; e0 < total; e0 += 4 * step) {
+      double vu[4], vl[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * step;
+        vu[u] = e < total ? save_U[off + e] : 0.0;
+        vl[u] = e < total ? save_Li[off + e] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * step;
+        if (e < total) { const int i = e / n, j = e - i * n; b0(i, j) = vu[u]; b1(i, j) = vl[u]; }
+      }
+    }
+    zero_padding(b0, n, m);
+    zero_padding(b1, n, m);
+    __syncthreads();
+  }
+  la_gemm(b2, b1.T(), b0, n, n, n, TRI_UPPER, TRI_FULL, TRI_FULL, 1.0, 0.0);        // Lt^-T U~
+  store_full_rows(save_K + off, b2, n, threadIdx.x, blockDim.x);
+}
+
 __global__ void __launch_bounds__(KL_THREADS)
 proj_kl_cov_bwd_sigma_kernel(const float *__restrict__ L, const double *__restrict__ gsig,
                              const double *__restrict__ save_M, const double *__restrict__ save_U,
                              const double *__restrict__ save_Li, const double *__restrict__ save_Sig,
                              const double *__restrict__ save_lam, const double *__restrict__ save_sc,
-                             float *__restrict__ grad_L, int n, int fused_entropy, double tr_coeff) {
+                             const double *__restrict__ save_K, float *__restrict__ grad_L, int n, int fused_entropy,
+                             double tr_coeff, const float *__restrict__ vec, long long ldb_vec,
+                             float *__restrict__ grad_vec) {
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
-  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
-  double *dinv = sd + 4 * MS, *lam = dinv + LA_DINV_DOUBLES, *rho = lam + m, *red = rho + m;
+  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1}, b4{sd + 4 * MS, LD, 1},
+      b5{sd + 5 * MS, LD, 1};
+  double *dinv = sd + 6 * MS, *lam = dinv + LA_DINV_DOUBLES, *rho = lam + m, *red = rho + m;
   const long long b = blockIdx.x;
   const size_t off = (size_t)b * n * n;
-  float *gl = grad_L + off;
+  float *gl = grad_L ? grad_L + off : nullptr;
+  // grad_vec != NULL: the adjoint of the policy head is fused in (head_bwd_kernel): the gradient is written w.r.t. the
+  // covariance vector -- strictly-lower entries copied, diagonal entries times sigmoid(v_i) -- instead of w.r.t. Lt
+  const float *vb = grad_vec ? vec + b * ldb_vec : nullptr;
+  float *gv = grad_vec ? grad_vec + b * (long long)(n + n * (n - 1) / 2) : nullptr;
+  auto emit = [&](int i, int j, double v) {
+    if (gv) {
+      if (j < i) gv[n + i * (i - 1) / 2 + j] = (float)v;
+      else if (j == i) gv[i] = (float)(v / (1.0 + exp(-(double)vb[i])));
+    } else {
+      gl[(size_t)i * n + j] = (float)v;
+    }
+  };
   const double eta = save_sc[b * KL_SC + 0];
   const bool kl_active = save_sc[b * KL_SC + 1] != 0.0;
   const double alpha = fused_entropy ? save_sc[b * KL_SC + 4] : 1.0, a2 = alpha * alpha;
   const bool ent_active = fused_entropy && save_sc[b * KL_SC + 5] != 0.0;
   KL_STAMP(16);
-  load_full_d(b0, gsig + off, n, m);                                               // Sbar_out
-  KL_STAMP(17);
   if (!kl_active) {
     // identity KL step: Sigma_proj = Lt Lt^T, grad_Lt = 2 alpha^2 tril(Sbar_out Lt) - (2 alpha^2 c / n) diag(1 / Lt_ii)
+    load_full_d(b0, gsig + off, n, m);                                             // Sbar_out
     load_lower_d(b1, L + off, n, m);                                               // Lt
     double c = 0.0;
     if (ent_active) {
@@ -902,57 +966,97 @@ proj_kl_cov_bwd_sigma_kernel(const float *__restrict__ L, const double *__restri
       double v = j <= i ? 2.0 * a2 * b2(i, j) : 0.0;
       if (i == j && ent_active) v -= 2.0 * a2 * c / (n * b1(i, i));
       if (i == j) v += tr_coeff * (1.0 / a2 - 1.0) / b1(i, i);      // trust-region term: Sigma_t = alpha^2 Sigma
-      gl[e] = (float)v;
+      emit(i, j, v);
     }
     return;
   }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) { lam[i] = save_lam[b * n + i]; rho[i] = 1.0 / (lam[i] + eta); }
-  load_full_d(b1, save_M + off, n, m);                                             // M
+  // Every matrix the backward needs is requested at once (eight loads in flight per thread): Sbar_out -> b0, M -> b1,
+  // U~ -> b4, and K = Lt^-T U~ -> b5 when tce_proj_kl_bwd_prep ran (else Lt^-1 -> b5).
+  {
+    const double *src3 = save_K ? save_K : save_Li;
+    const int total = n * n, step = (int)blockDim.x;
+    for (int e0 = threadIdx.x; e0 < total; e0 += 2 * step) {
+      double v0[2], v1[2], v2[2], v3[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int e = e0 + u * step;
+        const bool ok = e < total;
+        v0[u] = ok ? gsig[off + e] : 0.0; v1[u] = ok ? save_M[off + e] : 0.0;
+        v2[u] = ok ? save_U[off + e] : 0.0; v3[u] = ok ? src3[off + e] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int e = e0 + u * step;
+        if (e < total) {
+          const int i = e / n, j = e - i * n;
+          b0(i, j) = v0[u]; b1(i, j) = v1[u]; b4(i, j) = v2[u]; b5(i, j) = v3[u];
+        }
+      }
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { lam[i] = save_lam[b * n + i]; rho[i] = 1.0 / (lam[i] + eta); }
+    zero_padding(b0, n, m); zero_padding(b1, n, m); zero_padding(b4, n, m); zero_padding(b5, n, m);
+    __syncthreads();
+  }
+  KL_STAMP(17);
   KL_STAMP(18);
   la_gemm(b2, b0, b1, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);            // Sbar_out M
   KL_STAMP(19);
   la_gemm(b3, b1.T(), b2, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // F0 = M^T Sbar_out M
   KL_STAMP(20);
-  double c = 0.0;
-  if (ent_active) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) c += (1.0 + eta) * rho[i] * b3(i, i);
-    c = block_sum(c, red);
+  // c = <Sbar_out, Sigma_proj> = sum_i D_ii F0_ii (entropy adjoint), etabar, d f / d eta: one reduction
+  double v3s[3] = {0.0, 0.0, 0.0};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    v3s[0] += (1.0 + eta) * rho[i] * b3(i, i);
+    v3s[2] += 2.0 * rho[i] - (1.0 + eta) * rho[i] * rho[i] - 1.0 / (1.0 + eta);
   }
-  double eb = 0.0, dfe = 0.0;
+  block_sum_n<3>(v3s, red);
+  const double c = ent_active ? v3s[0] : 0.0, dfe = 0.5 * v3s[2];
+  double eb = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double ft = a2 * (b3(i, i) - (ent_active ? c / (n * (1.0 + eta) * rho[i]) : 0.0));
     eb += ft * (rho[i] - (1.0 + eta) * rho[i] * rho[i]);
-    dfe += 2.0 * rho[i] - (1.0 + eta) * rho[i] * rho[i] - 1.0 / (1.0 + eta);
   }
   eb = block_sum(eb, red);
-  dfe = 0.5 * block_sum(dfe, red);
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-    const int i = e / n, j = e - i * n;
-    double ft = a2 * 0.5 * (b3(i, j) + b3(j, i));
-    if (i == j && ent_active) ft -= a2 * c / (n * (1.0 + eta) * rho[i]);
-    double v = -(1.0 + eta) * rho[i] * rho[j] * ft;
-    if (i == j) v -= eb * (0.5 * (rho[i] - (1.0 + eta) * rho[i] * rho[i])) / dfe;
-    // trust-region regression term tr_coeff * KL_cov(N(Sigma) || N(Sigma_t)), Sigma_t = alpha^2 Sigma_proj DETACHED:
-    // d / d Lt = tr_coeff (Sigma_t^-1 Lt - Lt^-T), Sigma_t^-1 Lt = Lt^-T U~ diag(1 / (alpha^2 lam_i^2 D_ii)) U~^T
-    if (i == j) v -= 0.5 * tr_coeff / (a2 * (1.0 + eta) * rho[i] * lam[i] * lam[i]);
-    b2(i, j) = v;                                                                  // Nt
+  {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (int)(blockDim.x >> 5);
+    for (int i = w; i < n; i += nw)
+      for (int j = lane; j < n; j += 32) {
+        double ft = a2 * 0.5 * (b3(i, j) + b3(j, i));
+        if (i == j && ent_active) ft -= a2 * c / (n * (1.0 + eta) * rho[i]);
+        double v = -(1.0 + eta) * rho[i] * rho[j] * ft;
+        if (i == j) v -= eb * (0.5 * (rho[i] - (1.0 + eta) * rho[i] * rho[i])) / dfe;
+        // trust-region regression term tr_coeff * KL_cov(N(Sigma) || N(Sigma_t)), Sigma_t = alpha^2 Sigma_proj DETACHED:
+        // d / d Lt = tr_coeff (Sigma_t^-1 Lt - Lt^-T), Sigma_t^-1 Lt = Lt^-T U~ diag(1 / (alpha^2 lam_i^2 D_ii)) U~^T
+        if (i == j) v -= 0.5 * tr_coeff / (a2 * (1.0 + eta) * rho[i] * lam[i] * lam[i]);
+        b2(i, j) = v;                                                              // Nt
+      }
   }
+  __syncthreads();
   KL_STAMP(21);
-  load_full_d(b0, save_U + off, n, m);                                             // U~
   KL_STAMP(22);
-  la_gemm(b3, b0, b2, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);            // U~ Nt
-  KL_STAMP(23);
-  la_gemm(b1, b3, b0.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // U~ Nt U~^T
-  KL_STAMP(24);
-  load_full_d(b2, save_Li + off, n, m);                                            // Lt^-1
-  KL_STAMP(25);
-  la_gemm(b3, b2.T(), b1, n, n, n, TRI_UPPER, TRI_FULL, TRI_LOWER, 1.0, 0.0);      // Lt^-T (.)
+  if (save_K) {
+    la_gemm(b0, b2, b4.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);      // Nt U~^T
+    KL_STAMP(23);
+    la_gemm(b3, b5, b0, n, n, n, TRI_FULL, TRI_FULL, TRI_LOWER, 1.0, 0.0);         // K (Nt U~^T) = Lt^-T U~ Nt U~^T
+    KL_STAMP(24);
+    KL_STAMP(25);
+  } else {
+    la_gemm(b3, b4, b2, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);          // U~ Nt
+    KL_STAMP(23);
+    la_gemm(b1, b3, b4.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);      // U~ Nt U~^T
+    KL_STAMP(24);
+    KL_STAMP(25);
+    la_gemm(b3, b5.T(), b1, n, n, n, TRI_UPPER, TRI_FULL, TRI_LOWER, 1.0, 0.0);    // Lt^-T (.)
+  }
   KL_STAMP(26);
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-    const int i = e / n, j = e - i * n;
-    double v = j <= i ? -2.0 * b3(i, j) : 0.0;
-    if (i == j && tr_coeff != 0.0) v -= tr_coeff / (double)L[off + e];              // - tr_coeff (Lt^-T)_ii
-    gl[e] = (float)v;
+  {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (int)(blockDim.x >> 5);
+    for (int i = w; i < n; i += nw)
+      for (int j = lane; j < n; j += 32) {
+        double v = j <= i ? -2.0 * b3(i, j) : 0.0;
+        if (i == j && tr_coeff != 0.0) v -= tr_coeff / (double)L[off + (size_t)i * n + i];          // - tr_coeff (Lt^-T)_ii
+        emit(i, j, v);
+      }
   }
   KL_STAMP(27);
 }
@@ -1356,13 +1460,16 @@ extern "C" int tce_debug_kl_phase_cycles(long long *out32) {
 #endif
 }
 
-extern "C" size_t tce_proj_kl_save_doubles(int64_t B, int n) { return (size_t)B * (4 * (size_t)n * n + n + KL_SC); }
+// {M, U~, Lt^-1, Sigma_proj [B,n,n each], lam [B,n], scalars [B,KL_SC], K = Lt^-T U~ [B,n,n] (tce_proj_kl_bwd_prep)}
+extern "C" size_t tce_proj_kl_save_doubles(int64_t B, int n) { return (size_t)B * (5 * (size_t)n * n + n + KL_SC); }
 
 static int kl_fwd_launch(const float *L, const float *L_o, double eps_cov, const double *beta, int64_t ldb_beta,
                          int equality, float *proj_L, float *out_L, double *save, int32_t *info, int warm_start,
-                         int64_t B, int n, void *stream, int split = 0) {
+                         int64_t B, int n, void *stream, int split = 0, const float *vec = nullptr,
+                         int64_t ldb_vec = 0, float min_std = 0.f, float *L_built = nullptr) {
   if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
-  if (!L || !L_o || !proj_L || !save || B < 0 || !(eps_cov > 0)) return TCE_ERR_INVALID_ARGUMENT;
+  if ((!L && !vec) || (vec && !L_built) || !L_o || !proj_L || !save || B < 0 || !(eps_cov > 0))
+    return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
   const size_t smem = pj_smem_exclusive(pj_smem(n, 4) + sizeof(double) * LA_JACOBI_SCRATCH, B);
   int rc = set_smem(proj_kl_cov_fwd_kernel, smem);
@@ -1371,7 +1478,7 @@ static int kl_fwd_launch(const float *L, const float *L_o, double eps_cov, const
   double *M = save, *U = M + nn, *Li = U + nn, *Sig = Li + nn, *lam = Sig + nn, *sc = lam + (size_t)B * n;
   proj_kl_cov_fwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(
       L, L_o, eps_cov, proj_L, M, U, Li, Sig, lam, sc, info, n, warm_start, beta, (long long)ldb_beta, equality, out_L,
-      split);
+      split, vec, (long long)ldb_vec, min_std, L_built);
   TCE_CHECK_LAUNCH("proj_kl_cov_fwd_kernel");
   return TCE_OK;
 }
@@ -1422,6 +1529,17 @@ extern "C" int tce_proj_kl_entropy_fwd_sigma(const float *L, const float *L_o, d
                        1);
 }
 
+/* tce_proj_kl_entropy_fwd_sigma with the policy head fused in: the unprojected factor is built from the covariance
+ * vector(s) `vec` (batch stride ldb_vec, 0 = one shared vector) inside the kernel and also written to L_built [B,n,n]. */
+extern "C" int tce_proj_kl_entropy_fwd_sigma_vec(const float *vec, int64_t ldb_vec, float min_std, float *L_built,
+                                                 const float *L_o, double eps_cov, const double *beta, int64_t ldb_beta,
+                                                 int equality, float *proj_L, float *out_L, double *save, int32_t *info,
+                                                 int warm_start, int64_t B, int n, void *stream) {
+  if (B != 0 && (!out_L || !vec)) return TCE_ERR_INVALID_ARGUMENT;
+  return kl_fwd_launch(nullptr, L_o, eps_cov, beta, ldb_beta, equality, proj_L, out_L, save, info, warm_start, B, n, stream,
+                       1, vec, ldb_vec, min_std, L_built);
+}
+
 extern "C" int tce_proj_kl_entropy_fwd_chol(const double *save, float *proj_L, float *out_L, double *out_inv,
                                             int32_t *info, int64_t B, int n, void *stream) {
   if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
@@ -1450,20 +1568,57 @@ extern "C" int tce_proj_kl_entropy_bwd_tr(const float *L, const float *proj_L, c
 
 /* Backward of tce_proj_kl_cov_fwd (fused_entropy = 0) / tce_proj_kl_entropy_fwd* (fused_entropy = 1) given the gradient
  * w.r.t. the OUTPUT COVARIANCE Sigma_out = alpha^2 Sigma_proj [B,n,n] (symmetric, fp64) instead of w.r.t. its factor.  */
-extern "C" int tce_proj_kl_bwd_sigma(const float *L, const double *grad_sigma, const double *save, int fused_entropy,
-                                     double tr_coeff, float *grad_L, int64_t B, int n, void *stream) {
+static int kl_bwd_sigma_launch(const float *L, const double *grad_sigma, const double *save, int fused_entropy,
+                               double tr_coeff, float *grad_L, int64_t B, int n, void *stream, int use_K,
+                               const float *vec = nullptr, int64_t ldb_vec = 0, float *grad_vec = nullptr) {
   if (B == 0) return TCE_OK;
-  if (!L || !grad_sigma || !save || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
+  if (!L || !grad_sigma || !save || (!grad_L && !grad_vec) || (grad_vec && !vec) || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
-  const size_t smem = pj_smem_exclusive(pj_smem(n, 4), B);
+  const size_t smem = pj_smem_exclusive(pj_smem(n, 6), B);
   int rc = set_smem(proj_kl_cov_bwd_sigma_kernel, smem);
   if (rc) return rc;
   const size_t nn = (size_t)B * n * n;
   const double *M = save, *U = M + nn, *Li = U + nn, *Sig = Li + nn, *lam = Sig + nn, *sc = lam + (size_t)B * n;
+  const double *K = use_K ? sc + (size_t)B * KL_SC : nullptr;
   proj_kl_cov_bwd_sigma_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, grad_sigma, M, U, Li, Sig, lam,
-                                                                                       sc, grad_L, n, fused_entropy, tr_coeff);
+                                                                                       sc, K, grad_L, n, fused_entropy, tr_coeff,
+                                                                                       vec, (long long)ldb_vec, grad_vec);
   TCE_CHECK_LAUNCH("proj_kl_cov_bwd_sigma_kernel");
   return TCE_OK;
+}
+
+extern "C" int tce_proj_kl_bwd_sigma(const float *L, const double *grad_sigma, const double *save, int fused_entropy,
+                                     double tr_coeff, float *grad_L, int64_t B, int n, void *stream) {
+  return kl_bwd_sigma_launch(L, grad_sigma, save, fused_entropy, tr_coeff, grad_L, B, n, stream, 0);
+}
+
+/* K = Lt^-T U~ into the state (needs only the forward's outputs); then tce_proj_kl_bwd_sigma_k is tce_proj_kl_bwd_sigma
+ * with one GEMM and one load less on its critical path.  The pair must see the state of the SAME forward.      */
+extern "C" int tce_proj_kl_bwd_prep(double *save, int64_t B, int n, void *stream) {
+  if (B == 0) return TCE_OK;
+  if (!save || B < 0) return TCE_ERR_INVALID_ARGUMENT;
+  PJ_CHECK_N(n);
+  const size_t smem = pj_smem_exclusive(pj_smem(n, 3), B);
+  int rc = set_smem(kl_bwd_prep_kernel, smem);
+  if (rc) return rc;
+  const size_t nn = (size_t)B * n * n;
+  double *U = save + nn, *Li = U + nn, *sc = save + 4 * nn + (size_t)B * n, *K = sc + (size_t)B * KL_SC;
+  kl_bwd_prep_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(U, Li, sc, K, n);
+  TCE_CHECK_LAUNCH("kl_bwd_prep_kernel");
+  return TCE_OK;
+}
+
+extern "C" int tce_proj_kl_bwd_sigma_k(const float *L, const double *grad_sigma, const double *save, int fused_entropy,
+                                       double tr_coeff, float *grad_L, int64_t B, int n, void *stream) {
+  return kl_bwd_sigma_launch(L, grad_sigma, save, fused_entropy, tr_coeff, grad_L, B, n, stream, 1);
+}
+
+/* ..._k with the adjoint of the policy head fused in: the result is the gradient w.r.t. the covariance vector(s)
+ * [B, n + n(n-1)/2] (overwritten), L = the factor tce_proj_kl_entropy_fwd_sigma_vec built from `vec`.           */
+extern "C" int tce_proj_kl_bwd_sigma_k_vec(const float *L, const float *vec, int64_t ldb_vec, const double *grad_sigma,
+                                           const double *save, int fused_entropy, double tr_coeff, float *grad_vec,
+                                           int64_t B, int n, void *stream) {
+  return kl_bwd_sigma_launch(L, grad_sigma, save, fused_entropy, tr_coeff, nullptr, B, n, stream, 1, vec, ldb_vec, grad_vec);
 }
 
 extern "C" int tce_proj_kl_entropy_bwd_inv(const float *L, const float *proj_L, const float *grad_out,

@@ -891,7 +891,8 @@ def kl_state_scalars(state: Tensor, batch: int, n: int) -> Tensor:
     """[batch, 16] view: eta, KL step active, KL before the projection, fingerprint(L_old), alpha, entropy control
     active, alpha^2, [7:9] shape and volume part of KL_cov(N(Sigma_in) || N(Sigma_out)) (the trust-region loss),
     [9] entropy of the output, [10:12] shape / volume of KL(in || old), [12:14] shape / volume of KL(out || old)."""
-    return state[4 * batch * n * n + batch * n:].view(batch, KL_STATE_SCALARS)
+    o = 4 * batch * n * n + batch * n
+    return state[o:o + batch * KL_STATE_SCALARS].view(batch, KL_STATE_SCALARS)
 
 
 def kl_state(batch: int, n: int, device) -> Tensor:

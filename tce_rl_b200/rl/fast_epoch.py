@@ -76,17 +76,18 @@ class SharedCovKLEpoch:
         # ---- covariance chain, forward (side stream; needs neither the observations nor the mean net) ----------------
         cov.wait_stream(main)
         with torch.cuda.stream(cov):
-            L_new = torch.empty(1, n, n, device=dev, dtype=f32)
-            _lib.call("tce_policy_head_fwd", _p(vec), 0, float(pol.min_std), _p(L_new), 1, n, cov.cuda_stream)
+            L_new = torch.empty(1, n, n, device=dev, dtype=f32)         # built from the vector inside the KL kernel
             state = proj._state_for(L_new)
             beta = proj._entropy_bound(step, dev)
             scratch = torch.empty(2, n, n, device=dev, dtype=f32)                # factor outputs of an identity step
             info = torch.empty(1, device=dev, dtype=torch.int32)
-            _lib.call("tce_proj_kl_entropy_fwd_sigma", _p(L_new), _p(L_old1), float(proj.cov_bound), _p(beta), 0,
-                      int(proj.entropy_eq), _p(scratch[0]), _p(scratch[1]), _p(state), _p(info),
-                      int(proj.warm_start), 1, n, cov.cuda_stream)
+            _lib.call("tce_proj_kl_entropy_fwd_sigma_vec", _p(vec), 0, float(pol.min_std), _p(L_new), _p(L_old1),
+                      float(proj.cov_bound), _p(beta), 0, int(proj.entropy_eq), _p(scratch[0]), _p(scratch[1]), _p(state),
+                      _p(info), int(proj.warm_start), 1, n, cov.cuda_stream)
             sigma_ready = torch.cuda.Event()
             sigma_ready.record(cov)
+            # the gradient-independent part of the backward (K = L~^-T U~) while the likelihood is busy
+            _lib.call("tce_proj_kl_bwd_prep", _p(state), 1, n, cov.cuda_stream)
             for t in (L_new, scratch, info, acc):
                 t.record_stream(cov)
         ag._zero_policy_grads()
@@ -122,14 +123,11 @@ class SharedCovKLEpoch:
         # ---- covariance chain, backward --------------------------------------------------------------------------------
         with torch.cuda.stream(cov):
             cov.wait_event(lik_done)
-            g_L = torch.empty(1, n, n, device=dev, dtype=f32)
-            _lib.call("tce_proj_kl_bwd_sigma", _p(L_new), _p(g_S), _p(state), 1, coeff if with_cov else 0.0, _p(g_L), 1, n,
-                      cov.cuda_stream)
-            _lib.call("tce_policy_head_bwd", _p(vec), 0, _p(g_L), _p(vec.grad), 1, n, cov.cuda_stream)
+            _lib.call("tce_proj_kl_bwd_sigma_k_vec", _p(L_new), _p(vec), 0, _p(g_S), _p(state), 1,
+                      coeff if with_cov else 0.0, _p(vec.grad), 1, n, cov.cuda_stream)
             cov_done = torch.cuda.Event()
             cov_done.record(cov)
             g_S.record_stream(cov)
-            g_L.record_stream(cov)
         # ---- mean chain, backward ----------------------------------------------------------------------------------------
         tr_stream.wait_event(mean_fwd_done)          # maha_old, u_old
         tr_stream.wait_event(sigma_ready)            # the projection's state (L~^-1, eta, alpha)
