@@ -303,7 +303,9 @@ class Timer:
                 b.synchronize()
             events.append((a, b))
         self.barrier()
-        tt = torch.tensor([sum(a.elapsed_time(b) for a, b in events)], device=self.device, dtype=torch.float64)
+        per = sorted(a.elapsed_time(b) for a, b in events)
+        self.last_steps = {"min": round(per[0], 5), "median": round(per[len(per) // 2], 5), "max": round(per[-1], 5)}
+        tt = torch.tensor([sum(per)], device=self.device, dtype=torch.float64)
         if self.world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return tt.item() / K                                     # ms per step
@@ -562,6 +564,7 @@ def run_ours(args):
         t_wall0 = time.perf_counter()
         ms_per_step = timer.run(step_fn, K, W)
         t_wall = time.perf_counter() - t_wall0
+    step_spread = dict(timer.last_steps)
     value = world * B_PER_GPU / (ms_per_step * 1e-3)
     _mark("timed region done")
     final = metrics.cpu()
@@ -726,7 +729,7 @@ def run_ours(args):
                                             "activity of one replayed epoch incl. cuBLAS GEMMs of the MLP and ATen glue"},
             "roofline": roof,
             "also": also,
-            "wall_s_timed_region": round(t_wall, 3),
+            "wall_s_timed_region": round(t_wall, 3), "step_ms_rank0": step_spread,
             "loss": {"surrogate": round(final[0].item(), 6), "trust_region": round(final[2].item(), 6)},
         }
         if cpu is not None:

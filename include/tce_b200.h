@@ -77,6 +77,12 @@ int tce_prodmp_traj_fwd(const tce_tables_t *tables, const float *params, const f
 /* backward: grad_traj [B,T,2D] -> grad_params [B,Dp], grad_init_pos [B,D], grad_init_vel [B,D]
  * (any output may be NULL).  API-permitted, never exercised by the reference (sample runs under
  * no_grad, temporal_correlated_sampler.py:91,200).                                                */
+/* tce_prodmp_traj_fwd for a batch whose episodes share ONE time grid (same init_time and times row: every shipped TCE
+ * task): the basis rows are evaluated once (rows_ws: T * 2 * (K1 + 2) floats of workspace) and the batch becomes a
+ * small matrix product per episode.  times_row [T] / init_time [1]: episode 0's values.                        */
+int tce_prodmp_traj_fwd_uniform(const tce_tables_t *tables, const float *params, const float *times_row,
+                                const float *init_time, const float *init_pos, const float *init_vel,
+                                float *rows_ws, float *traj, int64_t B, int64_t T, void *stream);
 int tce_prodmp_traj_bwd(const tce_tables_t *tables, const float *grad_traj, const float *times,
                         const float *init_time, float *grad_params, float *grad_init_pos,
                         float *grad_init_vel, int64_t B, int64_t T, void *stream);
@@ -391,6 +397,27 @@ int tce_adam_step(int count, float *const *params, const int64_t *sizes, const f
  * this rank's buffer, which may then be overwritten.                                                         */
 int tce_p2p_allreduce_sumsq(int world, int rank, const void *const *peer_bufs, void *const *peer_pads, int64_t n,
                             float *avg_out, void *local2, double *state3, void *stream);
+/* The same exchange restricted to elements [offset, offset + n) of the buffers (offset a multiple of 4), so that an
+ * update can exchange the gradient in up to two ranges as they become final (the mean network's slice while the
+ * covariance chain is still in its backward, the covariance slice last): `phase` in {0, 1} selects the 2 * world
+ * signal-pad slots [2 * world * phase, ...) and the two uint64 local2[2 * phase ..]; pads need >= 4 * world uint64 and
+ * local2 four uint64 when phase 1 is used.  `bump_step`: this call increments state3[0] (once per optimiser step).
+ * Sums of squares of all ranges accumulate in state3[1].                                                     */
+int tce_p2p_allreduce_sumsq_range(int world, int rank, const void *const *peer_bufs, void *const *peer_pads,
+                                  int64_t offset, int64_t n, int phase, int bump_step, float *avg_out, void *local2,
+                                  double *state3, void *stream);
+
+/* Push variant (the one the agent uses): no arrival / departure barriers.  peer_xchg[r]: rank r's exchange area
+ * (tce_p2p_push_xchg_bytes(world, n_total) bytes of symmetric memory, zero-initialised once: per-block flags followed by
+ * receive slots [2 parities][world][n_total rounded up to 4]) as mapped into this process; grad: this rank's LOCAL flat
+ * gradient (n_total floats, padded with zeros to a multiple of 4, 16-byte aligned).  Each block stores its slice of
+ * grad[offset, offset + n) into every peer's slot, releases a per-block flag, waits for the peers' flags of the same
+ * block and reduces from local memory in rank order.  offset, n multiples of 4; phase / bump_step / local2 / state3 as
+ * for tce_p2p_allreduce_sumsq_range.  Every rank must launch the same sequence of calls.                       */
+size_t tce_p2p_push_xchg_bytes(int world, int64_t n_total);
+int tce_p2p_push_allreduce_sumsq(int world, int rank, void *const *peer_xchg, const float *grad, int64_t n_total,
+                                 int64_t offset, int64_t n, int phase, int bump_step, float *avg_out, void *local2,
+                                 double *state3, void *stream);
 
 /* ---- mean chain of a policy epoch with ONE shared covariance (csrc/tce_epoch.cu) -----------------------------
  * Replaces, for the non-contextual policies of every shipped config, the per-episode pieces between the policy

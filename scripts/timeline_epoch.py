@@ -5,9 +5,14 @@ import torch
 import bench
 from torch.profiler import profile, ProfilerActivity
 
-dev = torch.device("cuda", 0)
-torch.cuda.set_device(0)
-agent, dataset, times, pairs = bench.build_gpu_workload(dev, 0, 1)
+world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+dev = torch.device("cuda", local)
+torch.cuda.set_device(local)
+if world > 1:           # under torchrun: the data-parallel epoch (peer-memory gradient exchange), one timeline per rank
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+agent, dataset, times, pairs = bench.build_gpu_workload(dev, rank, world)
 side = torch.cuda.Stream()
 side.wait_stream(torch.cuda.current_stream())
 with torch.cuda.stream(side):
@@ -23,12 +28,15 @@ for _ in range(5):
     g.replay()
 torch.cuda.synchronize()
 out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/timeline.txt"
+if world > 1:
+    out = out.replace(".txt", f"_rank{rank}.txt")
+    dist.barrier()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     g.replay()
     torch.cuda.synchronize()
     g.replay()
     torch.cuda.synchronize()
-tmp = "/tmp/trace.json"
+tmp = f"/tmp/trace{rank}.json"
 prof.export_chrome_trace(tmp)
 ev = [e for e in json.load(open(tmp))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
 ev.sort(key=lambda e: e["ts"])
@@ -45,3 +53,6 @@ with open(out, "w") as f:
     for e in ev:
         f.write(f"{e['ts'] - t0:9.1f} {e['dur']:8.1f} s{e['args'].get('stream', '?'):<4} {e['name'][:90]}\n")
 print(open(out).read()[:300])
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()

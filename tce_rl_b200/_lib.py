@@ -38,6 +38,7 @@ SIGNATURES = {
     "tce_prodmp_tables_num_pc": (C.c_int, [_P]),
     "tce_prodmp_tables_export": (C.c_int, [_P] * 8),
     "tce_prodmp_traj_fwd": (C.c_int, [_P] * 7 + [_I64, _I64, _P]),
+    "tce_prodmp_traj_fwd_uniform": (C.c_int, [_P] * 8 + [_I64, _I64, _P]),
     "tce_prodmp_traj_bwd": (C.c_int, [_P] * 7 + [_I64, _I64, _P]),
     "tce_mvn_rsample": (C.c_int, [_P, _P, _I64, _P, _U64, _U64, _P, _I64, _I32, _P]),
     "tce_chol_fwd": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
@@ -96,6 +97,9 @@ SIGNATURES = {
                                           _I64, _I64, _P]),
     "tce_seglik_uniform_finish": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P, _I64, _P]),
     "tce_p2p_allreduce_sumsq": (C.c_int, [_I32, _I32, _P, _P, _I64, _P, _P, _P, _P]),
+    "tce_p2p_allreduce_sumsq_range": (C.c_int, [_I32, _I32, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P]),
+    "tce_p2p_push_xchg_bytes": (C.c_size_t, [_I32, _I64]),
+    "tce_p2p_push_allreduce_sumsq": (C.c_int, [_I32, _I32, _P, _P, _I64, _I64, _I64, _I32, _I32, _P, _P, _P, _P]),
     "tce_epoch_mean_fwd": (C.c_int, [_P, _P, _P, _D, _P, _P, _P, _P, _I64, _I32, _P]),
     "tce_epoch_tr_mean": (C.c_int, [_P, _P, _P, _P, _P, _P, _D, _D, _P, _P, _I64, _I32, _P]),
     "tce_epoch_mean_combine": (C.c_int, [_P, _P, _P, _P, _P, _P, _D, _P, _I64, _I32, _P]),

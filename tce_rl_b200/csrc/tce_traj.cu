@@ -233,6 +233,7 @@ traj_fwd_warp_kernel(TabDev tb, const float *__restrict__ params, const float *_
   }
 }
 
+
 // backward: one CTA per episode, thread (d, j) reduces over time.  Low priority path (the reference
 // only ever samples under no_grad), kept simple.
 template <int K1>
@@ -306,6 +307,143 @@ int num_sms() {
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   return g_num_sms;
+}
+
+
+// Common time grid (every episode has the same init_time and times row -- all shipped TCE tasks start their
+// trajectories at t = 0): the basis rows with initial conditions [xi1, xi2, hp[K1] | xi3, xi4, hv[K1]] are the same for
+// all episodes.  traj_rows_kernel evaluates them once (T threads); traj_uniform_kernel is then a batched
+// [T x (K1 + 2)] x [(K1 + 2) x D] product per episode: ~250 instructions per (episode, time) point instead of ~1200
+// (table lerps, fp64 index arithmetic and the initial-condition algebra are gone from the per-point work), which moves
+// the kernel from the issue limit towards the HBM roofline.
+template <int K1>
+__global__ void traj_rows_kernel(TabDev tb, const float *__restrict__ times_row, const float *__restrict__ init_time,
+                                 float *__restrict__ rows, int T) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  constexpr int RW = 2 * (K1 + 2);
+  const int stride = tb.row32_stride;
+  const double inv_tau = 1.0 / tb.tau;
+  int ib; float wb;
+  time_to_index_fast(tb, inv_tau, init_time[0], ib, wb);
+  const float *q0 = tb.row32 + (size_t)ib * stride, *q1 = q0 + stride;
+  const float y1b = lerp_t(q0[0], q1[0], wb), y2b = lerp_t(q0[1], q1[1], wb);
+  const float dy1b = lerp_t(q0[2], q1[2], wb), dy2b = lerp_t(q0[3], q1[3], wb);
+  const float inv_det = 1.0f / (y1b * dy2b - y2b * dy1b);
+  int i0; float wf;
+  time_to_index_fast(tb, inv_tau, times_row[t], i0, wf);
+  const float *r0 = tb.row32 + (size_t)i0 * stride, *r1 = r0 + stride;
+  const float y1 = lerp_t(r0[0], r1[0], wf), y2 = lerp_t(r0[1], r1[1], wf);
+  const float dy1 = lerp_t(r0[2], r1[2], wf), dy2 = lerp_t(r0[3], r1[3], wf);
+  const float xi1 = (dy2b * y1 - dy1b * y2) * inv_det, xi2 = (y1b * y2 - y2b * y1) * inv_det;
+  const float xi3 = (dy2b * dy1 - dy1b * dy2) * inv_det, xi4 = (y1b * dy2 - y2b * dy1) * inv_det;
+  float *o = rows + (size_t)t * RW;
+  o[0] = xi1; o[1] = xi2; o[K1 + 2] = xi3; o[K1 + 3] = xi4;
+#pragma unroll
+  for (int j = 0; j < K1; ++j) {
+    const float pbj = lerp_t(q0[4 + j], q1[4 + j], wb), vbj = lerp_t(q0[4 + K1 + j], q1[4 + K1 + j], wb);
+    const float pj = lerp_t(r0[4 + j], r1[4 + j], wf), vj = lerp_t(r0[4 + K1 + j], r1[4 + K1 + j], wf);
+    const float scj = (float)tb.scale[j];
+    o[2 + j] = (pj - xi1 * pbj - xi2 * vbj) * scj;
+    o[K1 + 4 + j] = (vj - xi3 * pbj - xi4 * vbj) * scj;
+  }
+}
+
+constexpr int TU_THREADS = 256;
+constexpr int TU_EPC = 8;            // episodes per CTA iteration
+template <int K1>
+__global__ void __launch_bounds__(TU_THREADS)
+traj_uniform_kernel(TabDev tb, const float *__restrict__ rows, const float *__restrict__ params,
+                    const float *__restrict__ init_pos, const float *__restrict__ init_vel, float *__restrict__ traj,
+                    long long B, int T) {
+  constexpr int RW = 2 * (K1 + 2), RS = RW | 1, PW = K1 + 2;
+  extern __shared__ __align__(16) float su[];
+  const int D = tb.D, D2 = 2 * D, Dp = D * K1;
+  float *srow = su;                         // [T][RS]: odd stride -> lanes (consecutive t) hit different banks
+  float *sP = su + (size_t)T * RS;          // [TU_EPC][D][PW]: y0, v0 * tau, theta (goal shifted for relative goals)
+  float *tile = su + (((size_t)T * RS + (size_t)TU_EPC * D * PW + 3) & ~(size_t)3);   // [TU_THREADS][2D], 16-byte aligned
+  for (int i = threadIdx.x; i < T * RW; i += TU_THREADS) srow[(i / RW) * RS + (i % RW)] = rows[i];
+  const float tau = (float)tb.tau, inv_tau_f = 1.0f / tau;
+  const float sc_g = (float)tb.scale[K1 - 1];
+  const float goal_shift_scale = tb.relative_goal ? (tb.relative_goal_scaled ? 1.0f : 1.0f / sc_g) : 0.0f;
+  const long long groups = (B + TU_EPC - 1) / TU_EPC;
+  for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
+    const long long b0 = g * TU_EPC;
+    const int ne = (int)((B - b0) < TU_EPC ? (B - b0) : TU_EPC);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ne * D * PW; i += TU_THREADS) {
+      const int e = i / (D * PW), r = i - e * D * PW, d = r / PW, k = r - d * PW;
+      const long long bb = b0 + e;
+      float v;
+      if (k == 0) v = init_pos[bb * D + d];
+      else if (k == 1) v = init_vel[bb * D + d] * tau;
+      else {
+        v = params[bb * Dp + d * K1 + (k - 2)];
+        if (k == PW - 1) v += goal_shift_scale * init_pos[bb * D + d];           // relative goal (0 otherwise)
+      }
+      sP[i] = v;
+    }
+    __syncthreads();
+    // 256 points per pass: results go through a shared tile so that the global stores are contiguous 128-bit (a
+    // thread-private 56-byte row written with 8-byte stores touches every 32-byte sector four times: L2 write bound)
+    for (int p0 = 0; p0 < ne * T; p0 += TU_THREADS) {
+      const int p = p0 + threadIdx.x;
+      if (p < ne * T) {
+        const int e = p / T, t = p - e * T;
+        float rp[PW], rv[PW];
+        const float *row = srow + t * RS;
+#pragma unroll
+        for (int k = 0; k < PW; ++k) { rp[k] = row[k]; rv[k] = row[PW + k]; }
+        const float *P = sP + e * D * PW;
+        float *o = tile + threadIdx.x * D2;
+        for (int d = 0; d < D; ++d) {
+          float a = 0.f, c = 0.f;
+#pragma unroll
+          for (int k = 0; k < PW; ++k) {
+            const float pk = P[d * PW + k];
+            a = fmaf(rp[k], pk, a);
+            c = fmaf(rv[k], pk, c);
+          }
+          o[d] = a;
+          o[D + d] = c * inv_tau_f;
+        }
+      }
+      __syncthreads();
+      const int npts = ne * T - p0 < TU_THREADS ? ne * T - p0 : TU_THREADS;
+      const long long g0 = (b0 * T + p0) * (long long)D2;
+      const int n_out = npts * D2;
+      if ((n_out & 3) == 0 && (g0 & 3) == 0) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(tile);
+        float4 *d4 = reinterpret_cast<float4 *>(traj + g0);
+        for (int i = threadIdx.x; i < n_out / 4; i += TU_THREADS) d4[i] = s4[i];
+      } else {
+        for (int i = threadIdx.x; i < n_out; i += TU_THREADS) traj[g0 + i] = tile[i];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <int K1>
+int launch_traj_uniform(const tce_tables *t, const float *params, const float *times_row, const float *init_time,
+                        const float *init_pos, const float *init_vel, float *rows_ws, float *traj, int64_t B, int64_t T,
+                        cudaStream_t st) {
+  constexpr int RW = 2 * (K1 + 2), RS = RW | 1;
+  traj_rows_kernel<K1><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(tab_dev(t), times_row, init_time, rows_ws, (int)T);
+  TCE_CHECK_LAUNCH("traj_rows_kernel");
+  const size_t smem = sizeof(float) * ((size_t)T * RS + (size_t)TU_EPC * t->D * (K1 + 2) + 8 +
+                                       (size_t)TU_THREADS * 2 * t->D);
+  if (smem > 200 * 1024) return TCE_ERR_UNSUPPORTED_SHAPE;
+  if (smem > 48 * 1024)
+    TCE_CUDA(cudaFuncSetAttribute(traj_uniform_kernel<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+             "traj uniform smem attr");
+  long long grid = (B + TU_EPC - 1) / TU_EPC;
+  const long long cap = 4LL * num_sms();
+  if (grid > cap) grid = cap;
+  traj_uniform_kernel<K1><<<(unsigned)grid, TU_THREADS, smem, st>>>(tab_dev(t), rows_ws, params, init_pos, init_vel, traj, B,
+                                                                  (int)T);
+  TCE_CHECK_LAUNCH("traj_uniform_kernel");
+  return TCE_OK;
 }
 
 bool g_traj_cta = false;
@@ -386,6 +524,19 @@ extern "C" int tce_prodmp_traj_fwd(const tce_tables_t *t, const float *params, c
     return TCE_ERR_INVALID_ARGUMENT;
   TCE_DISPATCH_K1(t->K1, return launch_traj_fwd<K1>(t, params, times, init_time, init_pos, init_vel, traj, B, T,
                                                     (cudaStream_t)stream));
+  return TCE_OK;
+}
+
+/* All episodes share ONE time grid: times_row [T] and init_time [1] describe it (episode 0's values); rows_ws
+ * [T * 2 * (K1 + 2)] floats of workspace.  Same results as tce_prodmp_traj_fwd on such inputs.               */
+extern "C" int tce_prodmp_traj_fwd_uniform(const tce_tables_t *t, const float *params, const float *times_row,
+                                           const float *init_time, const float *init_pos, const float *init_vel,
+                                           float *rows_ws, float *traj, int64_t B, int64_t T, void *stream) {
+  if (B == 0) return TCE_OK;
+  if (!t || !params || !times_row || !init_time || !init_pos || !init_vel || !rows_ws || !traj || B < 0 || T < 1)
+    return TCE_ERR_INVALID_ARGUMENT;
+  TCE_DISPATCH_K1(t->K1, return launch_traj_uniform<K1>(t, params, times_row, init_time, init_pos, init_vel, rows_ws, traj,
+                                                        B, T, (cudaStream_t)stream));
   return TCE_OK;
 }
 

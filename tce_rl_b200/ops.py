@@ -97,6 +97,9 @@ class Tables:
 
 
 # --------------------------------------------------------------------------------------------------
+UNIFORM_TRAJ = True      # common-time-grid fast path of the trajectory synthesis (False: always the general kernel)
+
+
 # (1) trajectory synthesis
 # --------------------------------------------------------------------------------------------------
 @torch.library.custom_op("tce::prodmp_traj", mutates_args=())
@@ -106,6 +109,14 @@ def prodmp_traj(params: Tensor, times: Tensor, init_time: Tensor, init_pos: Tens
     init_time, init_pos, init_vel = _chk(init_time), _chk(init_pos), _chk(init_vel)
     B, T = times.shape
     traj = torch.empty(B, T, 2 * num_dof, device=params.device, dtype=torch.float32)
+    # one time grid for the whole batch (a cached device read per tensor; never decided under graph capture): the
+    # basis rows are evaluated once and the batch becomes a small matrix product per episode
+    if UNIFORM_TRAJ and B >= 64 and times_uniform(init_time, times):
+        k1 = params.shape[-1] // num_dof
+        rows = torch.empty(T * 2 * (k1 + 2), device=params.device, dtype=torch.float32)
+        _lib.call("tce_prodmp_traj_fwd_uniform", tables, _p(params), _p(times), _p(init_time), _p(init_pos), _p(init_vel),
+                  _p(rows), _p(traj), B, T, _stream())
+        return traj
     _lib.call("tce_prodmp_traj_fwd", tables, _p(params), _p(times), _p(init_time), _p(init_pos), _p(init_vel),
               _p(traj), B, T, _stream())
     return traj

@@ -21,10 +21,15 @@ parts are closed forms of the same eigenvalues (``csrc/tce_proj.cu: save_tr_valu
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .. import _lib, ops, ops_seglik, util
 from .projection import KLProjectionLayer, _first
+
+
+EARLY_EXCHANGE = os.environ.get("TCE_P2P_EARLY", "1") != "0"    # data parallel: mean-net slice of the gradient goes ahead
 
 
 def _p(t):
@@ -143,6 +148,10 @@ class SharedCovKLEpoch:
                   float(proj.mean_bound), _p(g_mean), B, n, main.cuda_stream)
         torch.autograd.backward([mean], [g_mean])
         util.join_side_grads()
+        # data parallel: the mean network's slice of the flat gradient is final -- exchange it under the covariance
+        # chain's backward; only the covariance vector's slice trails the chain (FlatAdam.step)
+        if getattr(ag.policy_optimizer, "reducer", None) is not None and EARLY_EXCHANGE:
+            ag.policy_optimizer.exchange_early(sum(p.numel() for p in params[:-1]))
         main.wait_event(cov_done)
         ag._allreduce_grads(params)
         ag.policy_optimizer.step(max_norm=float(ag.clip_grad_norm))

@@ -31,6 +31,8 @@ class FlatAdam(torch.optim.Optimizer):
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=flat_grad.device)
         self.exp_avg_sq = torch.zeros_like(self.exp_avg)
         self.stats = torch.zeros(3, dtype=torch.float64, device=flat_grad.device)     # {step, sum g^2, p2p error flag}
+        self._early = 0            # elements already exchanged by exchange_early in the current step
+        self._xchg_stream = self._early_done = None
         self.reducer = None        # rl.p2p.P2PGradBuffer: all-reduce fused with the gradient norm (data parallel)
         self._params = params
         self._sizes = (C.c_int64 * len(params))(*[p.numel() for p in params])
@@ -78,6 +80,27 @@ class FlatAdam(torch.optim.Optimizer):
         self.stats[0] = step
         self.state.clear()
 
+    def exchange_early(self, n_first: int) -> bool:
+        """Data parallel: exchange the first ``n_first`` elements of the flat gradient NOW (they are final: the mean
+        network's slice once its backward has run); ``step`` then only exchanges the remainder.  No-op (False) without a
+        peer-memory reducer or when either part would be empty."""
+        n = self.flat_grad.numel()
+        n_first -= n_first % 4               # 128-bit words: up to three trailing elements travel with the remainder
+        if self.reducer is None or n_first <= 0 or n_first >= n:
+            return False
+        # on a stream of its own: the remainder's exchange (issued by ``step`` on the caller's stream once the rest of
+        # the gradient is final) must not queue behind this one -- the two overlap and ``step`` joins them
+        main = torch.cuda.current_stream()
+        if self._xchg_stream is None:
+            self._xchg_stream = torch.cuda.Stream(device=self.flat_grad.device)
+            self._early_done = torch.cuda.Event()
+        self._xchg_stream.wait_stream(main)
+        with torch.cuda.stream(self._xchg_stream):
+            self.reducer.allreduce_sumsq_range(self.stats, 0, n_first, 0, False)
+            self._early_done.record(self._xchg_stream)
+        self._early = int(n_first)
+        return True
+
     def begin(self):
         """Clear the gradients and the norm accumulator (call before backward; cheap, can be issued early)."""
         self.flat_grad.zero_()
@@ -97,7 +120,13 @@ class FlatAdam(torch.optim.Optimizer):
         st = torch.cuda.current_stream().cuda_stream
         ptrs = (C.c_void_p * len(self._params))(*[p.data_ptr() for p in self._params])
         if self.reducer is not None:           # averaged over the ranks through NVLink peer memory, norm in the same launch
-            grad = self.reducer.allreduce_sumsq(self.stats)
+            if self._early:                    # [0, _early) went ahead (exchange_early): only the rest trails
+                self.reducer.allreduce_sumsq_range(self.stats, self._early, self.flat_grad.numel() - self._early, 1, True)
+                grad = self.reducer.avg[:self.flat_grad.numel()]
+                torch.cuda.current_stream().wait_event(self._early_done)
+                self._early = 0
+            else:
+                grad = self.reducer.allreduce_sumsq(self.stats)
         else:
             grad = self.flat_grad
             _lib.call("tce_grad_sumsq", grad.data_ptr(), grad.numel(), self.stats.data_ptr(), st)

@@ -77,6 +77,54 @@ def test_trajectory_parity(name, B):
         assert (f64(got)[..., sl] - want[..., sl]).abs().max() <= 1e-5 * scale
 
 
+@pytest.mark.parametrize("name", list(MP_CONFIGS))
+def test_uniform_grid_trajectory_path_equals_general_kernel(name):
+    """One time grid for the whole batch: basis rows evaluated once + per-episode matrix product
+    (tce_prodmp_traj_fwd_uniform) against the general kernel and the oracle; a batch with per-episode start times must
+    not take it."""
+    B = 200
+    cfg, T, inp, times, _ = setup_case(name, B)
+    tabs = ops.Tables(**cfg)
+    c = lambda t: t.to(DEV)
+    args = (c(inp["mean"]), c(times), c(inp["init_time"]), c(inp["init_pos"]), c(inp["init_vel"]), tabs.handle, cfg["num_dof"])
+    n0 = _lib_launch_count("tce_prodmp_traj_fwd_uniform")
+    fast = ops.prodmp_traj(*args)
+    assert _lib_launch_count("tce_prodmp_traj_fwd_uniform") == n0 + 1
+    ops.UNIFORM_TRAJ = False
+    try:
+        general = ops.prodmp_traj(*args)
+    finally:
+        ops.UNIFORM_TRAJ = True
+    scale = general.abs().max().item()
+    assert (fast - general).abs().max().item() <= 2e-6 * scale
+    pol = make_oracle_policy(name)
+    want = pol.sample(False, inp["mean"].double(), inp["L"].double(), times.double(), inp["init_time"].double(),
+                      inp["init_pos"].double(), inp["init_vel"].double(), use_mean=True)
+    assert (f64(fast) - want).abs().max() <= 1e-5 * want.abs().max()
+    cfg, T, inp2, times2, _ = setup_case(name, B, init_time_spread=0.2)
+    n1 = _lib_launch_count("tce_prodmp_traj_fwd_uniform")
+    ops.prodmp_traj(c(inp2["mean"]), c(times2), c(inp2["init_time"]), c(inp2["init_pos"]), c(inp2["init_vel"]), tabs.handle,
+                    cfg["num_dof"])
+    assert _lib_launch_count("tce_prodmp_traj_fwd_uniform") == n1
+
+
+_COUNTS = {}
+
+
+def _lib_launch_count(name):
+    """Launches of one ABI entry so far (a counting wrapper installed on first use)."""
+    from tce_rl_b200 import _lib
+    if "installed" not in _COUNTS:
+        orig = _lib.call
+
+        def counting(n, *a):
+            _COUNTS[n] = _COUNTS.get(n, 0) + 1
+            return orig(n, *a)
+        _lib.call = counting
+        _COUNTS["installed"] = True
+    return _COUNTS.get(name, 0)
+
+
 def test_rsample_injected_and_philox():
     B, n = 257, 63
     inp = synthetic_inputs("box", B, dtype=torch.float32)
