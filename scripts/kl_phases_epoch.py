@@ -8,7 +8,8 @@ from tce_rl_b200 import _lib
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
-agent, dataset, times, pairs = bench.build_gpu_workload(dev, 0, 1)
+contextual = len(sys.argv) > 1 and sys.argv[1] == "contextual"        # per-episode covariance factors: 1024 projections per step
+agent, dataset, times, pairs = bench.build_gpu_workload(dev, 0, 1, contextual=contextual)
 step_fn, metrics, *_ = bench.capture_epoch(agent, dataset, times, pairs)
 for _ in range(10):
     step_fn()
