@@ -533,11 +533,18 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
                        double *__restrict__ save_sc, int32_t *__restrict__ info, int n, int warm_start,
                        const double *__restrict__ beta,
                        long long ldb_beta, int entropy_eq, float *__restrict__ out_L, int split,
-                       const float *__restrict__ vec, long long ldb_vec, float min_std, float *__restrict__ L_built) {
+                       const float *__restrict__ vec, long long ldb_vec, float min_std, float *__restrict__ L_built,
+                       int compact) {
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
-  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
-  double *dinv = sd + 4 * MS, *lam = dinv + LA_DINV_DOUBLES, *nrm = lam + m, *red = nrm + LA_JACOBI_SCRATCH;   // red: >= 48
+  // Four buffers: b0 = Lt throughout, b3 = Lo -> W -> U~.  `compact` (batches: two CTAs of 256 threads per SM instead of
+  // one of 512, so that one matrix's Jacobi phase -- four busy warps -- runs beside another's GEMMs): THREE buffers;
+  // Lo is staged where Lt^-1 goes next, W = Lt^-1 (basis) overwrites Lt, and the warps that idle during the Jacobi
+  // iteration fetch Lt again into the buffer the start basis has left (bL: where Lt is once U~ exists).
+  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{compact ? sd : sd + 3 * MS, LD, 1};
+  Mat bLo = compact ? b2 : b3, bL = compact ? b1 : b0, bS = compact ? b0 : b1;       // bS: Sigma of an identity step
+  double *dinv = sd + (compact ? 3 : 4) * MS, *lam = dinv + LA_DINV_DOUBLES, *nrm = lam + m,
+         *red = nrm + LA_JACOBI_SCRATCH;                                                               // red: >= 48
   __shared__ int s_bad;
   const long long b = blockIdx.x;
   const size_t off = (size_t)b * n * n;
@@ -580,7 +587,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
             L_built[off + e] = j <= i ? vt[u] : 0.f;
           }
           b0(i, j) = j <= i ? (double)vt[u] : 0.0;
-          b3(i, j) = j <= i ? (double)vo[u] : 0.0;
+          bLo(i, j) = j <= i ? (double)vo[u] : 0.0;
           b1(i, j) = vm[u];
           fp = fma((double)(e % 251 + 1), (double)vo[u], fp);
         }
@@ -588,12 +595,12 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
     }
     zero_padding(b0, n, m);
     zero_padding(b1, n, m);
-    zero_padding(b3, n, m);
+    zero_padding(bLo, n, m);
   }
   fp = block_sum(fp, red);
   const bool warm = warm_start && save_sc[b * KL_SC + 3] == fp;
   if (!warm) {                                                                      // cold: b1 = Lo (lower)
-    for (int e = threadIdx.x; e < m * m; e += blockDim.x) b1(e / m, e % m) = b3(e / m, e % m);
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) b1(e / m, e % m) = bLo(e / m, e % m);
     __syncthreads();
   }
   KL_STAMP(1);
@@ -604,11 +611,21 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   KL_STAMP(11);
   KL_STAMP(2);
   // the warps that hold no rows of the register-resident iteration write Lt^-1 to the state meanwhile
+  auto refetch_Lt = [&](int t, int nt) {              // compact: Lt (fp32 in HBM / L2; exact in fp64) -> bL, padding zeroed
+    for (int e = t; e < m * m; e += nt) {
+      const int i = e / m, j = e - i * m;
+      bL(i, j) = (i < n && j <= i) ? (double)Lt[(size_t)i * n + j] : 0.0;
+    }
+  };
   const int sweeps = la_jacobi_onesided(b3, lam, nrm, n, [&](int t, int nt) {
-    if (nt >= 32) store_full_rows(save_Li + off, b2, n, t, nt);
+    if (nt >= 32) {
+      store_full_rows(save_Li + off, b2, n, t, nt);
+      if (compact) refetch_Lt(t, nt);
+    }
   });                                                                               // b3 = U~
   if ((int)blockDim.x - 32 * ((n + LA_JACOBI_ROWS - 1) / LA_JACOBI_ROWS) < 32) {    // (no idle warp: all of them do it now)
     store_full_rows(save_Li + off, b2, n, threadIdx.x, blockDim.x);
+    if (compact) refetch_Lt(threadIdx.x, blockDim.x);
     __syncthreads();
   }
   KL_STAMP(3);
@@ -624,7 +641,7 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   const bool active = kl0 > eps_cov;
   const double eta = active ? kl_solve_eta(lam, n, eps_cov, red, warm && save_sc[b * KL_SC + 1] != 0.0 ? save_sc[b * KL_SC + 0] : 0.0) : 0.0;
   KL_STAMP(4);
-  la_gemm(b2, b0, b3, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // M = Lt U~
+  la_gemm(b2, bL, b3, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // M = Lt U~
   if (threadIdx.x == 0) {
     save_sc[b * KL_SC + 0] = eta; save_sc[b * KL_SC + 1] = active ? 1.0 : 0.0; save_sc[b * KL_SC + 2] = kl0; save_sc[b * KL_SC + 3] = fp;
     save_sc[b * KL_SC + 4] = 1.0; save_sc[b * KL_SC + 5] = 0.0;    // alpha, ent_active, alpha^2: overwritten by the fused
@@ -695,11 +712,11 @@ proj_kl_cov_fwd_kernel(const float *__restrict__ L, const float *__restrict__ L_
   // Sigma of the (pre-entropy) result goes to the state as well: with ONE covariance for the batch the
   // likelihood's stage 1 takes alpha^2 * Sigma from there instead of re-forming L L^T per episode.
   if (!active) {                                                                    // identity
-    la_gemm(b1, b0, b0.T(), n, n, n, TRI_LOWER, TRI_UPPER, TRI_FULL, 1.0, 0.0);      // Sigma = Lt Lt^T
-    store_full_rows(save_Sig + off, b1, n, threadIdx.x, blockDim.x);
-    const double alpha = tail_scalars([&](int i, double) { return log(b0(i, i)); }, false);
+    la_gemm(bS, bL, bL.T(), n, n, n, TRI_LOWER, TRI_UPPER, TRI_FULL, 1.0, 0.0);      // Sigma = Lt Lt^T
+    store_full_rows(save_Sig + off, bS, n, threadIdx.x, blockDim.x);
+    const double alpha = tail_scalars([&](int i, double) { return log(bL(i, i)); }, false);
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-      const float v = (e % n <= e / n) ? (float)b0(e / n, e % n) : 0.f;          // Lt (fp32 values, exact in fp64)
+      const float v = (e % n <= e / n) ? (float)bL(e / n, e % n) : 0.f;          // Lt (fp32 values, exact in fp64)
       out[e] = v;
       if (out_L) out_L[off + e] = (float)(alpha * (double)v);
     }
@@ -1307,6 +1324,26 @@ size_t pj_smem(int n, int nbuf) {
 // late and so does the chain).  Asking for (almost) all shared memory of the SM keeps the SM exclusive.
 size_t pj_smem_exclusive(size_t smem, int64_t B) { return B <= 16 && smem < 200 * 1024 ? 200 * 1024 : smem; }
 
+int num_sms_proj() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+bool kl_compact_enabled() {             // TCE_KL_COMPACT=0: always one 512-thread CTA per SM (cross-check)
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("TCE_KL_COMPACT");
+    on = !(e && e[0] == '0');
+  }
+  return on != 0;
+}
+
 template <typename K>
 int set_smem(K kernel, size_t smem) {
   if (smem > 220 * 1024) return TCE_ERR_UNSUPPORTED_SHAPE;
@@ -1471,14 +1508,16 @@ static int kl_fwd_launch(const float *L, const float *L_o, double eps_cov, const
   if ((!L && !vec) || (vec && !L_built) || !L_o || !proj_L || !save || B < 0 || !(eps_cov > 0))
     return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
-  const size_t smem = pj_smem_exclusive(pj_smem(n, 4) + sizeof(double) * LA_JACOBI_SCRATCH, B);
-  int rc = set_smem(proj_kl_cov_fwd_kernel, smem);
+  // more matrices than SMs: two CTAs of 256 threads per SM on three buffers each (`compact`), else one of 512 on four
+  const int compact = B > num_sms_proj() && kl_compact_enabled();
+  const size_t smem = pj_smem_exclusive(pj_smem(n, compact ? 3 : 4) + sizeof(double) * LA_JACOBI_SCRATCH, B);
+  int rc = set_smem(proj_kl_cov_fwd_kernel, compact ? pj_smem(n, 4) + sizeof(double) * LA_JACOBI_SCRATCH : smem);
   if (rc) return rc;
   const size_t nn = (size_t)B * n * n;
   double *M = save, *U = M + nn, *Li = U + nn, *Sig = Li + nn, *lam = Sig + nn, *sc = lam + (size_t)B * n;
-  proj_kl_cov_fwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(
+  proj_kl_cov_fwd_kernel<<<(unsigned)B, compact ? KL_THREADS / 2 : KL_THREADS, smem, (cudaStream_t)stream>>>(
       L, L_o, eps_cov, proj_L, M, U, Li, Sig, lam, sc, info, n, warm_start, beta, (long long)ldb_beta, equality, out_L,
-      split, vec, (long long)ldb_vec, min_std, L_built);
+      split, vec, (long long)ldb_vec, min_std, L_built, compact);
   TCE_CHECK_LAUNCH("proj_kl_cov_fwd_kernel");
   return TCE_OK;
 }

@@ -365,3 +365,36 @@ def test_kl_state_generation_guard():
     out_b.sum().backward()                                                     # the latest forward: fine
     with pytest.raises(RuntimeError, match="overwrote its state"):
         out_a.sum().backward()
+
+
+def test_kl_projection_large_batch_equals_small_batches():
+    """More matrices than SMs take the two-CTAs-per-SM variant of the KL forward (three shared-memory buffers, 256
+    threads; csrc/tce_proj.cu `compact`): projected factors, the saved state and the gradients equal those of the same
+    matrices projected in chunks that take the one-CTA-per-SM variant -- cold, warm-started, and with one identity step."""
+    B, name, Dp = 200, "box", 63
+    inp = case(name, B, True, seed=5)
+    inp["L"][3] = inp["L_old"][3] * (1 + 1e-4)                  # inside the trust region: identity branch
+    c = lambda k: inp[k].to(DEV).contiguous()
+    L, L_o = c("L"), c("L_old")
+    beta = torch.full((1,), -1e9, device=DEV, dtype=torch.float64)          # entropy control inactive
+    g = torch.tril(torch.randn(B, Dp, Dp, generator=torch.Generator().manual_seed(1))).to(DEV)
+
+    def run(lo, hi, state, warm):
+        Lr = L[lo:hi].clone().requires_grad_(True)
+        out, proj, info = ops.proj_kl_entropy(Lr, L_o[lo:hi], 5e-4, state, warm, beta, False)
+        assert int(info.abs().max()) == 0
+        (out * g[lo:hi]).sum().backward()
+        return out.detach(), Lr.grad
+
+    big_state = ops.kl_state(B, Dp, DEV)
+    chunk_states = [ops.kl_state(100, Dp, DEV) for _ in range(2)]
+    for warm in (False, True, True):                            # the second / third call start from the saved eigen-basis
+        out_big, grad_big = run(0, B, big_state, warm)
+        outs, grads = zip(*[run(100 * k, 100 * (k + 1), chunk_states[k], warm) for k in range(2)])
+        out_small, grad_small = torch.cat(outs), torch.cat(grads)
+        assert (out_big - out_small).abs().max().item() <= 2e-6 * out_small.abs().max().item()
+        assert (grad_big - grad_small).abs().max().item() <= 1e-5 * grad_small.abs().max().item()
+        sc_big = ops.kl_state_scalars(big_state, B, Dp)
+        sc_small = torch.cat([ops.kl_state_scalars(s, 100, Dp) for s in chunk_states])
+        assert (sc_big[:, :3] - sc_small[:, :3]).abs().max().item() <= 1e-9 * max(1.0, sc_small[:, :3].abs().max().item())
+    assert sc_big[3, 1].item() == 0.0 and sc_big[:, 1].sum().item() >= B - 20       # identity step seen, most are active
