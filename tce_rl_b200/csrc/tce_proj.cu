@@ -795,11 +795,11 @@ proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ pr
                        const double *__restrict__ save_M, const double *__restrict__ save_U,
                        const double *__restrict__ save_Li, const double *__restrict__ save_lam,
                        const double *__restrict__ save_sc, float *__restrict__ grad_L, int n, int fused_entropy,
-                       const double *__restrict__ out_inv, double tr_coeff) {
+                       const double *__restrict__ out_inv, double tr_coeff, int compact) {
   extern __shared__ double sd[];
   const int m = pad_even(n), LD = m + 1, MS = m * LD;
-  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};
-  double *dinv = sd + 4 * MS, *lam = dinv + LA_DINV_DOUBLES, *rho = lam + m, *red = rho + m;
+  Mat b0{sd, LD, 1}, b1{sd + MS, LD, 1}, b2{sd + 2 * MS, LD, 1}, b3{sd + 3 * MS, LD, 1};     // b3: not with `compact`
+  double *dinv = sd + (compact ? 3 : 4) * MS, *lam = dinv + LA_DINV_DOUBLES, *rho = lam + m, *red = rho + m;
   const long long b = blockIdx.x;
   const size_t off = (size_t)b * n * n;
   float *gl = grad_L + off;
@@ -847,47 +847,66 @@ proj_kl_cov_bwd_kernel(const float *__restrict__ L, const float *__restrict__ pr
     const int i = e / n, j = e - i * n;
     if (j > i) b2(i, j) = 0.0; else if (i == j) b2(i, j) *= 0.5;                   // Phi
   }
-  load_full_d(b1, save_M + off, n, m);                                             // M (G is consumed)
-  if (out_inv) {     // (alpha P)^-1 is already known (the trust-region loss inverts the layer's output): P^-1 = alpha (.)
+  // `compact` (batches: two CTAs of 256 threads per SM, three buffers): F' = M^T (P^-T Phi P^-1) M with the products
+  // ordered so that never more than two operands and one result are alive; bF = where F' ends up, bN = where Nt goes
+  Mat bF = compact ? b2 : b1, bN = compact ? b1 : b2, bT = compact ? b2 : b3;
+  auto load_out_inv = [&](Mat X) {   // (alpha P)^-1 is already known (the trust-region loss inverts the layer's output)
     const double alpha = fused_entropy ? save_sc[b * KL_SC + 4] : 1.0;
     batched_load(out_inv + off, n * n, [&](int e, double v) {
       const int i = e / n, j = e - i * n;
-      b3(i, j) = j <= i ? alpha * v : 0.0;
+      X(i, j) = j <= i ? alpha * v : 0.0;
     });
+    zero_padding(X, n, m);
     __syncthreads();
+  };
+  if (compact) {
+    __syncthreads();                                                               // Phi complete, G consumed
+    if (out_inv) load_out_inv(b1); else la_tri_inverse(b0, b1, dinv, n);           // P^-1 (over G)
+    la_gemm(b0, b2, b1, n, n, n, TRI_LOWER, TRI_LOWER, TRI_LOWER, 1.0, 0.0);       // Phi P^-1 (over P; lower x lower)
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {                        // (its strict upper triangle is zero)
+      const int i = e / n, j = e - i * n;
+      if (j > i) b0(i, j) = 0.0;
+    }
+    __syncthreads();
+    la_gemm(b2, b1.T(), b0, n, n, n, TRI_UPPER, TRI_LOWER, TRI_FULL, 1.0, 0.0);    // S' = P^-T Phi P^-1 (over Phi)
+    load_full_d(b0, save_M + off, n, m);                                           // M
+    la_gemm(b1, b2, b0, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);          // S' M
+    la_gemm(b2, b0.T(), b1, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);      // F' = M^T S' M ; Ft = sym(F')
   } else {
-    la_tri_inverse(b0, b3, dinv, n);                                               // P^-1
+    load_full_d(b1, save_M + off, n, m);                                           // M (G is consumed)
+    if (out_inv) load_out_inv(b3); else la_tri_inverse(b0, b3, dinv, n);           // P^-1
+    la_gemm(b0, b3, b1, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);         // Y = P^-1 M (P is consumed)
+    la_gemm(b3, b2, b0, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);         // Phi Y
+    la_gemm(b1, b0.T(), b3, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);      // F' = Y^T Phi Y ; Ft = sym(F')
   }
-  la_gemm(b0, b3, b1, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // Y = P^-1 M (P is consumed)
-  la_gemm(b3, b2, b0, n, n, n, TRI_LOWER, TRI_FULL, TRI_FULL, 1.0, 0.0);           // Phi Y
-  la_gemm(b1, b0.T(), b3, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // F' = Y^T Phi Y ; Ft = sym(F')
   double eb = 0.0, dfe = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    eb += b1(i, i) * (rho[i] - (1.0 + eta) * rho[i] * rho[i]);
+    eb += bF(i, i) * (rho[i] - (1.0 + eta) * rho[i] * rho[i]);
     dfe += 2.0 * rho[i] - (1.0 + eta) * rho[i] * rho[i] - 1.0 / (1.0 + eta);
   }
   eb = block_sum(eb, red);
   dfe = 0.5 * block_sum(dfe, red);
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     const int i = e / n, j = e - i * n;
-    double v = -(1.0 + eta) * rho[i] * rho[j] * (0.5 * (b1(i, j) + b1(j, i)));
+    double v = -(1.0 + eta) * rho[i] * rho[j] * (0.5 * (bF(i, j) + bF(j, i)));
     if (i == j) v -= eb * (0.5 * (rho[i] - (1.0 + eta) * rho[i] * rho[i])) / dfe;
     if (i == j && tr_coeff != 0.0) {                                               // trust-region term, as in the sigma kernel
       const double a2 = fused_entropy ? save_sc[b * KL_SC + 6] : 1.0;
       v -= 0.5 * tr_coeff / (a2 * (1.0 + eta) * rho[i] * lam[i] * lam[i]);
     }
-    b2(i, j) = v;                                                                  // Nt (Phi is consumed)
+    bN(i, j) = v;                                                                  // Nt (Phi / S' M is consumed)
   }
-  load_full_d(b0, save_U + off, n, m);                                             // U~ (Y is consumed)
-  la_gemm(b3, b0, b2, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);            // U~ Nt
-  la_gemm(b1, b3, b0.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // U~ Nt U~^T (F' is consumed)
-  load_full_d(b2, save_Li + off, n, m);                                            // Lt^-1 (Nt is consumed)
-  la_gemm(b3, b2.T(), b1, n, n, n, TRI_UPPER, TRI_FULL, TRI_LOWER, 1.0, 0.0);      // Lt^-T (.)
+  load_full_d(b0, save_U + off, n, m);                                             // U~ (Y / M is consumed)
+  la_gemm(bT, b0, bN, n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);            // U~ Nt (compact: over F', which Nt
+  la_gemm(b1, bT, b0.T(), n, n, n, TRI_FULL, TRI_FULL, TRI_FULL, 1.0, 0.0);        // has absorbed) ; U~ Nt U~^T (over F' / Nt)
+  Mat bI = compact ? b0 : b2, bG = compact ? b2 : b3;
+  load_full_d(bI, save_Li + off, n, m);                                            // Lt^-1 (Nt / U~ is consumed)
+  la_gemm(bG, bI.T(), b1, n, n, n, TRI_UPPER, TRI_FULL, TRI_LOWER, 1.0, 0.0);      // Lt^-T (.)
   if (tr_coeff != 0.0) {                                                           // - tr_coeff (Lt^-T)_ii  (scaled by -2 below)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) b3(i, i) += 0.5 * tr_coeff / (double)L[off + (size_t)i * n + i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) bG(i, i) += 0.5 * tr_coeff / (double)L[off + (size_t)i * n + i];
     __syncthreads();
   }
-  store_lower_f(gl, b3, n, -2.0);
+  store_lower_f(gl, bG, n, -2.0);
 }
 
 // Backward in COVARIANCE space: the consumer of the projected covariance (the segment likelihood, which reads
@@ -1528,13 +1547,14 @@ static int kl_bwd_launch(const float *L, const float *proj_L, const float *grad_
   if (B == 0) return TCE_OK;              /* empty shard: pointers may be NULL */
   if (!L || !proj_L || !grad_out || !save || !grad_L || B < 0) return TCE_ERR_INVALID_ARGUMENT;
   PJ_CHECK_N(n);
-  const size_t smem = pj_smem_exclusive(pj_smem(n, 4), B);
-  int rc = set_smem(proj_kl_cov_bwd_kernel, smem);
+  const int compact = B > num_sms_proj() && kl_compact_enabled();      // as kl_fwd_launch: two 256-thread CTAs per SM
+  const size_t smem = pj_smem_exclusive(pj_smem(n, compact ? 3 : 4), B);
+  int rc = set_smem(proj_kl_cov_bwd_kernel, compact ? pj_smem(n, 4) : smem);
   if (rc) return rc;
   const size_t nn = (size_t)B * n * n;
   const double *M = save, *U = M + nn, *Li = U + nn, *lam = Li + 2 * nn, *sc = lam + (size_t)B * n;
-  proj_kl_cov_bwd_kernel<<<(unsigned)B, KL_THREADS, smem, (cudaStream_t)stream>>>(L, proj_L, grad_out, M, U, Li, lam, sc, grad_L,
-                                                                                 n, fused_entropy, out_inv, tr_coeff);
+  proj_kl_cov_bwd_kernel<<<(unsigned)B, compact ? KL_THREADS / 2 : KL_THREADS, smem, (cudaStream_t)stream>>>(
+      L, proj_L, grad_out, M, U, Li, lam, sc, grad_L, n, fused_entropy, out_inv, tr_coeff, compact);
   TCE_CHECK_LAUNCH("proj_kl_cov_bwd_kernel");
   return TCE_OK;
 }
