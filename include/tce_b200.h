@@ -78,7 +78,8 @@ int tce_prodmp_traj_fwd(const tce_tables_t *tables, const float *params, const f
  * (any output may be NULL).  API-permitted, never exercised by the reference (sample runs under
  * no_grad, temporal_correlated_sampler.py:91,200).                                                */
 /* tce_prodmp_traj_fwd for a batch whose episodes share ONE time grid (same init_time and times row: every shipped TCE
- * task): the basis rows are evaluated once (rows_ws: T * 2 * (K1 + 2) floats of workspace) and the batch becomes a
+ * task): the basis rows are evaluated once (rows_ws: T * (2 * (K1 + 2) rounded up to a multiple of 4) floats of 16-byte
+ * aligned workspace) and the batch becomes a
  * small matrix product per episode.  times_row [T] / init_time [1]: episode 0's values.                        */
 int tce_prodmp_traj_fwd_uniform(const tce_tables_t *tables, const float *params, const float *times_row,
                                 const float *init_time, const float *init_pos, const float *init_vel,

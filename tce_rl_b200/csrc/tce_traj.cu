@@ -321,7 +321,7 @@ __global__ void traj_rows_kernel(TabDev tb, const float *__restrict__ times_row,
                                  float *__restrict__ rows, int T) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
-  constexpr int RW = 2 * (K1 + 2);
+  constexpr int RW = (2 * (K1 + 2) + 3) & ~3;            // rows padded to 128-bit words (pad = 0)
   const int stride = tb.row32_stride;
   const double inv_tau = 1.0 / tb.tau;
   int ib; float wb;
@@ -338,6 +338,8 @@ __global__ void traj_rows_kernel(TabDev tb, const float *__restrict__ times_row,
   const float xi1 = (dy2b * y1 - dy1b * y2) * inv_det, xi2 = (y1b * y2 - y2b * y1) * inv_det;
   const float xi3 = (dy2b * dy1 - dy1b * dy2) * inv_det, xi4 = (y1b * dy2 - y2b * dy1) * inv_det;
   float *o = rows + (size_t)t * RW;
+#pragma unroll
+  for (int k = 2 * (K1 + 2); k < RW; ++k) o[k] = 0.f;
   o[0] = xi1; o[1] = xi2; o[K1 + 2] = xi3; o[K1 + 3] = xi4;
 #pragma unroll
   for (int j = 0; j < K1; ++j) {
@@ -349,77 +351,96 @@ __global__ void traj_rows_kernel(TabDev tb, const float *__restrict__ times_row,
   }
 }
 
+// traj_uniform_kernel: thread (e, d) owns one degree of freedom of one episode of the CTA's group: its K1 + 2
+// coefficients [y0, tau v0, theta (goal shifted)] stay in registers for the whole trajectory, the basis row of time t is
+// read as six 128-bit BROADCAST loads (all lanes the same t), 2 (K1 + 2) FMAs give position and velocity.  Results go
+// through a shared tile [episode][TU_TT time steps][2 D] so that every episode's TU_TT * 2D floats leave as contiguous
+// 128-bit stores (56-byte rows written from registers touch every 32-byte sector several times: L2 write bound).
+// ~7 warp instructions and ~2 shared-memory wavefronts per (episode, time) point; at B = 16384 every group has its
+// own resident CTA.
 constexpr int TU_THREADS = 256;
-constexpr int TU_EPC = 8;            // episodes per CTA iteration
+constexpr int TU_TT = 20;            // time steps per tile pass
 template <int K1>
 __global__ void __launch_bounds__(TU_THREADS)
 traj_uniform_kernel(TabDev tb, const float *__restrict__ rows, const float *__restrict__ params,
                     const float *__restrict__ init_pos, const float *__restrict__ init_vel, float *__restrict__ traj,
-                    long long B, int T) {
-  constexpr int RW = 2 * (K1 + 2), RS = RW | 1, PW = K1 + 2;
+                    long long B, int T, int epc, int estride) {
+  constexpr int PW = K1 + 2, RWP = (2 * PW + 3) & ~3;
   extern __shared__ __align__(16) float su[];
   const int D = tb.D, D2 = 2 * D, Dp = D * K1;
-  float *srow = su;                         // [T][RS]: odd stride -> lanes (consecutive t) hit different banks
-  float *sP = su + (size_t)T * RS;          // [TU_EPC][D][PW]: y0, v0 * tau, theta (goal shifted for relative goals)
-  float *tile = su + (((size_t)T * RS + (size_t)TU_EPC * D * PW + 3) & ~(size_t)3);   // [TU_THREADS][2D], 16-byte aligned
-  for (int i = threadIdx.x; i < T * RW; i += TU_THREADS) srow[(i / RW) * RS + (i % RW)] = rows[i];
+  float *srow = su;                                   // [T][RWP]
+  float *tile = su + (size_t)T * RWP;                 // [epc][estride], estride >= TU_TT * D2 (multiple of 4, = 8 mod 32)
+  {                                                   // rows [T][RWP] (padded by traj_rows_kernel): straight 128-bit copy,
+    const float4 *src = reinterpret_cast<const float4 *>(rows);          // four loads in flight per thread
+    float4 *dst = reinterpret_cast<float4 *>(srow);
+    const int n4 = T * (RWP / 4), nth = (int)blockDim.x;
+    for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * nth) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (i0 + u * nth < n4) v[u] = src[i0 + u * nth];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (i0 + u * nth < n4) dst[i0 + u * nth] = v[u];
+    }
+  }
   const float tau = (float)tb.tau, inv_tau_f = 1.0f / tau;
   const float sc_g = (float)tb.scale[K1 - 1];
   const float goal_shift_scale = tb.relative_goal ? (tb.relative_goal_scaled ? 1.0f : 1.0f / sc_g) : 0.0f;
-  const long long groups = (B + TU_EPC - 1) / TU_EPC;
+  const int e = threadIdx.x / D, d = threadIdx.x - e * D;
+  const long long groups = (B + epc - 1) / epc;
   for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
-    const long long b0 = g * TU_EPC;
-    const int ne = (int)((B - b0) < TU_EPC ? (B - b0) : TU_EPC);
-    __syncthreads();
-    for (int i = threadIdx.x; i < ne * D * PW; i += TU_THREADS) {
-      const int e = i / (D * PW), r = i - e * D * PW, d = r / PW, k = r - d * PW;
-      const long long bb = b0 + e;
-      float v;
-      if (k == 0) v = init_pos[bb * D + d];
-      else if (k == 1) v = init_vel[bb * D + d] * tau;
-      else {
-        v = params[bb * Dp + d * K1 + (k - 2)];
-        if (k == PW - 1) v += goal_shift_scale * init_pos[bb * D + d];           // relative goal (0 otherwise)
-      }
-      sP[i] = v;
-    }
-    __syncthreads();
-    // 256 points per pass: results go through a shared tile so that the global stores are contiguous 128-bit (a
-    // thread-private 56-byte row written with 8-byte stores touches every 32-byte sector four times: L2 write bound)
-    for (int p0 = 0; p0 < ne * T; p0 += TU_THREADS) {
-      const int p = p0 + threadIdx.x;
-      if (p < ne * T) {
-        const int e = p / T, t = p - e * T;
-        float rp[PW], rv[PW];
-        const float *row = srow + t * RS;
+    const long long b0 = g * epc, bb = b0 + e;
+    const int ne = (int)((B - b0) < epc ? (B - b0) : epc);
+    const bool mine = e < ne;
+    float p[PW];
 #pragma unroll
-        for (int k = 0; k < PW; ++k) { rp[k] = row[k]; rv[k] = row[PW + k]; }
-        const float *P = sP + e * D * PW;
-        float *o = tile + threadIdx.x * D2;
-        for (int d = 0; d < D; ++d) {
+    for (int k = 0; k < PW; ++k) p[k] = 0.f;
+    if (mine) {
+      const float y0 = init_pos[bb * D + d];
+      p[0] = y0;
+      p[1] = init_vel[bb * D + d] * tau;
+#pragma unroll
+      for (int j = 0; j < K1; ++j) p[2 + j] = params[bb * Dp + d * K1 + j];
+      p[PW - 1] += goal_shift_scale * y0;                                        // relative goal (0 otherwise)
+    }
+    for (int t0 = 0; t0 < T; t0 += TU_TT) {
+      const int nt = T - t0 < TU_TT ? T - t0 : TU_TT;
+      __syncthreads();                                 // srow ready (first pass) / previous tile copied out
+      if (mine) {
+        float *o = tile + (size_t)e * estride + d;
+        for (int tl = 0; tl < nt; ++tl) {
+          const float4 *row = reinterpret_cast<const float4 *>(srow + (size_t)(t0 + tl) * RWP);
+          float r[RWP];
+#pragma unroll
+          for (int q = 0; q < RWP / 4; ++q) {
+            const float4 v = row[q];
+            r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+          }
           float a = 0.f, c = 0.f;
 #pragma unroll
           for (int k = 0; k < PW; ++k) {
-            const float pk = P[d * PW + k];
-            a = fmaf(rp[k], pk, a);
-            c = fmaf(rv[k], pk, c);
+            a = fmaf(r[k], p[k], a);
+            c = fmaf(r[PW + k], p[k], c);
           }
-          o[d] = a;
-          o[D + d] = c * inv_tau_f;
+          o[tl * D2] = a;
+          o[tl * D2 + D] = c * inv_tau_f;
         }
       }
       __syncthreads();
-      const int npts = ne * T - p0 < TU_THREADS ? ne * T - p0 : TU_THREADS;
-      const long long g0 = (b0 * T + p0) * (long long)D2;
-      const int n_out = npts * D2;
-      if ((n_out & 3) == 0 && (g0 & 3) == 0) {
-        const float4 *s4 = reinterpret_cast<const float4 *>(tile);
-        float4 *d4 = reinterpret_cast<float4 *>(traj + g0);
-        for (int i = threadIdx.x; i < n_out / 4; i += TU_THREADS) d4[i] = s4[i];
+      const int per = nt * D2;                         // contiguous floats per episode in this pass
+      const long long g0 = (b0 * T + t0) * (long long)D2;
+      if ((per & 3) == 0 && (g0 & 3) == 0 && (((long long)T * D2) & 3) == 0) {
+        const int per4 = per >> 2;
+        for (int i = threadIdx.x; i < ne * per4; i += blockDim.x) {
+          const int ee = i / per4, q = i - ee * per4;
+          reinterpret_cast<float4 *>(traj + g0 + (long long)ee * T * D2)[q] =
+              reinterpret_cast<const float4 *>(tile + (size_t)ee * estride)[q];
+        }
       } else {
-        for (int i = threadIdx.x; i < n_out; i += TU_THREADS) traj[g0 + i] = tile[i];
+        for (int i = threadIdx.x; i < ne * per; i += blockDim.x) {
+          const int ee = i / per, q = i - ee * per;
+          traj[g0 + (long long)ee * T * D2 + q] = tile[(size_t)ee * estride + q];
+        }
       }
-      __syncthreads();
     }
   }
 }
@@ -428,20 +449,29 @@ template <int K1>
 int launch_traj_uniform(const tce_tables *t, const float *params, const float *times_row, const float *init_time,
                         const float *init_pos, const float *init_vel, float *rows_ws, float *traj, int64_t B, int64_t T,
                         cudaStream_t st) {
-  constexpr int RW = 2 * (K1 + 2), RS = RW | 1;
+  constexpr int RW = 2 * (K1 + 2), RWP = (RW + 3) & ~3;
   traj_rows_kernel<K1><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(tab_dev(t), times_row, init_time, rows_ws, (int)T);
   TCE_CHECK_LAUNCH("traj_rows_kernel");
-  const size_t smem = sizeof(float) * ((size_t)T * RS + (size_t)TU_EPC * t->D * (K1 + 2) + 8 +
-                                       (size_t)TU_THREADS * 2 * t->D);
+  const int D = t->D, D2 = 2 * D;
+  if (D > TU_THREADS / 4) return TCE_ERR_UNSUPPORTED_SHAPE;
+  // episodes per CTA: up to 16 (<= 256 threads), fewer for small batches so that every SM gets a group
+  int epc = TU_THREADS / D;
+  if (epc > 16) epc = 16;
+  while (epc > 4 && (B + epc - 1) / epc < 2LL * num_sms()) epc >>= 1;
+  int estride = (TU_TT * D2 + 3) & ~3;                 // multiple of 4 and = 8 (mod 32): conflict-light tile rows
+  while ((estride & 31) != 8) estride += 4;
+  const size_t smem = sizeof(float) * ((size_t)T * RWP + (size_t)epc * estride);
   if (smem > 200 * 1024) return TCE_ERR_UNSUPPORTED_SHAPE;
   if (smem > 48 * 1024)
     TCE_CUDA(cudaFuncSetAttribute(traj_uniform_kernel<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
              "traj uniform smem attr");
-  long long grid = (B + TU_EPC - 1) / TU_EPC;
-  const long long cap = 4LL * num_sms();
+  int threads = ((epc * D + 31) / 32) * 32;            // >= 128: the extra threads help with the row copy and the stores
+  if (threads < 128) threads = 128;
+  long long grid = (B + epc - 1) / epc;
+  const long long cap = 8LL * num_sms();
   if (grid > cap) grid = cap;
-  traj_uniform_kernel<K1><<<(unsigned)grid, TU_THREADS, smem, st>>>(tab_dev(t), rows_ws, params, init_pos, init_vel, traj, B,
-                                                                  (int)T);
+  traj_uniform_kernel<K1><<<(unsigned)grid, threads, smem, st>>>(tab_dev(t), rows_ws, params, init_pos, init_vel, traj, B,
+                                                               (int)T, epc, estride);
   TCE_CHECK_LAUNCH("traj_uniform_kernel");
   return TCE_OK;
 }
@@ -528,7 +558,7 @@ extern "C" int tce_prodmp_traj_fwd(const tce_tables_t *t, const float *params, c
 }
 
 /* All episodes share ONE time grid: times_row [T] and init_time [1] describe it (episode 0's values); rows_ws
- * [T * 2 * (K1 + 2)] floats of workspace.  Same results as tce_prodmp_traj_fwd on such inputs.               */
+ * [T * (2 * (K1 + 2) rounded up to a multiple of 4)] floats of workspace, 16-byte aligned.  Same results as tce_prodmp_traj_fwd on such inputs.               */
 extern "C" int tce_prodmp_traj_fwd_uniform(const tce_tables_t *t, const float *params, const float *times_row,
                                            const float *init_time, const float *init_pos, const float *init_vel,
                                            float *rows_ws, float *traj, int64_t B, int64_t T, void *stream) {

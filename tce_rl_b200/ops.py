@@ -113,7 +113,7 @@ def prodmp_traj(params: Tensor, times: Tensor, init_time: Tensor, init_pos: Tens
     # basis rows are evaluated once and the batch becomes a small matrix product per episode
     if UNIFORM_TRAJ and B >= 64 and times_uniform(init_time, times):
         k1 = params.shape[-1] // num_dof
-        rows = torch.empty(T * 2 * (k1 + 2), device=params.device, dtype=torch.float32)
+        rows = torch.empty(T * ((2 * (k1 + 2) + 3) // 4 * 4), device=params.device, dtype=torch.float32)
         _lib.call("tce_prodmp_traj_fwd_uniform", tables, _p(params), _p(times), _p(init_time), _p(init_pos), _p(init_vel),
                   _p(rows), _p(traj), B, T, _stream())
         return traj
