@@ -13,6 +13,8 @@ Environment rollout (``sampler.run``) is out of scope: ``step()`` needs a sample
 """
 from __future__ import annotations
 
+import contextlib
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -89,8 +91,7 @@ class TemporalCorrelatedAgent:
         self.p2p_allreduce = bool(kwargs.get("p2p_allreduce", True))
         self._p2p = None
         self._fast = None
-        if self.overlap_logging and hasattr(policy, "mean_net") and hasattr(policy.mean_net, "side_wgrad"):
-            policy.mean_net.side_wgrad = True              # joined after every backward of policy_epoch
+        self._scope_depth = 0                              # _side_grad_scope (re-entrant)
         self._log_stream = None
         self._log_stream2 = None
         self._tr_stream = None
@@ -524,6 +525,10 @@ class TemporalCorrelatedAgent:
         """The balance check of temporal_correlated_agent.py:446-522 / black_box_agent.py:221-283: the gradient norm of
         the surrogate loss alone and of the trust-region loss alone (two extra forward + backward passes, no optimiser
         step).  -> device tensor [2] = (surrogate_grad_norm, trust_region_grad_norm)."""
+        with self._side_grad_scope():
+            return self._balance_norms(dataset, times, pred_pairs)
+
+    def _balance_norms(self, dataset, times, pred_pairs):
         old = (dataset["segment_params_mean"], dataset["segment_params_L"])
         obs = self._policy_obs(dataset)
         norms = []
@@ -547,9 +552,38 @@ class TemporalCorrelatedAgent:
                 norms.append(self._flat_grad_norm())
         return torch.stack(norms)
 
+    @contextlib.contextmanager
+    def _side_grad_scope(self):
+        """While the agent's own update code runs: weight / bias gradients of the mean network on side streams
+        (``MLP.side_wgrad``, joined by ``util.join_side_grads`` after every backward in here) and torch's
+        accumulate-grad stream-mismatch warning off (the covariance chain deliberately runs forward and backward on a
+        side stream).  Both are restored on exit, so user code around the agent (``torch.autograd.grad``, hooks, own
+        losses) sees stock autograd behaviour."""
+        net = getattr(self.policy, "mean_net", None)
+        use = bool(self.overlap_logging and net is not None and hasattr(net, "side_wgrad"))
+        prev = net.side_wgrad if use else None
+        warn = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if use:
+            net.side_wgrad = True
+        if warn is not None and self._scope_depth == 0:
+            warn(False)
+        self._scope_depth += 1
+        try:
+            yield
+        finally:
+            self._scope_depth -= 1
+            if use:
+                net.side_wgrad = prev
+            if warn is not None and self._scope_depth == 0:
+                warn(True)
+
     def policy_epoch(self, dataset, times, pred_pairs):
         """One epoch body of ``update_policy`` (temporal_correlated_agent.py:524-589): returns the metrics
         vector [7 + 12] (``_LOSS_KEYS`` then ``_KL_KEYS``) living on the device."""
+        with self._side_grad_scope():
+            return self._policy_epoch(dataset, times, pred_pairs)
+
+    def _policy_epoch(self, dataset, times, pred_pairs):
         if self.fast_epoch:
             from .fast_epoch import SharedCovKLEpoch
             if SharedCovKLEpoch.applicable(self, dataset):

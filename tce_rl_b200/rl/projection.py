@@ -16,9 +16,8 @@ import torch
 from .. import ops, util
 
 
-# the covariance chain deliberately runs (forward and backward) on a side stream, see _call_overlapped
-if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
-    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+# (the covariance chain deliberately runs forward and backward on a side stream, see _call_overlapped; torch's
+# accumulate-grad stream-mismatch warning is switched off only inside the agent's update scope: rl/agent.py)
 
 
 def _expand_first(t, batch):

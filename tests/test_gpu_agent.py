@@ -1,6 +1,7 @@
 """The drop-in agent API on the GPU: process_dataset -> update_critic -> update_policy (eager and CUDA graph)."""
 import copy
 
+import numpy as np
 import pytest
 import torch
 
@@ -277,3 +278,25 @@ def test_flat_adam_matches_torch_adam(max_norm, wd):
         for p, q in zip(ref, mine):
             assert (p - q).abs().max().item() <= 2e-6 * max(1.0, p.abs().max().item()), it
     assert opt.stats[0].item() == 6.0
+
+
+def test_side_stream_gradients_are_scoped_to_the_update():
+    """The agent switches the mean network's side-stream weight gradients on only while its own update code runs
+    (``_side_grad_scope``): outside, ``torch.autograd.grad`` / a user's own backward through the policy see stock
+    autograd (every parameter gets its gradient)."""
+    agent, dataset = build(epochs=1)
+    net = agent.policy.mean_net
+    assert net.side_wgrad is False
+    dataset = agent.process_dataset(dataset)
+    metrics = agent.update_policy(dataset)
+    assert net.side_wgrad is False and bool(np.isfinite(metrics["policy_loss_mean"]))
+    obs = dataset["segment_state"][..., :12]
+    params = list(net.parameters())
+    grads = torch.autograd.grad(net(obs).square().sum(), params)
+    assert all(g is not None and torch.isfinite(g).all() and g.abs().sum() > 0 for g in grads)
+    for p in params:                                            # .grad buffers exist (views of the flat buffer): a plain
+        assert p.grad is not None                               # backward accumulates into them on the current stream
+    before = [p.grad.clone() for p in params]
+    net(obs).square().sum().backward()
+    torch.cuda.synchronize()
+    assert all(((p.grad - b) - g).abs().max() <= 1e-4 * max(1.0, g.abs().max().item()) for p, b, g in zip(params, before, grads))
