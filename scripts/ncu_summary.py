@@ -36,8 +36,11 @@ txt = "\n".join(lines)
 out_txt = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles", "r02_ncu_summary.txt")
 open(out_txt, "w").write(txt + "\n")
 import bench
-abi = {"proj_kl_cov_fwd_kernel": ["tce_proj_kl_entropy_fwd_sigma", "tce_proj_kl_cov_fwd", "tce_proj_kl_entropy_fwd"],
-       "proj_kl_cov_bwd_sigma_kernel": ["tce_proj_kl_bwd_sigma"], "uniform_main_kernel<7, 9, 8>": ["tce_seglik_uniform_main"],
+abi = {"proj_kl_cov_fwd_kernel": ["tce_proj_kl_entropy_fwd_sigma", "tce_proj_kl_cov_fwd", "tce_proj_kl_entropy_fwd",
+                                  "tce_proj_kl_entropy_fwd_sigma_vec"],
+       "proj_kl_cov_bwd_sigma_kernel": ["tce_proj_kl_bwd_sigma", "tce_proj_kl_bwd_sigma_k", "tce_proj_kl_bwd_sigma_k_vec"],
+       "traj_uniform_kernel<9>": ["tce_prodmp_traj_fwd_uniform"], "maha_kernel": ["tce_gauss_maha"],
+       "rsample_kernel": ["tce_mvn_rsample"], "uniform_main_kernel<7, 9, 8>": ["tce_seglik_uniform_main"],
        "uniform_prep_kernel<7, 9, true>": ["tce_seglik_uniform_prep"], "uniform_finish_kernel<7, 9>": ["tce_seglik_uniform_finish"],
        "epoch_mean_fwd_kernel": ["tce_epoch_mean_fwd"], "epoch_tr_mean_kernel": ["tce_epoch_tr_mean"],
        "proj_kl_cov_bwd_kernel": ["tce_proj_kl_cov_bwd", "tce_proj_kl_entropy_bwd", "tce_proj_kl_entropy_bwd_tr"],

@@ -41,9 +41,11 @@ prof.export_chrome_trace(tmp)
 ev = [e for e in json.load(open(tmp))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
 ev.sort(key=lambda e: e["ts"])
 # keep the last replay: everything after the previous epoch's last kernel (metrics assembly / policy head as markers)
-ends = [i for i, e in enumerate(ev) if "epoch_metrics_kernel" in e["name"]]
+# (the metrics kernel runs beside the Adam kernel, which ends the epoch: cut after whichever of the two comes last)
+ends = [i for i, e in enumerate(ev) if "adam_kernel" in e["name"]]
+ends = [max(i, *[j for j in range(i - 2, min(i + 3, len(ev))) if "epoch_metrics_kernel" in ev[j]["name"]] or [i]) for i in ends]
 if len(ends) >= 2:
-    ev = ev[ends[-2] + 1:]
+    ev = ev[ends[-2] + 1:ends[-1] + 1]
 else:
     cut = max(i for i, e in enumerate(ev) if "head_fwd_kernel" in e["name"])
     ev = ev[cut:]

@@ -154,9 +154,20 @@ class SharedCovKLEpoch:
             ag.policy_optimizer.exchange_early(sum(p.numel() for p in params[:-1]))
         main.wait_event(cov_done)
         ag._allreduce_grads(params)
-        ag.policy_optimizer.step(max_norm=float(ag.clip_grad_norm))
         metrics = torch.empty(19, device=dev, dtype=f64)
-        _lib.call("tce_epoch_metrics", _p(acc), _p(lacc[1:]), _p(sc), _p(ag.policy_optimizer.stats), B, coeff,
-                  int(with_cov), float(ag.entropy_penalty_coef), _p(metrics), main.cuda_stream)
+        metrics_done = torch.cuda.Event()
+
+        def metrics_beside_adam():          # needs the gradient norm, not the update: runs next to the Adam kernel
+            norm_ready = torch.cuda.Event()
+            norm_ready.record(main)
+            tr_stream.wait_event(norm_ready)
+            _lib.call("tce_epoch_metrics", _p(acc), _p(lacc[1:]), _p(sc), _p(ag.policy_optimizer.stats), B, coeff,
+                      int(with_cov), float(ag.entropy_penalty_coef), _p(metrics), tr_stream.cuda_stream)
+            metrics_done.record(tr_stream)
+            for t in (acc, lacc, metrics):
+                t.record_stream(tr_stream)
+
+        ag.policy_optimizer.step(max_norm=float(ag.clip_grad_norm), after_norm=metrics_beside_adam)
+        main.wait_event(metrics_done)
         self.last = dict(logp=logp, info=linfo, proj_mean=proj_mean, state=state, mean=mean_d)
         return metrics

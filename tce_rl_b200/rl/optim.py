@@ -114,7 +114,9 @@ class FlatAdam(torch.optim.Optimizer):
         return self.stats[1].sqrt()
 
     @torch.no_grad()
-    def step(self, max_norm: float = 0.0):
+    def step(self, max_norm: float = 0.0, after_norm=None):
+        """``after_norm``: called once the gradient norm (and the data-parallel exchange) is queued and before the update
+        kernel -- a consumer of the norm (the epoch's metrics kernel) can be forked onto another stream there."""
         self._check_views()
         g = self.param_groups[0]
         st = torch.cuda.current_stream().cuda_stream
@@ -130,6 +132,8 @@ class FlatAdam(torch.optim.Optimizer):
         else:
             grad = self.flat_grad
             _lib.call("tce_grad_sumsq", grad.data_ptr(), grad.numel(), self.stats.data_ptr(), st)
+        if after_norm is not None:
+            after_norm()
         _lib.call("tce_adam_step", len(self._params), C.cast(ptrs, C.c_void_p), C.cast(self._sizes, C.c_void_p),
                   grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                   self.stats.data_ptr(), float(max_norm), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
