@@ -4,6 +4,7 @@
 // Otto et al., ICLR 2021), including the C++ cpp_projection (ITPAL) KL covariance projection, which the
 // reference runs on the CPU through numpy.  One CTA per matrix; all matrices live in shared memory in fp64
 // (bounds such as cov_bound = 5e-4 are differences of O(n) quantities -- fp32 cannot resolve them).
+#include <cuda_pipeline.h>
 #include <math.h>
 
 #include "tce_smem_la.cuh"
@@ -239,6 +240,83 @@ maha_kernel(const float *__restrict__ mean, const float *__restrict__ mean_o, co
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     const int i = e / n, j = e - i * n;
     gl[e] = j <= i ? (float)(-g2 * bv[i] * zv[j]) : 0.f;
+  }
+}
+
+// n <= 64: ONE WARP per episode (four episodes per 128-thread CTA, every warp busy -- the kernel above keeps three of its
+// four warps idle during the solves).  Lane l owns rows l and l + 32 of the system: right-hand side, solution and the
+// inverted diagonal live in registers; per step the owner lane broadcasts z_j with a shuffle and every lane updates its
+// two rows with the column entries it fetched from shared memory one step ahead: ~45 cycles per step instead of ~150.
+constexpr int MW_WARPS = 4;
+__global__ void __launch_bounds__(MW_WARPS * 32)
+maha_warp_kernel(const float *__restrict__ mean, const float *__restrict__ mean_o, const float *__restrict__ L_o,
+                 long long ldb_Lo, const double *__restrict__ gout, double *__restrict__ out,
+                 float *__restrict__ grad_mean, float *__restrict__ grad_L, int n, long long B) {
+  extern __shared__ __align__(16) unsigned char mw_raw[];
+  const int LD = n | 1, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t per_warp = (((size_t)n * LD * sizeof(float) + 15) & ~(size_t)15) + 2 * 64 * sizeof(double);
+  float *sL = reinterpret_cast<float *>(mw_raw + warp * per_warp);
+  double *sz = reinterpret_cast<double *>(mw_raw + warp * per_warp + (((size_t)n * LD * sizeof(float) + 15) & ~(size_t)15));
+  double *su = sz + 64;
+  const unsigned full = 0xffffffffu;
+  for (long long b = (long long)blockIdx.x * MW_WARPS + warp; b < B; b += (long long)gridDim.x * MW_WARPS) {
+    const float *Lo = L_o + b * ldb_Lo;
+    __syncwarp();
+    // lower triangle, row by row (lanes = consecutive columns), as asynchronous global -> shared copies: all ~2 n
+    // requests of a lane are in flight at once (staging through registers four rows at a time made this a chain of
+    // n / 4 memory round trips, 3/4 of the kernel's time)
+    for (int i = 0; i < n; ++i) {
+      if (lane <= i) __pipeline_memcpy_async(sL + i * LD + lane, Lo + (size_t)i * n + lane, sizeof(float));
+      if (lane + 32 <= i) __pipeline_memcpy_async(sL + i * LD + lane + 32, Lo + (size_t)i * n + lane + 32, sizeof(float));
+    }
+    __pipeline_commit();
+    const int r0 = lane, r1 = lane + 32;
+    double b0 = r0 < n ? (double)mean[b * n + r0] - (double)mean_o[b * n + r0] : 0.0;
+    double b1 = r1 < n ? (double)mean[b * n + r1] - (double)mean_o[b * n + r1] : 0.0;
+    __pipeline_wait_prior(0);
+    __syncwarp();
+    const double inv0 = r0 < n ? 1.0 / (double)sL[r0 * LD + r0] : 0.0, inv1 = r1 < n ? 1.0 / (double)sL[r1 * LD + r1] : 0.0;
+    double z0 = 0.0, z1 = 0.0, maha = 0.0;
+    // z = L_o^-1 diff (column oriented)
+    float c0 = (r0 > 0 && r0 < n) ? sL[r0 * LD] : 0.f, c1 = r1 < n ? sL[r1 * LD] : 0.f;
+    for (int j = 0; j < n; ++j) {
+      const double mine = (j < 32 ? b0 * inv0 : b1 * inv1);
+      const double zj = __shfl_sync(full, mine, j & 31);
+      const float n0 = (j + 1 < n && r0 > j + 1 && r0 < n) ? sL[r0 * LD + j + 1] : 0.f;      // next column, fetched ahead
+      const float n1 = (j + 1 < n && r1 > j + 1 && r1 < n) ? sL[r1 * LD + j + 1] : 0.f;
+      if (r0 > j) b0 = fma(-(double)c0, zj, b0);
+      if (r1 > j) b1 = fma(-(double)c1, zj, b1);
+      if (lane == (j & 31)) { if (j < 32) z0 = zj; else z1 = zj; }
+      maha = fma(zj, zj, maha);
+      c0 = n0; c1 = n1;
+    }
+    if (out && lane == 0) out[b] = maha;
+    if (!gout) continue;
+    const double g2 = 2.0 * gout[b];
+    // u = L_o^-T z: after u_i is known every lane k < i subtracts L_o[i][k] u_i from its rows (row i of L: consecutive lanes)
+    b0 = z0; b1 = z1;
+    for (int i = n - 1; i >= 0; --i) {
+      const double mine = (i < 32 ? b0 * inv0 : b1 * inv1);
+      const double ui = __shfl_sync(full, mine, i & 31);
+      const float l0 = r0 < i ? sL[i * LD + r0] : 0.f, l1 = r1 < i ? sL[i * LD + r1] : 0.f;
+      if (lane == (i & 31)) { if (i < 32) b0 = ui; else b1 = ui; }
+      if (r0 < i) b0 = fma(-(double)l0, ui, b0);
+      if (r1 < i) b1 = fma(-(double)l1, ui, b1);
+    }
+    if (grad_mean) {
+      if (r0 < n) grad_mean[b * n + r0] = (float)(g2 * b0);
+      if (r1 < n) grad_mean[b * n + r1] = (float)(g2 * b1);
+    }
+    if (grad_L) {                       // d maha / d L_o = -2 tril(u z^T)   (d(L^-1) = -L^-1 dL L^-1)
+      if (r0 < n) { sz[r0] = z0; su[r0] = b0; }
+      if (r1 < n) { sz[r1] = z1; su[r1] = b1; }
+      __syncwarp();
+      float *gl = grad_L + (size_t)b * n * n;
+      for (int i = 0; i < n; ++i) {
+        const double ui = -g2 * su[i];
+        for (int j = lane; j < n; j += 32) gl[(size_t)i * n + j] = j <= i ? (float)(ui * sz[j]) : 0.f;
+      }
+    }
   }
 }
 
@@ -1407,6 +1485,19 @@ extern "C" int tce_gauss_stats_bwd(const float *mean, const float *L, int64_t ld
 
 static int maha_launch(const float *mean, const float *mean_o, const float *L_o, int64_t ldb_Lo, const double *grad_out,
                        double *maha, float *grad_mean, float *grad_L, int64_t B, int n, void *stream) {
+  if (n <= 64 && B >= 2 * MW_WARPS) {                   // warp per episode (a handful of episodes: the CTA kernel's extra
+    const size_t per_warp = (((size_t)n * (n | 1) * sizeof(float) + 15) & ~(size_t)15) + 2 * 64 * sizeof(double);   // threads
+    const size_t smem_w = MW_WARPS * per_warp;          // help with the loads)
+    if (smem_w > 48 * 1024)
+      TCE_CUDA(cudaFuncSetAttribute(maha_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w), "maha attr");
+    long long grid = (B + MW_WARPS - 1) / MW_WARPS;
+    const long long cap = 6LL * num_sms_proj();
+    if (grid > cap) grid = cap;
+    maha_warp_kernel<<<(unsigned)grid, MW_WARPS * 32, smem_w, (cudaStream_t)stream>>>(mean, mean_o, L_o, ldb_Lo, grad_out, maha,
+                                                                                 grad_mean, grad_L, n, (long long)B);
+    TCE_CHECK_LAUNCH("maha_warp_kernel");
+    return TCE_OK;
+  }
   const size_t smem = 3 * (size_t)n * sizeof(double) + (size_t)n * (n | 1) * sizeof(float);
   if (smem > 48 * 1024)
     TCE_CUDA(cudaFuncSetAttribute(maha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "maha attr");

@@ -615,8 +615,8 @@ def _(x):
 def gauss_maha(mean: Tensor, mean_o: Tensor, L_o: Tensor) -> Tensor:
     """|L_o^-1 (mean - mean_o)|^2  [B] fp64 (``policy.maha``); differentiable w.r.t. all three arguments."""
     mean, mean_o = _chk(mean), _chk(mean_o)
-    L_o, ldbo = _batched_matrix(L_o, "L_o")
     B, n = mean.shape
+    L_o, ldbo = _batched_matrix(L_o, "L_o", batch=B)
     out = torch.empty(B, device=mean.device, dtype=torch.float64)
     _lib.call("tce_gauss_maha", _p(mean), _p(mean_o), _p(L_o), ldbo, None, _p(out), None, B, n, _stream())
     return out
@@ -630,8 +630,8 @@ def _(mean, mean_o, L_o):
 @torch.library.custom_op("tce::gauss_maha_bwd", mutates_args=())
 def gauss_maha_bwd(grad: Tensor, mean: Tensor, mean_o: Tensor, L_o: Tensor) -> Tensor:
     mean, mean_o = _chk(mean), _chk(mean_o)
-    L_o, ldbo = _batched_matrix(L_o, "L_o")
     B, n = mean.shape
+    L_o, ldbo = _batched_matrix(L_o, "L_o", batch=B)
     g = _chk(grad, torch.float64, "grad")
     g_mean = torch.empty_like(mean)
     _lib.call("tce_gauss_maha", _p(mean), _p(mean_o), _p(L_o), ldbo, _p(g), None, _p(g_mean), B, n, _stream())
@@ -647,8 +647,8 @@ def _(grad, mean, mean_o, L_o):
 def gauss_maha_bwd_full(grad: Tensor, mean: Tensor, mean_o: Tensor, L_o: Tensor, need_L: bool) -> Tuple[Tensor, Tensor]:
     """-> (d maha / d mean [B, n] (= -d maha / d mean_o), d maha / d L_o [B, n, n] or empty)."""
     mean, mean_o = _chk(mean), _chk(mean_o)
-    Lc, ldbo = _batched_matrix(L_o, "L_o")
     B, n = mean.shape
+    Lc, ldbo = _batched_matrix(L_o, "L_o", batch=B)
     g = _chk(grad, torch.float64, "grad")
     g_mean = torch.empty_like(mean)
     g_L = torch.empty(B, n, n, device=mean.device, dtype=torch.float32) if need_L else mean.new_empty(0)

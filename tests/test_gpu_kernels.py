@@ -341,3 +341,29 @@ def test_surrogate_single_factor_path_equals_broadcast_path():
     assert (gm0 - gm1).abs().max() <= 2e-5 * gm1.abs().max()
     assert gL0.shape == gL1.shape == (1,) + tuple(inp["L"].shape[1:])
     assert (gL0 - gL1).abs().max() <= 1e-4 * gL1.abs().max()
+
+
+@pytest.mark.parametrize("n,B", [(63, 200), (63, 9), (63, 3), (28, 37), (6, 64), (64, 16), (100, 12)])
+def test_gauss_maha_values_and_gradients(n, B):
+    """tce_gauss_maha / tce_gauss_maha_bwd_full (black_box_policy.py:183-224 ``maha``) against fp64 torch: value and the
+    gradients w.r.t. both means and the factor -- through the warp-per-episode kernel (n <= 64, B >= 8), the
+    CTA-per-episode kernel (few episodes, n > 64) and a broadcast factor [1, n, n]."""
+    g = torch.Generator().manual_seed(n * 1000 + B)
+    mean, mean_o = torch.randn(B, n, generator=g), torch.randn(B, n, generator=g)
+    L = torch.tril(0.1 * torch.randn(B, n, n, generator=g), -1) + torch.diag_embed(0.5 + torch.rand(B, n, generator=g))
+    w = torch.rand(B, generator=g, dtype=torch.float64)
+    for shared in (False, True):
+        Lc = L[:1].clone() if shared else L
+        m64, o64, L64 = (t.double().requires_grad_(True) for t in (mean, mean_o, Lc))
+        d = (m64 - o64)[..., None]
+        z = torch.linalg.solve_triangular(L64.expand(B, n, n), d, upper=False)
+        want = z.square().sum((1, 2))
+        gm, go, gL = torch.autograd.grad((want * w).sum(), [m64, o64, L64])
+        md, od, Ld = (t.to(DEV).requires_grad_(True) for t in (mean, mean_o, Lc))
+        got = ops.gauss_maha(md, od, Ld)
+        assert (got.cpu() - want.detach()).abs().max() <= 1e-5 * want.abs().max()
+        g_m, g_o, g_L = torch.autograd.grad((got * w.to(DEV)).sum(), [md, od, Ld])
+        assert (g_m.cpu().double() - gm).abs().max() <= 2e-5 * gm.abs().max()
+        assert (g_o.cpu().double() - go).abs().max() <= 2e-5 * go.abs().max()
+        assert (g_L.cpu().double() - torch.tril(gL)).abs().max() <= 5e-5 * gL.abs().max()
+        assert torch.triu(g_L, 1).abs().max().item() == 0.0
