@@ -57,10 +57,26 @@ rows = [
 out = [f"# HBM-bound family, {name} shape, B = {B}; CUDA events per launch (median of 20, L2 flushed); peak = {peak:.0f} GB/s "
        f"(MEASURED_PEAKS.json hbm_gbs); bytes = SURVEY 8(d) algorithmic bytes per episode x B",
        f"{'kernel':52s} {'us':>9s} {'alg MB':>9s} {'GB/s':>9s} {'frac':>7s}"]
+# bytes that MUST cross the HBM interface given the layout (factors are dense [n, n] fp32 in HBM, as the reference holds
+# them: the zero upper triangle travels with a contiguous block copy) -- only where that differs from the algorithmic figure
+moved = {"mvn_rsample (per-episode L)": 4 * (3 * Dp + Dp * Dp), "gauss_maha (per-episode L)": 4 * (Dp * Dp + 2 * Dp) + 8}
 for tag, fn, bpe in rows:
     t = timed(fn)
     mb = bpe * B / 1e6
-    out.append(f"{tag:52s} {t * 1e6:9.1f} {mb:9.1f} {mb / 1e3 / t:9.1f} {mb / 1e3 / t / peak:7.3f}")
+    line = f"{tag:52s} {t * 1e6:9.1f} {mb:9.1f} {mb / 1e3 / t:9.1f} {mb / 1e3 / t / peak:7.3f}"
+    if tag in moved:
+        line += f"   (dense-layout bytes {moved[tag] * B / 1e6:.1f} MB: {moved[tag] * B / 1e9 / t:.0f} GB/s = {moved[tag] * B / 1e9 / t / peak:.3f})"
+    out.append(line)
+# what this memory system sustains for one-sided traffic (same timing method, 1 GiB buffers): the 6544 GB/s peak is a
+# COPY (half reads, half writes); write-dominated kernels (policy head: 2/3 writes, trajectories: 9/10) see the write figure
+big = torch.empty(256 * 1024 * 1024, device=dev, dtype=torch.float32)
+big2 = torch.empty_like(big)
+t_w = timed(lambda: big.fill_(1.0))
+t_r = timed(lambda: big.sum())
+t_c = timed(lambda: big2.copy_(big))
+gb = big.numel() * 4 / 1e9
+out.append(f"# calibration (1 GiB fp32, torch kernels): write-only fill {gb / t_w:.0f} GB/s, read-only sum {gb / t_r:.0f} GB/s, "
+           f"copy {2 * gb / t_c:.0f} GB/s (read + write bytes)")
 txt = "\n".join(out)
 print(txt)
 dst = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "r02_hbm_kernels_summary.txt")

@@ -7,6 +7,7 @@
 #include <cuda_pipeline.h>
 #include <math.h>
 
+#include "tce_bulk.cuh"
 #include "tce_smem_la.cuh"
 
 // Profiling scaffolding, compiled in with -DTCE_PROFILE only (TCE_PROFILE=1 python -m tce_rl_b200._build --force):
@@ -247,34 +248,62 @@ maha_kernel(const float *__restrict__ mean, const float *__restrict__ mean_o, co
 // four warps idle during the solves).  Lane l owns rows l and l + 32 of the system: right-hand side, solution and the
 // inverted diagonal live in registers; per step the owner lane broadcasts z_j with a shuffle and every lane updates its
 // two rows with the column entries it fetched from shared memory one step ahead: ~45 cycles per step instead of ~150.
+//
+// BULK (odd n, contiguous factors, B a multiple of MW_WARPS): the dense factors of the CTA's MW_WARPS episodes are one
+// 16-byte-aligned block of 4 n^2 floats, requested by ONE bulk asynchronous copy (mbarrier completion) instead of
+// ~2 n four-byte copies per lane; row stride n is odd, so the column accesses of the forward solve stay conflict free.
+// One buffer per CTA, three CTAs per SM: the copies of two CTAs are in flight while the third solves.
 constexpr int MW_WARPS = 4;
+template <bool BULK>
 __global__ void __launch_bounds__(MW_WARPS * 32)
 maha_warp_kernel(const float *__restrict__ mean, const float *__restrict__ mean_o, const float *__restrict__ L_o,
                  long long ldb_Lo, const double *__restrict__ gout, double *__restrict__ out,
                  float *__restrict__ grad_mean, float *__restrict__ grad_L, int n, long long B) {
-  extern __shared__ __align__(16) unsigned char mw_raw[];
-  const int LD = n | 1, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t per_warp = (((size_t)n * LD * sizeof(float) + 15) & ~(size_t)15) + 2 * 64 * sizeof(double);
+  extern __shared__ __align__(128) unsigned char mw_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  const int LD = BULK ? n : (n | 1), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t mat_bytes = BULK ? (size_t)n * n * sizeof(float) : (((size_t)n * LD * sizeof(float) + 15) & ~(size_t)15);
+  const size_t per_warp = mat_bytes + (BULK ? 0 : 2 * 64 * sizeof(double));
   float *sL = reinterpret_cast<float *>(mw_raw + warp * per_warp);
-  double *sz = reinterpret_cast<double *>(mw_raw + warp * per_warp + (((size_t)n * LD * sizeof(float) + 15) & ~(size_t)15));
+  double *sz = reinterpret_cast<double *>(mw_raw + (BULK ? MW_WARPS * mat_bytes + warp * 2 * 64 * sizeof(double)
+                                                         : warp * per_warp + mat_bytes));
   double *su = sz + 64;
   const unsigned full = 0xffffffffu;
+  uint32_t parity = 0;
+  if (BULK) {
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+  }
   for (long long b = (long long)blockIdx.x * MW_WARPS + warp; b < B; b += (long long)gridDim.x * MW_WARPS) {
     const float *Lo = L_o + b * ldb_Lo;
-    __syncwarp();
-    // lower triangle, row by row (lanes = consecutive columns), as asynchronous global -> shared copies: all ~2 n
-    // requests of a lane are in flight at once (staging through registers four rows at a time made this a chain of
-    // n / 4 memory round trips, 3/4 of the kernel's time)
-    for (int i = 0; i < n; ++i) {
-      if (lane <= i) __pipeline_memcpy_async(sL + i * LD + lane, Lo + (size_t)i * n + lane, sizeof(float));
-      if (lane + 32 <= i) __pipeline_memcpy_async(sL + i * LD + lane + 32, Lo + (size_t)i * n + lane + 32, sizeof(float));
-    }
-    __pipeline_commit();
     const int r0 = lane, r1 = lane + 32;
-    double b0 = r0 < n ? (double)mean[b * n + r0] - (double)mean_o[b * n + r0] : 0.0;
-    double b1 = r1 < n ? (double)mean[b * n + r1] - (double)mean_o[b * n + r1] : 0.0;
-    __pipeline_wait_prior(0);
-    __syncwarp();
+    double b0, b1;
+    if (BULK) {                         // (B is a multiple of MW_WARPS: all warps of a CTA run the same iterations)
+      __syncthreads();                  // the previous iteration's reads of the buffer are done
+      if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)(MW_WARPS * mat_bytes);
+        mbar_arrive_expect_tx(&bar, bytes);
+        bulk_copy_g2s(mw_raw, L_o + (b - warp) * ldb_Lo, bytes, &bar);
+      }
+      b0 = r0 < n ? (double)mean[b * n + r0] - (double)mean_o[b * n + r0] : 0.0;
+      b1 = r1 < n ? (double)mean[b * n + r1] - (double)mean_o[b * n + r1] : 0.0;
+      mbar_wait(&bar, parity);
+      parity ^= 1;
+    } else {
+      __syncwarp();
+      // lower triangle, row by row (lanes = consecutive columns), as asynchronous global -> shared copies: all ~2 n
+      // requests of a lane are in flight at once (staging through registers four rows at a time made this a chain of
+      // n / 4 memory round trips, 3/4 of the kernel's time)
+      for (int i = 0; i < n; ++i) {
+        if (lane <= i) __pipeline_memcpy_async(sL + i * LD + lane, Lo + (size_t)i * n + lane, sizeof(float));
+        if (lane + 32 <= i) __pipeline_memcpy_async(sL + i * LD + lane + 32, Lo + (size_t)i * n + lane + 32, sizeof(float));
+      }
+      __pipeline_commit();
+      b0 = r0 < n ? (double)mean[b * n + r0] - (double)mean_o[b * n + r0] : 0.0;
+      b1 = r1 < n ? (double)mean[b * n + r1] - (double)mean_o[b * n + r1] : 0.0;
+      __pipeline_wait_prior(0);
+      __syncwarp();
+    }
     const double inv0 = r0 < n ? 1.0 / (double)sL[r0 * LD + r0] : 0.0, inv1 = r1 < n ? 1.0 / (double)sL[r1 * LD + r1] : 0.0;
     double z0 = 0.0, z1 = 0.0, maha = 0.0;
     // z = L_o^-1 diff (column oriented)
@@ -1486,15 +1515,34 @@ extern "C" int tce_gauss_stats_bwd(const float *mean, const float *L, int64_t ld
 static int maha_launch(const float *mean, const float *mean_o, const float *L_o, int64_t ldb_Lo, const double *grad_out,
                        double *maha, float *grad_mean, float *grad_L, int64_t B, int n, void *stream) {
   if (n <= 64 && B >= 2 * MW_WARPS) {                   // warp per episode (a handful of episodes: the CTA kernel's extra
-    const size_t per_warp = (((size_t)n * (n | 1) * sizeof(float) + 15) & ~(size_t)15) + 2 * 64 * sizeof(double);   // threads
-    const size_t smem_w = MW_WARPS * per_warp;          // help with the loads)
+    cudaStream_t st = (cudaStream_t)stream;             // threads help with the loads)
+    int64_t done = 0;
+    // contiguous per-episode factors of odd order: whole groups of MW_WARPS episodes through the bulk-copy variant
+    if ((n & 1) && ldb_Lo == (int64_t)n * n && B >= 8 * MW_WARPS && ((uintptr_t)L_o & 15) == 0) {
+      const size_t smem_b = MW_WARPS * ((size_t)n * n * sizeof(float) + 2 * 64 * sizeof(double));
+      if (smem_b > 48 * 1024)
+        TCE_CUDA(cudaFuncSetAttribute(maha_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b), "maha attr");
+      done = B / MW_WARPS * MW_WARPS;
+      long long grid = done / MW_WARPS;
+      const long long cap = 3LL * num_sms_proj();
+      if (grid > cap) grid = cap;
+      maha_warp_kernel<true><<<(unsigned)grid, MW_WARPS * 32, smem_b, st>>>(mean, mean_o, L_o, ldb_Lo, grad_out, maha, grad_mean,
+                                                                             grad_L, n, (long long)done);
+      TCE_CHECK_LAUNCH("maha_warp_kernel<bulk>");
+      if (done == B) return TCE_OK;
+    }
+    const size_t per_warp = (((size_t)n * (n | 1) * sizeof(float) + 15) & ~(size_t)15) + 2 * 64 * sizeof(double);
+    const size_t smem_w = MW_WARPS * per_warp;
     if (smem_w > 48 * 1024)
-      TCE_CUDA(cudaFuncSetAttribute(maha_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w), "maha attr");
-    long long grid = (B + MW_WARPS - 1) / MW_WARPS;
+      TCE_CUDA(cudaFuncSetAttribute(maha_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w), "maha attr");
+    const int64_t rest = B - done;                      // (the tail of a bulk launch: at most MW_WARPS - 1 episodes)
+    long long grid = (rest + MW_WARPS - 1) / MW_WARPS;
     const long long cap = 6LL * num_sms_proj();
     if (grid > cap) grid = cap;
-    maha_warp_kernel<<<(unsigned)grid, MW_WARPS * 32, smem_w, (cudaStream_t)stream>>>(mean, mean_o, L_o, ldb_Lo, grad_out, maha,
-                                                                                 grad_mean, grad_L, n, (long long)B);
+    maha_warp_kernel<false><<<(unsigned)grid, MW_WARPS * 32, smem_w, st>>>(
+        mean + done * n, mean_o + done * n, L_o + done * ldb_Lo, ldb_Lo, grad_out ? grad_out + done : nullptr,
+        maha ? maha + done : nullptr, grad_mean ? grad_mean + done * n : nullptr,
+        grad_L ? grad_L + (size_t)done * n * n : nullptr, n, (long long)rest);
     TCE_CHECK_LAUNCH("maha_warp_kernel");
     return TCE_OK;
   }

@@ -343,7 +343,7 @@ def test_surrogate_single_factor_path_equals_broadcast_path():
     assert (gL0 - gL1).abs().max() <= 1e-4 * gL1.abs().max()
 
 
-@pytest.mark.parametrize("n,B", [(63, 200), (63, 9), (63, 3), (28, 37), (6, 64), (64, 16), (100, 12)])
+@pytest.mark.parametrize("n,B", [(63, 200), (63, 203), (63, 9), (63, 3), (28, 37), (6, 64), (64, 16), (100, 12)])
 def test_gauss_maha_values_and_gradients(n, B):
     """tce_gauss_maha / tce_gauss_maha_bwd_full (black_box_policy.py:183-224 ``maha``) against fp64 torch: value and the
     gradients w.r.t. both means and the factor -- through the warp-per-episode kernel (n <= 64, B >= 8), the
@@ -367,3 +367,42 @@ def test_gauss_maha_values_and_gradients(n, B):
         assert (g_o.cpu().double() - go).abs().max() <= 2e-5 * go.abs().max()
         assert (g_L.cpu().double() - torch.tril(gL)).abs().max() <= 5e-5 * gL.abs().max()
         assert torch.triu(g_L, 1).abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("n,B", [(63, 2051), (63, 35), (24, 1203), (9, 64)])
+def test_bulk_copy_kernels_large_batches(n, B):
+    """The bulk-asynchronous-copy kernels (per-episode factors fetched / written as one contiguous block per group of
+    four episodes: rsample and maha for odd n, the policy head for every n) with several groups per CTA and a tail of
+    B % 4 episodes that runs through the row-wise kernels -- against fp64 torch."""
+    g = torch.Generator().manual_seed(7 * n + B)
+    mean, mean_o, eps = (torch.randn(B, n, generator=g) for _ in range(3))
+    nvec = n + n * (n - 1) // 2
+    vec = 0.3 * torch.randn(B, nvec, generator=g)
+    # policy head (abstract_policy.py:166-187): softplus(diagonal) + min_std, strict lower triangle row by row
+    L = ops.policy_head(vec.to(DEV), B, n, 1e-4)
+    want = torch.zeros(B, n, n, dtype=torch.float64)
+    r, c = torch.tril_indices(n, n, -1)
+    want[:, r, c] = vec[:, n:].double()
+    want += torch.diag_embed(torch.nn.functional.softplus(vec[:, :n].double()) + 1e-4)
+    assert (f64(L) - want).abs().max() < 1e-6
+    assert torch.triu(L, 1).abs().max().item() == 0.0
+    # rsample with injected noise and with Philox draws (the tail must continue the same counter sequence)
+    got = ops.mvn_rsample(mean.to(DEV), L, eps.to(DEV), 0, 0)
+    ref = mean.double() + torch.einsum('bij,bj->bi', want, eps.double())
+    assert (f64(got) - ref).abs().max() < 2e-5
+    z = ops.mvn_rsample(torch.zeros(B, n, device=DEV), torch.eye(n, device=DEV).repeat(B, 1, 1), None, 11, 3)
+    z_rows = ops.mvn_rsample(torch.zeros(B, n, device=DEV), torch.eye(n, device=DEV).expand(B, n, n), None, 11, 3)
+    assert torch.equal(z, z_rows)                       # stride-0 factors run through the row-wise kernel
+    # Mahalanobis term, value and gradients
+    md, od, Ld = (t.to(DEV).requires_grad_(True) for t in (mean, mean_o, L.detach()))
+    w = torch.rand(B, generator=g, dtype=torch.float64)
+    maha = ops.gauss_maha(md, od, Ld)
+    m64, L64 = mean.double().requires_grad_(True), want.clone().requires_grad_(True)
+    zz = torch.linalg.solve_triangular(L64, (m64 - mean_o.double())[..., None], upper=False)
+    mref = zz.square().sum((1, 2))
+    assert (maha.cpu() - mref.detach()).abs().max() <= 1e-5 * mref.abs().max()
+    gm, gL = torch.autograd.grad((mref * w).sum(), [m64, L64])
+    g_m, g_o, g_L = torch.autograd.grad((maha * w.to(DEV)).sum(), [md, od, Ld])
+    assert (g_m.cpu().double() - gm).abs().max() <= 2e-5 * gm.abs().max()
+    assert (g_o.cpu().double() + gm).abs().max() <= 2e-5 * gm.abs().max()
+    assert (g_L.cpu().double() - torch.tril(gL)).abs().max() <= 5e-5 * gL.abs().max()
