@@ -617,12 +617,13 @@ def run_ours(args):
         started.record(main_stream)
         if len(sets) == 1:
             upload(0)                                            # no second buffer: upload, then compute
-        else:
-            upload(e2e_count[0] % len(sets), after=started)      # next step's inputs, overlapped with this step
         main_stream.wait_event(uploaded[i])
         sets[i][1]()
         consumed[i].record(main_stream)
         out_host.copy_(sets[i][2], non_blocking=True)
+        if len(sets) > 1:                                        # next step's inputs, overlapped with this step; queued
+            upload(e2e_count[0] % len(sets), after=started)      # AFTER this step's replay so that the host's ~20
+                                                                 # copy calls do not delay the start of the epoch
 
     if len(sets) > 1:
         upload(0)

@@ -20,7 +20,10 @@ peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs",
 flush = torch.empty(192 * 1024 * 1024, device=dev, dtype=torch.int32)
 
 
-def timed(fn, reps=20, warm=5):
+REPS, WARM = int(os.environ.get("TCE_HBM_REPS", 20)), int(os.environ.get("TCE_HBM_WARM", 5))   # (profiling runs: 1 / 1)
+
+
+def timed(fn, reps=REPS, warm=WARM):
     for _ in range(warm):
         fn()
     ts = []
