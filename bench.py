@@ -583,16 +583,20 @@ def run_ours(args):
     # Double-buffered input pipeline (what a training loop around the agent does): two device copies of the
     # dataset, each with its own captured epoch; while step k runs on buffer k % 2 a copy stream uploads the
     # dataset of step k + 1 into the other buffer.  Every step's inputs still cross PCIe inside the timed region
-    # (K uploads in K timed steps) and every step's loss vector is read back and waited for.
+    # (K uploads in K timed steps) and every step's loss vector is read back and waited for (one step later: the host
+    # queues step k + 1 before it blocks on the loss of step k, as a training loop that logs its losses does).
     sets = [(dataset, step_fn, metrics)]
     if graph is not None:
         try:
             dataset_b = agent.dataset_to_device(pinned)
             torch.cuda.synchronize()
-            graph_b = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph_b):
-                metrics_b = agent.policy_epoch(dataset_b, times, pairs)
-            sets.append((dataset_b, graph_b.replay, metrics_b))
+            # same procedure as for the first buffer: the eager warm-up epochs also settle the per-dataset facts the
+            # epoch caches (common time grid: decided once per dataset with one device read, which a capture cannot
+            # do -- captured cold, this graph fell back to the general-grid likelihood, +50 us per replay)
+            step_b, metrics_b, _, mode_b, graph_b, _ = capture_epoch(agent, dataset_b, times, pairs, rank)
+            if mode_b != "cuda_graph":
+                raise RuntimeError("capture failed")
+            sets.append((dataset_b, step_b, metrics_b))
         except Exception as exc:                                 # pragma: no cover
             if rank == 0:
                 print(f"[bench] second epoch graph failed ({exc!r}); e2e without input prefetch", file=sys.stderr)
@@ -609,6 +613,10 @@ def run_ours(args):
             uploaded[i].record(copy_stream)
 
     e2e_count = [0]
+    out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
+    read_back = [torch.cuda.Event(), torch.cuda.Event()]
+    for ev in read_back:
+        ev.record(main_stream)
 
     def e2e_step():
         i = e2e_count[0] % len(sets)
@@ -620,7 +628,12 @@ def run_ours(args):
         main_stream.wait_event(uploaded[i])
         sets[i][1]()
         consumed[i].record(main_stream)
-        out_host.copy_(sets[i][2], non_blocking=True)
+        j = e2e_count[0] % 2
+        out_hosts[j].copy_(sets[i][2], non_blocking=True)       # the step's loss vector -> pinned host memory
+        read_back[j].record(main_stream)
+        read_back[1 - j].synchronize()                           # the PREVIOUS step's loss is on the host (owned by the
+                                                                 # caller) before the step after this one is queued:
+                                                                 # one step of look-ahead, no launch gap on the GPU
         if len(sets) > 1:                                        # next step's inputs, overlapped with this step; queued
             upload(e2e_count[0] % len(sets), after=started)      # AFTER this step's replay so that the host's ~20
                                                                  # copy calls do not delay the start of the epoch
@@ -631,8 +644,39 @@ def run_ours(args):
         e2e_step()
     timer.barrier()
     _mark("e2e warm-up done")
-    e2e_ms = timer.run(e2e_step, K, 0, sync_each=True)           # the caller owns the loss before the next step
+    e2e_ms = timer.run(e2e_step, K, 0)                           # (each step waits for the previous step's loss itself)
     e2e_value = world * B_PER_GPU / (e2e_ms * 1e-3)
+    if os.environ.get("TCE_E2E_DEBUG"):                          # where the e2e step's extra time goes (stderr only)
+        def variant(no_upload=False, no_readback=False, one_graph=False, which=0):
+            def f():
+                i = which if one_graph else e2e_count[0] % len(sets)
+                e2e_count[0] += 1
+                started = torch.cuda.Event(); started.record(main_stream)
+                if not no_upload:
+                    main_stream.wait_event(uploaded[i])
+                sets[i][1]()
+                consumed[i].record(main_stream)
+                if not no_readback:
+                    out_hosts[0].copy_(sets[i][2], non_blocking=True)
+                if not no_upload:
+                    upload(0 if one_graph else e2e_count[0] % len(sets), after=started)
+            return f
+        for tag, kw in (("full", {}), ("no_upload", dict(no_upload=True)), ("no_readback", dict(no_readback=True)),
+                        ("no_upload_no_readback", dict(no_upload=True, no_readback=True)),
+                        ("one_graph_no_upload_no_readback", dict(no_upload=True, no_readback=True, one_graph=True)),
+                        ("graph_b_only", dict(no_upload=True, no_readback=True, one_graph=True, which=len(sets) - 1))):
+            torch.cuda.synchronize()
+            print(f"[e2e debug] {tag}: {timer.run(variant(**kw), K, 3):.5f} ms", file=sys.stderr)
+    # the upload alone (same loader, same pinned dataset, nothing else running): what PCIe + ~20 copy calls cost per step
+    torch.cuda.synchronize()
+    ua, ub = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(copy_stream):
+        ua.record(copy_stream)
+        for _ in range(10):
+            agent.dataset_to_device(pinned, out=sets[0][0])
+        ub.record(copy_stream)
+    torch.cuda.synchronize()
+    upload_ms = ua.elapsed_time(ub) / 10
     _mark("e2e done")
 
     # ---- the other halves of config 2, and BASELINE configs 1 / 3 / 4 / 5 ------------------------------------------
@@ -719,10 +763,12 @@ def run_ours(args):
             "clocks": clocks.summary(),
             "e2e": {"value": round(e2e_value, 1), "unit": "episodes/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 5),
-                    "host_dataset_bytes": h2d_reference_layout,
+                    "host_dataset_bytes": h2d_reference_layout, "upload_alone_ms": round(upload_ms, 5),
+                    "host_tensors_per_step": sum(1 for v in pinned.values() if torch.is_tensor(v)),
                     "input_pipeline": "double_buffered" if len(sets) > 1 else "serial",
                     "note": "host dataset in the reference layout; the loader sends the shared old factor once; "
-                            "the upload of step k+1 overlaps step k (two device buffers, two captured epochs)"},
+                            "the upload of step k+1 overlaps step k (two device buffers, two captured epochs); every "
+                            "step's loss vector is copied to pinned host memory and waited for one step later"},
             "gpu_launches": (total_nodes if total_nodes is not None else launches_per_step) * K,
             "gpu_launches_per_step": total_nodes if total_nodes is not None else launches_per_step,
             "gpu_launches_detail": {"own_kernels_per_step": launches_per_step, "graph_nodes_per_step": kinds,
