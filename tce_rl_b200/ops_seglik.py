@@ -15,6 +15,7 @@ The gradient of the fused surrogate is produced in the FORWARD call (the upstrea
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 import weakref
 from typing import Optional, Tuple
 
@@ -124,6 +125,9 @@ def pairs_chained(pred_pairs: Tensor) -> bool:
     return res
 
 
+_WARNED_CAPTURE = False
+
+
 def times_uniform(init_time: Tensor, times: Tensor) -> bool:
     """Every episode has the same time grid (same init_time, same row of ``times``).  One device reduction + host read
     per tensor version; under graph capture an unknown tensor counts as non-uniform."""
@@ -132,6 +136,12 @@ def times_uniform(init_time: Tensor, times: Tensor) -> bool:
     if key is not None and key[0] == sig:
         return key[1]
     if times.is_cuda and torch.cuda.is_current_stream_capturing():
+        global _WARNED_CAPTURE
+        if not _WARNED_CAPTURE:                      # (a captured epoch keeps whatever path it was captured with)
+            _WARNED_CAPTURE = True
+            warnings.warn("tce_rl_b200: time grid of a dataset first seen during CUDA-graph capture -- the capture cannot "
+                          "read the device, so the general-grid likelihood is recorded (slower than the common-grid "
+                          "path); run one eager epoch on these tensors first or call ops_seglik.declare_uniform")
         return False
     res = bool(times.shape[0] >= 1 and bool(((times == times[:1]).all() & (init_time == init_time[:1]).all()).item()))
     _TIME_FACTS.put(times, (sig, res))
