@@ -91,7 +91,10 @@ int tce_prodmp_traj_bwd(const tce_tables_t *tables, const float *grad_traj, cons
 /* ---- (2) Gaussian policy over the MP parameters -----------------------------------------------------
  * out = mean + L eps : MultivariateNormal(loc, scale_tril).rsample (black_box_policy.py:82-84 and
  * mp_pytorch sample_trajectories).  eps [B, n] is injected when not NULL, otherwise drawn in-kernel
- * from Philox4x32-10 (seed, offset) with Box-Muller.                                               */
+ * from Philox4x32-10 (seed, offset) with Box-Muller (counter = element index: results do not depend on
+ * which kernel serves an episode).  Per-episode factors of odd order n <= 64 that are contiguous
+ * (ldb_L == n*n) and 16-byte aligned are streamed four episodes at a time by bulk asynchronous copies
+ * (cp.async.bulk + mbarrier); everything else (stride 0, even n, the last B % 4 episodes) row by row.  */
 int tce_mvn_rsample(const float *mean, const float *L, int64_t ldb_L, const float *eps, uint64_t seed,
                     uint64_t offset, float *out, int64_t B, int n, void *stream);
 /* Batched Cholesky A = L L^T, one CTA per matrix in shared memory, n <= 128
@@ -101,7 +104,8 @@ int tce_chol_fwd(const float *A, float *L, int32_t *info, int64_t B, int n, void
 int tce_chol_bwd(const float *L, const float *grad_L, float *grad_A, int64_t B, int n, void *stream);
 /* policy head: covariance vector [B or 1, n + n(n-1)/2] -> L [B, n, n]
  * diag = softplus(v) + min_std, strictly lower filled row-major (abstract_policy.py:166-187,
- * util_numerical.py:44-68, util_matrix.py:12-33); ldb_vec = 0 broadcasts one vector.              */
+ * util_numerical.py:44-68, util_matrix.py:12-33); ldb_vec = 0 broadcasts one vector.  Contiguous
+ * 16-byte-aligned per-episode vectors (ldb_vec == n + n(n-1)/2, B >= 32) take the bulk-copy kernel.  */
 int tce_policy_head_fwd(const float *vec, int64_t ldb_vec, float min_std, float *L, int64_t B, int n,
                         void *stream);
 /* grad_vec [Bv, nvec]: Bv = B (ldb_vec != 0) or 1 (sum over the batch, ldb_vec == 0)               */
@@ -123,7 +127,9 @@ int tce_gauss_stats_bwd(const float *mean, const float *L, int64_t ldb_L, const 
                         float *grad_L, int64_t B, int n, void *stream);
 
 /* maha [B] = |L_o^-1 (mean - mean_o)|^2 (policy.maha, black_box_policy.py:205-224) when grad_out == NULL;
- * otherwise grad_mean [B,n] = grad_out[b] * 2 Sigma_o^-1 (mean - mean_o) (maha may also be written).      */
+ * otherwise grad_mean [B,n] = grad_out[b] * 2 Sigma_o^-1 (mean - mean_o) (maha may also be written).
+ * n <= 64: one warp per episode (solves in registers); contiguous 16-byte-aligned factors of odd order are
+ * fetched four episodes at a time by one bulk asynchronous copy; ldb_Lo = 0 broadcasts one factor.         */
 int tce_gauss_maha(const float *mean, const float *mean_o, const float *L_o, int64_t ldb_Lo,
                    const double *grad_out, double *maha, float *grad_mean, int64_t B, int n, void *stream);
 /* backward of tce_gauss_maha w.r.t. ALL arguments (BlackBoxPolicy.log_prob differentiates the Mahalanobis term w.r.t.
