@@ -91,7 +91,7 @@ int tce_prodmp_traj_bwd(const tce_tables_t *tables, const float *grad_traj, cons
 /* ---- (2) Gaussian policy over the MP parameters -----------------------------------------------------
  * out = mean + L eps : MultivariateNormal(loc, scale_tril).rsample (black_box_policy.py:82-84 and
  * mp_pytorch sample_trajectories).  eps [B, n] is injected when not NULL, otherwise drawn in-kernel
- * from Philox4x32-10 (seed, offset) with Box-Muller (counter = element index: results do not depend on
+ * from Philox4x32-10 (seed, offset) with Box-Muller (counter = element index: the draws do not depend on
  * which kernel serves an episode).  Per-episode factors of odd order n <= 64 that are contiguous
  * (ldb_L == n*n) and 16-byte aligned are streamed four episodes at a time by bulk asynchronous copies
  * (cp.async.bulk + mbarrier); everything else (stride 0, even n, the last B % 4 episodes) row by row.  */
