@@ -314,12 +314,34 @@ class Timer:
 # =============================================================================================================
 # roofline: every kernel of the step, timed live
 # =============================================================================================================
-def csrc_hash():
+def csrc_hash(files=None):
+    """Hash of the kernel sources (all of csrc/, or the named files)."""
     h = hashlib.sha256()
     base = os.path.join(ROOT, "tce_rl_b200", "csrc")
-    for f in sorted(os.listdir(base)):
+    for f in sorted(files if files is not None else os.listdir(base)):
         h.update(open(os.path.join(base, f), "rb").read())
     return h.hexdigest()[:16]
+
+
+# which sources an entry point's kernels live in (first matching prefix; the shared headers always count): an ncu
+# capture of a kernel stays valid while THESE files are unchanged
+_SRC_OF = (("tce_seglik_uniform", "tce_seglik_fused.cu"), ("tce_seglik_prepass", "tce_seglik_fused.cu"),
+           ("tce_seglik_fused", "tce_seglik_fused.cu"), ("tce_seglik_dsigma_reduce", "tce_seglik_fused.cu"),
+           ("tce_seglik", "tce_seglik.cu"), ("tce_proj", "tce_proj.cu"), ("tce_gauss_maha", "tce_proj.cu"),
+           ("tce_gauss_kl", "tce_proj.cu"), ("tce_gauss_stats", "tce_proj.cu"), ("tce_tri_inverse", "tce_proj.cu"),
+           ("tce_epoch", "tce_epoch.cu"), ("tce_prodmp", "tce_traj.cu"), ("tce_mvn", "tce_gauss.cu"),
+           ("tce_chol", "tce_gauss.cu"), ("tce_policy_head", "tce_gauss.cu"), ("tce_adam", "tce_adam.cu"),
+           ("tce_grad_sumsq", "tce_adam.cu"), ("tce_p2p", "tce_p2p.cu"), ("tce_gae", "tce_adv.cu"),
+           ("tce_segment", "tce_adv.cu"), ("tce_normalize", "tce_adv.cu"))
+
+
+def src_hash_of(abi_name):
+    base = os.path.join(ROOT, "tce_rl_b200", "csrc")
+    headers = [f for f in os.listdir(base) if f.endswith(".cuh")]
+    for prefix, f in _SRC_OF:
+        if abi_name.startswith(prefix):
+            return csrc_hash(headers + [f])
+    return csrc_hash()
 
 
 def measure_fma_peaks(timer):
@@ -421,7 +443,8 @@ def roofline_numbers(agent, dataset, times, pairs, timer, peaks, ms_per_step, sh
         ent = tj.get("kernels", {}).get(dom)
         if ent is not None:                              # captures are keyed by launch grid (1 matrix / B matrices / CTAs)
             ent = ent.get(f"grid={n_cov}") or (next(iter(ent.values())) if len(ent) == 1 else None)
-        if ent is not None and tj.get("csrc_hash") == csrc_hash():
+        if ent is not None and (ent.get("src_hash") == src_hash_of(dom) if "src_hash" in ent
+                                else tj.get("csrc_hash") == csrc_hash()):
             traffic, traffic_src = ent["dram_bytes"], tj.get("source", "profiles/r02_ncu_traffic.json")
         elif ent is not None:
             traffic_src = "profiles/r02_ncu_traffic.json is stale (kernel sources changed since the capture)"

@@ -1,6 +1,6 @@
 """Summarise an `ncu --page raw --csv` export: one line per captured launch with duration, DRAM traffic, pipe
 utilisation, occupancy, bank conflicts -> profiles/r02_ncu_summary.txt, and per-kernel DRAM bytes (last instance)
--> profiles/r02_ncu_traffic.json (read by bench.py; carries the hash of csrc/ at capture time)."""
+-> profiles/r02_ncu_traffic.json (read by bench.py; every entry carries the hash of ITS kernel's sources at capture time)."""
 import csv, json, os, re, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -49,7 +49,7 @@ kern = {}
 for (name, grid), vals in last.items():
     for a in abi.get(name, []):
         kern.setdefault(a, {})[f"grid={grid}"] = {"kernel": name, "dram_bytes": int((vals["dram_rd_MB"] + vals["dram_wr_MB"]) * 1e6),
-                                                  "us_under_ncu": round(vals["us"], 2)}
+                                                  "us_under_ncu": round(vals["us"], 2), "src_hash": bench.src_hash_of(a)}
 json.dump({"source": os.path.relpath(out_txt, ROOT) + " (ncu --set full, last captured instance of each kernel; "
            "keyed by launch grid: grid=1 = the ONE matrix of the shared-covariance epoch, grid=1024 = per-episode covariances)",
            "csrc_hash": bench.csrc_hash(), "kernels": kern},
