@@ -337,23 +337,26 @@ __global__ void traj_rows_kernel(TabDev tb, const float *__restrict__ times_row,
   const float dy1 = lerp_t(r0[2], r1[2], wf), dy2 = lerp_t(r0[3], r1[3], wf);
   const float xi1 = (dy2b * y1 - dy1b * y2) * inv_det, xi2 = (y1b * y2 - y2b * y1) * inv_det;
   const float xi3 = (dy2b * dy1 - dy1b * dy2) * inv_det, xi4 = (y1b * dy2 - y2b * dy1) * inv_det;
+  // stored INTERLEAVED, (position coefficient k, velocity coefficient k) side by side: the consumer multiplies both by
+  // the same parameter with one packed FMA
   float *o = rows + (size_t)t * RW;
 #pragma unroll
   for (int k = 2 * (K1 + 2); k < RW; ++k) o[k] = 0.f;
-  o[0] = xi1; o[1] = xi2; o[K1 + 2] = xi3; o[K1 + 3] = xi4;
+  o[0] = xi1; o[1] = xi3; o[2] = xi2; o[3] = xi4;
 #pragma unroll
   for (int j = 0; j < K1; ++j) {
     const float pbj = lerp_t(q0[4 + j], q1[4 + j], wb), vbj = lerp_t(q0[4 + K1 + j], q1[4 + K1 + j], wb);
     const float pj = lerp_t(r0[4 + j], r1[4 + j], wf), vj = lerp_t(r0[4 + K1 + j], r1[4 + K1 + j], wf);
     const float scj = (float)tb.scale[j];
-    o[2 + j] = (pj - xi1 * pbj - xi2 * vbj) * scj;
-    o[K1 + 4 + j] = (vj - xi3 * pbj - xi4 * vbj) * scj;
+    o[2 * (2 + j)] = (pj - xi1 * pbj - xi2 * vbj) * scj;
+    o[2 * (2 + j) + 1] = (vj - xi3 * pbj - xi4 * vbj) * scj;
   }
 }
 
 // traj_uniform_kernel: thread (e, d) owns one degree of freedom of one episode of the CTA's group: its K1 + 2
 // coefficients [y0, tau v0, theta (goal shifted)] stay in registers for the whole trajectory, the basis row of time t is
-// read as six 128-bit BROADCAST loads (all lanes the same t), 2 (K1 + 2) FMAs give position and velocity.  Results go
+// read as six 128-bit BROADCAST loads (all lanes the same t), K1 + 2 packed FMAs (FFMA2: position and velocity
+// coefficient of the row side by side, the parameter in both halves) give position and velocity.  Results go
 // through a shared tile [episode][TU_TT time steps][2 D] so that every episode's TU_TT * 2D floats leave as contiguous
 // 128-bit stores (56-byte rows written from registers touch every 32-byte sector several times: L2 write bound).
 // ~7 warp instructions and ~2 shared-memory wavefronts per (episode, time) point; at B = 16384 every group has its
@@ -409,20 +412,15 @@ traj_uniform_kernel(TabDev tb, const float *__restrict__ rows, const float *__re
         float *o = tile + (size_t)e * estride + d;
         for (int tl = 0; tl < nt; ++tl) {
           const float4 *row = reinterpret_cast<const float4 *>(srow + (size_t)(t0 + tl) * RWP);
-          float r[RWP];
-#pragma unroll
+          float2 ac = make_float2(0.f, 0.f);           // (position, velocity * tau): one packed FP32 FMA (FFMA2, sm_100)
+#pragma unroll                                         // per coefficient instead of two scalar ones
           for (int q = 0; q < RWP / 4; ++q) {
             const float4 v = row[q];
-            r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+            if (2 * q < PW) ac = __ffma2_rn(make_float2(v.x, v.y), make_float2(p[2 * q], p[2 * q]), ac);
+            if (2 * q + 1 < PW) ac = __ffma2_rn(make_float2(v.z, v.w), make_float2(p[2 * q + 1], p[2 * q + 1]), ac);
           }
-          float a = 0.f, c = 0.f;
-#pragma unroll
-          for (int k = 0; k < PW; ++k) {
-            a = fmaf(r[k], p[k], a);
-            c = fmaf(r[PW + k], p[k], c);
-          }
-          o[tl * D2] = a;
-          o[tl * D2 + D] = c * inv_tau_f;
+          o[tl * D2] = ac.x;
+          o[tl * D2 + D] = ac.y * inv_tau_f;
         }
       }
       __syncthreads();
