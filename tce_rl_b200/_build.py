@@ -55,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs])   # static cudart (nvcc default)
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs])   # static cudart (nvcc default)
     return LIB
 
 
