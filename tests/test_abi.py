@@ -70,3 +70,36 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "from .. import oracle" not in src and "/root/reference" not in src
+
+
+def test_library_contains_the_sm100_instructions_the_design_names():
+    """DESIGN.md section 4 / profiles/r02_sass_evidence.txt: the factor-streaming kernels request their data with bulk
+    asynchronous copies (UBLKCP + mbarrier SYNCS), the common-grid trajectory kernel uses packed fp32x2 FMAs (FFMA2), and
+    nothing is on the tensor cores.  Checked on the object files of the in-tree build (cuobjdump, no GPU needed)."""
+    import shutil
+    import subprocess
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    build = os.path.join(ROOT, "tce_rl_b200", "build")
+    objs = {f: os.path.join(build, f) for f in ("tce_gauss.o", "tce_traj.o")}
+    if not os.path.exists(tool) or not all(os.path.exists(p) for p in objs.values()):
+        pytest.skip("cuobjdump or the object files of the in-tree build are not here")
+    sass = {f: subprocess.run([tool, "-sass", p], capture_output=True, text=True, check=True).stdout for f, p in objs.items()}
+    assert "UBLKCP.S.G" in sass["tce_gauss.o"] and "SYNCS.ARRIVE.TRANS64" in sass["tce_gauss.o"]
+    assert "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass["tce_gauss.o"]
+    assert "FFMA2" in sass["tce_traj.o"]
+    opcodes = {op for s in sass.values() for op in re.findall(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", s)}
+    assert "FFMA" in opcodes and not [op for op in opcodes if "MMA" in op]
+
+
+def test_traffic_json_entries_name_existing_sources():
+    """bench.py reports ``roofline.traffic`` from profiles/r02_ncu_traffic.json only while the sources of THAT kernel
+    are unchanged: every prefix of the source map points at a file that exists, and every entry carries its hash."""
+    import json
+    import bench
+    csrc = os.path.join(ROOT, "tce_rl_b200", "csrc")
+    assert all(os.path.exists(os.path.join(csrc, f)) for _, f in bench._SRC_OF)
+    tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+    for name, grids in tj["kernels"].items():
+        assert any(name.startswith(p) for p, _ in bench._SRC_OF), name
+        assert all(len(e["src_hash"]) == 16 and e["dram_bytes"] > 0 for e in grids.values())
+    assert bench.src_hash_of("tce_proj_kl_entropy_fwd_sigma_vec") != bench.src_hash_of("tce_prodmp_traj_fwd")
