@@ -21,6 +21,7 @@ import torch.distributed as dist
 from torch.optim.lr_scheduler import LinearLR
 
 from .. import ops, util
+from .._lib import TceError
 from .projection import KLProjectionLayer, gaussian_kl_details
 
 _KL_KEYS = ["new_old_mean_diff", "new_old_cov_diff", "new_old_shape_diff", "new_old_volume_diff",
@@ -481,8 +482,11 @@ class TemporalCorrelatedAgent:
         if old.state:                                   # already stepped with torch's Adam: keep it
             return
         g = old.param_groups[0]
-        opt = FlatAdam(self.policy_net_params, self._flat_grad, lr=g["lr"], betas=g["betas"], eps=g["eps"],
-                       weight_decay=g["weight_decay"])
+        try:
+            opt = FlatAdam(self.policy_net_params, self._flat_grad, lr=g["lr"], betas=g["betas"], eps=g["eps"],
+                           weight_decay=g["weight_decay"])
+        except TceError:                                # e.g. more than 32 parameter tensors: torch's Adam stays
+            return
         if "initial_lr" in g:
             opt.param_groups[0]["initial_lr"] = g["initial_lr"]
         if self.policy_lr_scheduler is not None:
