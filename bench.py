@@ -19,8 +19,10 @@ One JSON line is printed by rank 0:
                   step and the loss vector read back;
 * ``config.variants``  the other halves of SURVEY 8(d) config 2, same step, same timing: per-episode covariance
                   factors (contextual layout, nothing amortised by broadcasting) and the literal 25-segment pair set;
-* ``also``        BASELINE configs 1, 3, 4, 5 (B = 152 GPU next to CPU fp32 / fp64; metaworld B = 4096 KL, strong
-                  scaled at N > 1; table tennis W2 1024 episodes / GPU; likelihood sweep with roofline fractions);
+* ``also``        BASELINE configs 1, 3, 4, 5 (B = 152 GPU next to CPU fp32 / fp64; metaworld B = 4096 KL; table
+                  tennis W2 1024 episodes / GPU; likelihood sweep with roofline fractions).  ``config.variants`` and
+                  ``also`` are N = 1 lines; at N > 1 they run only with ``--multi-extras`` (config 3 is then strong
+                  scaled, 4096 / N episodes per GPU);
 * ``roofline``    the dominant kernel over ALL kernels of the step, timed inside this run with CUDA events on the
                   launching stream, next to the whole-step fraction of SURVEY 8(d);
 * ``cpu_baseline`` the CPU oracle (a port of the reference path) on the box's host cores, same config.
@@ -928,7 +930,12 @@ def main():
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-also", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--multi-extras", action="store_true",
+                    help="N > 1: also run config.variants / also on every rank (by default they are N = 1 lines: at "
+                         "N > 1 the run is the headline step, e2e and the roofline, i.e. what the scaling curve needs)")
     args = ap.parse_args()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not args.multi_extras:
+        args.no_variants = args.no_also = True
     if args.impl == "reference":
         run_reference(args)
     else:
