@@ -103,3 +103,31 @@ def test_traffic_json_entries_name_existing_sources():
         assert any(name.startswith(p) for p, _ in bench._SRC_OF), name
         assert all(len(e["src_hash"]) == 16 and e["dram_bytes"] > 0 for e in grids.values())
     assert bench.src_hash_of("tce_proj_kl_entropy_fwd_sigma_vec") != bench.src_hash_of("tce_prodmp_traj_fwd")
+
+
+def test_header_is_plain_c_and_links_against_the_library(lib, tmp_path):
+    """include/tce_b200.h is what a cgo / JNI / ctypes binding reads: it must compile as C99 and as C++, and a C program
+    that only knows the header must link against libtce_b200.so and get answers from the calls that need no GPU."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", HEADER], check=True)
+    gxx = shutil.which("g++")
+    if gxx:
+        subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-x", "c++", HEADER], check=True)
+    src = tmp_path / "demo.c"
+    src.write_text('#include <stdio.h>\n#include "tce_b200.h"\n'
+                   'int main(void) {\n'
+                   '  /* NULL pointers: rejected before any CUDA call */\n'
+                   '  int rc = tce_mvn_rsample(0, 0, 0, 0, 0, 0, 0, 4, 3, 0);\n'
+                   '  printf("%d %d %s\\n", tce_version(), rc, tce_strerror(rc));\n'
+                   '  return rc == TCE_ERR_INVALID_ARGUMENT ? 0 : 1;\n}\n')
+    libdir = os.path.join(ROOT, "tce_rl_b200")
+    exe = tmp_path / "demo"
+    subprocess.run([gcc, "-std=c99", "-I", os.path.dirname(HEADER), str(src), "-o", str(exe), "-L", libdir,
+                    "-l:libtce_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert int(out.stdout.split()[0]) >= 100
